@@ -1,0 +1,297 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes bindings of the CPU oracle (``libhemelb_oracle.so``, our
+restatement) and of ``_ref/libhemelb_ref*.so`` (the unmodified reference headers compiled by
+``oracle/Makefile``).  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+cpu_baseline / ``--impl reference`` legs may import this package; ``hemelb_b200`` never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KERNELS = {"LBGK": 0, "MRT": 1, "TRT": 2}
+WALLS = {"SBB": 0, "BFL": 1, "GZS": 2}
+IOLETS = {"NASH": 0, "LADD": 1}
+CACHE_BITS = {"density": 1, "velocity": 2, "wall_shear_stress": 4, "von_mises": 8, "shear_rate": 16,
+              "stress_tensor": 32, "traction": 64, "tangential_traction": 128}
+TABLE_DTYPES = {
+    "counts": np.int64, "neighbourIndices": np.int64, "wallMask": np.uint32, "ioletMask": np.uint32,
+    "siteType": np.int32, "ioletId": np.int32, "distanceToWall": np.float64, "wallNormal": np.float64,
+    "globalCoords": np.int64, "inputIndex": np.int64, "streamingIndices": np.int64,
+}
+
+
+def build(force: bool = False) -> None:
+    """Compile the oracle (and oracle/_ref when /root/reference is present)."""
+    if force:
+        subprocess.run(["make", "-C", HERE, "clean"], check=True, capture_output=True)
+    subprocess.run(["make", "-C", HERE, "all"], check=True, capture_output=True)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _d(a):
+    return _ptr(a, C.c_double)
+
+
+_oracle = None
+
+
+def oracle_lib():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(HERE, "libhemelb_oracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.hlbo_geometry_create.restype = C.c_void_p
+        L.hlbo_sim_create.restype = C.c_void_p
+        L.hlbo_domain_get.restype = C.c_int64
+        L.hlbo_sim_get_cache.restype = C.c_int64
+        L.hlbo_sim_f_size.restype = C.c_int64
+        L.hlbo_sim_get_time.restype = C.c_uint64
+        L.hlbo_tau.restype = C.c_double
+        L.hlbo_cosine_density.restype = C.c_double
+        _oracle = L
+    return _oracle
+
+
+_refs = {}
+
+
+def ref_lib(sse3: bool = False):
+    """The compiled reference, or None when oracle/_ref was not built/shipped."""
+    if sse3 not in _refs:
+        path = os.path.join(HERE, "_ref", "libhemelb_ref_sse3.so" if sse3 else "libhemelb_ref.so")
+        if not os.path.exists(path):
+            _refs[sse3] = None
+        else:
+            L = C.CDLL(path)
+            L.href_sim_create.restype = C.c_void_p
+            L.href_sim_get_cache.restype = C.c_int64
+            L.href_sim_f_size.restype = C.c_int64
+            L.href_tau.restype = C.c_double
+            L.href_sim_get_tau.restype = C.c_double
+            L.href_cosine_density.restype = C.c_double
+            _refs[sse3] = L
+    return _refs[sse3]
+
+
+def iolet_record(kind=0, normal=(0, 0, 1), position=(0, 0, 0), radius=1.0, max_speed=0.0,
+                 density_mean=1.0, density_amp=0.0, phase=0.0, period=1000.0, warmup=0.0,
+                 min_density=1.0):
+    """The 16-double iolet descriptor shared by the oracle, the reference driver and the C ABI."""
+    return np.array([kind, *normal, *position, radius, max_speed, density_mean, density_amp, phase,
+                     period, warmup, min_density, 0.0], np.float64)
+
+
+def _recs(lst):
+    if not lst:
+        return np.zeros((1, 16), np.float64), 0
+    return np.ascontiguousarray(np.stack(lst)), len(lst)
+
+
+# ------------------------------------------------------------------------------- pointwise
+def lattice(Q, lib=None):
+    c = np.zeros((Q, 3), np.int32)
+    w = np.zeros(Q)
+    inv = np.zeros(Q, np.int32)
+    if lib is None:
+        oracle_lib().hlbo_lattice(Q, _ptr(c, C.c_int), _d(w), _ptr(inv, C.c_int))
+    else:
+        lib.href_lattice(Q, _ptr(c, C.c_int), _d(w), _ptr(inv, C.c_int))
+    return c, w, inv
+
+
+def collide(Q, kernel, tau, f):
+    f = np.ascontiguousarray(f, np.float64)
+    fpost, feq, fneq, rmu = np.zeros(Q), np.zeros(Q), np.zeros(Q), np.zeros(7)
+    oracle_lib().hlbo_collide(Q, KERNELS[kernel], C.c_double(tau), _d(f), _d(fpost), _d(feq), _d(fneq), _d(rmu))
+    return dict(fpost=fpost, feq=feq, fneq=fneq, rho=rmu[0], m=rmu[1:4].copy(), u=rmu[4:7].copy())
+
+
+def ref_collide(lib, Q, kernel, dt, dx, rho, eta, f, rates=None):
+    f = np.ascontiguousarray(f, np.float64)
+    fpost, feq, fneq, rmu = np.zeros(Q), np.zeros(Q), np.zeros(Q), np.zeros(7)
+    r = None if rates is None else _d(np.ascontiguousarray(rates, np.float64))
+    rc = lib.href_collide(Q, KERNELS[kernel], C.c_double(dt), C.c_double(dx), C.c_double(rho),
+                          C.c_double(eta), _d(f), _d(fpost), _d(feq), _d(fneq), _d(rmu), r)
+    if rc:
+        raise ValueError("combination not buildable from the reference")
+    return dict(fpost=fpost, feq=feq, fneq=fneq, rho=rmu[0], m=rmu[1:4].copy(), u=rmu[4:7].copy())
+
+
+def stress_functions(Q, rho, tau, fneq, normal, lib=None):
+    out = np.zeros(18)
+    fneq = np.ascontiguousarray(fneq, np.float64)
+    normal = np.ascontiguousarray(normal, np.float64)
+    fn = oracle_lib().hlbo_stress_functions if lib is None else lib.href_stress_functions
+    fn(Q, C.c_double(rho), C.c_double(tau), _d(fneq), _d(normal), _d(out))
+    return dict(von_mises=out[0], wall_shear_stress=out[1], shear_rate=out[2],
+                stress_tensor=out[3:12].copy(), traction=out[12:15].copy(), tangential_traction=out[15:18].copy())
+
+
+# ------------------------------------------------------------------------------- tables
+class OracleDomains:
+    """Per-rank ``geometry::Domain`` tables built by the oracle from a Geometry + site->rank map."""
+
+    def __init__(self, geom, Q, rank_of_site=None, nranks=1):
+        L = oracle_lib()
+        self.Q, self.R = Q, nranks
+        rank = np.zeros(geom.n_sites, np.int32) if rank_of_site is None else np.ascontiguousarray(rank_of_site, np.int32)
+        bd = np.ascontiguousarray(geom.block_dims, np.int32)
+        coords = np.ascontiguousarray(geom.coords, np.int32)
+        self._keep = (bd, coords, rank)
+        self.h = C.c_void_p(L.hlbo_geometry_create(
+            Q, nranks, _ptr(bd, C.c_int), geom.block_size, C.c_int64(geom.n_sites), _ptr(coords, C.c_int32),
+            _ptr(rank, C.c_int32), C.c_int64(geom.bsite.size),
+            _ptr(np.ascontiguousarray(geom.bsite, np.int64), C.c_int64),
+            _ptr(np.ascontiguousarray(geom.btype, np.uint8), C.c_uint8),
+            _ptr(np.ascontiguousarray(geom.biolet, np.int32), C.c_int32),
+            _ptr(np.ascontiguousarray(geom.bdist, np.float32), C.c_float),
+            _ptr(np.ascontiguousarray(geom.bnavail, np.uint8), C.c_uint8),
+            _ptr(np.ascontiguousarray(geom.bnormal, np.float32), C.c_float)))
+
+    def tables(self, r=0):
+        L = oracle_lib()
+        out = {"N": int(L.hlbo_domain_get(self.h, r, b"N", None)),
+               "totalSharedFs": int(L.hlbo_domain_get(self.h, r, b"totalSharedFs", None)), "Q": self.Q}
+        for name, dt in TABLE_DTYPES.items():
+            n = L.hlbo_domain_get(self.h, r, name.encode(), None)
+            a = np.zeros(n, dt)
+            L.hlbo_domain_get(self.h, r, name.encode(), a.ctypes.data_as(C.c_void_p))
+            out[name] = a
+        n = L.hlbo_domain_get(self.h, r, b"procs", None)
+        p = np.zeros(3 * n, np.int64)
+        L.hlbo_domain_get(self.h, r, b"procs", p.ctypes.data_as(C.c_void_p))
+        out["procs"] = p.reshape(n, 3)
+        out["mid"] = out["counts"][:6].copy()
+        out["edge"] = out["counts"][6:].copy()
+        return out
+
+    def __del__(self):
+        try:
+            oracle_lib().hlbo_geometry_destroy(self.h)
+        except Exception:
+            pass
+
+
+class _SimCommon:
+    prefix = ""
+
+    def _fn(self, name):
+        return getattr(self.L, self.prefix + name)
+
+    def f_size(self, r=0):
+        return int(self._fn("sim_f_size")(self.h, r))
+
+    def set_f(self, f, r=0, which=0):
+        f = np.ascontiguousarray(f, np.float64)
+        assert f.size == self.f_size(r)
+        self._fn("sim_set_f")(self.h, r, which, _d(f))
+
+    def get_f(self, r=0, which=0):
+        f = np.zeros(self.f_size(r))
+        self._fn("sim_get_f")(self.h, r, which, _d(f))
+        return f
+
+    def set_time(self, t):
+        self._fn("sim_set_time")(self.h, C.c_uint64(t))
+
+    def set_cache_mask(self, mask):
+        self._fn("sim_set_cache_mask")(self.h, C.c_uint(mask))
+
+    def get_cache(self, name, r=0):
+        bit = CACHE_BITS[name]
+        n = self._fn("sim_get_cache")(self.h, r, bit, None) if self.prefix == "hlbo_" else None
+        if n is None:
+            per = {1: 1, 2: 3, 4: 1, 8: 1, 16: 1, 32: 9, 64: 3, 128: 3}[bit]
+            n = per * self.N[r]
+        out = np.zeros(n)
+        self._fn("sim_get_cache")(self.h, r, bit, _d(out))
+        return out
+
+    def stream_and_collide(self, slot, first, count, r=0):
+        self._fn("sim_stream_and_collide")(self.h, r, slot, C.c_int64(first), C.c_int64(count))
+
+    def post_step(self, slot, first, count, r=0):
+        self._fn("sim_post_step")(self.h, r, slot, C.c_int64(first), C.c_int64(count))
+
+    def step(self, n=1):
+        self._fn("sim_step")(self.h, n)
+
+
+class OracleSim(_SimCommon):
+    """The restated LBM phase loop over all emulated ranks of an OracleDomains."""
+    prefix = "hlbo_"
+
+    def __init__(self, domains, kernel="LBGK", wall="SBB", inlet="NASH", outlet="NASH", tau=0.8,
+                 inlets=(), outlets=()):
+        self.L = oracle_lib()
+        self.domains = domains
+        self.N = [int(self.L.hlbo_domain_get(domains.h, r, b"N", None)) for r in range(domains.R)]
+        ri, ni = _recs(list(inlets))
+        ro, no = _recs(list(outlets))
+        self.h = C.c_void_p(self.L.hlbo_sim_create(domains.h, KERNELS[kernel], WALLS[wall], IOLETS[inlet],
+                                                   IOLETS[outlet], C.c_double(tau), ni, _d(ri), no, _d(ro)))
+
+    def set_equilibrium(self, rho=1.0, m=(0.0, 0.0, 0.0)):
+        m = np.ascontiguousarray(m, np.float64)
+        self.L.hlbo_sim_set_equilibrium(self.h, C.c_double(rho), _d(m))
+
+    def __del__(self):
+        try:
+            self.L.hlbo_sim_destroy(self.h)
+        except Exception:
+            pass
+
+
+class RefSim(_SimCommon):
+    """The reference's own streamers/kernels (oracle/_ref) run over supplied tables."""
+    prefix = "href_"
+
+    def __init__(self, tables_per_rank, Q, kernel="LBGK", wall="SBB", inlet="NASH", outlet="NASH",
+                 dt=1e-4, dx=1e-4, rho=1000.0, eta=0.004, inlets=(), outlets=(), sse3=False):
+        self.L = ref_lib(sse3)
+        if self.L is None:
+            raise RuntimeError("oracle/_ref not built")
+        ri, ni = _recs(list(inlets))
+        ro, no = _recs(list(outlets))
+        R = len(tables_per_rank)
+        h = self.L.href_sim_create(Q, KERNELS[kernel], WALLS[wall], IOLETS[inlet], IOLETS[outlet],
+                                   C.c_double(dt), C.c_double(dx), C.c_double(rho), C.c_double(eta), R,
+                                   ni, _d(ri), no, _d(ro))
+        if not h:
+            raise ValueError("combination not buildable from the reference")
+        self.h = C.c_void_p(h)
+        self.N = []
+        for r, t in enumerate(tables_per_rank):
+            self.N.append(int(t["N"]))
+            procs = np.ascontiguousarray(t["procs"], np.int64).reshape(-1)
+            self.L.href_sim_set_domain(
+                self.h, r, C.c_int64(t["N"]), _ptr(np.ascontiguousarray(t["counts"], np.int64), C.c_int64),
+                _ptr(np.ascontiguousarray(t["neighbourIndices"], np.int64), C.c_int64),
+                _ptr(np.ascontiguousarray(t["wallMask"], np.uint32), C.c_uint32),
+                _ptr(np.ascontiguousarray(t["ioletMask"], np.uint32), C.c_uint32),
+                _ptr(np.ascontiguousarray(t["siteType"], np.int32), C.c_int32),
+                _ptr(np.ascontiguousarray(t["ioletId"], np.int32), C.c_int32),
+                _d(np.ascontiguousarray(t["distanceToWall"], np.float64)),
+                _d(np.ascontiguousarray(t["wallNormal"], np.float64)),
+                _ptr(np.ascontiguousarray(t["globalCoords"], np.int64), C.c_int64),
+                _ptr(np.ascontiguousarray(t["inputIndex"], np.int64), C.c_int64),
+                C.c_int64(t["totalSharedFs"]), int(t["procs"].shape[0]),
+                _ptr(procs if procs.size else np.zeros(3, np.int64), C.c_int64),
+                _ptr(np.ascontiguousarray(t["streamingIndices"], np.int64) if t["totalSharedFs"] else np.zeros(1, np.int64), C.c_int64))
+        self.L.href_sim_init(self.h)
+        self.tau = float(self.L.href_sim_get_tau(self.h))
+
+    def __del__(self):
+        try:
+            self.L.href_sim_destroy(self.h)
+        except Exception:
+            pass

@@ -1,0 +1,17 @@
+// Shadow header (oracle/_ref build only): the three members of lb::BoundaryValues the iolet
+// link streamers call (Code/lb/iolets/BoundaryValues.h:50-70, .cc:162-165).
+#pragma once
+#include <vector>
+#include "lb/iolets/InOutLet.h"
+#include "lb/SimulationState.h"
+namespace hemelb::lb {
+  class BoundaryValues {
+  public:
+    std::vector<InOutLet*> iolets;
+    SimulationState* state = nullptr;
+    LatticeDensity GetBoundaryDensity(int i) { return iolets[i]->GetDensity(state->Get0IndexedTimeStep()); }
+    InOutLet* GetLocalIolet(unsigned i) { return iolets[i]; }
+    unsigned GetLocalIoletCount() const { return iolets.size(); }
+    LatticeTimeStep GetTimeStep() const { return state->GetTimeStep(); }
+  };
+}
