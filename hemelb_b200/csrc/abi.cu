@@ -1,0 +1,1122 @@
+// C ABI of the B200 collide-and-stream engine (see include/hemelb_b200.h for the contract and
+// the reference interfaces each entry point replaces).
+//
+// Device layout per handle (one reference rank = one GPU):
+//   f[2]      : Q*stride + 1 + S doubles each.  Population d of site s at d*stride + s (SoA;
+//               stride = N rounded up to 64 so every plane is 512 B aligned), the reference's
+//               rubbish slot at Q*stride, the per-neighbour halo slices after it in the
+//               reference's own order (FieldData.cc:14-25, Domain.cc:404-419), so NCCL sends /
+//               receives straight out of / into the arrays with no pack step.
+//   nbr       : (Q-1) planes of stride uint32: internal target index of each push.
+//   boundary  : masks, iolet ids, float cut distances, normals, coordinates -- only for the
+//               wall / inlet / outlet typed sites (two contiguous id ranges), plane-major.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hemelb_b200.h"
+#include "kernels.cuh"
+
+namespace hlb {
+// per-(lattice, kernel) launchers, defined in cs_q*_*.cu
+#define HLB_DECL(Q, K) \
+  extern template void launch_collide_stream<Q, K>(int, int, const StepArgs&, const void*, int64_t, int64_t, void*);
+HLB_DECL(15, K_LBGK) HLB_DECL(15, K_MRT) HLB_DECL(15, K_TRT)
+HLB_DECL(19, K_LBGK) HLB_DECL(19, K_MRT) HLB_DECL(19, K_TRT)
+HLB_DECL(27, K_LBGK) HLB_DECL(27, K_TRT)
+#undef HLB_DECL
+}  // namespace hlb
+
+using namespace hlb;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string& m) {
+  g_err = m;
+  return 1;
+}
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                    \
+  } while (0)
+
+// ---------------------------------------------------------------- NCCL through dlopen
+typedef struct { char internal[128]; } NcclUniqueId;
+typedef void* NcclComm;
+struct Nccl {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool Load() {
+    if (lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) return false;
+#define SYM(f, n) f = (decltype(f))dlsym(lib, n)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return GetUniqueId && CommInitRank && Send && Recv && GroupStart && GroupEnd;
+  }
+} g_nccl;
+const int kNcclDouble = 8;  // ncclFloat64
+
+// ---------------------------------------------------------------- host-side iolet providers
+// InOutLetCosine::GetDensity, Code/lb/iolets/InOutLetCosine.cc:26-43
+struct IoletHost {
+  int kind;
+  double densityMean, densityAmp, phase, period, warmUpLength, minimumSimulationDensity;
+  double Density(uint64_t time_step) const {
+    if (kind == 1) return 1.0;  // InOutLetVelocity::GetDensity
+    const double PI = 3.14159265358979323846264338327950288;
+    const double w = 2.0 * PI / period;
+    const double target = densityMean + densityAmp * std::cos(w * time_step + phase);
+    if ((double)time_step >= warmUpLength) return target;
+    const double interpolationFactor = ((double)time_step) / ((double)warmUpLength);
+    return interpolationFactor * target + (1. - interpolationFactor) * minimumSimulationDensity;
+  }
+};
+
+struct Neighbour {
+  int rank;
+  int64_t count, first;  // first = reference index (N*Q + 1 + offset)
+};
+
+}  // namespace
+
+struct hlb_gpu_handle {
+  hlb_gpu_config cfg;
+  int Q = 0;
+  int64_t N = 0, stride = 0, S = 0, fLen = 0;
+  int64_t mid[6], edge[6], midTotal = 0, midBulk = 0, edgeBulk = 0, NB = 0, bStride = 0;
+  cudaStream_t compute = nullptr, comm = nullptr;
+  cudaEvent_t evEdge = nullptr, evComm = nullptr, evT0 = nullptr, evT1 = nullptr;
+  double* f[2] = {nullptr, nullptr};
+  int cur = 0;
+  uint32_t* nbr = nullptr;
+  uint32_t *wallMask = nullptr, *ioletMask = nullptr;
+  int32_t* ioletId = nullptr;
+  float* cutDist = nullptr;
+  double* wallNormal = nullptr;
+  int32_t* coords = nullptr;
+  int32_t* gzsNeighbour = nullptr;
+  uint32_t* streamIdx = nullptr;
+  IoletDev* ioletsDev[2] = {nullptr, nullptr};
+  double* ioletDensityDev[2] = {nullptr, nullptr};
+  double* ioletDensityPinned[2] = {nullptr, nullptr};
+  uint64_t pinnedCursor[2] = {0, 0};
+  std::vector<IoletHost> ioletsHost[2];
+  std::vector<Neighbour> neighbours;
+  double* cache[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint32_t cacheMask = 0;
+  uint64_t timeStep = 1;  // SimulationState.cc:16
+  std::vector<char> mrt;
+  LaunchFn launch = nullptr;
+  double omegaMinus = 0;
+  // host staging of the boundary tables until finalise
+  std::vector<uint32_t> hWall, hIolet;
+  std::vector<int32_t> hIoletId, hCoords;
+  std::vector<float> hCut;
+  std::vector<double> hNormal;
+  bool haveNbr = false, haveSiteData = false, haveCut = false, haveNormal = false, haveCoords = false,
+       haveNeighbours = false, haveStream = false, haveIolets[2] = {false, false}, finalised = false;
+  bool edgePending = false, commPosted = false;
+  NcclComm comm_nccl = nullptr;
+  void* staging = nullptr;
+  size_t stagingBytes = 0;
+  uint32_t* siteListDev = nullptr;
+  int64_t siteListCap = 0;
+  double* monitorDev = nullptr;
+  int64_t launches = 0;
+  bool profileBulk = false;
+  std::vector<cudaEvent_t> profEv;  // pairs around the mid-fluid (bulk) range launches
+  size_t profUsed = 0;
+  int64_t profSites = 0;
+};
+
+namespace {
+
+const int64_t kChunkSites = 1 << 20;
+const int kPinnedSlots = 256;
+
+int ensure_staging(hlb_gpu_t h, size_t bytes) {
+  if (h->stagingBytes >= bytes) return 0;
+  if (h->staging) cudaFree(h->staging);
+  h->staging = nullptr;
+  h->stagingBytes = 0;
+  CU(cudaMalloc(&h->staging, bytes));
+  h->stagingBytes = bytes;
+  return 0;
+}
+
+// boundary ordinal of a site, or -1 for bulk-typed sites
+inline int64_t host_bidx(const hlb_gpu_handle* h, int64_t site) {
+  if (site < h->midBulk) return -1;
+  if (site < h->midTotal) return site - h->midBulk;
+  if (site < h->midTotal + h->edgeBulk) return -1;
+  return site - h->midTotal - h->edgeBulk + (h->midTotal - h->midBulk);
+}
+
+__global__ void convert_nbr_kernel(const int64_t* __restrict__ aos, uint32_t* __restrict__ nbr, int64_t first,
+                                   int64_t n, int Q, int64_t N, int64_t stride, int* bad) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n * Q) return;
+  const int d = (int)(tid / n);
+  const int64_t s = tid % n;
+  const int64_t v = aos[s * Q + d];
+  const int64_t site = first + s;
+  if (d == 0) {
+    if (v != site * Q) atomicExch(bad, 1);  // Domain.cc:449: direction 0 streams to itself
+    return;
+  }
+  int64_t internal;
+  if (v < 0 || v > N * Q + ((int64_t)1 << 40)) {
+    atomicExch(bad, 2);
+    return;
+  }
+  if (v < N * Q) internal = (v % Q) * stride + v / Q;
+  else internal = v - N * Q + (int64_t)Q * stride;
+  nbr[(int64_t)(d - 1) * stride + site] = (uint32_t)internal;
+}
+
+__global__ void nbr_to_ref_kernel(const uint32_t* __restrict__ nbr, int64_t* __restrict__ aos, int64_t first, int64_t n,
+                                  int Q, int64_t N, int64_t stride) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n * Q) return;
+  const int d = (int)(tid / n);
+  const int64_t s = tid % n;
+  const int64_t site = first + s;
+  int64_t v;
+  if (d == 0) v = site * Q;
+  else {
+    const int64_t in = nbr[(int64_t)(d - 1) * stride + site];
+    if (in < (int64_t)Q * stride) v = (in % stride) * Q + in / stride;
+    else v = in - (int64_t)Q * stride + N * Q;
+  }
+  aos[s * Q + d] = v;
+}
+
+__global__ void aos_to_soa_kernel(const double* __restrict__ aos, double* __restrict__ f, int64_t first, int64_t n,
+                                  int Q, int64_t stride) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n * Q) return;
+  const int d = (int)(tid / n);
+  const int64_t s = tid % n;
+  f[(int64_t)d * stride + first + s] = aos[s * Q + d];
+}
+__global__ void soa_to_aos_kernel(const double* __restrict__ f, double* __restrict__ aos, int64_t first, int64_t n,
+                                  int Q, int64_t stride) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n * Q) return;
+  const int d = (int)(tid / n);
+  const int64_t s = tid % n;
+  aos[s * Q + d] = f[(int64_t)d * stride + first + s];
+}
+__global__ void fill_planes_kernel(double* __restrict__ f0, double* __restrict__ f1, int64_t N, int64_t stride, int Q,
+                                   const double* __restrict__ feq) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= N * Q) return;
+  const int d = (int)(tid / N);
+  const int64_t s = tid % N;
+  f0[(int64_t)d * stride + s] = feq[d];
+  f1[(int64_t)d * stride + s] = feq[d];
+}
+// FieldData::CopyReceived, FieldData.cc:41-48
+__global__ void copy_received_kernel(double* __restrict__ fNew, const double* __restrict__ fOldShared,
+                                     const uint32_t* __restrict__ streamIdx, int64_t S) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= S) return;
+  fNew[streamIdx[tid]] = fOldShared[tid];
+}
+__global__ void gzs_neighbour_kernel(const uint32_t* __restrict__ nbr, int32_t* __restrict__ out, int Q, int64_t stride,
+                                     int64_t bStride, int64_t NB, int64_t midBulk, int64_t midTotal, int64_t edgeBulk) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= NB * (Q - 1)) return;
+  const int d = (int)(tid / NB) + 1;
+  const int64_t b = tid % NB;
+  const int64_t nbMid = midTotal - midBulk;
+  const int64_t site = b < nbMid ? b + midBulk : b - nbMid + midTotal + edgeBulk;
+  const int64_t in = nbr[(int64_t)(d - 1) * stride + site];
+  int32_t v = INT32_MIN;  // not a local fluid neighbour (rubbish / remote)
+  if (in < (int64_t)Q * stride) v = (int32_t)(in - (int64_t)d * stride);
+  out[(int64_t)(d - 1) * bStride + b] = v;
+}
+
+// {min f_old, min rho, max rho, max |u|^2} -- block reduce then atomics on ordered-int encodings
+__device__ __forceinline__ unsigned long long enc(double x) {
+  unsigned long long u = __double_as_longlong(x);
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dec(unsigned long long u) {
+  u = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+  return __longlong_as_double(u);
+}
+__global__ void monitor_kernel(const double* __restrict__ f, int64_t N, int64_t stride, int Q,
+                               unsigned long long* __restrict__ out) {
+  double fmin = 1e300, rmin = 1e300, rmax = -1e300, umax = 0.0;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
+    double rho = 0, mx = 0, my = 0, mz = 0;
+    for (int d = 0; d < Q; ++d) {
+      const double v = f[(int64_t)d * stride + s];
+      fmin = fmin < v ? fmin : v;
+      rho += v;
+      int cx, cy, cz;
+      if (Q == 15) { cx = Lat<15>::cx(d); cy = Lat<15>::cy(d); cz = Lat<15>::cz(d); }
+      else { cx = Lat<27>::cx(d); cy = Lat<27>::cy(d); cz = Lat<27>::cz(d); }
+      mx += cx * v;
+      my += cy * v;
+      mz += cz * v;
+    }
+    rmin = rmin < rho ? rmin : rho;
+    rmax = rmax > rho ? rmax : rho;
+    const double u2 = (mx * mx + my * my + mz * mz) / (rho * rho);
+    umax = umax > u2 ? umax : u2;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    fmin = fmin < __shfl_xor_sync(0xffffffffu, fmin, o) ? fmin : __shfl_xor_sync(0xffffffffu, fmin, o);
+    rmin = rmin < __shfl_xor_sync(0xffffffffu, rmin, o) ? rmin : __shfl_xor_sync(0xffffffffu, rmin, o);
+    rmax = rmax > __shfl_xor_sync(0xffffffffu, rmax, o) ? rmax : __shfl_xor_sync(0xffffffffu, rmax, o);
+    umax = umax > __shfl_xor_sync(0xffffffffu, umax, o) ? umax : __shfl_xor_sync(0xffffffffu, umax, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(out + 0, enc(fmin));
+    atomicMin(out + 1, enc(rmin));
+    atomicMax(out + 2, enc(rmax));
+    atomicMax(out + 3, enc(umax));
+  }
+}
+__global__ void monitor_decode_kernel(unsigned long long* io) {
+  if (threadIdx.x < 4) {
+    double v = dec(io[threadIdx.x]);
+    if (threadIdx.x == 3) v = sqrt(v);
+    ((double*)io)[4 + threadIdx.x] = v;
+  }
+}
+
+inline unsigned blocks_for(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+StepArgs make_args(hlb_gpu_t h, int which /*0 inlet BoundaryValues, 1 outlet*/) {
+  StepArgs A;
+  std::memset(&A, 0, sizeof(A));
+  A.fOld = h->f[h->cur];
+  A.fNew = h->f[h->cur ^ 1];
+  A.nbr = h->nbr;
+  A.stride = h->stride;
+  A.wallMask = h->wallMask;
+  A.ioletMask = h->ioletMask;
+  A.ioletId = h->ioletId;
+  A.cutDist = h->cutDist;
+  A.wallNormal = h->wallNormal;
+  A.coords = h->coords;
+  A.bStride = h->bStride;
+  A.midBulk = h->midBulk;
+  A.midTotal = h->midTotal;
+  A.edgeBulk = h->edgeBulk;
+  A.gzsNeighbour = h->gzsNeighbour;
+  A.gzsGhost = nullptr;
+  A.ghostStride = 0;
+  A.iolets = h->ioletsDev[which];
+  A.ioletDensity = h->ioletDensityDev[which];
+  A.timeStep = h->timeStep;
+  A.tau = h->cfg.tau;
+  A.omega = -1.0 / h->cfg.tau;  // LbmParameters.h:36
+  A.stressParameter = (1.0 - 1.0 / (2.0 * h->cfg.tau)) / std::sqrt(2.0);
+  A.omegaMinus = h->omegaMinus;
+  A.cacheMask = h->cacheMask;
+  A.cDensity = h->cache[0];
+  A.cVelocity = h->cache[1];
+  A.cWss = h->cache[2];
+  A.cVonMises = h->cache[3];
+  A.cShearRate = h->cache[4];
+  A.cStress = h->cache[5];
+  A.cTraction = h->cache[6];
+  A.cTangTraction = h->cache[7];
+  A.refSiteOf = nullptr;
+  A.siteList = nullptr;
+  return A;
+}
+
+int ensure_caches(hlb_gpu_t h, uint32_t mask) {
+  static const int per[8] = {1, 3, 1, 1, 1, 9, 3, 3};
+  for (int i = 0; i < 8; ++i)
+    if ((mask >> i) & 1u)
+      if (!h->cache[i]) {
+        CU(cudaMalloc(&h->cache[i], sizeof(double) * per[i] * std::max<int64_t>(h->N, 1)));
+        CU(cudaMemset(h->cache[i], 0, sizeof(double) * per[i] * std::max<int64_t>(h->N, 1)));
+      }
+  return 0;
+}
+
+template <int Q>
+void fill_mrt(hlb_gpu_t h) {
+  h->mrt.assign(sizeof(MrtArgs<Q>), 0);
+  MrtArgs<Q>& M = *reinterpret_cast<MrtArgs<Q>*>(h->mrt.data());
+  if constexpr (mrt_k<Q>() > 0) {
+    const double tau = h->cfg.tau;
+    double S[15];
+    if (Q == 15) {  // DHumieresD3Q15MRTBasis.cc:10-25
+      const double s[11] = {1.6, 1.2, 1.6, 1.6, 1.6, 1.0 / tau, 1.0 / tau, 1.0 / tau, 1.0 / tau, 1.0 / tau, 1.2};
+      for (int k = 0; k < 11; ++k) S[k] = s[k];
+    } else {  // DHumieresD3Q19MRTBasis.cc:11-37
+      const double s[15] = {1.19, 1.4, 1.2, 1.2, 1.2, 1.0 / tau, 1.4, 1.0 / tau, 1.4, 1.0 / tau,
+                            1.0 / tau, 1.0 / tau, 1.98, 1.98, 1.98};
+      for (int k = 0; k < 15; ++k) S[k] = s[k];
+    }
+    for (int k = 0; k < mrt_k<Q>(); ++k)
+      for (int d = 0; d < Q; ++d) M.SMn[k][d] = S[k] * mrt_mn<Q>(k, d);
+  }
+}
+
+// site range of a streamer slot -> is it a whole range (fast path) or an arbitrary sub-range
+int launch_range(hlb_gpu_t h, int slot, int64_t first, int64_t count, bool post) {
+  if (!h->finalised) return fail("handle not finalised");
+  if (slot < 0 || slot > 5) return fail("streamer slot out of range");
+  if (count <= 0) return 0;
+  if (first < 0 || first + count > h->N) return fail("site range outside the local fluid sites");
+  const bool isBoundarySlot = slot != 0;
+  if (isBoundarySlot) {
+    // boundary streamers read per-site tables that only exist for boundary-typed sites
+    if (host_bidx(h, first) < 0 || host_bidx(h, first + count - 1) < 0 ||
+        (first < h->midTotal && first + count > h->midTotal))
+      return fail("boundary streamer called on bulk-typed sites");
+  }
+  const bool isInletSlot = (slot == 2 || slot == 4);
+  StepArgs A = make_args(h, isInletSlot ? 0 : 1);
+  const bool canWall = (slot == 1 || slot == 4 || slot == 5);
+  const bool canIolet = slot >= 2;
+  if (post) {
+    // StreamerTypeFactory::PostStep: only the BFL wall link does anything
+    if (!canWall || h->cfg.wall != HLB_WALL_BFL) return 0;
+    switch (h->Q) {
+      case 15: bfl_post_step_kernel<15><<<blocks_for(count), 256, 0, h->compute>>>(A, first, count); break;
+      case 19: bfl_post_step_kernel<19><<<blocks_for(count), 256, 0, h->compute>>>(A, first, count); break;
+      case 27: bfl_post_step_kernel<27><<<blocks_for(count), 256, 0, h->compute>>>(A, first, count); break;
+    }
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+  }
+  const int wall = canWall ? h->cfg.wall : W_NONE;
+  const int iolet = canIolet ? (isInletSlot ? h->cfg.inlet : h->cfg.outlet) : I_NONE;
+  const bool prof = h->profileBulk && slot == 0;
+  if (prof) {
+    while (h->profEv.size() < h->profUsed + 2) {
+      cudaEvent_t e;
+      CU(cudaEventCreate(&e));
+      h->profEv.push_back(e);
+    }
+    CU(cudaEventRecord(h->profEv[h->profUsed], h->compute));
+  }
+  h->launch(wall, iolet, A, h->mrt.data(), first, count, h->compute);
+  if (prof) {
+    CU(cudaEventRecord(h->profEv[h->profUsed + 1], h->compute));
+    h->profUsed += 2;
+    h->profSites += count;
+  }
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int post_comms(hlb_gpu_t h) {
+  // FieldData::SendAndReceive (FieldData.cc:27-39): per neighbour, receive into the slice of
+  // f_old and send the same slice of f_new, on the comm stream after the edge ranges finished.
+  if (h->neighbours.empty()) return 0;
+  if (!h->comm_nccl) return fail("neighbours present but hlb_gpu_comm_init was not called");
+  CU(cudaEventRecord(h->evEdge, h->compute));
+  CU(cudaStreamWaitEvent(h->comm, h->evEdge, 0));
+  double* fOld = h->f[h->cur];
+  double* fNew = h->f[h->cur ^ 1];
+  const int64_t base = (int64_t)h->Q * h->stride - h->N * h->Q;  // reference index -> internal
+  int rc = g_nccl.GroupStart();
+  for (auto& nb : h->neighbours) {
+    if (rc) break;
+    rc = g_nccl.Recv(fOld + nb.first + base, (size_t)nb.count, kNcclDouble, nb.rank, h->comm_nccl, h->comm);
+    if (rc) break;
+    rc = g_nccl.Send(fNew + nb.first + base, (size_t)nb.count, kNcclDouble, nb.rank, h->comm_nccl, h->comm);
+  }
+  int rc2 = g_nccl.GroupEnd();
+  if (rc || rc2) return fail(std::string("NCCL send/recv: ") + g_nccl.GetErrorString(rc ? rc : rc2));
+  CU(cudaEventRecord(h->evComm, h->comm));
+  h->commPosted = true;
+  return 0;
+}
+
+int upload_densities(hlb_gpu_t h, int which, const double* d) {
+  const int n = which ? h->cfg.n_outlets : h->cfg.n_inlets;
+  if (n == 0) return 0;
+  if (!d) return fail("iolet densities missing");
+  // ring of pinned slots: a slot is reused only after the stream drained (every kPinnedSlots steps)
+  const int slot = (int)(h->pinnedCursor[which]++ % kPinnedSlots);
+  if (slot == 0 && h->pinnedCursor[which] > 1) CU(cudaStreamSynchronize(h->compute));
+  double* src = h->ioletDensityPinned[which] + (size_t)slot * n;
+  std::memcpy(src, d, sizeof(double) * n);
+  CU(cudaMemcpyAsync(h->ioletDensityDev[which], src, sizeof(double) * n, cudaMemcpyHostToDevice, h->compute));
+  return 0;
+}
+
+int one_step(hlb_gpu_t h) {
+  // BoundaryValues::GetBoundaryDensity -> iolet->GetDensity(Get0IndexedTimeStep())
+  for (int w = 0; w < 2; ++w) {
+    const int n = w ? h->cfg.n_outlets : h->cfg.n_inlets;
+    if (!n) continue;
+    std::vector<double> dens(n);
+    for (int i = 0; i < n; ++i) dens[i] = h->ioletsHost[w][i].Density(h->timeStep - 1);
+    if (upload_densities(h, w, dens.data())) return 1;
+  }
+  int64_t off = h->midTotal;
+  for (int t = 0; t < 6; ++t) {  // LBM::PreSend, lb.hpp:176-212
+    if (launch_range(h, t, off, h->edge[t], false)) return 1;
+    off += h->edge[t];
+  }
+  if (post_comms(h)) return 1;  // RequestComms + Net::Receive/Send
+  off = 0;
+  for (int t = 0; t < 6; ++t) {  // LBM::PreReceive, lb.hpp:215-251
+    if (launch_range(h, t, off, h->mid[t], false)) return 1;
+    off += h->mid[t];
+  }
+  if (hlb_gpu_copy_received(h)) return 1;  // LBM::PostReceive, lb.hpp:254-309
+  off = h->midTotal;
+  for (int t = 0; t < 6; ++t) {
+    if (launch_range(h, t, off, h->edge[t], true)) return 1;
+    off += h->edge[t];
+  }
+  off = 0;
+  for (int t = 0; t < 6; ++t) {
+    if (launch_range(h, t, off, h->mid[t], true)) return 1;
+    off += h->mid[t];
+  }
+  h->cur ^= 1;    // FieldData::SwapOldAndNew
+  h->timeStep++;  // SimulationState::Increment
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hlb_gpu_last_error(void) { return g_err.c_str(); }
+
+int hlb_gpu_device_count(int* count) {
+  CU(cudaGetDeviceCount(count));
+  return 0;
+}
+
+int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
+  if (!cfg || !out) return fail("null argument");
+  const int Q = cfg->lattice;
+  if (Q != 15 && Q != 19 && Q != 27) return fail("lattice must be 15, 19 or 27");
+  if (cfg->kernel < 0 || cfg->kernel > 2) return fail("unknown kernel");
+  if (cfg->kernel == HLB_KERNEL_MRT && Q == 27)
+    return fail("No MRT basis for D3Q27 (Code/lb/Kernels.h:32-39)");
+  if (cfg->wall < 0 || cfg->wall > 2) return fail("unknown wall boundary");
+  if (cfg->inlet < 0 || cfg->inlet > 1 || cfg->outlet < 0 || cfg->outlet > 1) return fail("unknown iolet boundary");
+  if (!(cfg->tau > 0.5)) return fail("tau must exceed 0.5");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device: the collide-and-stream engine has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("CUDA device ordinal out of range");
+  CU(cudaSetDevice(cfg->device));
+  hlb_gpu_handle* h = new hlb_gpu_handle();
+  h->cfg = *cfg;
+  h->Q = Q;
+  h->N = cfg->n_sites;
+  h->S = cfg->total_shared_fs;
+  int64_t tot = 0;
+  h->midTotal = 0;
+  for (int t = 0; t < 6; ++t) {
+    h->mid[t] = cfg->mid_count[t];
+    h->edge[t] = cfg->edge_count[t];
+    if (h->mid[t] < 0 || h->edge[t] < 0) { delete h; return fail("negative collision count"); }
+    h->midTotal += h->mid[t];
+    tot += h->mid[t] + h->edge[t];
+  }
+  if (tot != h->N) { delete h; return fail("collision counts do not sum to n_sites"); }
+  h->midBulk = h->mid[0];
+  h->edgeBulk = h->edge[0];
+  h->NB = h->N - h->midBulk - h->edgeBulk;
+  h->bStride = ((h->NB + 63) / 64) * 64;
+  if (h->bStride == 0) h->bStride = 64;
+  h->stride = ((h->N + 63) / 64) * 64;
+  if (h->stride == 0) h->stride = 64;
+  h->fLen = (int64_t)Q * h->stride + 1 + h->S;
+  if (h->fLen >= ((int64_t)1 << 32)) { delete h; return fail("too many sites for 32-bit streaming indices on one GPU"); }
+  CU(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&h->comm, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&h->evEdge, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&h->evComm, cudaEventDisableTiming));
+  CU(cudaEventCreate(&h->evT0));
+  CU(cudaEventCreate(&h->evT1));
+  for (int i = 0; i < 2; ++i) {
+    CU(cudaMalloc(&h->f[i], sizeof(double) * h->fLen));
+    CU(cudaMemset(h->f[i], 0, sizeof(double) * h->fLen));
+  }
+  CU(cudaMalloc(&h->nbr, sizeof(uint32_t) * (Q - 1) * h->stride));
+  CU(cudaMemset(h->nbr, 0xff, sizeof(uint32_t) * (Q - 1) * h->stride));
+  CU(cudaMalloc(&h->wallMask, sizeof(uint32_t) * h->bStride));
+  CU(cudaMalloc(&h->ioletMask, sizeof(uint32_t) * h->bStride));
+  CU(cudaMalloc(&h->ioletId, sizeof(int32_t) * h->bStride));
+  CU(cudaMalloc(&h->cutDist, sizeof(float) * (Q - 1) * h->bStride));
+  CU(cudaMalloc(&h->wallNormal, sizeof(double) * 3 * h->bStride));
+  CU(cudaMalloc(&h->coords, sizeof(int32_t) * 3 * h->bStride));
+  CU(cudaMalloc(&h->streamIdx, sizeof(uint32_t) * std::max<int64_t>(h->S, 1)));
+  CU(cudaMalloc(&h->monitorDev, 64));
+  for (int w = 0; w < 2; ++w) {
+    const int n = std::max(1, w ? cfg->n_outlets : cfg->n_inlets);
+    CU(cudaMalloc(&h->ioletsDev[w], sizeof(IoletDev) * n));
+    CU(cudaMalloc(&h->ioletDensityDev[w], sizeof(double) * n));
+    CU(cudaMallocHost(&h->ioletDensityPinned[w], sizeof(double) * n * 256));
+  }
+  h->hWall.assign(h->bStride, 0);
+  h->hIolet.assign(h->bStride, 0);
+  h->hIoletId.assign(h->bStride, -1);
+  h->hCut.assign((size_t)(Q - 1) * h->bStride, -1.0f);
+  h->hNormal.assign((size_t)3 * h->bStride, 0.0);
+  h->hCoords.assign((size_t)3 * h->bStride, 0);
+  h->omegaMinus = -1.0 / (0.5 + (3.0 / 16.0) / (cfg->tau - 0.5));  // TRT.h:100-107
+#define HLB_PICK(QQ, KK, KE)                                      \
+  if (Q == QQ && cfg->kernel == KK) {                             \
+    h->launch = &launch_collide_stream<QQ, KE>;                   \
+    fill_mrt<QQ>(h);                                              \
+  }
+  HLB_PICK(15, 0, K_LBGK) HLB_PICK(15, 1, K_MRT) HLB_PICK(15, 2, K_TRT)
+  HLB_PICK(19, 0, K_LBGK) HLB_PICK(19, 1, K_MRT) HLB_PICK(19, 2, K_TRT)
+  HLB_PICK(27, 0, K_LBGK) HLB_PICK(27, 2, K_TRT)
+#undef HLB_PICK
+  if (cfg->n_neighbours == 0) h->haveNeighbours = true;
+  if (h->S == 0) h->haveStream = true;
+  if (cfg->n_inlets == 0) h->haveIolets[0] = true;
+  if (cfg->n_outlets == 0) h->haveIolets[1] = true;
+  *out = h;
+  return 0;
+}
+
+int hlb_gpu_destroy(hlb_gpu_t h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  if (h->comm_nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm_nccl);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(h->f[i]);
+    cudaFree(h->ioletsDev[i]);
+    cudaFree(h->ioletDensityDev[i]);
+    cudaFreeHost(h->ioletDensityPinned[i]);
+  }
+  for (int i = 0; i < 8; ++i) cudaFree(h->cache[i]);
+  cudaFree(h->nbr);
+  cudaFree(h->wallMask);
+  cudaFree(h->ioletMask);
+  cudaFree(h->ioletId);
+  cudaFree(h->cutDist);
+  cudaFree(h->wallNormal);
+  cudaFree(h->coords);
+  cudaFree(h->gzsNeighbour);
+  cudaFree(h->streamIdx);
+  cudaFree(h->staging);
+  cudaFree(h->siteListDev);
+  cudaFree(h->monitorDev);
+  cudaEventDestroy(h->evEdge);
+  cudaEventDestroy(h->evComm);
+  cudaEventDestroy(h->evT0);
+  cudaEventDestroy(h->evT1);
+  cudaStreamDestroy(h->compute);
+  cudaStreamDestroy(h->comm);
+  delete h;
+  return 0;
+}
+
+int hlb_gpu_set_neighbour_indices(hlb_gpu_t h, int64_t first, int64_t n, const int64_t* idx) {
+  if (!h || !idx) return fail("null argument");
+  if (first < 0 || n < 0 || first + n > h->N) return fail("site range outside the local fluid sites");
+  CU(cudaSetDevice(h->cfg.device));
+  const int Q = h->Q;
+  if (ensure_staging(h, sizeof(int64_t) * kChunkSites * Q + 16)) return 1;
+  int* bad = (int*)((char*)h->staging + sizeof(int64_t) * kChunkSites * Q);
+  CU(cudaMemset(bad, 0, sizeof(int)));
+  for (int64_t s0 = 0; s0 < n; s0 += kChunkSites) {
+    const int64_t m = std::min(kChunkSites, n - s0);
+    CU(cudaMemcpy(h->staging, idx + s0 * Q, sizeof(int64_t) * m * Q, cudaMemcpyHostToDevice));
+    convert_nbr_kernel<<<blocks_for(m * Q), 256>>>((const int64_t*)h->staging, h->nbr, first + s0, m, Q, h->N,
+                                                   h->stride, bad);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+  }
+  int hb = 0;
+  CU(cudaMemcpy(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost));
+  if (hb == 1) return fail("neighbourIndices: direction 0 must stream to the site itself");
+  if (hb) return fail("neighbourIndices: value outside the distribution array");
+  h->haveNbr = true;
+  return 0;
+}
+
+int hlb_gpu_get_neighbour_indices(hlb_gpu_t h, int64_t* idx) {
+  if (!h || !idx) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  const int Q = h->Q;
+  if (ensure_staging(h, sizeof(int64_t) * kChunkSites * Q + 16)) return 1;
+  for (int64_t s0 = 0; s0 < h->N; s0 += kChunkSites) {
+    const int64_t m = std::min(kChunkSites, h->N - s0);
+    nbr_to_ref_kernel<<<blocks_for(m * Q), 256>>>(h->nbr, (int64_t*)h->staging, s0, m, Q, h->N, h->stride);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(idx + s0 * Q, h->staging, sizeof(int64_t) * m * Q, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+int hlb_gpu_set_site_data(hlb_gpu_t h, int64_t first, int64_t n, const uint32_t* wall, const uint32_t* iolet,
+                          const int32_t* ioletId) {
+  if (!h || !wall || !iolet || !ioletId) return fail("null argument");
+  if (first < 0 || n < 0 || first + n > h->N) return fail("site range outside the local fluid sites");
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t b = host_bidx(h, first + i);
+    if (b < 0) {
+      if (wall[i] || iolet[i]) return fail("site data: a bulk-typed site has cut links");
+      continue;
+    }
+    h->hWall[b] = wall[i];
+    h->hIolet[b] = iolet[i];
+    h->hIoletId[b] = ioletId[i];
+  }
+  h->haveSiteData = true;
+  return 0;
+}
+
+int hlb_gpu_set_wall_distances(hlb_gpu_t h, int64_t first, int64_t n, const double* dist) {
+  if (!h || !dist) return fail("null argument");
+  if (first < 0 || n < 0 || first + n > h->N) return fail("site range outside the local fluid sites");
+  const int Q = h->Q;
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t b = host_bidx(h, first + i);
+    if (b < 0) continue;
+    for (int d = 1; d < Q; ++d) {
+      const double v = dist[i * (Q - 1) + d - 1];
+      const float fv = (float)v;
+      // cut distances originate as float32 in the .gmy (GeometrySiteLink.h:29); keep them so
+      if ((double)fv != v) return fail("wall distance is not float32-representable");
+      h->hCut[(size_t)(d - 1) * h->bStride + b] = fv;
+    }
+  }
+  h->haveCut = true;
+  return 0;
+}
+
+int hlb_gpu_set_wall_normals(hlb_gpu_t h, int64_t first, int64_t n, const double* normals) {
+  if (!h || !normals) return fail("null argument");
+  if (first < 0 || n < 0 || first + n > h->N) return fail("site range outside the local fluid sites");
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t b = host_bidx(h, first + i);
+    if (b < 0) continue;
+    for (int k = 0; k < 3; ++k) h->hNormal[(size_t)k * h->bStride + b] = normals[3 * i + k];
+  }
+  h->haveNormal = true;
+  return 0;
+}
+
+int hlb_gpu_set_site_coords(hlb_gpu_t h, int64_t first, int64_t n, const int64_t* coords) {
+  if (!h || !coords) return fail("null argument");
+  if (first < 0 || n < 0 || first + n > h->N) return fail("site range outside the local fluid sites");
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t b = host_bidx(h, first + i);
+    if (b < 0) continue;
+    for (int k = 0; k < 3; ++k) h->hCoords[(size_t)k * h->bStride + b] = (int32_t)coords[3 * i + k];
+  }
+  h->haveCoords = true;
+  return 0;
+}
+
+int hlb_gpu_set_neighbours(hlb_gpu_t h, const int* rank, const int64_t* count, const int64_t* first) {
+  if (!h) return fail("null argument");
+  h->neighbours.clear();
+  int64_t expect = h->N * h->Q + 1, total = 0;
+  for (int i = 0; i < h->cfg.n_neighbours; ++i) {
+    if (first[i] != expect) return fail("FirstSharedDistribution is not the running prefix (Domain.cc:412-419)");
+    if (rank[i] < 0 || rank[i] >= h->cfg.nranks || rank[i] == h->cfg.rank) return fail("bad neighbour rank");
+    h->neighbours.push_back({rank[i], count[i], first[i]});
+    expect += count[i];
+    total += count[i];
+  }
+  if (total != h->S) return fail("SharedDistributionCounts do not sum to totalSharedFs");
+  h->haveNeighbours = true;
+  return 0;
+}
+
+int hlb_gpu_set_streaming_indices(hlb_gpu_t h, const int64_t* idx) {
+  if (!h || (!idx && h->S)) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  std::vector<uint32_t> v(h->S);
+  for (int64_t i = 0; i < h->S; ++i) {
+    if (idx[i] < 0 || idx[i] >= h->N * h->Q) return fail("streamingIndicesForReceivedDistributions out of range");
+    v[i] = (uint32_t)((idx[i] % h->Q) * h->stride + idx[i] / h->Q);
+  }
+  if (h->S) CU(cudaMemcpy(h->streamIdx, v.data(), sizeof(uint32_t) * h->S, cudaMemcpyHostToDevice));
+  h->haveStream = true;
+  return 0;
+}
+
+int hlb_gpu_set_iolets(hlb_gpu_t h, int which, int n, const double* rec) {
+  if (!h || which < 0 || which > 1) return fail("bad argument");
+  if (n != (which ? h->cfg.n_outlets : h->cfg.n_inlets)) return fail("iolet count differs from the config");
+  CU(cudaSetDevice(h->cfg.device));
+  std::vector<IoletDev> dev(n);
+  h->ioletsHost[which].resize(n);
+  for (int i = 0; i < n; ++i) {
+    const double* r = rec + HLB_IOLET_RECORD_DOUBLES * i;
+    IoletDev& d = dev[i];
+    std::memset(&d, 0, sizeof(d));
+    d.kind = (int)r[0];
+    const double mag = std::sqrt(r[1] * r[1] + r[2] * r[2] + r[3] * r[3]);  // InOutLet.h:160-163
+    if (!(mag > 0)) return fail("iolet normal has zero length");
+    for (int k = 0; k < 3; ++k) {
+      d.normal[k] = r[1 + k] / mag;
+      d.position[k] = r[4 + k];
+    }
+    d.radius = r[7];
+    d.maxSpeed = r[8];
+    d.warmUpLength = r[13];
+    IoletHost& hh = h->ioletsHost[which][i];
+    hh.kind = d.kind;
+    hh.densityMean = r[9];
+    hh.densityAmp = r[10];
+    hh.phase = r[11];
+    hh.period = r[12];
+    hh.warmUpLength = r[13];
+    hh.minimumSimulationDensity = r[14];
+  }
+  if (n) CU(cudaMemcpy(h->ioletsDev[which], dev.data(), sizeof(IoletDev) * n, cudaMemcpyHostToDevice));
+  h->haveIolets[which] = true;
+  return 0;
+}
+
+int hlb_gpu_set_gzs_remote(hlb_gpu_t, int64_t n, const int64_t*, const int32_t*, const int32_t*, const int64_t*) {
+  if (n == 0) return 0;
+  return fail("GZS extrapolation from sites on another rank is not implemented yet");
+}
+
+int hlb_gpu_finalise(hlb_gpu_t h) {
+  if (!h) return fail("null argument");
+  if (!h->haveNbr && h->N) return fail("neighbourIndices not set");
+  if (h->NB && !h->haveSiteData) return fail("site data not set");
+  if (h->NB && !h->haveCut && h->cfg.wall != HLB_WALL_SIMPLEBOUNCEBACK) return fail("wall distances not set");
+  if (!h->haveNeighbours) return fail("neighbouring processors not set");
+  if (!h->haveStream) return fail("streaming indices for received distributions not set");
+  if (!h->haveIolets[0] || !h->haveIolets[1]) return fail("iolets not set");
+  CU(cudaSetDevice(h->cfg.device));
+  const int Q = h->Q;
+  for (int64_t b = 0; b < h->NB; ++b)
+    if (h->hIolet[b] && (h->hIoletId[b] < 0)) return fail("iolet site without an iolet id");
+  CU(cudaMemcpy(h->wallMask, h->hWall.data(), sizeof(uint32_t) * h->bStride, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->ioletMask, h->hIolet.data(), sizeof(uint32_t) * h->bStride, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->ioletId, h->hIoletId.data(), sizeof(int32_t) * h->bStride, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->cutDist, h->hCut.data(), sizeof(float) * (Q - 1) * h->bStride, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->wallNormal, h->hNormal.data(), sizeof(double) * 3 * h->bStride, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->coords, h->hCoords.data(), sizeof(int32_t) * 3 * h->bStride, cudaMemcpyHostToDevice));
+  if (h->cfg.wall == HLB_WALL_GZS && h->NB) {
+    CU(cudaMalloc(&h->gzsNeighbour, sizeof(int32_t) * (Q - 1) * h->bStride));
+    gzs_neighbour_kernel<<<blocks_for(h->NB * (Q - 1)), 256>>>(h->nbr, h->gzsNeighbour, Q, h->stride, h->bStride,
+                                                               h->NB, h->midBulk, h->midTotal, h->edgeBulk);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    // a GZS link that would extrapolate from a site on another rank needs the phase-0 site halo
+    std::vector<int32_t> g((size_t)(Q - 1) * h->bStride);
+    CU(cudaMemcpy(g.data(), h->gzsNeighbour, sizeof(int32_t) * g.size(), cudaMemcpyDeviceToHost));
+    for (int64_t b = 0; b < h->NB; ++b)
+      for (int d = 1; d < Q; ++d) {
+        if (!((h->hWall[b] >> (d - 1)) & 1u)) continue;
+        const int i = inv_dir(d);
+        if (((h->hWall[b] >> (i - 1)) & 1u) || ((h->hIolet[b] >> (i - 1)) & 1u)) continue;
+        if (!(h->hCut[(size_t)(d - 1) * h->bStride + b] < 0.75f)) continue;
+        if (g[(size_t)(i - 1) * h->bStride + b] < 0)
+          return fail("GZS wall link extrapolates from a site on another rank: not implemented yet");
+      }
+  }
+  h->finalised = true;
+  return 0;
+}
+
+int hlb_gpu_comm_unique_id(void* id128) {
+  if (!g_nccl.Load()) return fail("libnccl.so.2 could not be loaded");
+  NcclUniqueId id;
+  int rc = g_nccl.GetUniqueId(&id);
+  if (rc) return fail(std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc));
+  std::memcpy(id128, &id, 128);
+  return 0;
+}
+
+int hlb_gpu_comm_init(hlb_gpu_t h, const void* id128) {
+  if (!h || !id128) return fail("null argument");
+  if (!g_nccl.Load()) return fail("libnccl.so.2 could not be loaded");
+  CU(cudaSetDevice(h->cfg.device));
+  NcclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  int rc = g_nccl.CommInitRank(&h->comm_nccl, h->cfg.nranks, id, h->cfg.rank);
+  if (rc) return fail(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc));
+  return 0;
+}
+
+int hlb_gpu_set_f(hlb_gpu_t h, int which, const double* f) {
+  if (!h || !f) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->compute));
+  double* dst = h->f[which ? h->cur ^ 1 : h->cur];
+  const int Q = h->Q;
+  if (ensure_staging(h, sizeof(int64_t) * kChunkSites * Q + 16)) return 1;
+  for (int64_t s0 = 0; s0 < h->N; s0 += kChunkSites) {
+    const int64_t m = std::min(kChunkSites, h->N - s0);
+    CU(cudaMemcpy(h->staging, f + s0 * Q, sizeof(double) * m * Q, cudaMemcpyHostToDevice));
+    aos_to_soa_kernel<<<blocks_for(m * Q), 256>>>((const double*)h->staging, dst, s0, m, Q, h->stride);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+  }
+  CU(cudaMemcpy(dst + (int64_t)Q * h->stride, f + h->N * Q, sizeof(double) * (1 + h->S), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int hlb_gpu_get_f(hlb_gpu_t h, int which, double* f) {
+  if (!h || !f) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->compute));
+  CU(cudaStreamSynchronize(h->comm));
+  const double* src = h->f[which ? h->cur ^ 1 : h->cur];
+  const int Q = h->Q;
+  if (ensure_staging(h, sizeof(int64_t) * kChunkSites * Q + 16)) return 1;
+  for (int64_t s0 = 0; s0 < h->N; s0 += kChunkSites) {
+    const int64_t m = std::min(kChunkSites, h->N - s0);
+    soa_to_aos_kernel<<<blocks_for(m * Q), 256>>>(src, (double*)h->staging, s0, m, Q, h->stride);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(f + s0 * Q, h->staging, sizeof(double) * m * Q, cudaMemcpyDeviceToHost));
+  }
+  CU(cudaMemcpy(f + h->N * Q, src + (int64_t)Q * h->stride, sizeof(double) * (1 + h->S), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int hlb_gpu_get_halo(hlb_gpu_t h, int which, double* out) {
+  if (!h || (!out && h->S)) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->compute));
+  const double* src = h->f[which ? h->cur ^ 1 : h->cur] + (int64_t)h->Q * h->stride + 1;
+  if (h->S) CU(cudaMemcpy(out, src, sizeof(double) * h->S, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int hlb_gpu_set_halo(hlb_gpu_t h, int which, const double* in) {
+  if (!h || (!in && h->S)) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->compute));
+  double* dst = h->f[which ? h->cur ^ 1 : h->cur] + (int64_t)h->Q * h->stride + 1;
+  if (h->S) CU(cudaMemcpy(dst, in, sizeof(double) * h->S, cudaMemcpyHostToDevice));
+  h->edgePending = false;  // the caller moved the halo itself (host-staged exchange)
+  return 0;
+}
+
+int hlb_gpu_set_equilibrium(hlb_gpu_t h, double rho, const double* m) {
+  if (!h || !m) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  // Lattice::CalculateFeq (scalar path) on the host, then broadcast to every site of both arrays
+  double feq[27];
+  const double density_1 = 1. / rho;
+  const double mm = m[0] * m[0] + m[1] * m[1] + m[2] * m[2];
+  for (int i = 0; i < h->Q; ++i) {
+    int cx, cy, cz;
+    double w;
+    if (h->Q == 15) { cx = Lat<15>::cx(i); cy = Lat<15>::cy(i); cz = Lat<15>::cz(i); w = Lat<15>::W(i); }
+    else if (h->Q == 19) { cx = Lat<19>::cx(i); cy = Lat<19>::cy(i); cz = Lat<19>::cz(i); w = Lat<19>::W(i); }
+    else { cx = Lat<27>::cx(i); cy = Lat<27>::cy(i); cz = Lat<27>::cz(i); w = Lat<27>::W(i); }
+    const double mde = cx * m[0] + cy * m[1] + cz * m[2];
+    feq[i] = w * (rho - (3. / 2.) * mm * density_1 + (9. / 2.) * density_1 * mde * mde + 3. * mde);
+  }
+  if (ensure_staging(h, 512)) return 1;
+  CU(cudaMemcpy(h->staging, feq, sizeof(double) * h->Q, cudaMemcpyHostToDevice));
+  if (h->N) fill_planes_kernel<<<blocks_for(h->N * h->Q), 256>>>(h->f[0], h->f[1], h->N, h->stride, h->Q, (const double*)h->staging);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  return 0;
+}
+
+int hlb_gpu_set_step_scalars(hlb_gpu_t h, uint64_t timeStep, const double* inDens, const double* outDens,
+                             uint32_t cacheMask) {
+  if (!h) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  h->timeStep = timeStep;
+  if (ensure_caches(h, cacheMask)) return 1;
+  h->cacheMask = cacheMask;
+  if (upload_densities(h, 0, inDens)) return 1;
+  if (upload_densities(h, 1, outDens)) return 1;
+  return 0;
+}
+
+int hlb_gpu_stream_and_collide(hlb_gpu_t h, int slot, int64_t first, int64_t count) {
+  if (!h) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  return launch_range(h, slot, first, count, false);
+}
+
+int hlb_gpu_post_step(hlb_gpu_t h, int slot, int64_t first, int64_t count) {
+  if (!h) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  return launch_range(h, slot, first, count, true);
+}
+
+int hlb_gpu_request_comms(hlb_gpu_t h) {
+  // LBM::RequestComms only *registers* the sends/receives with the Net (lb.hpp:162-173); they are
+  // issued after PreSend.  Mirror that: remember, and post when the edge ranges have been issued.
+  if (!h) return fail("null argument");
+  h->edgePending = true;
+  return 0;
+}
+
+int hlb_gpu_edge_done(hlb_gpu_t h) {
+  if (!h) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  if (h->edgePending) {
+    h->edgePending = false;
+    return post_comms(h);
+  }
+  return 0;
+}
+
+int hlb_gpu_copy_received(hlb_gpu_t h) {
+  if (!h) return fail("null argument");
+  if (!h->finalised) return fail("handle not finalised");
+  CU(cudaSetDevice(h->cfg.device));
+  if (h->edgePending) {  // caller never marked the end of PreSend: post now (no overlap)
+    h->edgePending = false;
+    if (post_comms(h)) return 1;
+  }
+  if (h->S == 0) return 0;
+  if (h->commPosted) {
+    CU(cudaStreamWaitEvent(h->compute, h->evComm, 0));  // Net::Wait
+    h->commPosted = false;
+  }
+  copy_received_kernel<<<blocks_for(h->S), 256, 0, h->compute>>>(
+      h->f[h->cur ^ 1], h->f[h->cur] + (int64_t)h->Q * h->stride + 1, h->streamIdx, h->S);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int hlb_gpu_swap(hlb_gpu_t h) {
+  if (!h) return fail("null argument");
+  h->cur ^= 1;
+  return 0;
+}
+
+int hlb_gpu_get_cache(hlb_gpu_t h, uint32_t which, double* out) {
+  if (!h || !out) return fail("null argument");
+  static const int per[8] = {1, 3, 1, 1, 1, 9, 3, 3};
+  CU(cudaSetDevice(h->cfg.device));
+  for (int i = 0; i < 8; ++i)
+    if (which == (1u << i)) {
+      if (!h->cache[i]) return fail("cache was never requested");
+      CU(cudaStreamSynchronize(h->compute));
+      CU(cudaMemcpy(out, h->cache[i], sizeof(double) * per[i] * h->N, cudaMemcpyDeviceToHost));
+      return 0;
+    }
+  return fail("unknown cache");
+}
+
+int hlb_gpu_step(hlb_gpu_t h, int nsteps) {
+  if (!h) return fail("null argument");
+  if (!h->finalised) return fail("handle not finalised");
+  CU(cudaSetDevice(h->cfg.device));
+  for (int i = 0; i < nsteps; ++i)
+    if (one_step(h)) return 1;
+  return 0;
+}
+
+int hlb_gpu_get_time_step(hlb_gpu_t h, uint64_t* t) {
+  if (!h || !t) return fail("null argument");
+  *t = h->timeStep;
+  return 0;
+}
+
+int hlb_gpu_sync(hlb_gpu_t h) {
+  if (!h) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->compute));
+  CU(cudaStreamSynchronize(h->comm));
+  return 0;
+}
+
+int hlb_gpu_time_steps(hlb_gpu_t h, int nsteps, float* ms) {
+  if (!h || !ms) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->compute));
+  CU(cudaStreamSynchronize(h->comm));
+  CU(cudaEventRecord(h->evT0, h->compute));
+  for (int i = 0; i < nsteps; ++i)
+    if (one_step(h)) return 1;
+  CU(cudaEventRecord(h->evT1, h->compute));
+  CU(cudaEventSynchronize(h->evT1));
+  CU(cudaStreamSynchronize(h->comm));
+  CU(cudaEventElapsedTime(ms, h->evT0, h->evT1));
+  return 0;
+}
+
+int hlb_gpu_time_steps_detail(hlb_gpu_t h, int nsteps, float* total_ms, float* bulk_ms, int64_t* bulk_sites) {
+  if (!h || !total_ms || !bulk_ms || !bulk_sites) return fail("null argument");
+  h->profileBulk = true;
+  h->profUsed = 0;
+  h->profSites = 0;
+  int rc = hlb_gpu_time_steps(h, nsteps, total_ms);
+  h->profileBulk = false;
+  if (rc) return rc;
+  float acc = 0.f;
+  for (size_t i = 0; i + 1 < h->profUsed; i += 2) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, h->profEv[i], h->profEv[i + 1]));
+    acc += ms;
+  }
+  *bulk_ms = acc;
+  *bulk_sites = h->profSites;
+  return 0;
+}
+
+int hlb_gpu_monitor(hlb_gpu_t h, double* out4) {
+  if (!h || !out4) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  unsigned long long init[4] = {~0ull, ~0ull, 0ull, 0ull};
+  CU(cudaMemcpyAsync(h->monitorDev, init, sizeof(init), cudaMemcpyHostToDevice, h->compute));
+  if (h->N) {
+    monitor_kernel<<<148 * 8, 256, 0, h->compute>>>(h->f[h->cur], h->N, h->stride, h->Q,
+                                                    (unsigned long long*)h->monitorDev);
+    h->launches++;
+  }
+  monitor_decode_kernel<<<1, 32, 0, h->compute>>>((unsigned long long*)h->monitorDev);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out4, h->monitorDev + 4, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->compute));
+  CU(cudaStreamSynchronize(h->compute));
+  return 0;
+}
+
+int hlb_gpu_launch_count(hlb_gpu_t h, int64_t* n) {
+  if (!h || !n) return fail("null argument");
+  *n = h->launches;
+  return 0;
+}
+
+}  // extern "C"

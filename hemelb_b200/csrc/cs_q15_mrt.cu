@@ -1,0 +1,5 @@
+// D3Q15 MRT: collide-and-stream kernels for all wall / iolet link policies.
+#include "instantiate.cuh"
+namespace hlb {
+template void launch_collide_stream<15, K_MRT>(int, int, const StepArgs&, const void*, int64_t, int64_t, void*);
+}

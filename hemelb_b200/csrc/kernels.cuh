@@ -1,0 +1,522 @@
+// Fused collide-and-stream kernels over HemeLB's type-ordered sparse site ranges (sm_100a).
+//
+// One kernel instantiation per (lattice, collision kernel, wall link, iolet link) policy bundle --
+// the device-side counterpart of the reference's
+//   lb::BulkStreamer<C>                       Code/lb/streamers/BulkStreamer.h:57-99
+//   lb::StreamerTypeFactory<WallLink,IoletLink> Code/lb/streamers/StreamerTypeFactory.h:24-109
+// with C = lb::Normal<LBGK|MRT|TRT>.  One thread owns one site: it loads the Q pre-collision
+// populations from the structure-of-arrays f_old (plane d at f + d*stride: every warp load is one
+// fully coalesced 256 B request), collides in registers, and pushes each post-collision
+// population through the 32-bit neighbour table into f_new.  Macroscopic-moment extraction
+// (UpdateCachePostCollision, Common.h:21-130) is fused behind a run-time mask.
+//
+// HBM traffic per site update: Q*8 B read + Q*8 B written + (Q-1)*4 B of indices.
+#pragma once
+#include <cstdint>
+#include <cfloat>
+#include "lattice.cuh"
+
+namespace hlb {
+
+enum KernelKind { K_LBGK = 0, K_MRT = 1, K_TRT = 2 };
+enum WallKind { W_SBB = 0, W_BFL = 1, W_GZS = 2, W_NONE = 3 };
+enum IoletKind { I_NASH = 0, I_LADD = 1, I_NONE = 2 };
+enum CacheBit {
+  C_DENSITY = 1, C_VELOCITY = 2, C_WSS = 4, C_VONMISES = 8, C_SHEARRATE = 16, C_STRESS = 32,
+  C_TRACTION = 64, C_TANGTRACTION = 128
+};
+
+struct IoletDev {  // lb::iolets::InOutLet{Cosine,ParabolicVelocity} as the kernels see them
+  double normal[3];    // normalised in double (InOutLet.h:160-163)
+  double position[3];
+  double radius, maxSpeed, warmUpLength;
+  int kind;            // 0 pressure (cosine), 1 parabolic velocity
+  int pad;
+};
+
+struct StepArgs {
+  // distributions (SoA): population d of site s at f[d*stride + s]; f[Q*stride] is the rubbish
+  // slot, f[Q*stride+1 ...] the halo slots (FieldData.cc:14-25 re-laid-out)
+  const double* __restrict__ fOld;
+  double* __restrict__ fNew;
+  const uint32_t* __restrict__ nbr;  // (Q-1) planes: target of direction d at nbr[(d-1)*stride + s]
+  int64_t stride;
+  // boundary-site tables, indexed by boundary ordinal b (see bidx())
+  const uint32_t* __restrict__ wallMask;
+  const uint32_t* __restrict__ ioletMask;
+  const int32_t* __restrict__ ioletId;
+  const float* __restrict__ cutDist;     // (Q-1) planes of bStride
+  const double* __restrict__ wallNormal; // 3 planes of bStride
+  const int32_t* __restrict__ coords;    // 3 planes of bStride
+  int64_t bStride;
+  int64_t midBulk, midTotal, edgeBulk;   // bulk counts / mid-domain total, for bidx()
+  // GZS: whole-site f_old rows of remote neighbours (NeighbouringDataManager) live after the
+  // local planes: ghost row g of direction d at fOld[...]; not used unless WALL == W_GZS
+  const int32_t* __restrict__ gzsNeighbour;  // (Q-1) planes of bStride: local site id, or -(g+1)
+  const double* __restrict__ gzsGhost;       // Q planes of ghostStride
+  int64_t ghostStride;
+  // iolets of this range's BoundaryValues object + per-step scalars
+  const IoletDev* __restrict__ iolets;
+  const double* __restrict__ ioletDensity;   // GetBoundaryDensity(id) for this step
+  uint64_t timeStep;                         // SimulationState::GetTimeStep() (1-indexed)
+  // LbmParameters
+  double tau, omega, stressParameter, omegaMinus;
+  // caches (MacroscopicPropertyCache), site-major like the reference
+  uint32_t cacheMask;
+  double* __restrict__ cDensity;
+  double* __restrict__ cVelocity;
+  double* __restrict__ cWss;
+  double* __restrict__ cVonMises;
+  double* __restrict__ cShearRate;
+  double* __restrict__ cStress;
+  double* __restrict__ cTraction;
+  double* __restrict__ cTangTraction;
+  const int64_t* __restrict__ refSiteOf;  // internal site -> reference site id (cache rows), or null
+  // optional explicit site list (sub-range calls that are not whole ranges)
+  const uint32_t* __restrict__ siteList;
+};
+
+template <int Q> struct MrtArgs {
+  double SMn[mrt_k<Q>() > 0 ? mrt_k<Q>() : 1][Q];  // collisionMatrixDiagonals[k] * normalisedReducedMomentBasis[k][d]
+};
+
+__device__ __forceinline__ int64_t bidx(const StepArgs& A, int64_t site) {
+  // boundary-typed sites are [midBulk, midTotal) and [midTotal+edgeBulk, N)
+  return site < A.midTotal ? site - A.midBulk : site - A.midTotal - A.edgeBulk + (A.midTotal - A.midBulk);
+}
+
+// ---------------------------------------------------------------------------------- collisions
+template <int Q, int KERNEL> struct HydroVars {
+  double rho, m[3], u[3];
+  double f[Q], fneq[Q], fpost[Q];
+};
+
+// MRT.h:123-134
+template <int Q>
+__device__ __forceinline__ void mrt_project(const double (&v)[Q], double (&mom)[mrt_k<Q>() > 0 ? mrt_k<Q>() : 1]) {
+#pragma unroll
+  for (int k = 0; k < mrt_k<Q>(); ++k) {
+    double acc = 0.;
+#pragma unroll
+    for (int d = 0; d < Q; ++d)
+      if (mrt_m<Q>(k, d) != 0) acc += double(mrt_m<Q>(k, d)) * v[d];
+    mom[k] = acc;
+  }
+}
+
+// LBGK.h:56-63 / MRT.h:88-105 / TRT.h:94-121 on (f, fneq) -> fpost
+template <int Q, int KERNEL>
+__device__ __forceinline__ void collide(const StepArgs& A, const MrtArgs<Q>& M, const double (&f)[Q],
+                                        const double (&fneq)[Q], double (&fpost)[Q]) {
+  if constexpr (KERNEL == K_LBGK) {
+#pragma unroll
+    for (int d = 0; d < Q; ++d) fpost[d] = f[d] + fneq[d] * A.omega;
+  } else if constexpr (KERNEL == K_MRT) {
+    double mneq[mrt_k<Q>() > 0 ? mrt_k<Q>() : 1];
+    mrt_project<Q>(fneq, mneq);
+#pragma unroll
+    for (int d = 0; d < Q; ++d) {
+      double collision = 0.;
+#pragma unroll
+      for (int k = 0; k < mrt_k<Q>(); ++k)
+        if (mrt_m<Q>(k, d) != 0) collision += M.SMn[k][d] * mneq[k];
+      fpost[d] = f[d] - collision;
+    }
+  } else {
+    fpost[0] = f[0] + A.omega * fneq[0];
+#pragma unroll
+    for (int i = 1; i < Q; i += 2) {
+      const int ib = i + 1;
+      const double sym = 0.5 * A.omega * (fneq[i] + fneq[ib]);
+      const double asym = 0.5 * A.omegaMinus * (fneq[i] - fneq[ib]);
+      fpost[i] = f[i] + sym + asym;
+      fpost[ib] = f[ib] + sym - asym;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- stresses
+// Lattice.h:716-746 CalculatePiTensor (lower triangle, then mirrored)
+template <int Q>
+__device__ __forceinline__ void pi_tensor(const double (&f)[Q], double (&pi)[3][3]) {
+#pragma unroll
+  for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+    for (int jj = 0; jj <= ii; ++jj) {
+      double acc = 0.0;
+#pragma unroll
+      for (int l = 0; l < Q; ++l) {
+        const int ci = ii == 0 ? Lat<Q>::cx(l) : (ii == 1 ? Lat<Q>::cy(l) : Lat<Q>::cz(l));
+        const int cj = jj == 0 ? Lat<Q>::cx(l) : (jj == 1 ? Lat<Q>::cy(l) : Lat<Q>::cz(l));
+        if (ci * cj != 0) acc += cmul(ci * cj, f[l]);  // (f*ci)*cj with ci,cj in {-1,0,1}
+      }
+      pi[ii][jj] = acc;
+    }
+  pi[0][1] = pi[1][0];
+  pi[0][2] = pi[2][0];
+  pi[1][2] = pi[2][1];
+}
+
+template <int Q>
+__device__ __forceinline__ void stress_tensor(double rho, double tau, const double (&fneq)[Q], double (&s)[3][3]) {
+  pi_tensor<Q>(fneq, s);  // Lattice.h:622-637
+  const double fac = 1 - 1 / (2 * tau);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s[r][c] *= fac;
+  const double pressure = (rho - 1) * kCs2;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) s[r][r] += pressure;
+}
+
+template <int Q, int KERNEL>
+__device__ __noinline__ void update_caches(const StepArgs& A, int64_t site, bool boundaryTyped, double rho,
+                                           const double (&u)[3], const double (&fneq)[Q]) {
+  // UpdateCachePostCollision, Common.h:21-130
+  const int64_t row = A.refSiteOf ? A.refSiteOf[site] : site;
+  const uint32_t mask = A.cacheMask;
+  bool isWall = false;
+  double nor[3] = {0, 0, 0};
+  if (boundaryTyped) {
+    const int64_t b = bidx(A, site);
+    isWall = A.wallMask[b] != 0;
+    nor[0] = A.wallNormal[b];
+    nor[1] = A.wallNormal[A.bStride + b];
+    nor[2] = A.wallNormal[2 * A.bStride + b];
+  }
+  if (mask & C_DENSITY) A.cDensity[row] = rho;
+  if (mask & C_VELOCITY) {
+    A.cVelocity[3 * row] = u[0];
+    A.cVelocity[3 * row + 1] = u[1];
+    A.cVelocity[3 * row + 2] = u[2];
+  }
+  if (mask & C_WSS) {
+    double stress = DBL_MAX;  // NO_VALUE
+    if (isWall) {  // Lattice.h:650-688
+      double sv[3] = {0.0, 0.0, 0.0};
+      double sq = 0.0, ns = 0.0;
+      const double temp = A.stressParameter * (-sqrt(2.0));
+      double pi[3][3];
+      pi_tensor<Q>(fneq, pi);
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) sv[i] += pi[i][j] * nor[j] * temp;
+        sq += sv[i] * sv[i];
+        ns += sv[i] * nor[i];
+      }
+      stress = sqrt(sq - ns * ns);
+    }
+    A.cWss[row] = stress;
+  }
+  if (mask & C_VONMISES) {  // Lattice.h:510-551
+    double xx_yy = 0.0, yy_zz = 0.0, xx_zz = 0.0, xy = 0.0, xz = 0.0, yz = 0.0;
+#pragma unroll
+    for (int d = 0; d < Q; ++d) {
+      const int cx = Lat<Q>::cx(d), cy = Lat<Q>::cy(d), cz = Lat<Q>::cz(d);
+      if (cx * cx - cy * cy != 0) xx_yy += cmul(cx * cx - cy * cy, fneq[d]);
+      if (cy * cy - cz * cz != 0) yy_zz += cmul(cy * cy - cz * cz, fneq[d]);
+      if (cx * cx - cz * cz != 0) xx_zz += cmul(cx * cx - cz * cz, fneq[d]);
+      if (cx * cy != 0) xy += cmul(cx * cy, fneq[d]);
+      if (cx * cz != 0) xz += cmul(cx * cz, fneq[d]);
+      if (cy * cz != 0) yz += cmul(cy * cz, fneq[d]);
+    }
+    const double a = xx_yy * xx_yy + yy_zz * yy_zz + xx_zz * xx_zz;
+    const double b = xy * xy + xz * xz + yz * yz;
+    A.cVonMises[row] = A.stressParameter * sqrt(a + 6.0 * b);
+  }
+  if (mask & C_SHEARRATE) {  // Lattice.h:748-770, 890-908
+    double shear = 0.0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = r; c < 3; ++c) {
+        double s = 0.0;
+#pragma unroll
+        for (int v = 0; v < Q; ++v) {
+          const int cr = r == 0 ? Lat<Q>::cx(v) : (r == 1 ? Lat<Q>::cy(v) : Lat<Q>::cz(v));
+          const int cc = c == 0 ? Lat<Q>::cx(v) : (c == 1 ? Lat<Q>::cy(v) : Lat<Q>::cz(v));
+          if (cr * cc != 0) s += cmul(cr * cc, fneq[v]);
+        }
+        s *= -1.0 / (2.0 * A.tau * rho * kCs2);
+        shear += (c == r) ? s * s : 2 * s * s;
+      }
+    A.cShearRate[row] = sqrt(2 * shear);
+  }
+  if (mask & (C_STRESS | C_TRACTION | C_TANGTRACTION)) {
+    double s[3][3];
+    stress_tensor<Q>(rho, A.tau, fneq, s);
+    if (mask & C_STRESS)
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) A.cStress[9 * row + 3 * a + b] = s[a][b];
+    double t[3] = {0, 0, 0}, tt[3] = {0, 0, 0};
+    if (isWall) {  // Lattice.h:566-608
+      double mag = 0.0;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        double acc = 0.0;
+#pragma unroll
+        for (int b = 0; b < 3; ++b) acc += s[a][b] * nor[b];
+        t[a] = acc;
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) mag += t[a] * nor[a];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) tt[a] = t[a] - nor[a] * mag;
+    }
+    if (mask & C_TRACTION)
+      for (int a = 0; a < 3; ++a) A.cTraction[3 * row + a] = t[a];
+    if (mask & C_TANGTRACTION)
+      for (int a = 0; a < 3; ++a) A.cTangTraction[3 * row + a] = tt[a];
+  }
+}
+
+// ---------------------------------------------------------------------------------- iolet links
+// InOutLetParabolicVelocity.cc:23-43
+__device__ __forceinline__ void parabolic_velocity(const IoletDev& io, const double (&x)[3], uint64_t t, double (&v)[3]) {
+  const double d0 = x[0] - io.position[0], d1 = x[1] - io.position[1], d2 = x[2] - io.position[2];
+  double z = 0.0;
+  z += d0 * io.normal[0];
+  z += d1 * io.normal[1];
+  z += d2 * io.normal[2];
+  double mag2 = 0.0;
+  mag2 += d0 * d0;
+  mag2 += d1 * d1;
+  mag2 += d2 * d2;
+  const double rSq = (mag2 - z * z) / (io.radius * io.radius);
+  double mx = io.maxSpeed;
+  if ((double)t < io.warmUpLength) mx *= t / io.warmUpLength;
+  const double s = mx * (1. - rSq);
+  v[0] = io.normal[0] * s;
+  v[1] = io.normal[1] * s;
+  v[2] = io.normal[2] * s;
+}
+
+// ---------------------------------------------------------------------------------- GZS wall link
+// GuoZhengShi.h:123-284 for wall direction iPrime of one site.  Kept out of line with run-time
+// direction: it re-runs a whole collision per wall link and would explode the unrolled site loop.
+template <int Q, int KERNEL, int IOLET>
+__device__ __noinline__ void gzs_link(const StepArgs& A, const MrtArgs<Q>& M, int64_t site, int64_t b, int iPrime,
+                                      uint32_t wallMask, uint32_t ioletMask, double rho, const double (&m)[3],
+                                      const double* fneqIn, const double* fpostIn) {
+  const int i = inv_dir(iPrime);
+  const double q = (double)A.cutDist[(int64_t)(iPrime - 1) * A.bStride + b];
+  double mw[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) mw[k] = m[k] * (1. - 1. / q);
+  double fneqW[Q];
+#pragma unroll
+  for (int j = 0; j < Q; ++j) fneqW[j] = fneqIn[j];
+  bool sbb = false;
+  if (q < 0.75) {
+    const bool hasIoletI = (ioletMask >> (i - 1)) & 1u;
+    const bool hasWallI = (wallMask >> (i - 1)) & 1u;
+    if (IOLET != I_NONE && hasIoletI) {
+      const IoletDev& io = A.iolets[A.ioletId[b]];
+      if (io.kind != 1) {
+        sbb = true;
+      } else {
+        double np[3], nv[3];
+        np[0] = (double)A.coords[b] + (double)Lat<Q>::cx(i);
+        np[1] = (double)A.coords[A.bStride + b] + (double)Lat<Q>::cy(i);
+        np[2] = (double)A.coords[2 * A.bStride + b] + (double)Lat<Q>::cz(i);
+        parabolic_velocity(io, np, A.timeStep, nv);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double second = nv[k] * (q - 1) / (q + 1);
+          mw[k] = q * mw[k] + (1. - q) * rho * second;
+        }
+      }
+    } else if (hasWallI) {
+      sbb = true;
+    } else {
+      // neighbour site's f_old: local plane read, or the phase-0 ghost row of a remote site
+      double nf[Q];
+      const int32_t n = A.gzsNeighbour[(int64_t)(i - 1) * A.bStride + b];
+      if (n >= 0) {
+#pragma unroll
+        for (int j = 0; j < Q; ++j) nf[j] = A.fOld[(int64_t)j * A.stride + n];
+      } else {
+        const int64_t g = -(int64_t)n - 1;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) nf[j] = A.gzsGhost[(int64_t)j * A.ghostStride + g];
+      }
+      double nrho, nm[3], nu[3], nfeq[Q];
+      density_momentum<Q>(nf, nrho, nm);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) nu[k] = nm[k] / nrho;
+      feq_all<Q>(nrho, nm, nfeq);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double second = nu[k] * (q - 1) / (q + 1);
+        mw[k] = q * mw[k] + (1. - q) * rho * second;
+      }
+#pragma unroll
+      for (int j = 0; j < Q; ++j) fneqW[j] = q * fneqW[j] + (1. - q) * (nf[j] - nfeq[j]);
+    }
+  }
+  double out;
+  if (sbb) {
+    out = fpostIn[iPrime];
+  } else {
+    double fW[Q], feqW[Q], fpostW[Q];
+    feq_all<Q>(rho, mw, feqW);
+#pragma unroll
+    for (int j = 0; j < Q; ++j) fW[j] = feqW[j] + fneqW[j];
+    // (the reference leaves m_neq of this HydroVars unset for MRT; we project its f_neq)
+    collide<Q, KERNEL>(A, M, fW, fneqW, fpostW);
+    out = fpostW[i];
+  }
+  A.fNew[(int64_t)i * A.stride + site] = out;
+}
+
+// ---------------------------------------------------------------------------------- the site kernel
+template <int Q, int KERNEL, int WALL, int IOLET>
+__global__ void __launch_bounds__(256) collide_stream_kernel(const StepArgs A, const MrtArgs<Q> M, int64_t first, int64_t count) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= count) return;
+  const int64_t site = A.siteList ? (int64_t)A.siteList[tid] : first + tid;
+  constexpr bool HAS_WALL = WALL != W_NONE;
+  constexpr bool HAS_IOLET = IOLET != I_NONE;
+
+  double f[Q];
+#pragma unroll
+  for (int d = 0; d < Q; ++d) f[d] = __ldcs(A.fOld + (int64_t)d * A.stride + site);
+  uint32_t target[Q];
+  target[0] = (uint32_t)site;
+#pragma unroll
+  for (int d = 1; d < Q; ++d) target[d] = __ldcs(A.nbr + (int64_t)(d - 1) * A.stride + site);
+
+  // CalculatePreCollision (Normal.h:29-33 -> kernel.CalculateDensityMomentumFeq)
+  double rho, m[3], u[3];
+  density_momentum<Q>(f, rho, m);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) u[k] = m[k] / rho;
+  double fneq[Q], fpost[Q];
+  {
+    const double density_1 = 1. / rho;
+    const double mm = m[0] * m[0] + m[1] * m[1] + m[2] * m[2];
+#pragma unroll
+    for (int d = 0; d < Q; ++d) fneq[d] = f[d] - feq_i<Q>(d, rho, density_1, mm, m);
+  }
+  collide<Q, KERNEL>(A, M, f, fneq, fpost);
+
+  uint32_t wallMask = 0, ioletMask = 0;
+  int64_t b = 0;
+  if constexpr (HAS_WALL || HAS_IOLET) {
+    b = bidx(A, site);
+    if constexpr (HAS_WALL) wallMask = A.wallMask[b];
+    if constexpr (HAS_IOLET) ioletMask = A.ioletMask[b];
+  }
+
+  // per-site iolet quantities (NashZerothOrderPressure.h:27-60 / LaddIolet.h:29-66)
+  double ghostRho = 0, ghostM[3] = {0, 0, 0}, ghostD1 = 0, ghostMM = 0;
+  double wallMom[3] = {0, 0, 0};
+  double sx = 0, sy = 0, sz = 0;
+  const IoletDev* io = nullptr;
+  if constexpr (HAS_IOLET) {
+    if (ioletMask) {
+      const int id = A.ioletId[b];
+      io = A.iolets + id;
+      if constexpr (IOLET == I_NASH) {
+        ghostRho = A.ioletDensity[id];
+        const float nf0 = (float)io->normal[0], nf1 = (float)io->normal[1], nf2 = (float)io->normal[2];
+        double dot = 0.0;
+        dot += m[0] * (double)nf0;
+        dot += m[1] * (double)nf1;
+        dot += m[2] * (double)nf2;
+        const double component = dot / rho;
+        ghostM[0] = ((double)nf0 * component) * ghostRho;
+        ghostM[1] = ((double)nf1 * component) * ghostRho;
+        ghostM[2] = ((double)nf2 * component) * ghostRho;
+        ghostD1 = 1. / ghostRho;
+        ghostMM = ghostM[0] * ghostM[0] + ghostM[1] * ghostM[1] + ghostM[2] * ghostM[2];
+      } else {
+        sx = (double)A.coords[b];
+        sy = (double)A.coords[A.bStride + b];
+        sz = (double)A.coords[2 * A.bStride + b];
+      }
+    }
+  }
+
+  // stream: iolet link, else wall link, else bulk push (StreamerTypeFactory.h:65-79)
+  A.fNew[target[0]] = fpost[0];
+#pragma unroll
+  for (int d = 1; d < Q; ++d) {
+    constexpr int dummy = 0;
+    (void)dummy;
+    const int id = inv_dir(d);
+    const bool hasIolet = HAS_IOLET && ((ioletMask >> (d - 1)) & 1u);
+    const bool hasWall = HAS_WALL && ((wallMask >> (d - 1)) & 1u);
+    if (hasIolet) {
+      if constexpr (IOLET == I_NASH) {
+        A.fNew[(int64_t)id * A.stride + site] = feq_i<Q>(id, ghostRho, ghostD1, ghostMM, ghostM);
+      } else if constexpr (IOLET == I_LADD) {
+        double x[3] = {sx + 0.5 * Lat<Q>::cx(d), sy + 0.5 * Lat<Q>::cy(d), sz + 0.5 * Lat<Q>::cz(d)};
+        parabolic_velocity(*io, x, A.timeStep, wallMom);
+        wallMom[0] *= rho;
+        wallMom[1] *= rho;
+        wallMom[2] *= rho;
+        double dot = 0.0;
+        dot += wallMom[0] * (double)Lat<Q>::cx(d);
+        dot += wallMom[1] * (double)Lat<Q>::cy(d);
+        dot += wallMom[2] * (double)Lat<Q>::cz(d);
+        const double correction = 2. * Lat<Q>::W(d) * dot / kCs2;
+        A.fNew[(int64_t)id * A.stride + site] = fpost[d] - correction;
+      }
+    } else if (hasWall) {
+      if constexpr (WALL == W_SBB) {  // SimpleBounceBack.h:23-42
+        A.fNew[(int64_t)id * A.stride + site] = fpost[d];
+      } else if constexpr (WALL == W_BFL) {  // BouzidiFirdaousLallemand.h:41-70
+        const double q = (double)A.cutDist[(int64_t)(d - 1) * A.bStride + b];
+        const bool invWall = (wallMask >> (id - 1)) & 1u;
+        double v;
+        if (invWall || q < 0.5) v = fpost[d];
+        else v = (fpost[d] + (2.0 * q - 1) * fpost[id]) / (2.0 * q);
+        A.fNew[(int64_t)id * A.stride + site] = v;
+      } else if constexpr (WALL == W_GZS) {
+        gzs_link<Q, KERNEL, IOLET>(A, M, site, b, d, wallMask, ioletMask, rho, m, fneq, fpost);
+      }
+    } else {
+      A.fNew[target[d]] = fpost[d];  // BulkStreamer.h:31-39
+    }
+  }
+
+  if (A.cacheMask) update_caches<Q, KERNEL>(A, site, HAS_WALL || HAS_IOLET, rho, u, fneq);
+}
+
+// PostStep: only BFL does work (BouzidiFirdaousLallemand.h:72-91); runs after all streaming and
+// the halo unpack, one thread per boundary-typed site of the range.
+template <int Q>
+__global__ void __launch_bounds__(256) bfl_post_step_kernel(const StepArgs A, int64_t first, int64_t count) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= count) return;
+  const int64_t site = A.siteList ? (int64_t)A.siteList[tid] : first + tid;
+  const int64_t b = bidx(A, site);
+  const uint32_t wallMask = A.wallMask[b];
+  if (!wallMask) return;
+#pragma unroll
+  for (int d = 1; d < Q; ++d) {
+    if (!((wallMask >> (d - 1)) & 1u)) continue;
+    const int id = inv_dir(d);
+    if ((wallMask >> (id - 1)) & 1u) continue;
+    const double q = (double)A.cutDist[(int64_t)(d - 1) * A.bStride + b];
+    if (q < 0.5) {
+      double* fi = A.fNew + (int64_t)id * A.stride + site;
+      const double fd = A.fNew[(int64_t)d * A.stride + site];
+      *fi = 2.0 * q * (*fi) + (1.0 - 2.0 * q) * fd;
+    }
+  }
+}
+
+// Host-side launch entry, one per (Q, KERNEL) translation unit
+typedef void (*LaunchFn)(int wall, int iolet, const StepArgs& A, const void* mrt, int64_t first, int64_t count,
+                         void* stream);
+template <int Q, int KERNEL>
+void launch_collide_stream(int wall, int iolet, const StepArgs& A, const void* mrt, int64_t first, int64_t count,
+                           void* stream);
+
+}  // namespace hlb

@@ -1,0 +1,150 @@
+/* hemelb_b200.h -- C ABI of the B200-native collide-and-stream engine.
+ *
+ * This is the drop-in boundary for HemeLB's lattice-Boltzmann hot path.  The reference has no
+ * FFI: its seam is the C++ policy-template API (lb::streamer concept, Code/lb/concepts.h:90-103;
+ * Traits<>, Code/Traits.h:17-39; geometry::FieldData, Code/geometry/FieldData.h:117-212).  Each
+ * entry point below names the reference interface it replaces; the header-only C++ policy classes
+ * in hemelb_b200/host/ forward to these calls.
+ *
+ * Conventions: every function returns 0 on success and non-zero on error, with the message
+ * available from hlb_gpu_last_error() (thread-local).  All pointers are HOST pointers to arrays
+ * laid out exactly as the reference holds them; they are borrowed for the duration of the call
+ * only.  The handle owns all device memory.  There is no CPU fallback: without a CUDA device
+ * hlb_gpu_create fails.  One handle = one MPI rank of the reference = one GPU.
+ */
+#ifndef HEMELB_B200_H
+#define HEMELB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hlb_gpu_handle* hlb_gpu_t;
+
+/* build_info strings of the reference (CMake/HemeLbOptions.cmake:54-68) as enums */
+enum { HLB_KERNEL_LBGK = 0, HLB_KERNEL_MRT = 1, HLB_KERNEL_TRT = 2 };
+enum { HLB_WALL_SIMPLEBOUNCEBACK = 0, HLB_WALL_BFL = 1, HLB_WALL_GZS = 2 };
+enum { HLB_IOLET_NASHZEROTHORDERPRESSURE = 0, HLB_IOLET_LADD = 1 };
+/* MacroscopicPropertyCache members (Code/lb/MacroscopicPropertyCache.h:50-90) */
+enum {
+  HLB_CACHE_DENSITY = 1, HLB_CACHE_VELOCITY = 2, HLB_CACHE_WALL_SHEAR_STRESS = 4,
+  HLB_CACHE_VON_MISES_STRESS = 8, HLB_CACHE_SHEAR_RATE = 16, HLB_CACHE_STRESS_TENSOR = 32,
+  HLB_CACHE_TRACTION = 64, HLB_CACHE_TANGENTIAL_TRACTION = 128
+};
+
+typedef struct {
+  int lattice;            /* 15, 19 or 27 (HEMELB_LATTICE) */
+  int kernel;             /* HLB_KERNEL_* (HEMELB_KERNEL) */
+  int wall;               /* HLB_WALL_* (HEMELB_WALL_BOUNDARY) */
+  int inlet, outlet;      /* HLB_IOLET_* (HEMELB_INLET_BOUNDARY / HEMELB_OUTLET_BOUNDARY) */
+  double tau;             /* LbmParameters::GetTau(), Code/lb/LbmParameters.h:34-39 */
+  int device;             /* CUDA ordinal */
+  int rank, nranks;       /* Domain::GetLocalRank(), communicator size */
+  int64_t n_sites;        /* Domain::GetLocalFluidSiteCount() */
+  int64_t mid_count[6];   /* Domain::GetMidDomainCollisionCount(t), t = 0..5 */
+  int64_t edge_count[6];  /* Domain::GetDomainEdgeCollisionCount(t) */
+  int64_t total_shared_fs;/* Domain::totalSharedFs */
+  int n_neighbours;       /* Domain::neighbouringProcs.size() */
+  int n_inlets, n_outlets;/* BoundaryValues::GetLocalIoletCount() of the two objects */
+} hlb_gpu_config;
+
+/* Iolet descriptor: 16 doubles {kind (0 cosine pressure / 1 parabolic velocity), normal[3],
+ * position[3], radius, maxSpeed, densityMean, densityAmp, phase, period, warmUpLength,
+ * minimumSimulationDensity, reserved}  (Code/lb/iolets/InOutLet{,Cosine,ParabolicVelocity}.h) */
+#define HLB_IOLET_RECORD_DOUBLES 16
+
+const char* hlb_gpu_last_error(void);
+int hlb_gpu_device_count(int* count);
+
+/* ---- construction: what SimBuilder / LBM::InitCollisions hand the streamers
+ *      (Code/configuration/SimBuilder.h:115-269, Code/lb/lb.hpp:75-124) */
+int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out);
+int hlb_gpu_destroy(hlb_gpu_t h);
+/* Domain::neighbourIndices (Code/geometry/Domain.h:526), reference form: int64, site-major,
+ * values site*Q+dir | N*Q (rubbish) | N*Q+1+k (send slot).  May be called in site chunks. */
+int hlb_gpu_set_neighbour_indices(hlb_gpu_t h, int64_t first_site, int64_t n, const int64_t* idx);
+/* SiteData per site (Code/geometry/SiteDataBare.h:66-74): wall / iolet intersection masks
+ * (bit d-1 <-> direction d) and iolet id */
+int hlb_gpu_set_site_data(hlb_gpu_t h, int64_t first_site, int64_t n, const uint32_t* wall_mask,
+                          const uint32_t* iolet_mask, const int32_t* iolet_id);
+/* Domain::distanceToWall, n*(Q-1) doubles (Code/geometry/Domain.h:406-409,519) */
+int hlb_gpu_set_wall_distances(hlb_gpu_t h, int64_t first_site, int64_t n, const double* dist);
+/* Domain::wallNormalAtSite, n*3 doubles */
+int hlb_gpu_set_wall_normals(hlb_gpu_t h, int64_t first_site, int64_t n, const double* normals);
+/* Domain::globalSiteCoords, n*3 int64 */
+int hlb_gpu_set_site_coords(hlb_gpu_t h, int64_t first_site, int64_t n, const int64_t* coords);
+/* Domain::neighbouringProcs {Rank, SharedDistributionCount, FirstSharedDistribution}
+ * (Code/geometry/NeighbouringProcessor.h:24-28) and streamingIndicesForReceivedDistributions */
+int hlb_gpu_set_neighbours(hlb_gpu_t h, const int* rank, const int64_t* count, const int64_t* first);
+int hlb_gpu_set_streaming_indices(hlb_gpu_t h, const int64_t* idx);
+/* iolets of the inlet (which = 0) / outlet (which = 1) BoundaryValues object */
+int hlb_gpu_set_iolets(hlb_gpu_t h, int which, int n, const double* records);
+/* remote sites GZS extrapolates from (NeighbouringDataManager::RegisterNeededSite,
+ * Code/lb/streamers/GuoZhengShi.h:93-99): for each boundary link needing a remote f_old row,
+ * (local site, direction, owner rank, owner's local site id).  Optional. */
+int hlb_gpu_set_gzs_remote(hlb_gpu_t h, int64_t n, const int64_t* local_site, const int32_t* direction,
+                           const int32_t* owner_rank, const int64_t* owner_site);
+int hlb_gpu_finalise(hlb_gpu_t h);
+
+/* ---- multi-GPU: replaces net::Net's MPI point-to-point (Code/net/mixins/pointpoint/
+ *      CoalescePointPoint.cc:23-132) with NCCL send/recv over NVLink */
+int hlb_gpu_comm_unique_id(void* id128);
+int hlb_gpu_comm_init(hlb_gpu_t h, const void* id128);
+
+/* ---- FieldData (Code/geometry/FieldData.h:117-167, .cc:27-48) */
+/* which = 0: f_old, 1: f_new; reference layout, N*Q + 1 + totalSharedFs doubles */
+int hlb_gpu_set_f(hlb_gpu_t h, int which, const double* f);
+int hlb_gpu_get_f(hlb_gpu_t h, int which, double* f);
+/* the halo region alone (totalSharedFs doubles after the rubbish slot): lets a host keep the
+ * reference's own net::Net / MPI for the exchange (host-staged) instead of NCCL.  get: the send
+ * slices of f_new (which = 1); set: the receive slices of f_old (which = 0). */
+int hlb_gpu_get_halo(hlb_gpu_t h, int which, double* out);
+int hlb_gpu_set_halo(hlb_gpu_t h, int which, const double* in);
+/* EquilibriumInitialCondition::SetFs (Code/lb/InitialCondition.hpp:40-52) */
+int hlb_gpu_set_equilibrium(hlb_gpu_t h, double density, const double* momentum3);
+int hlb_gpu_request_comms(hlb_gpu_t h);   /* FieldData::SendAndReceive + Net::Receive/Send */
+int hlb_gpu_copy_received(hlb_gpu_t h);   /* Net::Wait + FieldData::CopyReceived */
+int hlb_gpu_swap(hlb_gpu_t h);            /* FieldData::SwapOldAndNew */
+
+/* ---- per-step scalars: SimulationState::GetTimeStep() (1-indexed), BoundaryValues::
+ *      GetBoundaryDensity(i) for each inlet / outlet, and the refresh flags of the property cache
+ *      (Code/SimulationMaster.impl.h:223-241) */
+int hlb_gpu_set_step_scalars(hlb_gpu_t h, uint64_t time_step, const double* inlet_density,
+                             const double* outlet_density, uint32_t cache_mask);
+
+/* ---- lb::streamer concept: slot 0..5 = mid-fluid, wall, inlet, outlet, inlet-wall,
+ *      outlet-wall streamer of LBM (Code/lb/lb.h:102-107); (first, count) as LBM passes them */
+int hlb_gpu_stream_and_collide(hlb_gpu_t h, int slot, int64_t first, int64_t count);
+int hlb_gpu_post_step(hlb_gpu_t h, int slot, int64_t first, int64_t count);
+/* mark the end of LBM::PreSend (all domain-edge ranges issued): lets the halo send start while
+ * the mid-domain ranges run */
+int hlb_gpu_edge_done(hlb_gpu_t h);
+
+/* ---- MacroscopicPropertyCache read-back (site-major doubles as the reference's caches) */
+int hlb_gpu_get_cache(hlb_gpu_t h, uint32_t which, double* out);
+
+/* ---- whole steps: the phase sequence of LBM (RequestComms, PreSend, PreReceive, PostReceive,
+ *      EndIteration; Code/lb/lb.hpp:162-314) + SwapOldAndNew + SimulationState::Increment, with
+ *      cosine iolet densities evaluated on the host as InOutLetCosine::GetDensity does */
+int hlb_gpu_step(hlb_gpu_t h, int nsteps);
+int hlb_gpu_get_time_step(hlb_gpu_t h, uint64_t* t);
+int hlb_gpu_sync(hlb_gpu_t h);
+/* CUDA-event timing of nsteps whole steps on the engine's own streams (ms) */
+int hlb_gpu_time_steps(hlb_gpu_t h, int nsteps, float* ms);
+/* same, also returning the summed CUDA-event duration of the mid-fluid (bulk) range launches and
+ * the number of sites they updated -- the roofline kernel, timed live inside the step */
+int hlb_gpu_time_steps_detail(hlb_gpu_t h, int nsteps, float* total_ms, float* bulk_ms, int64_t* bulk_sites);
+/* device-side monitors (StabilityTester / IncompressibilityChecker inputs): {min f_old, min
+ * density, max density, max |u|} of the last cached density/velocity; D2H of 4 doubles */
+int hlb_gpu_monitor(hlb_gpu_t h, double* out4);
+/* number of kernels launched by this handle so far */
+int hlb_gpu_launch_count(hlb_gpu_t h, int64_t* n);
+/* the device-resident tables, converted back to reference form (for parity tests) */
+int hlb_gpu_get_neighbour_indices(hlb_gpu_t h, int64_t* idx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEMELB_B200_H */

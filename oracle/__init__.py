@@ -225,6 +225,10 @@ class _SimCommon:
     def step(self, n=1):
         self._fn("sim_step")(self.h, n)
 
+    def step_mt(self, n=1):
+        """one thread per emulated rank (reference driver only)"""
+        self._fn("sim_step_mt")(self.h, n)
+
 
 class OracleSim(_SimCommon):
     """The restated LBM phase loop over all emulated ranks of an OracleDomains."""

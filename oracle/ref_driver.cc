@@ -15,6 +15,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -625,6 +626,47 @@ void href_sim_stream_and_collide(void* sp, int r, int slot, int64_t first, int64
 void href_sim_post_step(void* sp, int r, int slot, int64_t first, int64_t count) {
   ((SimBase*)sp)->PostStep(r, slot, first, count);
 }
+// One std::thread per emulated rank (the reference is one single-threaded MPI process per rank):
+// phases separated by joins stand in for the MPI waits.  Used for the CPU baseline only.
+void href_sim_step_mt(void* sp, int n) {
+  SimBase* S = (SimBase*)sp;
+  const int R = S->R, Q = S->Q;
+  auto par = [&](auto fn) {
+    std::vector<std::thread> th;
+    for (int r = 0; r < R; ++r) th.emplace_back(fn, r);
+    for (auto& t : th) t.join();
+  };
+  for (int it = 0; it < n; ++it) {
+    S->ApplyCacheMask();
+    par([&](int r) {
+      RankState& X = *S->ranks[r];
+      site_t off = 0;
+      for (int t = 0; t < 6; ++t) off += X.mid[t];
+      for (int t = 0; t < 6; ++t) { S->StreamAndCollide(r, t, off, X.edge[t]); off += X.edge[t]; }
+      off = 0;
+      for (int t = 0; t < 6; ++t) { S->StreamAndCollide(r, t, off, X.mid[t]); off += X.mid[t]; }
+    });
+    par([&](int r) {  // receive side pulls its slices, then CopyReceived + PostStep
+      RankState& X = *S->ranks[r];
+      for (auto& p : X.procs) {
+        RankState& O = *S->ranks[p.rank];
+        for (auto& po : O.procs)
+          if (po.rank == r)
+            for (site_t i = 0; i < p.count; ++i) X.fd.fOld[p.first + i] = O.fd.fNew[po.first + i];
+      }
+      for (site_t i = 0; i < X.totalSharedFs; ++i)
+        X.fd.fNew[X.streamingIndices[i]] = X.fd.fOld[X.dom.nSites * Q + 1 + i];
+      site_t off = 0;
+      for (int t = 0; t < 6; ++t) off += X.mid[t];
+      for (int t = 0; t < 6; ++t) { S->PostStep(r, t, off, X.edge[t]); off += X.edge[t]; }
+      off = 0;
+      for (int t = 0; t < 6; ++t) { S->PostStep(r, t, off, X.mid[t]); off += X.mid[t]; }
+    });
+    for (int r = 0; r < R; ++r) S->ranks[r]->fd.fOld.swap(S->ranks[r]->fd.fNew);
+    S->state.Increment();
+  }
+}
+
 void href_sim_step(void* sp, int n) {
   for (int i = 0; i < n; ++i) ((SimBase*)sp)->Step();
 }

@@ -1,0 +1,208 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): per-step distributions <= 1e-13 absolute.  The kernels are built
+with -fmad=false and follow the reference's scalar operation order, so in practice the match is
+bit-exact; EXACT=True asserts that too.
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+from hemelb_b200 import geometry as G
+from hemelb_b200.domain import build_domains
+from hemelb_b200.lbm import GpuLBM
+from tests.cases import TOL_F, anisotropic_f, geometry, iolets_for, perturbed_equilibrium, valid_combo
+
+pytestmark = pytest.mark.gpu
+EXACT = True
+
+
+def _check(a, b, what):
+    err = np.abs(a - b).max() if a.size else 0.0
+    assert err <= TOL_F, "%s: max abs err %g" % (what, err)
+    if EXACT:
+        assert np.array_equal(a, b), "%s: not bit-identical (max abs err %g)" % (what, err)
+
+
+def _run_pair(geom, Q, kernel, wall, inlet, outlet, steps, tau=0.62, mask=255, init="anisotropic"):
+    inlets, outlets = iolets_for(geom, inlet, outlet)
+    dom = build_domains(geom, Q)[0]
+    odom = O.OracleDomains(geom, Q)
+    sim = O.OracleSim(odom, kernel, wall, inlet, outlet, tau=tau, inlets=inlets, outlets=outlets)
+    gpu = GpuLBM(dom, kernel, wall, inlet, outlet, tau=tau, inlets=inlets, outlets=outlets)
+    if init == "anisotropic":
+        f0 = anisotropic_f(dom.N, Q, 0)
+    else:
+        _, w, _ = O.lattice(Q)
+        f0 = perturbed_equilibrium(dom.N, Q, 0, w)
+    sim.set_f(f0)
+    gpu.set_f(f0)
+    sim.set_cache_mask(mask)
+    gpu.set_cache_mask(mask)
+    sim.step(steps)
+    gpu.step(steps)
+    return sim, gpu, dom
+
+
+COMBOS = [(Q, k, w, i, o)
+          for Q in (15, 19, 27) for k in ("LBGK", "MRT", "TRT") for w in ("SBB", "BFL", "GZS")
+          for (i, o) in (("NASH", "NASH"), ("LADD", "NASH"), ("LADD", "LADD"))
+          if valid_combo(Q, k, w, i, o)]
+
+
+@pytest.mark.parametrize("Q,kernel,wall,inlet,outlet", COMBOS)
+def test_four_cube_all_policies(Q, kernel, wall, inlet, outlet):
+    """configs[0] geometry, every policy bundle, 5 steps from LbTestsHelper's anisotropic data."""
+    sim, gpu, dom = _run_pair(geometry("four_cube"), Q, kernel, wall, inlet, outlet, 5)
+    _check(gpu.get_f()[:dom.N * Q], sim.get_f()[:dom.N * Q], "f_old after 5 steps")
+    for name in O.CACHE_BITS:
+        _check(gpu.get_cache(name), sim.get_cache(name), "cache " + name)
+
+
+@pytest.mark.parametrize("geom_name", ["cylinder", "tree", "sac"])
+@pytest.mark.parametrize("Q,kernel,wall,inlet,outlet", [
+    (19, "LBGK", "BFL", "NASH", "NASH"),   # configs[1], configs[2]
+    (19, "MRT", "GZS", "LADD", "NASH"),    # configs[3]
+    (27, "TRT", "BFL", "NASH", "NASH"),    # configs[4]
+    (15, "LBGK", "SBB", "NASH", "NASH"),   # configs[0] policies
+    (19, "LBGK", "GZS", "LADD", "LADD"),
+    (15, "MRT", "BFL", "LADD", "LADD"),
+])
+def test_baseline_configs_small(geom_name, Q, kernel, wall, inlet, outlet):
+    sim, gpu, dom = _run_pair(geometry(geom_name), Q, kernel, wall, inlet, outlet, 20, tau=0.8, init="equilibrium")
+    _check(gpu.get_f()[:dom.N * Q], sim.get_f()[:dom.N * Q], "f_old after 20 steps")
+    _check(gpu.get_cache("density"), sim.get_cache("density"), "density")
+    _check(gpu.get_cache("velocity"), sim.get_cache("velocity"), "velocity")
+
+
+def test_thousand_steps_density_velocity():
+    """north_star: density / velocity agree to <= 1e-10 relative after 1000 steps."""
+    geom = geometry("cylinder")
+    sim, gpu, dom = _run_pair(geom, 19, "LBGK", "BFL", "NASH", "NASH", 1000, tau=0.8, mask=3, init="equilibrium")
+    rho_g, rho_o = gpu.get_cache("density"), sim.get_cache("density")
+    u_g, u_o = gpu.get_cache("velocity"), sim.get_cache("velocity")
+    assert np.abs(rho_g / rho_o - 1).max() <= 1e-10
+    scale = np.abs(u_o).max()
+    assert scale > 1e-6  # the flow actually developed
+    assert np.abs(u_g - u_o).max() / scale <= 1e-10
+    if EXACT:
+        assert np.array_equal(gpu.get_f()[:dom.N * 19], sim.get_f()[:dom.N * 19])
+
+
+@pytest.mark.parametrize("slot", range(6))
+def test_single_ranges_like_streamer_tests(slot):
+    """StreamerTests.cc pattern: one streamer over one site range, then PostStep, on the four-cube
+    fixture (D3Q15 LBGK; BFL walls so PostStep does work)."""
+    geom, Q = geometry("four_cube"), 15
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    dom = build_domains(geom, Q)[0]
+    odom = O.OracleDomains(geom, Q)
+    sim = O.OracleSim(odom, "LBGK", "BFL", tau=0.62, inlets=inlets, outlets=outlets)
+    gpu = GpuLBM(dom, "LBGK", "BFL", tau=0.62, inlets=inlets, outlets=outlets)
+    f0 = anisotropic_f(dom.N, Q, 0)
+    for s in (sim, gpu):
+        s.set_f(f0, which=0)
+        s.set_f(np.full_like(f0, -7.0), which=1)
+    first = int(dom.mid[:slot].sum())
+    count = int(dom.mid[slot])
+    assert count > 0
+    # a sub-range first, then the rest of the range
+    half = count // 2
+    for s in (sim, gpu):
+        s.stream_and_collide(slot, first, half)
+        s.stream_and_collide(slot, first + half, count - half)
+        s.post_step(slot, first, count)
+    _check(gpu.get_f(which=1)[:dom.N * Q], sim.get_f(which=1)[:dom.N * Q], "f_new")
+
+
+def test_phase_api_equals_whole_step():
+    """RequestComms / PreSend / PreReceive / PostReceive / EndIteration driven from the host equal
+    hlb_gpu_step."""
+    geom, Q = geometry("cylinder"), 19
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    dom = build_domains(geom, Q)[0]
+    a = GpuLBM(dom, "LBGK", "BFL", tau=0.8, inlets=inlets, outlets=outlets)
+    b = GpuLBM(dom, "LBGK", "BFL", tau=0.8, inlets=inlets, outlets=outlets)
+    f0 = anisotropic_f(dom.N, Q, 0)
+    a.set_f(f0)
+    b.set_f(f0)
+    for _ in range(7):
+        a.do_time_step()
+    b.step(7)
+    assert np.array_equal(a.get_f(), b.get_f())
+
+
+def test_tables_round_trip_on_device():
+    """neighbourIndices uploaded in reference form come back bit-identical."""
+    geom = geometry("tree")
+    for Q in (15, 19, 27):
+        dom = build_domains(geom, Q)[0]
+        gpu = GpuLBM(dom)
+        assert np.array_equal(gpu.get_neighbour_indices(), dom.neighbour_indices())
+
+
+@pytest.mark.parametrize("R,decomp", [(2, "slab"), (3, "slab"), (4, "basic")])
+def test_multi_rank_host_staged_halo(R, decomp):
+    """R emulated ranks on one GPU, halo moved through hlb_gpu_get_halo / set_halo (the host-staged
+    exchange a reference build can keep using net::Net for): matches the oracle's R-rank run."""
+    geom, Q = geometry("cylinder_long"), 19
+    rank = G.slab_decomposition(geom, R) if decomp == "slab" else G.basic_decomposition(geom, R)
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    doms = build_domains(geom, Q, rank, R)
+    odom = O.OracleDomains(geom, Q, rank, R)
+    sim = O.OracleSim(odom, "LBGK", "BFL", tau=0.8, inlets=inlets, outlets=outlets)
+    gpus = [GpuLBM(d, "LBGK", "BFL", tau=0.8, inlets=inlets, outlets=outlets) for d in doms]
+    for r, d in enumerate(doms):
+        f0 = anisotropic_f(d.N, Q, d.totalSharedFs, site_offset=7 * r)
+        sim.set_f(f0, r)
+        gpus[r].set_f(f0)
+    for _ in range(6):
+        for g in gpus:
+            g.request_comms()
+            g.pre_send()
+            g.pre_receive()
+        sends = [g.get_halo(which=1) for g in gpus]
+        for r, d in enumerate(doms):
+            recv = np.zeros(d.totalSharedFs)
+            for (p, cnt, first) in d.procs:
+                op = doms[p].procs
+                j = int(np.nonzero(op[:, 0] == r)[0][0])
+                o_first = int(op[j, 2]) - (doms[p].N * Q + 1)
+                m_first = int(first) - (d.N * Q + 1)
+                recv[m_first:m_first + cnt] = sends[p][o_first:o_first + cnt]
+            gpus[r].set_halo(recv, which=0)
+        for g in gpus:
+            g.post_receive()
+            g.end_iteration()
+            g.swap_old_and_new()
+            g.state.increment()
+    sim.step(6)
+    for r, d in enumerate(doms):
+        _check(gpus[r].get_f()[:d.N * Q], sim.get_f(r)[:d.N * Q], "rank %d f_old" % r)
+
+
+def test_error_paths():
+    from hemelb_b200.capi import HlbError
+    geom = geometry("four_cube")
+    dom = build_domains(geom, 27)[0]
+    with pytest.raises(HlbError, match="No MRT basis for D3Q27"):
+        GpuLBM(dom, "MRT")
+    dom = build_domains(geom, 15)[0]
+    gpu = GpuLBM(dom)
+    with pytest.raises(HlbError, match="outside the local fluid sites"):
+        gpu.stream_and_collide(0, 0, dom.N + 1)
+    with pytest.raises(HlbError, match="bulk-typed"):
+        gpu.stream_and_collide(1, 0, 4)
+
+
+def test_monitor_matches_numpy():
+    geom, Q = geometry("cylinder"), 19
+    dom = build_domains(geom, Q)[0]
+    gpu = GpuLBM(dom)
+    f0 = anisotropic_f(dom.N, Q, 0)
+    gpu.set_f(f0)
+    m = gpu.monitor()
+    f = f0[:dom.N * Q].reshape(dom.N, Q)
+    rho = f.sum(1)
+    assert m["min_f"] == f.min()
+    assert abs(m["min_density"] - rho.min()) < 1e-12 and abs(m["max_density"] - rho.max()) < 1e-12
