@@ -144,7 +144,7 @@ struct hlb_gpu_handle {
   std::vector<double> hNormal;
   bool haveNbr = false, haveSiteData = false, haveCut = false, haveNormal = false, haveCoords = false,
        haveNeighbours = false, haveStream = false, haveIolets[2] = {false, false}, finalised = false;
-  bool edgePending = false, commPosted = false;
+  bool edgePending = false, commPosted = false, haloProvided = false;
   NcclComm comm_nccl = nullptr;
   void* staging = nullptr;
   size_t stagingBytes = 0;
@@ -275,32 +275,35 @@ __device__ __forceinline__ double dec(unsigned long long u) {
   u = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
   return __longlong_as_double(u);
 }
-__global__ void monitor_kernel(const double* __restrict__ f, int64_t N, int64_t stride, int Q,
-                               unsigned long long* __restrict__ out) {
+template <int Q>
+__global__ void __launch_bounds__(256) monitor_kernel(const double* __restrict__ f, int64_t N, int64_t stride,
+                                                      unsigned long long* __restrict__ out) {
   double fmin = 1e300, rmin = 1e300, rmax = -1e300, umax = 0.0;
   for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
+    double v[Q];
+#pragma unroll
+    for (int d = 0; d < Q; ++d) v[d] = __ldcs(f + (int64_t)d * stride + s);
     double rho = 0, mx = 0, my = 0, mz = 0;
+#pragma unroll
     for (int d = 0; d < Q; ++d) {
-      const double v = f[(int64_t)d * stride + s];
-      fmin = fmin < v ? fmin : v;
-      rho += v;
-      int cx, cy, cz;
-      if (Q == 15) { cx = Lat<15>::cx(d); cy = Lat<15>::cy(d); cz = Lat<15>::cz(d); }
-      else { cx = Lat<27>::cx(d); cy = Lat<27>::cy(d); cz = Lat<27>::cz(d); }
-      mx += cx * v;
-      my += cy * v;
-      mz += cz * v;
+      fmin = fmin < v[d] ? fmin : v[d];
+      rho += v[d];
+      mx += Lat<Q>::cx(d) * v[d];
+      my += Lat<Q>::cy(d) * v[d];
+      mz += Lat<Q>::cz(d) * v[d];
     }
     rmin = rmin < rho ? rmin : rho;
     rmax = rmax > rho ? rmax : rho;
     const double u2 = (mx * mx + my * my + mz * mz) / (rho * rho);
     umax = umax > u2 ? umax : u2;
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    fmin = fmin < __shfl_xor_sync(0xffffffffu, fmin, o) ? fmin : __shfl_xor_sync(0xffffffffu, fmin, o);
-    rmin = rmin < __shfl_xor_sync(0xffffffffu, rmin, o) ? rmin : __shfl_xor_sync(0xffffffffu, rmin, o);
-    rmax = rmax > __shfl_xor_sync(0xffffffffu, rmax, o) ? rmax : __shfl_xor_sync(0xffffffffu, rmax, o);
-    umax = umax > __shfl_xor_sync(0xffffffffu, umax, o) ? umax : __shfl_xor_sync(0xffffffffu, umax, o);
+  for (int o = 16; o > 0; o >>= 1) {  // shuffles must stay convergent: fetch, then select
+    const double a = __shfl_xor_sync(0xffffffffu, fmin, o), b = __shfl_xor_sync(0xffffffffu, rmin, o);
+    const double c = __shfl_xor_sync(0xffffffffu, rmax, o), d = __shfl_xor_sync(0xffffffffu, umax, o);
+    fmin = fmin < a ? fmin : a;
+    rmin = rmin < b ? rmin : b;
+    rmax = rmax > c ? rmax : c;
+    umax = umax > d ? umax : d;
   }
   if ((threadIdx.x & 31) == 0) {
     atomicMin(out + 0, enc(fmin));
@@ -446,7 +449,7 @@ int post_comms(hlb_gpu_t h) {
   // FieldData::SendAndReceive (FieldData.cc:27-39): per neighbour, receive into the slice of
   // f_old and send the same slice of f_new, on the comm stream after the edge ranges finished.
   if (h->neighbours.empty()) return 0;
-  if (!h->comm_nccl) return fail("neighbours present but hlb_gpu_comm_init was not called");
+  if (!h->comm_nccl) return 0;  // host-staged exchange: the caller moves the halo (get_halo / set_halo)
   CU(cudaEventRecord(h->evEdge, h->compute));
   CU(cudaStreamWaitEvent(h->comm, h->evEdge, 0));
   double* fOld = h->f[h->cur];
@@ -929,6 +932,7 @@ int hlb_gpu_set_halo(hlb_gpu_t h, int which, const double* in) {
   double* dst = h->f[which ? h->cur ^ 1 : h->cur] + (int64_t)h->Q * h->stride + 1;
   if (h->S) CU(cudaMemcpy(dst, in, sizeof(double) * h->S, cudaMemcpyHostToDevice));
   h->edgePending = false;  // the caller moved the halo itself (host-staged exchange)
+  if (which == 0) h->haloProvided = true;
   return 0;
 }
 
@@ -1010,6 +1014,10 @@ int hlb_gpu_copy_received(hlb_gpu_t h) {
   if (h->commPosted) {
     CU(cudaStreamWaitEvent(h->compute, h->evComm, 0));  // Net::Wait
     h->commPosted = false;
+  } else if (h->haloProvided) {
+    h->haloProvided = false;
+  } else {
+    return fail("halo neither exchanged (hlb_gpu_comm_init + request_comms) nor provided (hlb_gpu_set_halo)");
   }
   copy_received_kernel<<<blocks_for(h->S), 256, 0, h->compute>>>(
       h->f[h->cur ^ 1], h->f[h->cur] + (int64_t)h->Q * h->stride + 1, h->streamIdx, h->S);
@@ -1101,8 +1109,13 @@ int hlb_gpu_monitor(hlb_gpu_t h, double* out4) {
   unsigned long long init[4] = {~0ull, ~0ull, 0ull, 0ull};
   CU(cudaMemcpyAsync(h->monitorDev, init, sizeof(init), cudaMemcpyHostToDevice, h->compute));
   if (h->N) {
-    monitor_kernel<<<148 * 8, 256, 0, h->compute>>>(h->f[h->cur], h->N, h->stride, h->Q,
-                                                    (unsigned long long*)h->monitorDev);
+    const unsigned grid = (unsigned)std::min<int64_t>((h->N + 255) / 256, 148 * 16);
+    unsigned long long* mo = (unsigned long long*)h->monitorDev;
+    switch (h->Q) {
+      case 15: monitor_kernel<15><<<grid, 256, 0, h->compute>>>(h->f[h->cur], h->N, h->stride, mo); break;
+      case 19: monitor_kernel<19><<<grid, 256, 0, h->compute>>>(h->f[h->cur], h->N, h->stride, mo); break;
+      case 27: monitor_kernel<27><<<grid, 256, 0, h->compute>>>(h->f[h->cur], h->N, h->stride, mo); break;
+    }
     h->launches++;
   }
   monitor_decode_kernel<<<1, 32, 0, h->compute>>>((unsigned long long*)h->monitorDev);

@@ -32,15 +32,15 @@ def iolets_for(geom, inlet_bc: str, outlet_bc: str):
     for LADD (as a SimConfig would pair them)."""
     meta = geom.meta
     if meta.get("kind") == "four_cube":
-        ins = [dict(position=(2.5, 2.5, 0.5), normal=(0, 0, 1), radius=2.0)]
-        outs = [dict(position=(2.5, 2.5, 4.5), normal=(0, 0, -1), radius=2.0)]
+        ins = [dict(position=(2.5, 2.5, 0.5), normal=(0, 0, 1), radius=2.5)]
+        outs = [dict(position=(2.5, 2.5, 4.5), normal=(0, 0, -1), radius=2.5)]
     else:
         ins = [dict(position=tuple(p.position), normal=tuple(p.normal), radius=p.radius - 2) for p in meta["inlets"]]
         outs = [dict(position=tuple(p.position), normal=tuple(p.normal), radius=p.radius - 2) for p in meta["outlets"]]
 
     def rec(spec, bc, k, inlet):
         if bc == "LADD":
-            return iolet_record(1, spec["normal"], spec["position"], radius=spec["radius"] + 0.7,
+            return iolet_record(1, spec["normal"], spec["position"], radius=spec["radius"] + 1.0,
                                 max_speed=0.02 if inlet else 0.015)
         return iolet_record(0, spec["normal"], spec["position"], radius=spec["radius"],
                             density_mean=1.01 if inlet else 0.995 - 0.0005 * k, density_amp=0.004,
