@@ -76,7 +76,7 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def build_workload(radius, length, rank, nranks):
+def build_workload(radius, length, rank, nranks, block_size=8):
     """Geometry + this rank's Domain tables.  N > 1: z-slabs of a cylinder nranks times longer; each
     rank voxelises only its own slab plus one halo layer either side (global coordinates)."""
     from hemelb_b200 import geometry as G
@@ -85,10 +85,10 @@ def build_workload(radius, length, rank, nranks):
     from hemelb_b200.lbm import prepare_boundary_objects
     total_len = length * nranks
     if nranks == 1:
-        geom = G.cylinder_extruded(radius, total_len)
+        geom = G.cylinder_extruded(radius, total_len, block_size)
         rank_of_site = None
     else:
-        geom, rank_of_site = G.cylinder_slab(radius, total_len, nranks, rank)
+        geom, rank_of_site = G.cylinder_slab(radius, total_len, nranks, rank, block_size)
     dom = DomainBuilder(geom, Q, rank_of_site, nranks).domains[rank]
     meta = geom.meta
     inl, outl = meta["inlets"][0], meta["outlets"][0]
@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--radius", type=float, default=146.0)
     ap.add_argument("--length", type=int, default=1500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--block-size", type=int, default=8, help="sites per block side of the synthetic .gmy (HemeLB default 8)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,7 +191,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     t_setup = time.time()
-    geom, dom, inlets, outlets = build_workload(args.radius, args.length, rank, world)
+    geom, dom, inlets, outlets = build_workload(args.radius, args.length, rank, world, args.block_size)
     gpu = GpuLBM(dom, "LBGK", "BFL", "NASH", "NASH", tau=TAU, inlets=inlets, outlets=outlets, device=local_rank)
     if world > 1:
         import torch

@@ -52,30 +52,38 @@ def gmy_link_of_direction(Q: int) -> np.ndarray:
 
 
 class _Lookup:
-    """global voxel coordinates -> input site index (or -1)."""
+    """global voxel coordinates -> input site index (or -1), over the sites' bounding box padded by
+    one voxel (so every lattice neighbour of a site falls inside the window)."""
 
     def __init__(self, geom: Geometry):
         c = geom.coords.astype(np.int64)
-        self.dims = geom.block_dims.astype(np.int64) * geom.block_size
+        if geom.n_sites:
+            self.origin = c.min(0) - 1
+            self.dims = c.max(0) - c.min(0) + 3
+        else:
+            self.origin = np.zeros(3, np.int64)
+            self.dims = np.ones(3, np.int64)
+        self.full = geom.block_dims.astype(np.int64) * geom.block_size
         nvox = int(self.dims.prod())
         self.dense = None
-        self.key_of_site = (c[:, 0] * self.dims[1] + c[:, 1]) * self.dims[2] + c[:, 2]
-        self.rimmed = bool(geom.n_sites == 0 or ((c.min(0) >= 1).all() and (c.max(0) <= self.dims - 2).all()))
+        q = c - self.origin
+        self.key_of_site = (q[:, 0] * self.dims[1] + q[:, 1]) * self.dims[2] + q[:, 2]
+        self.rimmed = True
         if nvox <= 3_000_000_000 and nvox <= 64 * max(geom.n_sites, 1) + 10_000_000:
             dt = np.int32 if geom.n_sites < 2**31 else np.int64
             self.dense = np.full(nvox, -1, dt)
             self.dense[self.key_of_site] = np.arange(geom.n_sites, dtype=dt)
         else:
-            key = (c[:, 0] * self.dims[1] + c[:, 1]) * self.dims[2] + c[:, 2]
-            self.order = np.argsort(key, kind="stable")
-            self.keys = key[self.order]
+            self.order = np.argsort(self.key_of_site, kind="stable")
+            self.keys = self.key_of_site[self.order]
 
     def key_offset(self, c) -> int:
         return int((c[0] * self.dims[1] + c[1]) * self.dims[2] + c[2])
 
     def __call__(self, p: np.ndarray) -> np.ndarray:
-        inside = ((p >= 0) & (p < self.dims)).all(1)
-        q = np.where(inside[:, None], p, 0)
+        q = p - self.origin
+        inside = ((q >= 0) & (q < self.dims)).all(1)
+        q = np.where(inside[:, None], q, 0)
         key = (q[:, 0] * self.dims[1] + q[:, 1]) * self.dims[2] + q[:, 2]
         if self.dense is not None:
             out = self.dense[key].astype(np.int64)

@@ -351,7 +351,21 @@ def cylinder(radius: float, length: int, block_size: int = 8, margin: int = 2) -
     return g
 
 
-def cylinder_extruded(radius: float, length: int, block_size: int = 8, margin: int = 2) -> Geometry:
+def cylinder_slab(radius: float, length: int, nranks: int, rank: int, block_size: int = 8, margin: int = 2):
+    """Rank ``rank``'s share of ``cylinder(radius, length)`` cut into ``nranks`` equal z-slabs, plus one
+    halo slice either side: (sub-geometry in global coordinates, site -> rank).  Enough to build
+    this rank's Domain tables exactly (the pair lists only involve the adjacent slices)."""
+    per = length // nranks
+    lo = rank * per
+    hi = length if rank == nranks - 1 else (rank + 1) * per
+    a, b = max(0, lo - 1), min(length, hi + 1)
+    g = cylinder_extruded(radius, length, block_size, margin, z_range=(a, b))
+    zi = g.coords[:, 2].astype(np.int64) - margin
+    ranks = np.minimum(zi // per, nranks - 1).astype(np.int32)
+    return g, ranks
+
+
+def cylinder_extruded(radius: float, length: int, block_size: int = 8, margin: int = 2, z_range=None) -> Geometry:
     """The same geometry as ``cylinder`` built by extruding the three distinct z-slices (inlet cap,
     interior, outlet cap) of a short template -- O(N) and fast enough for the 1e8-site benchmark."""
     if length < 3:
@@ -364,21 +378,27 @@ def cylinder_extruded(radius: float, length: int, block_size: int = 8, margin: i
     parts_c, parts_b = [], []
     sl = {k: np.nonzero(tz == z0 + k)[0] for k in range(3)}
     xy_mid = t.coords[sl[1]][:, :2]
-    nmid = length - 2
+    za, zb = (0, length) if z_range is None else z_range  # slice indices kept, [za, zb)
+    m_lo, m_hi = max(za, 1), min(zb, length - 1)
+    nmid = max(0, m_hi - m_lo)
     # interior slices replicate the template's middle slice
-    zs = np.arange(z0 + 1, z0 + 1 + nmid, dtype=np.int32)
+    zs = np.arange(z0 + m_lo, z0 + m_lo + nmid, dtype=np.int32)
     cm = np.empty((nmid, xy_mid.shape[0], 3), np.int32)
     cm[:, :, :2] = xy_mid[None]
     cm[:, :, 2] = zs[:, None]
     c0 = t.coords[sl[0]].copy()
     c2 = t.coords[sl[2]].copy()
     c2[:, 2] = z0 + length - 1
+    if za > 0:
+        c0 = c0[:0]
+    if zb < length:
+        c2 = c2[:0]
     coords = np.concatenate([c0, cm.reshape(-1, 3), c2], 0)
     # boundary records
-    b0 = brec[sl[0]]
+    b0 = brec[sl[0]] if za == 0 else brec[sl[0]][:0]
     b1 = brec[sl[1]]
-    b2 = brec[sl[2]]
-    n0, n1 = sl[0].size, sl[1].size
+    b2 = brec[sl[2]] if zb == length else brec[sl[2]][:0]
+    n0, n1 = c0.shape[0], sl[1].size
     has1 = np.nonzero(b1 >= 0)[0]
     bsite = np.concatenate([
         np.nonzero(b0 >= 0)[0],

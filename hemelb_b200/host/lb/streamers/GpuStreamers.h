@@ -1,0 +1,259 @@
+// lb/streamers/GpuStreamers.h -- lb::streamer policy classes that run on the B200 engine.
+//
+// Drop-in for the reference's streamer policies (Code/lb/streamers/BulkStreamer.h:57-99,
+// StreamerTypeFactory.h:24-109): same constructor (InitParams&), same
+//   StreamAndCollide(first, count, lbmParams, latDat, propertyCache) / PostStep(...)
+// so `Traits<LATTICE, KERNEL, Normal, GpuBulk, GpuWall<W>::type, GpuInlet<I>::type, ...>` feeds
+// lb::LBM<Traits> unchanged.  Each class forwards (slot, first, count) to the C ABI; the work
+// happens in hand-written sm_100a kernels.  Policy names follow CMake/HemeLbOptions.cmake.
+#ifndef HEMELB_LB_STREAMERS_GPUSTREAMERS_H
+#define HEMELB_LB_STREAMERS_GPUSTREAMERS_H
+
+#include <type_traits>
+#include <vector>
+
+#include "geometry/FieldData.h"
+#include "lb/concepts.h"
+#include "lb/LbmParameters.h"
+#include "lb/MacroscopicPropertyCache.h"
+#include "lb/iolets/BoundaryValues.h"
+#include "lb/iolets/InOutLetCosine.h"
+#include "lb/iolets/InOutLetParabolicVelocity.h"
+#include "lb/kernels/LBGK.h"
+#include "lb/kernels/MRT.h"
+#include "lb/kernels/TRT.h"
+#include "lb/streamers/Common.h"
+
+namespace hemelb::lb::gpu {
+
+  // ---- compile-time policy -> C ABI enums ------------------------------------------------------
+  template <class K> struct kernel_id;
+  template <lattice_type L> struct kernel_id<LBGK<L>> { static constexpr int value = HLB_KERNEL_LBGK; };
+  template <moment_basis M> struct kernel_id<MRT<M>> { static constexpr int value = HLB_KERNEL_MRT; };
+  template <lattice_type L> struct kernel_id<TRT<L>> { static constexpr int value = HLB_KERNEL_TRT; };
+
+  struct SimpleBounceBack { static constexpr int value = HLB_WALL_SIMPLEBOUNCEBACK; };
+  struct BouzidiFirdaousLallemand { static constexpr int value = HLB_WALL_BFL; };
+  struct GuoZhengShi { static constexpr int value = HLB_WALL_GZS; };
+  struct NashZerothOrderPressure { static constexpr int value = HLB_IOLET_NASHZEROTHORDERPRESSURE; };
+  struct LaddIolet { static constexpr int value = HLB_IOLET_LADD; };
+  struct NoLink { static constexpr int value = -1; };
+
+  inline uint32_t CacheMask(MacroscopicPropertyCache& c) {  // SimulationMaster.impl.h:223-241
+    uint32_t m = 0;
+    if (c.densityCache.RequiresRefresh()) m |= HLB_CACHE_DENSITY;
+    if (c.velocityCache.RequiresRefresh()) m |= HLB_CACHE_VELOCITY;
+    if (c.wallShearStressMagnitudeCache.RequiresRefresh()) m |= HLB_CACHE_WALL_SHEAR_STRESS;
+    if (c.vonMisesStressCache.RequiresRefresh()) m |= HLB_CACHE_VON_MISES_STRESS;
+    if (c.shearRateCache.RequiresRefresh()) m |= HLB_CACHE_SHEAR_RATE;
+    if (c.stressTensorCache.RequiresRefresh()) m |= HLB_CACHE_STRESS_TENSOR;
+    if (c.tractionCache.RequiresRefresh()) m |= HLB_CACHE_TRACTION;
+    if (c.tangentialProjectionTractionCache.RequiresRefresh()) m |= HLB_CACHE_TANGENTIAL_TRACTION;
+    return m;
+  }
+
+  // One streamer class for all six LBM slots: SLOT 0 mid-fluid, 1 wall, 2 inlet, 3 outlet,
+  // 4 inlet-wall, 5 outlet-wall (Code/lb/lb.h:102-107).
+  template <collision_type C, int SLOT, class WALL, class IOLET>
+  class GpuStreamer {
+  public:
+    using CollisionType = C;
+    using KernelType = typename C::KernelType;
+    using LatticeType = typename C::LatticeType;
+    using VarsType = typename C::VarsType;
+
+    explicit GpuStreamer(InitParams& ip) : boundary(ip.boundaryObject), tau(ip.lbmParams->GetTau()) {}
+
+    void StreamAndCollide(const site_t first, const site_t count, const LbmParameters* lbmParams,
+                          geometry::FieldData& latDat, MacroscopicPropertyCache& cache) {
+      Register(latDat, lbmParams);
+      hlb_gpu_t h = latDat.Engine();
+      PushStepScalars(h, latDat, cache);
+      geometry::FieldData::Check(hlb_gpu_stream_and_collide(h, SLOT, first, count));
+      // the last domain-edge range of LBM::PreSend (lb.hpp:176-212) releases the halo send
+      if (SLOT == 5 && first >= latDat.GetDomain().GetMidDomainSiteCount())
+        geometry::FieldData::Check(hlb_gpu_edge_done(h));
+    }
+
+    void PostStep(const site_t first, const site_t count, const LbmParameters*, geometry::FieldData& latDat,
+                  MacroscopicPropertyCache& cache) {
+      geometry::FieldData::Check(hlb_gpu_post_step(latDat.Engine(), SLOT, first, count));
+      // after the last PostStep of LBM::PostReceive the refreshed caches are brought to the host
+      if (SLOT == 5 && first < latDat.GetDomain().GetMidDomainSiteCount()) PullCaches(latDat, cache);
+    }
+
+  private:
+    void Register(geometry::FieldData& latDat, const LbmParameters* p) {
+      auto& pol = latDat.Policy();
+      pol.kernel = kernel_id<KernelType>::value;
+      pol.tau = p->GetTau();
+      if constexpr (WALL::value >= 0) pol.wall = WALL::value;
+      if constexpr (IOLET::value >= 0) {
+        if (SLOT == 2 || SLOT == 4) { pol.inlet = IOLET::value; pol.inletValues = boundary; }
+        else { pol.outlet = IOLET::value; pol.outletValues = boundary; }
+      }
+    }
+    static void PushStepScalars(hlb_gpu_t h, geometry::FieldData& latDat, MacroscopicPropertyCache& cache) {
+      auto& pol = latDat.Policy();
+      std::vector<double> in, out;
+      if (pol.inletValues)
+        for (unsigned i = 0; i < pol.inletValues->GetLocalIoletCount(); ++i) in.push_back(pol.inletValues->GetBoundaryDensity(i));
+      if (pol.outletValues)
+        for (unsigned i = 0; i < pol.outletValues->GetLocalIoletCount(); ++i) out.push_back(pol.outletValues->GetBoundaryDensity(i));
+      const auto t = pol.inletValues ? pol.inletValues->GetTimeStep() : (pol.outletValues ? pol.outletValues->GetTimeStep() : 1);
+      geometry::FieldData::Check(hlb_gpu_set_step_scalars(h, t, in.data(), out.data(), CacheMask(cache)));
+    }
+    static void PullCaches(geometry::FieldData& latDat, MacroscopicPropertyCache& cache) {
+      hlb_gpu_t h = latDat.Engine();
+      const site_t n = latDat.GetDomain().GetLocalFluidSiteCount();
+      std::vector<double> buf;
+      auto scalar = [&](auto& c, uint32_t bit) {
+        if (!c.RequiresRefresh()) return;
+        buf.resize(n);
+        geometry::FieldData::Check(hlb_gpu_get_cache(h, bit, buf.data()));
+        for (site_t i = 0; i < n; ++i) c.Put(i, buf[i]);
+      };
+      auto vec = [&](auto& c, uint32_t bit) {
+        if (!c.RequiresRefresh()) return;
+        buf.resize(3 * n);
+        geometry::FieldData::Check(hlb_gpu_get_cache(h, bit, buf.data()));
+        for (site_t i = 0; i < n; ++i) c.Put(i, util::Vector3D<distribn_t>(buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]));
+      };
+      scalar(cache.densityCache, HLB_CACHE_DENSITY);
+      vec(cache.velocityCache, HLB_CACHE_VELOCITY);
+      scalar(cache.wallShearStressMagnitudeCache, HLB_CACHE_WALL_SHEAR_STRESS);
+      scalar(cache.vonMisesStressCache, HLB_CACHE_VON_MISES_STRESS);
+      scalar(cache.shearRateCache, HLB_CACHE_SHEAR_RATE);
+      vec(cache.tractionCache, HLB_CACHE_TRACTION);
+      vec(cache.tangentialProjectionTractionCache, HLB_CACHE_TANGENTIAL_TRACTION);
+      if (cache.stressTensorCache.RequiresRefresh()) {
+        buf.resize(9 * n);
+        geometry::FieldData::Check(hlb_gpu_get_cache(h, HLB_CACHE_STRESS_TENSOR, buf.data()));
+        for (site_t i = 0; i < n; ++i) {
+          util::Matrix3D m;
+          for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) m[a][b] = buf[9 * i + 3 * a + b];
+          cache.stressTensorCache.Put(i, m);
+        }
+      }
+    }
+    BoundaryValues* boundary;
+    distribn_t tau;
+  };
+
+  // Traits-ready aliases: STREAMER, WALL_BOUNDARY, INLET_BOUNDARY, OUTLET_BOUNDARY template
+  // template parameters of hemelb::Traits (Code/Traits.h:17-39)
+  template <class C> using Bulk = GpuStreamer<C, 0, NoLink, NoLink>;
+  template <class W> struct Wall { template <class C> using type = GpuStreamer<C, 1, W, NoLink>; };
+  template <class I> struct Inlet { template <class C> using type = GpuStreamer<C, 2, NoLink, I>; };
+  template <class I> struct Outlet { template <class C> using type = GpuStreamer<C, 3, NoLink, I>; };
+}
+
+namespace hemelb::lb {
+  // primary template lives in Code/lb/Streamers.h:71-74 (re-declared so this header stands alone)
+  template <typename WS, typename IS> struct CombineWallAndIoletStreamers;
+  // wall + iolet combination (Code/lb/Streamers.h:71-99): inlet-wall is slot 4, outlet-wall slot 5
+  template <class C, class W, class I>
+  struct CombineWallAndIoletStreamers<gpu::GpuStreamer<C, 1, W, gpu::NoLink>, gpu::GpuStreamer<C, 2, gpu::NoLink, I>> {
+    using type = gpu::GpuStreamer<C, 4, W, I>;
+  };
+  template <class C, class W, class I>
+  struct CombineWallAndIoletStreamers<gpu::GpuStreamer<C, 1, W, gpu::NoLink>, gpu::GpuStreamer<C, 3, gpu::NoLink, I>> {
+    using type = gpu::GpuStreamer<C, 5, W, I>;
+  };
+}
+
+namespace hemelb::geometry {
+  // Build the device engine from the Domain's tables the first time a streamer needs it.
+  inline void FieldData::EnsureEngine() {
+    if (m_gpu) return;
+    Domain& d = *m_domain;
+    const int Q = d.latticeInfo.GetNumVectors();
+    const site_t N = d.GetLocalFluidSiteCount();
+    hlb_gpu_config cfg{};
+    cfg.lattice = Q;
+    cfg.kernel = m_policy.kernel;
+    cfg.wall = m_policy.wall < 0 ? HLB_WALL_SIMPLEBOUNCEBACK : m_policy.wall;
+    cfg.inlet = m_policy.inlet < 0 ? HLB_IOLET_NASHZEROTHORDERPRESSURE : m_policy.inlet;
+    cfg.outlet = m_policy.outlet < 0 ? HLB_IOLET_NASHZEROTHORDERPRESSURE : m_policy.outlet;
+    cfg.tau = m_policy.tau;
+    cfg.rank = d.GetLocalRank();
+    cfg.nranks = d.GetCommunicator().Size();
+    int ndev = 1;
+    Check(hlb_gpu_device_count(&ndev));
+    cfg.device = cfg.rank % ndev;  // rank r -> GPU r on the NVSwitch box
+    cfg.n_sites = N;
+    for (unsigned t = 0; t < COLLISION_TYPES; ++t) {
+      cfg.mid_count[t] = d.GetMidDomainCollisionCount(t);
+      cfg.edge_count[t] = d.GetDomainEdgeCollisionCount(t);
+    }
+    cfg.total_shared_fs = d.totalSharedFs;
+    cfg.n_neighbours = (int)d.neighbouringProcs.size();
+    auto records = [](lb::BoundaryValues* bv) {
+      std::vector<double> r;
+      if (!bv) return r;
+      for (unsigned i = 0; i < bv->GetLocalIoletCount(); ++i) {
+        lb::InOutLet* io = bv->GetLocalIolet(i);
+        double rec[HLB_IOLET_RECORD_DOUBLES] = {0};
+        auto const& n = io->GetNormal();
+        auto const& p = io->GetPosition();
+        for (int k = 0; k < 3; ++k) { rec[1 + k] = n[k]; rec[4 + k] = p[k]; }
+        if (auto* v = dynamic_cast<lb::InOutLetParabolicVelocity*>(io)) {
+          rec[0] = 1; rec[7] = v->GetRadius(); rec[8] = v->GetMaxSpeed();
+        } else if (auto* c = dynamic_cast<lb::InOutLetCosine*>(io)) {
+          rec[9] = c->GetDensityMean(); rec[10] = c->GetDensityAmp(); rec[11] = c->GetPhase(); rec[12] = c->GetPeriod();
+        } else {
+          rec[9] = io->GetDensityMin(); rec[12] = 1.0;  // densities still arrive per step from BoundaryValues
+        }
+        rec[14] = io->GetDensityMin();
+        r.insert(r.end(), rec, rec + HLB_IOLET_RECORD_DOUBLES);
+      }
+      return r;
+    };
+    auto rin = records(m_policy.inletValues), rout = records(m_policy.outletValues);
+    cfg.n_inlets = (int)(rin.size() / HLB_IOLET_RECORD_DOUBLES);
+    cfg.n_outlets = (int)(rout.size() / HLB_IOLET_RECORD_DOUBLES);
+    Check(hlb_gpu_create(&cfg, &m_gpu));
+    Check(hlb_gpu_set_neighbour_indices(m_gpu, 0, N, d.neighbourIndices.data()));
+    std::vector<uint32_t> wall(N), iol(N);
+    std::vector<int32_t> ioid(N);
+    std::vector<double> normals(3 * N);
+    std::vector<int64_t> coords(3 * N);
+    for (site_t i = 0; i < N; ++i) {
+      auto const& sd = d.GetSiteData(i);
+      wall[i] = sd.GetWallIntersectionData();
+      iol[i] = sd.GetIoletIntersectionData();
+      ioid[i] = sd.GetIoletId();
+      for (int k = 0; k < 3; ++k) { normals[3 * i + k] = d.GetNormalToWall(i)[k]; coords[3 * i + k] = d.GetGlobalSiteCoords(i)[k]; }
+    }
+    // only the boundary-typed id ranges carry cut links: [mid0, midTotal) and [midTotal+edge0, N)
+    const site_t midTotal = d.GetMidDomainSiteCount();
+    const site_t ranges[2][2] = {{d.GetMidDomainCollisionCount(0), midTotal},
+                                 {midTotal + d.GetDomainEdgeCollisionCount(0), N}};
+    for (auto& r : ranges) {
+      const site_t a = r[0], n = r[1] - r[0];
+      if (n <= 0) continue;
+      Check(hlb_gpu_set_site_data(m_gpu, a, n, wall.data() + a, iol.data() + a, ioid.data() + a));
+      Check(hlb_gpu_set_wall_distances(m_gpu, a, n, d.distanceToWall.data() + a * (Q - 1)));
+      Check(hlb_gpu_set_wall_normals(m_gpu, a, n, normals.data() + 3 * a));
+      Check(hlb_gpu_set_site_coords(m_gpu, a, n, coords.data() + 3 * a));
+    }
+    std::vector<int> nr;
+    std::vector<int64_t> nc, nf;
+    for (auto const& p : d.neighbouringProcs) { nr.push_back(p.Rank); nc.push_back(p.SharedDistributionCount); nf.push_back(p.FirstSharedDistribution); }
+    if (!nr.empty()) {
+      Check(hlb_gpu_set_neighbours(m_gpu, nr.data(), nc.data(), nf.data()));
+      Check(hlb_gpu_set_streaming_indices(m_gpu, d.streamingIndicesForReceivedDistributions.data()));
+    }
+    if (cfg.n_inlets) Check(hlb_gpu_set_iolets(m_gpu, 0, cfg.n_inlets, rin.data()));
+    if (cfg.n_outlets) Check(hlb_gpu_set_iolets(m_gpu, 1, cfg.n_outlets, rout.data()));
+    Check(hlb_gpu_finalise(m_gpu));
+    if (cfg.nranks > 1) {
+      // NCCL bootstrap over the reference's own MPI communicator: rank 0 creates the id
+      char id[128];
+      if (cfg.rank == 0) Check(hlb_gpu_comm_unique_id(id));
+      d.GetCommunicator().Broadcast(std::span<char>(id, 128), 0);
+      Check(hlb_gpu_comm_init(m_gpu, id));
+    }
+  }
+}
+#endif

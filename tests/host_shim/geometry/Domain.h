@@ -1,0 +1,56 @@
+// Test-only stand-in for geometry::Domain carrying the member NAMES the drop-in FieldData reads
+// through `friend class FieldData` (Code/geometry/Domain.h:55,71-82,257-282,340,495-530), so the
+// host headers can be compile-checked here without MPI / Boost.
+#pragma once
+#include <memory>
+#include <span>
+#include <vector>
+#include "units.h"
+#include "constants.h"
+#include "util/Vector3D.h"
+#include "geometry/SiteData.h"
+#include "geometry/Site.h"
+#include "geometry/neighbouring/NeighbouringDomain.h"
+#include "lb/lattices/LatticeInfo.h"
+namespace hemelb::geometry {
+  struct NeighbouringProcessor { proc_t Rank; site_t SharedDistributionCount; site_t FirstSharedDistribution; };
+  struct FakeComm {
+    int Size() const { return 1; }
+    template <class T, std::size_t N> void Broadcast(std::span<T, N>, int) const {}
+  };
+  class FieldData;
+  class Domain {
+    friend class FieldData;
+    template <class> friend class Site;
+  public:
+    explicit Domain(const lb::LatticeInfo& li) : latticeInfo(li) {}
+    FakeComm const& GetCommunicator() const { return comms; }
+    site_t const& GetLocalFluidSiteCount() const { return nSites; }
+    site_t GetMidDomainSiteCount() const { return 0; }
+    site_t const& GetMidDomainCollisionCount(unsigned t) const { return mid[t]; }
+    site_t const& GetDomainEdgeCollisionCount(unsigned t) const { return edge[t]; }
+    int GetLocalRank() const { return 0; }
+    Site<Domain> GetSite(site_t i) { return Site<Domain>(i, *this); }
+    template <class L> distribn_t GetCutDistance(site_t i, int d) const { return distanceToWall[i * (L::NUMVECTORS - 1) + d - 1]; }
+    distribn_t* GetCutDistances(site_t i) { return &distanceToWall[i]; }
+    const distribn_t* GetCutDistances(site_t i) const { return &distanceToWall[i]; }
+    util::Vector3D<distribn_t>& GetNormalToWall(site_t i) { return wallNormalAtSite[i]; }
+    const util::Vector3D<distribn_t>& GetNormalToWall(site_t i) const { return wallNormalAtSite[i]; }
+    template <class L> site_t GetStreamedIndex(site_t i, unsigned d) const { return neighbourIndices[i * L::NUMVECTORS + d]; }
+    SiteData& GetSiteData(site_t i) { return siteData[i]; }
+    const SiteData& GetSiteData(site_t i) const { return siteData[i]; }
+    const util::Vector3D<site_t>& GetGlobalSiteCoords(site_t i) const { return globalSiteCoords[i]; }
+  private:
+    const lb::LatticeInfo& latticeInfo;
+    site_t nSites = 0, mid[COLLISION_TYPES] = {}, edge[COLLISION_TYPES] = {};
+    site_t totalSharedFs = 0;
+    std::vector<NeighbouringProcessor> neighbouringProcs;
+    std::vector<distribn_t> distanceToWall;
+    std::vector<util::Vector3D<distribn_t>> wallNormalAtSite;
+    std::vector<SiteData> siteData;
+    std::vector<util::Vector3D<site_t>> globalSiteCoords;
+    std::vector<site_t> neighbourIndices, streamingIndicesForReceivedDistributions;
+    std::shared_ptr<neighbouring::NeighbouringDomain> neighbouringData;
+    FakeComm comms;
+  };
+}
