@@ -152,6 +152,17 @@ struct hlb_gpu_handle {
   int64_t siteListCap = 0;
   double* monitorDev = nullptr;
   int64_t launches = 0;
+  // internal renumbering: sites of each of the 12 ranges sorted into long z-runs
+  uint32_t* perm = nullptr;    // reference site -> internal site (null = identity)
+  uint32_t* iperm = nullptr;   // internal site -> reference site
+  int32_t* coordsAll = nullptr;  // 3 planes of stride, reference order, until finalise
+  int64_t coordsCovered = 0;
+  // run-compressed neighbour table, per whole range
+  uint32_t* nbrFlags = nullptr;
+  uint32_t* nbrBase = nullptr;
+  int64_t groupStride = 0;
+  int64_t groupOffset[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t rangeFirst[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   bool profileBulk = false;
   std::vector<cudaEvent_t> profEv;  // pairs around the mid-fluid (bulk) range launches
   size_t profUsed = 0;

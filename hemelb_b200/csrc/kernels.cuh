@@ -71,9 +71,15 @@ struct StepArgs {
   double* __restrict__ cStress;
   double* __restrict__ cTraction;
   double* __restrict__ cTangTraction;
-  const int64_t* __restrict__ refSiteOf;  // internal site -> reference site id (cache rows), or null
+  const uint32_t* __restrict__ refSiteOf;  // internal site -> reference site id (cache rows), or null
   // optional explicit site list (sub-range calls that are not whole ranges)
   const uint32_t* __restrict__ siteList;
+  // run-compressed neighbour table (whole-range launches only): for the g-th group of 32 sites of
+  // this launch, bit d-1 of nbrFlags says "the 32 targets of direction d are consecutive", and
+  // nbrBase then holds the first one -- one 4 B load per warp instead of 128 B
+  const uint32_t* __restrict__ nbrFlags;
+  const uint32_t* __restrict__ nbrBase;  // (Q-1) planes of groupStride
+  int64_t groupStride, groupOffset;
 };
 
 template <int Q> struct MrtArgs {
@@ -171,7 +177,7 @@ __device__ __forceinline__ void stress_tensor(double rho, double tau, const doub
 }
 
 template <int Q, int KERNEL>
-__device__ __noinline__ void update_caches(const StepArgs& A, int64_t site, bool boundaryTyped, double rho,
+__device__ __forceinline__ void update_caches(const StepArgs& A, int64_t site, bool boundaryTyped, double rho,
                                            const double (&u)[3], const double (&fneq)[Q]) {
   // UpdateCachePostCollision, Common.h:21-130
   const int64_t row = A.refSiteOf ? A.refSiteOf[site] : site;
@@ -387,8 +393,19 @@ __global__ void __launch_bounds__(256) collide_stream_kernel(const StepArgs A, c
   for (int d = 0; d < Q; ++d) f[d] = __ldcs(A.fOld + (int64_t)d * A.stride + site);
   uint32_t target[Q];
   target[0] = (uint32_t)site;
+  if (A.nbrFlags) {
+    const int64_t g = A.groupOffset + (tid >> 5);
+    const uint32_t flags = __ldg(A.nbrFlags + g);
+    const uint32_t lane = (uint32_t)(tid & 31);
 #pragma unroll
-  for (int d = 1; d < Q; ++d) target[d] = __ldcs(A.nbr + (int64_t)(d - 1) * A.stride + site);
+    for (int d = 1; d < Q; ++d) {
+      if ((flags >> (d - 1)) & 1u) target[d] = __ldg(A.nbrBase + (int64_t)(d - 1) * A.groupStride + g) + lane;
+      else target[d] = __ldcs(A.nbr + (int64_t)(d - 1) * A.stride + site);
+    }
+  } else {
+#pragma unroll
+    for (int d = 1; d < Q; ++d) target[d] = __ldcs(A.nbr + (int64_t)(d - 1) * A.stride + site);
+  }
 
   // CalculatePreCollision (Normal.h:29-33 -> kernel.CalculateDensityMomentumFeq)
   double rho, m[3], u[3];
