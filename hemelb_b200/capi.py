@@ -38,7 +38,7 @@ class HlbConfig(C.Structure):
                 ("outlet", C.c_int), ("tau", C.c_double), ("device", C.c_int), ("rank", C.c_int),
                 ("nranks", C.c_int), ("n_sites", C.c_int64), ("mid_count", C.c_int64 * 6),
                 ("edge_count", C.c_int64 * 6), ("total_shared_fs", C.c_int64), ("n_neighbours", C.c_int),
-                ("n_inlets", C.c_int), ("n_outlets", C.c_int)]
+                ("n_inlets", C.c_int), ("n_outlets", C.c_int), ("reorder", C.c_int)]
 
 
 class HlbError(RuntimeError):

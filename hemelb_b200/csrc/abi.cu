@@ -11,6 +11,7 @@
 //   boundary  : masks, iolet ids, float cut distances, normals, coordinates -- only for the
 //               wall / inlet / outlet typed sites (two contiguous id ranges), plane-major.
 #include <cuda_runtime.h>
+#include <cub/cub.cuh>
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -215,37 +216,114 @@ __global__ void convert_nbr_kernel(const int64_t* __restrict__ aos, uint32_t* __
 }
 
 __global__ void nbr_to_ref_kernel(const uint32_t* __restrict__ nbr, int64_t* __restrict__ aos, int64_t first, int64_t n,
-                                  int Q, int64_t N, int64_t stride) {
+                                  int Q, int64_t N, int64_t stride, const uint32_t* __restrict__ perm,
+                                  const uint32_t* __restrict__ iperm) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= n * Q) return;
   const int d = (int)(tid / n);
   const int64_t s = tid % n;
-  const int64_t site = first + s;
+  const int64_t site = first + s;  // reference id
   int64_t v;
   if (d == 0) v = site * Q;
   else {
-    const int64_t in = nbr[(int64_t)(d - 1) * stride + site];
-    if (in < (int64_t)Q * stride) v = (in % stride) * Q + in / stride;
-    else v = in - (int64_t)Q * stride + N * Q;
+    const int64_t isite = perm ? (int64_t)perm[site] : site;
+    const int64_t in = nbr[(int64_t)(d - 1) * stride + isite];
+    if (in < (int64_t)Q * stride) {
+      const int64_t t = in % stride;
+      v = (iperm ? (int64_t)iperm[t] : t) * Q + in / stride;
+    } else v = in - (int64_t)Q * stride + N * Q;
   }
   aos[s * Q + d] = v;
 }
 
+// ---------------------------------------------------------------- internal renumbering
+__global__ void coords_to_planes_kernel(const int64_t* __restrict__ aos, int32_t* __restrict__ planes, int64_t first,
+                                        int64_t n, int64_t stride) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n * 3) return;
+  const int k = (int)(tid / n);
+  const int64_t s = tid % n;
+  planes[(int64_t)k * stride + first + s] = (int32_t)aos[s * 3 + k];
+}
+struct RangeTable { int64_t first[13]; };
+// sort key: (site range, x, y, z) -- sites stay inside their (mid/edge x collision type) range and
+// become long z-runs, so the pushes of a warp land on consecutive addresses
+__global__ void sort_keys_kernel(const int32_t* __restrict__ coords, int64_t stride, int64_t N, RangeTable R, int lox,
+                                 int loy, int loz, int64_t Ly, int64_t Lz, uint64_t* __restrict__ keys,
+                                 uint32_t* __restrict__ vals) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= N) return;
+  int r = 0;
+  while (r < 11 && s >= R.first[r + 1]) ++r;
+  const int64_t x = coords[s] - lox, y = coords[stride + s] - loy, z = coords[2 * stride + s] - loz;
+  keys[s] = ((uint64_t)r << 58) | (uint64_t)((x * Ly + y) * Lz + z);
+  vals[s] = (uint32_t)s;
+}
+__global__ void invert_perm_kernel(const uint32_t* __restrict__ iperm, uint32_t* __restrict__ perm, int64_t N) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < N) perm[iperm[j]] = (uint32_t)j;
+}
+__global__ void permute_nbr_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                   const uint32_t* __restrict__ perm, int Q, int64_t N, int64_t stride) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= N * (Q - 1)) return;
+  const int64_t d1 = tid / N, s = tid % N;
+  uint32_t v = in[d1 * stride + s];
+  if ((int64_t)v < (int64_t)Q * stride) v = (uint32_t)(((int64_t)v / stride) * stride + perm[(int64_t)v % stride]);
+  out[d1 * stride + perm[s]] = v;
+}
+__global__ void remap_stream_kernel(uint32_t* __restrict__ idx, const uint32_t* __restrict__ perm, int64_t S,
+                                    int64_t stride) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S) return;
+  const int64_t v = idx[i];
+  idx[i] = (uint32_t)((v / stride) * stride + perm[v % stride]);
+}
+__global__ void site_list_kernel(const uint32_t* __restrict__ perm, uint32_t* __restrict__ out, int64_t first, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = perm[first + i];
+}
+// one warp per group of 32 consecutive sites of a range: which directions push to 32 consecutive
+// targets?  (flags, first target) per group
+__global__ void compress_nbr_kernel(const uint32_t* __restrict__ nbr, int Q, int64_t stride, int64_t rangeFirst,
+                                    int64_t rangeCount, int64_t groupOffset, int64_t groupStride,
+                                    uint32_t* __restrict__ flags, uint32_t* __restrict__ base) {
+  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t nGroups = (rangeCount + 31) / 32;
+  if (g >= nGroups) return;
+  const int64_t site = rangeFirst + g * 32 + lane;
+  const bool valid = site < rangeFirst + rangeCount;
+  uint32_t bits = 0;
+  for (int d = 1; d < Q; ++d) {
+    const uint32_t v = valid ? nbr[(int64_t)(d - 1) * stride + site] : 0u;
+    const uint32_t v0 = __shfl_sync(0xffffffffu, v, 0);
+    const bool ok = !valid || v == v0 + (uint32_t)lane;
+    if (__all_sync(0xffffffffu, ok)) {
+      bits |= 1u << (d - 1);
+      if (lane == 0) base[(int64_t)(d - 1) * groupStride + groupOffset + g] = v0;
+    }
+  }
+  if (lane == 0) flags[groupOffset + g] = bits;
+}
+
 __global__ void aos_to_soa_kernel(const double* __restrict__ aos, double* __restrict__ f, int64_t first, int64_t n,
-                                  int Q, int64_t stride) {
+                                  int Q, int64_t stride, const uint32_t* __restrict__ perm) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= n * Q) return;
   const int d = (int)(tid / n);
   const int64_t s = tid % n;
-  f[(int64_t)d * stride + first + s] = aos[s * Q + d];
+  const int64_t site = perm ? (int64_t)perm[first + s] : first + s;
+  f[(int64_t)d * stride + site] = aos[s * Q + d];
 }
 __global__ void soa_to_aos_kernel(const double* __restrict__ f, double* __restrict__ aos, int64_t first, int64_t n,
-                                  int Q, int64_t stride) {
+                                  int Q, int64_t stride, const uint32_t* __restrict__ perm) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= n * Q) return;
   const int d = (int)(tid / n);
   const int64_t s = tid % n;
-  aos[s * Q + d] = f[(int64_t)d * stride + first + s];
+  const int64_t site = perm ? (int64_t)perm[first + s] : first + s;
+  aos[s * Q + d] = f[(int64_t)d * stride + site];
 }
 __global__ void fill_planes_kernel(double* __restrict__ f0, double* __restrict__ f1, int64_t N, int64_t stride, int Q,
                                    const double* __restrict__ feq) {
@@ -369,7 +447,7 @@ StepArgs make_args(hlb_gpu_t h, int which /*0 inlet BoundaryValues, 1 outlet*/) 
   A.cStress = h->cache[5];
   A.cTraction = h->cache[6];
   A.cTangTraction = h->cache[7];
-  A.refSiteOf = nullptr;
+  A.refSiteOf = h->iperm;
   A.siteList = nullptr;
   return A;
 }
@@ -405,6 +483,124 @@ void fill_mrt(hlb_gpu_t h) {
   }
 }
 
+// Renumber the sites inside each of the 12 ranges by (x, y, z): long z-runs.  Everything indexed by
+// site moves with it: the neighbour table (positions and values), the streaming indices of the
+// received distributions and the staged boundary tables.  Halo slots and range bounds do not move.
+int build_permutation(hlb_gpu_t h) {
+  const int Q = h->Q;
+  const int64_t N = h->N;
+  // bounding box of the coordinates
+  int lo[3], hi[3];
+  {
+    void* tmp = nullptr;
+    size_t tmpBytes = 0;
+    int* dres = nullptr;
+    CU(cudaMalloc(&dres, sizeof(int) * 6));
+    cub::DeviceReduce::Min(tmp, tmpBytes, h->coordsAll, dres, (int)N);
+    CU(cudaMalloc(&tmp, tmpBytes + 16));
+    for (int k = 0; k < 3; ++k) {
+      cub::DeviceReduce::Min(tmp, tmpBytes, h->coordsAll + (int64_t)k * h->stride, dres + k, (int)N);
+      cub::DeviceReduce::Max(tmp, tmpBytes, h->coordsAll + (int64_t)k * h->stride, dres + 3 + k, (int)N);
+    }
+    int res[6];
+    CU(cudaMemcpy(res, dres, sizeof(res), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3; ++k) { lo[k] = res[k]; hi[k] = res[3 + k]; }
+    cudaFree(tmp);
+    cudaFree(dres);
+  }
+  const int64_t Ly = (int64_t)hi[1] - lo[1] + 1, Lz = (int64_t)hi[2] - lo[2] + 1, Lx = (int64_t)hi[0] - lo[0] + 1;
+  if ((double)Lx * (double)Ly * (double)Lz >= 2.8e17) return fail("coordinate bounding box too large to renumber");
+  uint64_t *keysIn = nullptr, *keysOut = nullptr;
+  uint32_t* valsIn = nullptr;
+  CU(cudaMalloc(&keysIn, sizeof(uint64_t) * N));
+  CU(cudaMalloc(&keysOut, sizeof(uint64_t) * N));
+  CU(cudaMalloc(&valsIn, sizeof(uint32_t) * N));
+  CU(cudaMalloc(&h->iperm, sizeof(uint32_t) * N));
+  CU(cudaMalloc(&h->perm, sizeof(uint32_t) * N));
+  RangeTable R;
+  for (int k = 0; k < 13; ++k) R.first[k] = h->rangeFirst[k];
+  sort_keys_kernel<<<blocks_for(N), 256>>>(h->coordsAll, h->stride, N, R, lo[0], lo[1], lo[2], Ly, Lz, keysIn, valsIn);
+  CU(cudaGetLastError());
+  {
+    void* tmp = nullptr;
+    size_t tmpBytes = 0;
+    cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keysIn, keysOut, valsIn, h->iperm, (int)N);
+    CU(cudaMalloc(&tmp, tmpBytes + 16));
+    cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, keysIn, keysOut, valsIn, h->iperm, (int)N);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    cudaFree(tmp);
+  }
+  cudaFree(keysIn);
+  cudaFree(keysOut);
+  cudaFree(valsIn);
+  invert_perm_kernel<<<blocks_for(N), 256>>>(h->iperm, h->perm, N);
+  CU(cudaGetLastError());
+  // neighbour table
+  uint32_t* nbr2 = nullptr;
+  CU(cudaMalloc(&nbr2, sizeof(uint32_t) * (Q - 1) * h->stride));
+  CU(cudaMemset(nbr2, 0xff, sizeof(uint32_t) * (Q - 1) * h->stride));
+  permute_nbr_kernel<<<blocks_for(N * (Q - 1)), 256>>>(h->nbr, nbr2, h->perm, Q, N, h->stride);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  cudaFree(h->nbr);
+  h->nbr = nbr2;
+  if (h->S) {
+    remap_stream_kernel<<<blocks_for(h->S), 256>>>(h->streamIdx, h->perm, h->S, h->stride);
+    CU(cudaGetLastError());
+  }
+  // staged boundary tables: reference boundary ordinal -> internal boundary ordinal
+  if (h->NB) {
+    std::vector<uint32_t> hp(h->NB);
+    const int64_t nbMid = h->midTotal - h->midBulk;
+    if (nbMid) CU(cudaMemcpy(hp.data(), h->perm + h->midBulk, sizeof(uint32_t) * nbMid, cudaMemcpyDeviceToHost));
+    if (h->NB - nbMid)
+      CU(cudaMemcpy(hp.data() + nbMid, h->perm + h->midTotal + h->edgeBulk, sizeof(uint32_t) * (h->NB - nbMid),
+                    cudaMemcpyDeviceToHost));
+    std::vector<int64_t> to(h->NB);
+    for (int64_t b = 0; b < h->NB; ++b) {
+      to[b] = host_bidx(h, (int64_t)hp[b]);
+      if (to[b] < 0 || to[b] >= h->NB) return fail("internal error: renumbering moved a site out of its range");
+    }
+    auto move = [&](auto& v, int planes) {
+      auto old = v;
+      for (int k = 0; k < planes; ++k)
+        for (int64_t b = 0; b < h->NB; ++b) v[(size_t)k * h->bStride + to[b]] = old[(size_t)k * h->bStride + b];
+    };
+    move(h->hWall, 1);
+    move(h->hIolet, 1);
+    move(h->hIoletId, 1);
+    move(h->hCut, Q - 1);
+    move(h->hNormal, 3);
+    move(h->hCoords, 3);
+  }
+  return 0;
+}
+
+int build_compressed(hlb_gpu_t h) {
+  const int Q = h->Q;
+  int64_t total = 0;
+  for (int k = 0; k < 12; ++k) {
+    h->groupOffset[k] = total;
+    total += (h->rangeFirst[k + 1] - h->rangeFirst[k] + 31) / 32;
+  }
+  h->groupStride = ((total + 63) / 64) * 64;
+  if (h->groupStride == 0) h->groupStride = 64;
+  CU(cudaMalloc(&h->nbrFlags, sizeof(uint32_t) * h->groupStride));
+  CU(cudaMalloc(&h->nbrBase, sizeof(uint32_t) * (Q - 1) * h->groupStride));
+  CU(cudaMemset(h->nbrFlags, 0, sizeof(uint32_t) * h->groupStride));
+  for (int k = 0; k < 12; ++k) {
+    const int64_t cnt = h->rangeFirst[k + 1] - h->rangeFirst[k];
+    if (cnt <= 0) continue;
+    const int64_t groups = (cnt + 31) / 32;
+    compress_nbr_kernel<<<blocks_for(groups * 32), 256>>>(h->nbr, Q, h->stride, h->rangeFirst[k], cnt,
+                                                          h->groupOffset[k], h->groupStride, h->nbrFlags, h->nbrBase);
+    CU(cudaGetLastError());
+  }
+  CU(cudaDeviceSynchronize());
+  return 0;
+}
+
 // site range of a streamer slot -> is it a whole range (fast path) or an arbitrary sub-range
 int launch_range(hlb_gpu_t h, int slot, int64_t first, int64_t count, bool post) {
   if (!h->finalised) return fail("handle not finalised");
@@ -420,6 +616,27 @@ int launch_range(hlb_gpu_t h, int slot, int64_t first, int64_t count, bool post)
   }
   const bool isInletSlot = (slot == 2 || slot == 4);
   StepArgs A = make_args(h, isInletSlot ? 0 : 1);
+  // whole ranges run on the internal order with the run-compressed table; an arbitrary sub-range
+  // (reference ids) goes through an explicit site list when the sites were renumbered
+  int whole = -1;
+  for (int k = 0; k < 12; ++k)
+    if (first == h->rangeFirst[k] && first + count == h->rangeFirst[k + 1]) whole = k;
+  if (whole >= 0 && h->nbrFlags && !post) {
+    A.nbrFlags = h->nbrFlags;
+    A.nbrBase = h->nbrBase;
+    A.groupStride = h->groupStride;
+    A.groupOffset = h->groupOffset[whole];
+  } else if (whole < 0 && h->perm) {
+    if (h->siteListCap < count) {
+      if (h->siteListDev) cudaFree(h->siteListDev);
+      h->siteListDev = nullptr;
+      CU(cudaMalloc(&h->siteListDev, sizeof(uint32_t) * count));
+      h->siteListCap = count;
+    }
+    // (stream-ordered: a previous launch may still read the list)
+    site_list_kernel<<<blocks_for(count), 256, 0, h->compute>>>(h->perm, h->siteListDev, first, count);
+    A.siteList = h->siteListDev;
+  }
   const bool canWall = (slot == 1 || slot == 4 || slot == 5);
   const bool canIolet = slot >= 2;
   if (post) {
@@ -570,6 +787,12 @@ int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
     tot += h->mid[t] + h->edge[t];
   }
   if (tot != h->N) { delete h; return fail("collision counts do not sum to n_sites"); }
+  {
+    int64_t acc = 0;
+    for (int t = 0; t < 6; ++t) { h->rangeFirst[t] = acc; acc += h->mid[t]; }
+    for (int t = 0; t < 6; ++t) { h->rangeFirst[6 + t] = acc; acc += h->edge[t]; }
+    h->rangeFirst[12] = acc;
+  }
   h->midBulk = h->mid[0];
   h->edgeBulk = h->edge[0];
   h->NB = h->N - h->midBulk - h->edgeBulk;
@@ -653,6 +876,11 @@ int hlb_gpu_destroy(hlb_gpu_t h) {
   cudaFree(h->staging);
   cudaFree(h->siteListDev);
   cudaFree(h->monitorDev);
+  cudaFree(h->perm);
+  cudaFree(h->iperm);
+  cudaFree(h->coordsAll);
+  cudaFree(h->nbrFlags);
+  cudaFree(h->nbrBase);
   cudaEventDestroy(h->evEdge);
   cudaEventDestroy(h->evComm);
   cudaEventDestroy(h->evT0);
@@ -694,7 +922,8 @@ int hlb_gpu_get_neighbour_indices(hlb_gpu_t h, int64_t* idx) {
   if (ensure_staging(h, sizeof(int64_t) * kChunkSites * Q + 16)) return 1;
   for (int64_t s0 = 0; s0 < h->N; s0 += kChunkSites) {
     const int64_t m = std::min(kChunkSites, h->N - s0);
-    nbr_to_ref_kernel<<<blocks_for(m * Q), 256>>>(h->nbr, (int64_t*)h->staging, s0, m, Q, h->N, h->stride);
+    nbr_to_ref_kernel<<<blocks_for(m * Q), 256>>>(h->nbr, (int64_t*)h->staging, s0, m, Q, h->N, h->stride, h->perm,
+                                                  h->iperm);
     CU(cudaGetLastError());
     CU(cudaMemcpy(idx + s0 * Q, h->staging, sizeof(int64_t) * m * Q, cudaMemcpyDeviceToHost));
   }
@@ -759,6 +988,20 @@ int hlb_gpu_set_site_coords(hlb_gpu_t h, int64_t first, int64_t n, const int64_t
     for (int k = 0; k < 3; ++k) h->hCoords[(size_t)k * h->bStride + b] = (int32_t)coords[3 * i + k];
   }
   h->haveCoords = true;
+  if (h->cfg.reorder) {
+    CU(cudaSetDevice(h->cfg.device));
+    if (!h->coordsAll) CU(cudaMalloc(&h->coordsAll, sizeof(int32_t) * 3 * h->stride));
+    if (ensure_staging(h, sizeof(int64_t) * kChunkSites * h->Q + 16)) return 1;
+    for (int64_t s0 = 0; s0 < n; s0 += kChunkSites) {
+      const int64_t m = std::min(kChunkSites, n - s0);
+      CU(cudaMemcpy(h->staging, coords + 3 * s0, sizeof(int64_t) * 3 * m, cudaMemcpyHostToDevice));
+      coords_to_planes_kernel<<<blocks_for(3 * m), 256>>>((const int64_t*)h->staging, h->coordsAll, first + s0, m,
+                                                          h->stride);
+      CU(cudaGetLastError());
+      CU(cudaDeviceSynchronize());
+    }
+    h->coordsCovered += n;
+  }
   return 0;
 }
 
@@ -842,6 +1085,11 @@ int hlb_gpu_finalise(hlb_gpu_t h) {
   const int Q = h->Q;
   for (int64_t b = 0; b < h->NB; ++b)
     if (h->hIolet[b] && (h->hIoletId[b] < 0)) return fail("iolet site without an iolet id");
+  if (h->cfg.reorder && h->N > 0) {
+    if (h->coordsCovered != h->N)
+      return fail("reorder requested but hlb_gpu_set_site_coords did not cover every site exactly once");
+    if (build_permutation(h)) return 1;
+  }
   CU(cudaMemcpy(h->wallMask, h->hWall.data(), sizeof(uint32_t) * h->bStride, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->ioletMask, h->hIolet.data(), sizeof(uint32_t) * h->bStride, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->ioletId, h->hIoletId.data(), sizeof(int32_t) * h->bStride, cudaMemcpyHostToDevice));
@@ -866,6 +1114,11 @@ int hlb_gpu_finalise(hlb_gpu_t h) {
         if (g[(size_t)(i - 1) * h->bStride + b] < 0)
           return fail("GZS wall link extrapolates from a site on another rank: not implemented yet");
       }
+  }
+  if (h->N > 0 && build_compressed(h)) return 1;
+  if (h->coordsAll) {
+    cudaFree(h->coordsAll);
+    h->coordsAll = nullptr;
   }
   h->finalised = true;
   return 0;
@@ -893,6 +1146,7 @@ int hlb_gpu_comm_init(hlb_gpu_t h, const void* id128) {
 
 int hlb_gpu_set_f(hlb_gpu_t h, int which, const double* f) {
   if (!h || !f) return fail("null argument");
+  if (!h->finalised) return fail("hlb_gpu_set_f before hlb_gpu_finalise");
   CU(cudaSetDevice(h->cfg.device));
   CU(cudaStreamSynchronize(h->compute));
   double* dst = h->f[which ? h->cur ^ 1 : h->cur];
@@ -901,7 +1155,7 @@ int hlb_gpu_set_f(hlb_gpu_t h, int which, const double* f) {
   for (int64_t s0 = 0; s0 < h->N; s0 += kChunkSites) {
     const int64_t m = std::min(kChunkSites, h->N - s0);
     CU(cudaMemcpy(h->staging, f + s0 * Q, sizeof(double) * m * Q, cudaMemcpyHostToDevice));
-    aos_to_soa_kernel<<<blocks_for(m * Q), 256>>>((const double*)h->staging, dst, s0, m, Q, h->stride);
+    aos_to_soa_kernel<<<blocks_for(m * Q), 256>>>((const double*)h->staging, dst, s0, m, Q, h->stride, h->perm);
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
   }
@@ -919,7 +1173,7 @@ int hlb_gpu_get_f(hlb_gpu_t h, int which, double* f) {
   if (ensure_staging(h, sizeof(int64_t) * kChunkSites * Q + 16)) return 1;
   for (int64_t s0 = 0; s0 < h->N; s0 += kChunkSites) {
     const int64_t m = std::min(kChunkSites, h->N - s0);
-    soa_to_aos_kernel<<<blocks_for(m * Q), 256>>>(src, (double*)h->staging, s0, m, Q, h->stride);
+    soa_to_aos_kernel<<<blocks_for(m * Q), 256>>>(src, (double*)h->staging, s0, m, Q, h->stride, h->perm);
     CU(cudaGetLastError());
     CU(cudaMemcpy(f + s0 * Q, h->staging, sizeof(double) * m * Q, cudaMemcpyDeviceToHost));
   }

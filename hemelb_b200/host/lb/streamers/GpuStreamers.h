@@ -187,6 +187,7 @@ namespace hemelb::geometry {
       cfg.edge_count[t] = d.GetDomainEdgeCollisionCount(t);
     }
     cfg.total_shared_fs = d.totalSharedFs;
+    cfg.reorder = 1;
     cfg.n_neighbours = (int)d.neighbouringProcs.size();
     auto records = [](lb::BoundaryValues* bv) {
       std::vector<double> r;
@@ -235,8 +236,8 @@ namespace hemelb::geometry {
       Check(hlb_gpu_set_site_data(m_gpu, a, n, wall.data() + a, iol.data() + a, ioid.data() + a));
       Check(hlb_gpu_set_wall_distances(m_gpu, a, n, d.distanceToWall.data() + a * (Q - 1)));
       Check(hlb_gpu_set_wall_normals(m_gpu, a, n, normals.data() + 3 * a));
-      Check(hlb_gpu_set_site_coords(m_gpu, a, n, coords.data() + 3 * a));
     }
+    Check(hlb_gpu_set_site_coords(m_gpu, 0, N, coords.data()));  // every site: internal z-run renumbering
     std::vector<int> nr;
     std::vector<int64_t> nc, nf;
     for (auto const& p : d.neighbouringProcs) { nr.push_back(p.Rank); nc.push_back(p.SharedDistributionCount); nf.push_back(p.FirstSharedDistribution); }

@@ -75,7 +75,7 @@ class GpuLBM:
     """One rank's collide-and-stream engine on one B200."""
 
     def __init__(self, domain: RankDomain, kernel="LBGK", wall="SBB", inlet="NASH", outlet="NASH", tau=0.8,
-                 inlets=(), outlets=(), device=0, chunk=1 << 21):
+                 inlets=(), outlets=(), device=0, chunk=1 << 21, reorder=True):
         self.L = lib()
         self.domain = domain
         self.Q = domain.Q
@@ -103,6 +103,7 @@ class GpuLBM:
         cfg.n_neighbours = int(domain.procs.shape[0])
         cfg.n_inlets = len(inlets)
         cfg.n_outlets = len(outlets)
+        cfg.reorder = 1 if reorder else 0
         self.cfg = cfg
         h = C.c_void_p()
         check(self.L.hlb_gpu_create(C.byref(cfg), C.byref(h)))
@@ -127,8 +128,14 @@ class GpuLBM:
             check(L.hlb_gpu_set_wall_distances(h, C.c_int64(first), C.c_int64(n), ptr(d, C.c_double)))
             nr = np.ascontiguousarray(domain.wall_normal(first, n))
             check(L.hlb_gpu_set_wall_normals(h, C.c_int64(first), C.c_int64(n), ptr(nr, C.c_double)))
-            gc = np.ascontiguousarray(domain.globalCoords[sl], np.int64)
-            check(L.hlb_gpu_set_site_coords(h, C.c_int64(first), C.c_int64(n), ptr(gc, C.c_int64)))
+            if not reorder:
+                gc = np.ascontiguousarray(domain.globalCoords[sl], np.int64)
+                check(L.hlb_gpu_set_site_coords(h, C.c_int64(first), C.c_int64(n), ptr(gc, C.c_int64)))
+        if reorder:  # the renumbering needs every site's coordinates
+            for s0 in range(0, N, chunk):
+                n = min(chunk, N - s0)
+                gc = np.ascontiguousarray(domain.globalCoords[s0:s0 + n], np.int64)
+                check(L.hlb_gpu_set_site_coords(h, C.c_int64(s0), C.c_int64(n), ptr(gc, C.c_int64)))
         if cfg.n_neighbours:
             pr = domain.procs
             check(L.hlb_gpu_set_neighbours(h, ptr(np.ascontiguousarray(pr[:, 0], np.int32), C.c_int),

@@ -48,6 +48,9 @@ typedef struct {
   int64_t total_shared_fs;/* Domain::totalSharedFs */
   int n_neighbours;       /* Domain::neighbouringProcs.size() */
   int n_inlets, n_outlets;/* BoundaryValues::GetLocalIoletCount() of the two objects */
+  int reorder;            /* 1: renumber sites internally into long z-runs inside each site range
+                             (needs hlb_gpu_set_site_coords for EVERY site); the API keeps speaking
+                             reference site ids.  0: keep the reference order on the device. */
 } hlb_gpu_config;
 
 /* Iolet descriptor: 16 doubles {kind (0 cosine pressure / 1 parabolic velocity), normal[3],

@@ -181,6 +181,35 @@ def test_multi_rank_host_staged_halo(R, decomp):
         _check(gpus[r].get_f()[:d.N * Q], sim.get_f(r)[:d.N * Q], "rank %d f_old" % r)
 
 
+@pytest.mark.parametrize("geom_name,Q,kernel,wall,inlet,outlet", [
+    ("tree", 19, "LBGK", "BFL", "NASH", "NASH"), ("sac", 27, "TRT", "GZS", "LADD", "NASH"),
+    ("cylinder", 15, "MRT", "SBB", "LADD", "LADD")])
+def test_internal_renumbering_is_invisible(geom_name, Q, kernel, wall, inlet, outlet):
+    """cfg.reorder renumbers sites on the device only: distributions, caches, sub-range calls and
+    the neighbour table read back in reference form are identical with and without it."""
+    geom = geometry(geom_name)
+    inlets, outlets = iolets_for(geom, inlet, outlet)
+    dom = build_domains(geom, Q)[0]
+    a = GpuLBM(dom, kernel, wall, inlet, outlet, tau=0.7, inlets=inlets, outlets=outlets, reorder=True)
+    b = GpuLBM(dom, kernel, wall, inlet, outlet, tau=0.7, inlets=inlets, outlets=outlets, reorder=False)
+    assert np.array_equal(a.get_neighbour_indices(), dom.neighbour_indices())
+    assert np.array_equal(b.get_neighbour_indices(), dom.neighbour_indices())
+    f0 = anisotropic_f(dom.N, Q, 0)
+    for g in (a, b):
+        g.set_f(f0)
+        assert np.array_equal(g.get_f(), f0)
+        g.set_cache_mask(255)
+        g.step(4)
+        # a ragged sub-range of the wall streamer on top (goes through the site-list path)
+        first, count = int(dom.mid[0]) + 3, int(dom.mid[1]) - 7
+        g.stream_and_collide(1, first, count)
+        g.post_step(1, first, count)
+    assert np.array_equal(a.get_f(), b.get_f())
+    assert np.array_equal(a.get_f(which=1), b.get_f(which=1))
+    for name in O.CACHE_BITS:
+        assert np.array_equal(a.get_cache(name), b.get_cache(name)), name
+
+
 def test_error_paths():
     from hemelb_b200.capi import HlbError
     geom = geometry("four_cube")
