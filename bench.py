@@ -160,6 +160,7 @@ def main():
     ap.add_argument("--radius", type=float, default=146.0)
     ap.add_argument("--length", type=int, default=1500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reorder", action="store_true")
     ap.add_argument("--block-size", type=int, default=8, help="sites per block side of the synthetic .gmy (HemeLB default 8)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -192,7 +193,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     t_setup = time.time()
     geom, dom, inlets, outlets = build_workload(args.radius, args.length, rank, world, args.block_size)
-    gpu = GpuLBM(dom, "LBGK", "BFL", "NASH", "NASH", tau=TAU, inlets=inlets, outlets=outlets, device=local_rank)
+    gpu = GpuLBM(dom, "LBGK", "BFL", "NASH", "NASH", tau=TAU, inlets=inlets, outlets=outlets, device=local_rank,
+                 reorder=not args.no_reorder)
     if world > 1:
         import torch
         uid = [GpuLBM.comm_unique_id() if rank == 0 else None]

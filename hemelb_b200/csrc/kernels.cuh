@@ -397,11 +397,13 @@ __global__ void __launch_bounds__(256) collide_stream_kernel(const StepArgs A, c
     const int64_t g = A.groupOffset + (tid >> 5);
     const uint32_t flags = __ldg(A.nbrFlags + g);
     const uint32_t lane = (uint32_t)(tid & 31);
+    // the per-group bases are fetched unconditionally (warp-uniform, independent of the flags, so
+    // they overlap the f loads); only the rare non-consecutive group pays a dependent table load
 #pragma unroll
-    for (int d = 1; d < Q; ++d) {
-      if ((flags >> (d - 1)) & 1u) target[d] = __ldg(A.nbrBase + (int64_t)(d - 1) * A.groupStride + g) + lane;
-      else target[d] = __ldcs(A.nbr + (int64_t)(d - 1) * A.stride + site);
-    }
+    for (int d = 1; d < Q; ++d) target[d] = __ldg(A.nbrBase + (int64_t)(d - 1) * A.groupStride + g) + lane;
+#pragma unroll
+    for (int d = 1; d < Q; ++d)
+      if (!((flags >> (d - 1)) & 1u)) target[d] = __ldcs(A.nbr + (int64_t)(d - 1) * A.stride + site);
   } else {
 #pragma unroll
     for (int d = 1; d < Q; ++d) target[d] = __ldcs(A.nbr + (int64_t)(d - 1) * A.stride + site);
