@@ -236,6 +236,9 @@ def main():
     mlups = n_sites_global * args.steps / (ms * 1e-3) / 1e6
 
     # ---- end to end through the phase API with host scalars every step
+    gpu.set_cache_mask(256)  # HLB_CACHE_MONITOR: stability / incompressibility monitors gathered in-kernel
+    gpu.do_time_step()
+    gpu.monitor()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):

@@ -153,6 +153,8 @@ struct hlb_gpu_handle {
   uint32_t* siteListDev = nullptr;
   int64_t siteListCap = 0;
   double* monitorDev = nullptr;
+  unsigned long long* monitorSlots = nullptr;
+  bool monitorFused = false;  // the slots hold a complete step's worth of data
   int64_t launches = 0;
   // internal renumbering: sites of each of the 12 ranges sorted into long z-runs
   uint32_t* perm = nullptr;    // reference site -> internal site (null = identity)
@@ -356,15 +358,9 @@ __global__ void gzs_neighbour_kernel(const uint32_t* __restrict__ nbr, int32_t* 
   out[(int64_t)(d - 1) * bStride + b] = v;
 }
 
-// {min f_old, min rho, max rho, max |u|^2} -- block reduce then atomics on ordered-int encodings
-__device__ __forceinline__ unsigned long long enc(double x) {
-  unsigned long long u = __double_as_longlong(x);
-  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double dec(unsigned long long u) {
-  u = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
-  return __longlong_as_double(u);
-}
+// {min f_old, min rho, max rho, max |u|^2}: stand-alone pass (when the fused monitor was not on)
+#define enc mon_enc
+#define dec mon_dec
 template <int Q>
 __global__ void __launch_bounds__(256) monitor_kernel(const double* __restrict__ f, int64_t N, int64_t stride,
                                                       unsigned long long* __restrict__ out) {
@@ -400,6 +396,27 @@ __global__ void __launch_bounds__(256) monitor_kernel(const double* __restrict__
     atomicMin(out + 1, enc(rmin));
     atomicMax(out + 2, enc(rmax));
     atomicMax(out + 3, enc(umax));
+  }
+}
+// fold the spread slots of the fused monitor into slot 0..3 of `io` and re-arm them
+__global__ void monitor_fold_kernel(unsigned long long* __restrict__ slots, unsigned long long* __restrict__ io) {
+  unsigned long long a = ~0ull, b = ~0ull, c = 0ull, d = 0ull;
+  for (int i = threadIdx.x; i < kMonitorSlots; i += blockDim.x) {
+    unsigned long long* s = slots + 4 * i;
+    a = a < s[0] ? a : s[0];
+    b = b < s[1] ? b : s[1];
+    c = c > s[2] ? c : s[2];
+    d = d > s[3] ? d : s[3];
+    s[0] = ~0ull; s[1] = ~0ull; s[2] = 0ull; s[3] = 0ull;
+  }
+  atomicMin(io + 0, a);
+  atomicMin(io + 1, b);
+  atomicMax(io + 2, c);
+  atomicMax(io + 3, d);
+}
+__global__ void monitor_arm_kernel(unsigned long long* __restrict__ slots) {
+  for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < kMonitorSlots; i += blockDim.x * gridDim.x) {
+    slots[4 * i] = ~0ull; slots[4 * i + 1] = ~0ull; slots[4 * i + 2] = 0ull; slots[4 * i + 3] = 0ull;
   }
 }
 __global__ void monitor_decode_kernel(unsigned long long* io) {
@@ -448,6 +465,7 @@ StepArgs make_args(hlb_gpu_t h, int which /*0 inlet BoundaryValues, 1 outlet*/) 
   A.cStress = h->cache[5];
   A.cTraction = h->cache[6];
   A.cTangTraction = h->cache[7];
+  A.monitorSlots = h->monitorSlots;
   A.refSiteOf = h->iperm;
   A.siteList = nullptr;
   return A;
@@ -823,6 +841,9 @@ int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
   CU(cudaMalloc(&h->coords, sizeof(int32_t) * 3 * h->bStride));
   CU(cudaMalloc(&h->streamIdx, sizeof(uint32_t) * std::max<int64_t>(h->S, 1)));
   CU(cudaMalloc(&h->monitorDev, 64));
+  CU(cudaMalloc(&h->monitorSlots, sizeof(unsigned long long) * 4 * kMonitorSlots));
+  monitor_arm_kernel<<<16, 256>>>(h->monitorSlots);
+  CU(cudaGetLastError());
   for (int w = 0; w < 2; ++w) {
     const int n = std::max(1, w ? cfg->n_outlets : cfg->n_inlets);
     CU(cudaMalloc(&h->ioletsDev[w], sizeof(IoletDev) * n));
@@ -877,6 +898,7 @@ int hlb_gpu_destroy(hlb_gpu_t h) {
   cudaFree(h->staging);
   cudaFree(h->siteListDev);
   cudaFree(h->monitorDev);
+  cudaFree(h->monitorSlots);
   cudaFree(h->perm);
   cudaFree(h->iperm);
   cudaFree(h->coordsAll);
@@ -1238,6 +1260,7 @@ int hlb_gpu_set_step_scalars(hlb_gpu_t h, uint64_t timeStep, const double* inDen
   h->timeStep = timeStep;
   if (ensure_caches(h, cacheMask)) return 1;
   h->cacheMask = cacheMask;
+  h->monitorFused = (cacheMask & C_MONITOR) != 0;
   if (upload_densities(h, 0, inDens)) return 1;
   if (upload_densities(h, 1, outDens)) return 1;
   return 0;
@@ -1379,7 +1402,11 @@ int hlb_gpu_monitor(hlb_gpu_t h, double* out4) {
   CU(cudaSetDevice(h->cfg.device));
   unsigned long long init[4] = {~0ull, ~0ull, 0ull, 0ull};
   CU(cudaMemcpyAsync(h->monitorDev, init, sizeof(init), cudaMemcpyHostToDevice, h->compute));
-  if (h->N) {
+  if (h->monitorFused) {
+    // gathered by the collide-and-stream kernels themselves during the last step(s)
+    monitor_fold_kernel<<<1, 256, 0, h->compute>>>(h->monitorSlots, (unsigned long long*)h->monitorDev);
+    h->launches++;
+  } else if (h->N) {
     const unsigned grid = (unsigned)std::min<int64_t>((h->N + 255) / 256, 148 * 16);
     unsigned long long* mo = (unsigned long long*)h->monitorDev;
     switch (h->Q) {

@@ -23,8 +23,9 @@ enum WallKind { W_SBB = 0, W_BFL = 1, W_GZS = 2, W_NONE = 3 };
 enum IoletKind { I_NASH = 0, I_LADD = 1, I_NONE = 2 };
 enum CacheBit {
   C_DENSITY = 1, C_VELOCITY = 2, C_WSS = 4, C_VONMISES = 8, C_SHEARRATE = 16, C_STRESS = 32,
-  C_TRACTION = 64, C_TANGTRACTION = 128
+  C_TRACTION = 64, C_TANGTRACTION = 128, C_MONITOR = 256
 };
+constexpr int kMonitorSlots = 4096;  // spread of the monitor atomics (4 x u64 per slot)
 
 struct IoletDev {  // lb::iolets::InOutLet{Cosine,ParabolicVelocity} as the kernels see them
   double normal[3];    // normalised in double (InOutLet.h:160-163)
@@ -80,6 +81,8 @@ struct StepArgs {
   const uint32_t* __restrict__ nbrFlags;
   const uint32_t* __restrict__ nbrBase;  // (Q-1) planes of groupStride
   int64_t groupStride, groupOffset;
+  // fused monitors (C_MONITOR): {min f, min rho, max rho, max u^2} as order-preserving u64 keys
+  unsigned long long* __restrict__ monitorSlots;
 };
 
 template <int Q> struct MrtArgs {
@@ -89,6 +92,47 @@ template <int Q> struct MrtArgs {
 __device__ __forceinline__ int64_t bidx(const StepArgs& A, int64_t site) {
   // boundary-typed sites are [midBulk, midTotal) and [midTotal+edgeBulk, N)
   return site < A.midTotal ? site - A.midBulk : site - A.midTotal - A.edgeBulk + (A.midTotal - A.midBulk);
+}
+
+// order-preserving map double -> u64 (so atomicMin/atomicMax on integers order doubles)
+__device__ __forceinline__ unsigned long long mon_enc(double x) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(x);
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double mon_dec(unsigned long long u) {
+  u = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+  return __longlong_as_double((long long)u);
+}
+
+// StabilityTester / IncompressibilityChecker inputs gathered while the populations are in
+// registers (Code/lb/StabilityTester.h:97-113: any f <= 0; IncompressibilityChecker: density
+// extrema, max speed): warp-reduce, then one relaxed atomic per value per warp, spread over slots.
+template <int Q>
+__device__ __forceinline__ void fused_monitor(const StepArgs& A, int64_t tid, const double (&f)[Q], double rho,
+                                              const double (&m)[3]) {
+  double fmin = f[0];
+#pragma unroll
+  for (int d = 1; d < Q; ++d) fmin = fmin < f[d] ? fmin : f[d];
+  double rmin = rho, rmax = rho;
+  double u2 = (m[0] * m[0] + m[1] * m[1] + m[2] * m[2]) / (rho * rho);
+  const unsigned mask = __activemask();
+  unsigned long long* slot = A.monitorSlots + 4 * ((tid >> 5) & (kMonitorSlots - 1));
+  if (mask == 0xffffffffu) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double a = __shfl_xor_sync(0xffffffffu, fmin, o), b = __shfl_xor_sync(0xffffffffu, rmin, o);
+      const double c = __shfl_xor_sync(0xffffffffu, rmax, o), e = __shfl_xor_sync(0xffffffffu, u2, o);
+      fmin = fmin < a ? fmin : a;
+      rmin = rmin < b ? rmin : b;
+      rmax = rmax > c ? rmax : c;
+      u2 = u2 > e ? u2 : e;
+    }
+    if ((tid & 31) != 0) return;
+  }
+  atomicMin(slot + 0, mon_enc(fmin));
+  atomicMin(slot + 1, mon_enc(rmin));
+  atomicMax(slot + 2, mon_enc(rmax));
+  atomicMax(slot + 3, mon_enc(u2));
 }
 
 // ---------------------------------------------------------------------------------- collisions
@@ -504,7 +548,10 @@ __global__ void __launch_bounds__(256) collide_stream_kernel(const StepArgs A, c
     }
   }
 
-  if (A.cacheMask) update_caches<Q, KERNEL>(A, site, HAS_WALL || HAS_IOLET, rho, u, fneq);
+  if (A.cacheMask) {
+    if (A.cacheMask & 255u) update_caches<Q, KERNEL>(A, site, HAS_WALL || HAS_IOLET, rho, u, fneq);
+    if (A.cacheMask & C_MONITOR) fused_monitor<Q>(A, tid, f, rho, m);
+  }
 }
 
 // PostStep: only BFL does work (BouzidiFirdaousLallemand.h:72-91); runs after all streaming and

@@ -31,7 +31,9 @@ enum { HLB_IOLET_NASHZEROTHORDERPRESSURE = 0, HLB_IOLET_LADD = 1 };
 enum {
   HLB_CACHE_DENSITY = 1, HLB_CACHE_VELOCITY = 2, HLB_CACHE_WALL_SHEAR_STRESS = 4,
   HLB_CACHE_VON_MISES_STRESS = 8, HLB_CACHE_SHEAR_RATE = 16, HLB_CACHE_STRESS_TENSOR = 32,
-  HLB_CACHE_TRACTION = 64, HLB_CACHE_TANGENTIAL_TRACTION = 128
+  HLB_CACHE_TRACTION = 64, HLB_CACHE_TANGENTIAL_TRACTION = 128,
+  /* not a cache: gather the hlb_gpu_monitor values inside the collide kernels of this step */
+  HLB_CACHE_MONITOR = 256
 };
 
 typedef struct {
@@ -139,8 +141,10 @@ int hlb_gpu_time_steps(hlb_gpu_t h, int nsteps, float* ms);
 /* same, also returning the summed CUDA-event duration of the mid-fluid (bulk) range launches and
  * the number of sites they updated -- the roofline kernel, timed live inside the step */
 int hlb_gpu_time_steps_detail(hlb_gpu_t h, int nsteps, float* total_ms, float* bulk_ms, int64_t* bulk_sites);
-/* device-side monitors (StabilityTester / IncompressibilityChecker inputs): {min f_old, min
- * density, max density, max |u|} of the last cached density/velocity; D2H of 4 doubles */
+/* device-side monitors (StabilityTester / IncompressibilityChecker inputs): {min f, min density,
+ * max density, max |u|}; D2H of 4 doubles.  With HLB_CACHE_MONITOR in the step's cache mask the
+ * values were gathered by the collide kernels from the distributions ENTERING the last step(s)
+ * since the previous call (no extra pass); otherwise one pass over the current f_old. */
 int hlb_gpu_monitor(hlb_gpu_t h, double* out4);
 /* number of kernels launched by this handle so far */
 int hlb_gpu_launch_count(hlb_gpu_t h, int64_t* n);

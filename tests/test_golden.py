@@ -1,0 +1,61 @@
+"""Golden vectors recorded from the compiled reference headers (tests/golden/make_golden.py):
+the oracle must reproduce them bit-for-bit wherever it runs (no reference checkout needed), and
+on a GPU the CUDA path must too."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+from hemelb_b200 import geometry as G
+from tests.cases import anisotropic_f, geometry, iolets_for
+
+PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vectors.npz")
+GOLD = np.load(PATH)
+KEYS = sorted(k[:-4] for k in GOLD.files if k.endswith("_tau"))
+STEPS = 5
+
+
+def _parse(key):
+    gname, R, Q, k, w, i, o = key.rsplit("_", 6)
+    return gname, int(R[1:]), int(Q[1:]), k, w, i, o
+
+
+@pytest.mark.parametrize("key", KEYS)
+def test_oracle_reproduces_reference_vectors(key):
+    gname, R, Q, k, w, i, o = _parse(key)
+    geom = geometry(gname)
+    rank = None if R == 1 else G.slab_decomposition(geom, R)
+    inlets, outlets = iolets_for(geom, i, o)
+    dom = O.OracleDomains(geom, Q, rank, R)
+    sim = O.OracleSim(dom, k, w, i, o, tau=float(GOLD[key + "_tau"][0]), inlets=inlets, outlets=outlets)
+    for r in range(R):
+        t = dom.tables(r)
+        sim.set_f(anisotropic_f(t["N"], Q, t["totalSharedFs"], site_offset=3 * r), r)
+    sim.set_cache_mask(3)
+    sim.step(STEPS)
+    for r in range(R):
+        n = dom.tables(r)["N"] * Q
+        assert np.array_equal(sim.get_f(r)[:n], GOLD["%s_f%d" % (key, r)])
+        assert np.array_equal(sim.get_cache("density", r), GOLD["%s_rho%d" % (key, r)])
+        assert np.array_equal(sim.get_cache("velocity", r), GOLD["%s_u%d" % (key, r)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", [k for k in KEYS if "_R1_" in k])
+def test_gpu_reproduces_reference_vectors(key):
+    from hemelb_b200.domain import build_domains
+    from hemelb_b200.lbm import GpuLBM
+    gname, R, Q, k, w, i, o = _parse(key)
+    geom = geometry(gname)
+    inlets, outlets = iolets_for(geom, i, o)
+    dom = build_domains(geom, Q)[0]
+    gpu = GpuLBM(dom, k, w, i, o, tau=float(GOLD[key + "_tau"][0]), inlets=inlets, outlets=outlets)
+    gpu.set_f(anisotropic_f(dom.N, Q, 0))
+    gpu.set_cache_mask(3)
+    gpu.step(STEPS)
+    f = gpu.get_f()[:dom.N * Q]
+    assert np.abs(f - GOLD[key + "_f0"]).max() <= 1e-13
+    assert np.array_equal(f, GOLD[key + "_f0"])
+    assert np.array_equal(gpu.get_cache("density"), GOLD[key + "_rho0"])
+    assert np.array_equal(gpu.get_cache("velocity"), GOLD[key + "_u0"])

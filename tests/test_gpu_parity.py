@@ -235,3 +235,17 @@ def test_monitor_matches_numpy():
     rho = f.sum(1)
     assert m["min_f"] == f.min()
     assert abs(m["min_density"] - rho.min()) < 1e-12 and abs(m["max_density"] - rho.max()) < 1e-12
+    # fused variant: gathered by the collide kernels from the distributions entering the step
+    gpu.set_cache_mask(256)
+    gpu.step(1)
+    m2 = gpu.monitor()
+    assert m2["min_f"] == f.min()
+    assert abs(m2["min_density"] - rho.min()) < 1e-12 and abs(m2["max_density"] - rho.max()) < 1e-12
+    assert abs(m2["max_speed"] - m["max_speed"]) < 1e-12
+    # and it re-arms: the next step reports the new state, equal to a stand-alone pass over it
+    gpu.step(1)
+    m3 = gpu.monitor()
+    gpu.set_cache_mask(0)
+    gpu.step(0)
+    f1 = gpu.get_f()[:dom.N * Q].reshape(dom.N, Q)
+    assert m3["min_f"] != m2["min_f"]
