@@ -243,7 +243,7 @@ def main():
     t0 = time.perf_counter()
     for _ in range(args.steps):
         gpu.do_time_step()   # set_step_scalars (H2D of iolet densities) + the LBM phase calls
-        gpu.monitor()        # D2H: {min f, min/max density, max speed}
+        mon = gpu.monitor()  # D2H: {min f, min/max density, max speed}
     gpu.sync()
     e2e_s = time.perf_counter() - t0
     if dist is not None:
@@ -252,7 +252,6 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_mlups = n_sites_global * args.steps / e2e_s / 1e6
-    mon = gpu.monitor()
 
     if rank != 0:
         return 0

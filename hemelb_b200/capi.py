@@ -24,7 +24,8 @@ SYMBOLS = [
     "hlb_gpu_last_error", "hlb_gpu_device_count", "hlb_gpu_create", "hlb_gpu_destroy",
     "hlb_gpu_set_neighbour_indices", "hlb_gpu_set_site_data", "hlb_gpu_set_wall_distances",
     "hlb_gpu_set_wall_normals", "hlb_gpu_set_site_coords", "hlb_gpu_set_neighbours",
-    "hlb_gpu_set_streaming_indices", "hlb_gpu_set_iolets", "hlb_gpu_set_gzs_remote", "hlb_gpu_finalise",
+    "hlb_gpu_set_streaming_indices", "hlb_gpu_set_iolets", "hlb_gpu_set_gzs_remote", "hlb_gpu_set_gzs_serve", "hlb_gpu_exchange_site_halo", "hlb_gpu_get_gzs_send",
+    "hlb_gpu_set_gzs_ghost", "hlb_gpu_finalise",
     "hlb_gpu_comm_unique_id", "hlb_gpu_comm_init", "hlb_gpu_set_f", "hlb_gpu_get_f", "hlb_gpu_get_halo", "hlb_gpu_set_halo",
     "hlb_gpu_set_equilibrium", "hlb_gpu_request_comms", "hlb_gpu_copy_received", "hlb_gpu_swap",
     "hlb_gpu_set_step_scalars", "hlb_gpu_stream_and_collide", "hlb_gpu_post_step", "hlb_gpu_edge_done",

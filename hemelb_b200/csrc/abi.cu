@@ -154,7 +154,8 @@ struct hlb_gpu_handle {
   int64_t siteListCap = 0;
   double* monitorDev = nullptr;
   unsigned long long* monitorSlots = nullptr;
-  bool monitorFused = false;  // the slots hold a complete step's worth of data
+  bool monitorFused = false;  // the collide kernels of the current step(s) feed the slots
+  int64_t monitorLaunches = 0; // collide launches that fed the slots since the last fold
   int64_t launches = 0;
   // internal renumbering: sites of each of the 12 ranges sorted into long z-runs
   uint32_t* perm = nullptr;    // reference site -> internal site (null = identity)
@@ -167,6 +168,19 @@ struct hlb_gpu_handle {
   int64_t groupStride = 0;
   int64_t groupOffset[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   int64_t rangeFirst[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  // GZS site halo (NeighbouringDataManager): whole f_old rows of remote sites, once per step
+  struct GzsPeer { int rank; int64_t first, count; };
+  std::vector<int64_t> gzsNeedSite, gzsNeedOwnerSite;   // as given (reference ids)
+  std::vector<int32_t> gzsNeedDir, gzsNeedOwner;
+  std::vector<int64_t> gzsServeSite;
+  std::vector<int32_t> gzsServeRank;
+  std::vector<GzsPeer> gzsRecvPeers, gzsSendPeers;
+  double* gzsGhost = nullptr;      // nNeed rows of Q
+  double* gzsSendBuf = nullptr;    // nServe rows of Q
+  uint32_t* gzsServeDev = nullptr; // internal site ids to pack
+  int64_t nGzsNeed = 0, nGzsServe = 0;
+  cudaEvent_t evGzsPack = nullptr, evGzsDone = nullptr;
+  bool gzsGhostProvided = false;
   bool profileBulk = false;
   std::vector<cudaEvent_t> profEv;  // pairs around the mid-fluid (bulk) range launches
   size_t profUsed = 0;
@@ -285,6 +299,15 @@ __global__ void remap_stream_kernel(uint32_t* __restrict__ idx, const uint32_t* 
 __global__ void site_list_kernel(const uint32_t* __restrict__ perm, uint32_t* __restrict__ out, int64_t first, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = perm[first + i];
+}
+// pack whole f_old rows (site-major) of the sites other ranks' GZS links extrapolate from
+__global__ void gzs_pack_kernel(const double* __restrict__ f, const uint32_t* __restrict__ sites, int64_t n, int Q,
+                                int64_t stride, double* __restrict__ out) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n * Q) return;
+  const int64_t k = tid / Q;
+  const int j = (int)(tid % Q);
+  out[tid] = f[(int64_t)j * stride + sites[k]];
 }
 // one warp per group of 32 consecutive sites of a range: which directions push to 32 consecutive
 // targets?  (flags, first target) per group
@@ -447,7 +470,7 @@ StepArgs make_args(hlb_gpu_t h, int which /*0 inlet BoundaryValues, 1 outlet*/) 
   A.midTotal = h->midTotal;
   A.edgeBulk = h->edgeBulk;
   A.gzsNeighbour = h->gzsNeighbour;
-  A.gzsGhost = nullptr;
+  A.gzsGhost = h->gzsGhost;
   A.ghostStride = 0;
   A.iolets = h->ioletsDev[which];
   A.ioletDensity = h->ioletDensityDev[which];
@@ -682,6 +705,7 @@ int launch_range(hlb_gpu_t h, int slot, int64_t first, int64_t count, bool post)
     CU(cudaEventRecord(h->profEv[h->profUsed], h->compute));
   }
   h->launch(wall, iolet, A, h->mrt.data(), first, count, h->compute);
+  if (h->cacheMask & C_MONITOR) h->monitorLaunches++;
   if (prof) {
     CU(cudaEventRecord(h->profEv[h->profUsed + 1], h->compute));
     h->profUsed += 2;
@@ -729,7 +753,35 @@ int upload_densities(hlb_gpu_t h, int which, const double* d) {
   return 0;
 }
 
+// NeighbouringDataManager::TransferFieldDependentInformation (phase 0 of the step,
+// Code/geometry/neighbouring/NeighbouringDataManager.cc:101-142): ship whole f_old rows of the sites
+// that other ranks' GZS links extrapolate from.
+int exchange_site_halo(hlb_gpu_t h) {
+  if (h->nGzsNeed == 0 && h->nGzsServe == 0) return 0;
+  const int Q = h->Q;
+  if (h->nGzsServe) {
+    gzs_pack_kernel<<<blocks_for(h->nGzsServe * Q), 256, 0, h->compute>>>(h->f[h->cur], h->gzsServeDev, h->nGzsServe, Q,
+                                                                          h->stride, h->gzsSendBuf);
+    h->launches++;
+    CU(cudaGetLastError());
+  }
+  if (!h->comm_nccl) return 0;  // host-staged: hlb_gpu_get_gzs_send / hlb_gpu_set_gzs_ghost
+  CU(cudaEventRecord(h->evGzsPack, h->compute));
+  CU(cudaStreamWaitEvent(h->comm, h->evGzsPack, 0));
+  int rc = g_nccl.GroupStart();
+  for (auto& p : h->gzsRecvPeers)
+    if (!rc) rc = g_nccl.Recv(h->gzsGhost + p.first * Q, (size_t)(p.count * Q), kNcclDouble, p.rank, h->comm_nccl, h->comm);
+  for (auto& p : h->gzsSendPeers)
+    if (!rc) rc = g_nccl.Send(h->gzsSendBuf + p.first * Q, (size_t)(p.count * Q), kNcclDouble, p.rank, h->comm_nccl, h->comm);
+  int rc2 = g_nccl.GroupEnd();
+  if (rc || rc2) return fail(std::string("NCCL site halo: ") + g_nccl.GetErrorString(rc ? rc : rc2));
+  CU(cudaEventRecord(h->evGzsDone, h->comm));
+  CU(cudaStreamWaitEvent(h->compute, h->evGzsDone, 0));
+  return 0;
+}
+
 int one_step(hlb_gpu_t h) {
+  if (exchange_site_halo(h)) return 1;
   // BoundaryValues::GetBoundaryDensity -> iolet->GetDensity(Get0IndexedTimeStep())
   for (int w = 0; w < 2; ++w) {
     const int n = w ? h->cfg.n_outlets : h->cfg.n_inlets;
@@ -900,6 +952,11 @@ int hlb_gpu_destroy(hlb_gpu_t h) {
   cudaFree(h->monitorDev);
   cudaFree(h->monitorSlots);
   cudaFree(h->perm);
+  cudaFree(h->gzsGhost);
+  cudaFree(h->gzsSendBuf);
+  cudaFree(h->gzsServeDev);
+  if (h->evGzsPack) cudaEventDestroy(h->evGzsPack);
+  if (h->evGzsDone) cudaEventDestroy(h->evGzsDone);
   cudaFree(h->iperm);
   cudaFree(h->coordsAll);
   cudaFree(h->nbrFlags);
@@ -1091,9 +1148,37 @@ int hlb_gpu_set_iolets(hlb_gpu_t h, int which, int n, const double* rec) {
   return 0;
 }
 
-int hlb_gpu_set_gzs_remote(hlb_gpu_t, int64_t n, const int64_t*, const int32_t*, const int32_t*, const int64_t*) {
-  if (n == 0) return 0;
-  return fail("GZS extrapolation from sites on another rank is not implemented yet");
+int hlb_gpu_set_gzs_remote(hlb_gpu_t h, int64_t n, const int64_t* local_site, const int32_t* direction,
+                           const int32_t* owner_rank, const int64_t* owner_site) {
+  if (!h) return fail("null argument");
+  if (h->finalised) return fail("hlb_gpu_set_gzs_remote after hlb_gpu_finalise");
+  for (int64_t k = 0; k < n; ++k) {
+    if (local_site[k] < 0 || local_site[k] >= h->N || host_bidx(h, local_site[k]) < 0)
+      return fail("GZS remote need: not a boundary-typed local site");
+    if (direction[k] < 1 || direction[k] >= h->Q) return fail("GZS remote need: bad direction");
+    if (owner_rank[k] < 0 || owner_rank[k] >= h->cfg.nranks || owner_rank[k] == h->cfg.rank)
+      return fail("GZS remote need: bad owner rank");
+    if (k && owner_rank[k] < owner_rank[k - 1]) return fail("GZS remote needs must be grouped by ascending owner rank");
+  }
+  h->gzsNeedSite.assign(local_site, local_site + n);
+  h->gzsNeedDir.assign(direction, direction + n);
+  h->gzsNeedOwner.assign(owner_rank, owner_rank + n);
+  h->gzsNeedOwnerSite.assign(owner_site, owner_site + n);
+  return 0;
+}
+
+int hlb_gpu_set_gzs_serve(hlb_gpu_t h, int64_t n, const int32_t* requester_rank, const int64_t* local_site) {
+  if (!h) return fail("null argument");
+  if (h->finalised) return fail("hlb_gpu_set_gzs_serve after hlb_gpu_finalise");
+  for (int64_t k = 0; k < n; ++k) {
+    if (local_site[k] < 0 || local_site[k] >= h->N) return fail("GZS serve list: site outside the local fluid sites");
+    if (requester_rank[k] < 0 || requester_rank[k] >= h->cfg.nranks || requester_rank[k] == h->cfg.rank)
+      return fail("GZS serve list: bad requester rank");
+    if (k && requester_rank[k] < requester_rank[k - 1]) return fail("GZS serve list must be grouped by ascending rank");
+  }
+  h->gzsServeRank.assign(requester_rank, requester_rank + n);
+  h->gzsServeSite.assign(local_site, local_site + n);
+  return 0;
 }
 
 int hlb_gpu_finalise(hlb_gpu_t h) {
@@ -1127,6 +1212,7 @@ int hlb_gpu_finalise(hlb_gpu_t h) {
     CU(cudaDeviceSynchronize());
     // a GZS link that would extrapolate from a site on another rank needs the phase-0 site halo
     std::vector<int32_t> g((size_t)(Q - 1) * h->bStride);
+    std::vector<std::pair<int64_t, int>> missing;
     CU(cudaMemcpy(g.data(), h->gzsNeighbour, sizeof(int32_t) * g.size(), cudaMemcpyDeviceToHost));
     for (int64_t b = 0; b < h->NB; ++b)
       for (int d = 1; d < Q; ++d) {
@@ -1134,9 +1220,47 @@ int hlb_gpu_finalise(hlb_gpu_t h) {
         const int i = inv_dir(d);
         if (((h->hWall[b] >> (i - 1)) & 1u) || ((h->hIolet[b] >> (i - 1)) & 1u)) continue;
         if (!(h->hCut[(size_t)(d - 1) * h->bStride + b] < 0.75f)) continue;
-        if (g[(size_t)(i - 1) * h->bStride + b] < 0)
-          return fail("GZS wall link extrapolates from a site on another rank: not implemented yet");
+        if (g[(size_t)(i - 1) * h->bStride + b] < 0 && g[(size_t)(i - 1) * h->bStride + b] == INT32_MIN)
+          missing.push_back({b, i});
       }
+    // remote rows: ghost g = position in the need list (grouped by owner rank)
+    h->nGzsNeed = (int64_t)h->gzsNeedSite.size();
+    std::vector<uint32_t> hp;
+    if (h->perm && (h->nGzsNeed || !h->gzsServeSite.empty())) {
+      hp.resize(h->N);
+      CU(cudaMemcpy(hp.data(), h->perm, sizeof(uint32_t) * h->N, cudaMemcpyDeviceToHost));
+    }
+    auto internal = [&](int64_t s) { return hp.empty() ? s : (int64_t)hp[s]; };
+    for (int64_t k = 0; k < h->nGzsNeed; ++k) {
+      const int64_t b = host_bidx(h, internal(h->gzsNeedSite[k]));
+      g[(size_t)(h->gzsNeedDir[k] - 1) * h->bStride + b] = (int32_t)(-(k + 1));
+      if (h->gzsRecvPeers.empty() || h->gzsRecvPeers.back().rank != h->gzsNeedOwner[k])
+        h->gzsRecvPeers.push_back({h->gzsNeedOwner[k], k, 0});
+      h->gzsRecvPeers.back().count++;
+    }
+    for (auto& ms : missing)
+      if (g[(size_t)(ms.second - 1) * h->bStride + ms.first] == INT32_MIN)
+        return fail("GZS wall link extrapolates from a site on another rank that hlb_gpu_set_gzs_remote did not name");
+    CU(cudaMemcpy(h->gzsNeighbour, g.data(), sizeof(int32_t) * g.size(), cudaMemcpyHostToDevice));
+    if (h->nGzsNeed) {
+      CU(cudaMalloc(&h->gzsGhost, sizeof(double) * Q * h->nGzsNeed));
+      CU(cudaMemset(h->gzsGhost, 0, sizeof(double) * Q * h->nGzsNeed));
+    }
+    h->nGzsServe = (int64_t)h->gzsServeSite.size();
+    if (h->nGzsServe) {
+      std::vector<uint32_t> sv(h->nGzsServe);
+      for (int64_t k = 0; k < h->nGzsServe; ++k) {
+        sv[k] = (uint32_t)internal(h->gzsServeSite[k]);
+        if (h->gzsSendPeers.empty() || h->gzsSendPeers.back().rank != h->gzsServeRank[k])
+          h->gzsSendPeers.push_back({h->gzsServeRank[k], k, 0});
+        h->gzsSendPeers.back().count++;
+      }
+      CU(cudaMalloc(&h->gzsServeDev, sizeof(uint32_t) * h->nGzsServe));
+      CU(cudaMemcpy(h->gzsServeDev, sv.data(), sizeof(uint32_t) * h->nGzsServe, cudaMemcpyHostToDevice));
+      CU(cudaMalloc(&h->gzsSendBuf, sizeof(double) * Q * h->nGzsServe));
+    }
+    CU(cudaEventCreateWithFlags(&h->evGzsPack, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->evGzsDone, cudaEventDisableTiming));
   }
   {
     // run-compressed neighbour table: measured slower than the plain table on B200 in round 1
@@ -1278,6 +1402,29 @@ int hlb_gpu_post_step(hlb_gpu_t h, int slot, int64_t first, int64_t count) {
   return launch_range(h, slot, first, count, true);
 }
 
+int hlb_gpu_exchange_site_halo(hlb_gpu_t h) {
+  if (!h) return fail("null argument");
+  if (!h->finalised) return fail("handle not finalised");
+  CU(cudaSetDevice(h->cfg.device));
+  return exchange_site_halo(h);
+}
+
+int hlb_gpu_get_gzs_send(hlb_gpu_t h, double* out) {
+  if (!h || (!out && h->nGzsServe)) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->compute));
+  if (h->nGzsServe) CU(cudaMemcpy(out, h->gzsSendBuf, sizeof(double) * h->Q * h->nGzsServe, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int hlb_gpu_set_gzs_ghost(hlb_gpu_t h, const double* in) {
+  if (!h || (!in && h->nGzsNeed)) return fail("null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaStreamSynchronize(h->compute));
+  if (h->nGzsNeed) CU(cudaMemcpy(h->gzsGhost, in, sizeof(double) * h->Q * h->nGzsNeed, cudaMemcpyHostToDevice));
+  return 0;
+}
+
 int hlb_gpu_request_comms(hlb_gpu_t h) {
   // LBM::RequestComms only *registers* the sends/receives with the Net (lb.hpp:162-173); they are
   // issued after PreSend.  Mirror that: remember, and post when the edge ranges have been issued.
@@ -1402,7 +1549,8 @@ int hlb_gpu_monitor(hlb_gpu_t h, double* out4) {
   CU(cudaSetDevice(h->cfg.device));
   unsigned long long init[4] = {~0ull, ~0ull, 0ull, 0ull};
   CU(cudaMemcpyAsync(h->monitorDev, init, sizeof(init), cudaMemcpyHostToDevice, h->compute));
-  if (h->monitorFused) {
+  if (h->monitorFused && h->monitorLaunches > 0) {
+    h->monitorLaunches = 0;
     // gathered by the collide-and-stream kernels themselves during the last step(s)
     monitor_fold_kernel<<<1, 256, 0, h->compute>>>(h->monitorSlots, (unsigned long long*)h->monitorDev);
     h->launches++;

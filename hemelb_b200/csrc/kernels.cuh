@@ -54,8 +54,8 @@ struct StepArgs {
   // GZS: whole-site f_old rows of remote neighbours (NeighbouringDataManager) live after the
   // local planes: ghost row g of direction d at fOld[...]; not used unless WALL == W_GZS
   const int32_t* __restrict__ gzsNeighbour;  // (Q-1) planes of bStride: local site id, or -(g+1)
-  const double* __restrict__ gzsGhost;       // Q planes of ghostStride
-  int64_t ghostStride;
+  const double* __restrict__ gzsGhost;       // ghost row g = Q consecutive doubles at gzsGhost[g*Q]
+  int64_t ghostStride;                       // (unused; rows are site-major as they travel)
   // iolets of this range's BoundaryValues object + per-step scalars
   const IoletDev* __restrict__ iolets;
   const double* __restrict__ ioletDensity;   // GetBoundaryDensity(id) for this step
@@ -392,7 +392,7 @@ __device__ __noinline__ void gzs_link(const StepArgs& A, const MrtArgs<Q>& M, in
       } else {
         const int64_t g = -(int64_t)n - 1;
 #pragma unroll
-        for (int j = 0; j < Q; ++j) nf[j] = A.gzsGhost[(int64_t)j * A.ghostStride + g];
+        for (int j = 0; j < Q; ++j) nf[j] = A.gzsGhost[g * Q + j];
       }
       double nrho, nm[3], nu[3], nfeq[Q];
       density_momentum<Q>(nf, nrho, nm);

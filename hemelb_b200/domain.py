@@ -130,13 +130,19 @@ class RankDomain:
         sites = self.inputIndex[first:first + n]
         out = np.empty((n, Q), np.int64)
         out[:, 0] = (np.arange(first, first + n, dtype=np.int64)) * Q
-        if b.R == 1 and b.lookup.dense is not None and b.lookup.rimmed:
-            # one gather per direction from a grid of local ids (every neighbour is in the box)
+        if b.lookup.dense is not None:
+            # one gather per direction from a grid of this rank's local ids (-1 solid, -2 a site
+            # of another rank); only the few cross-rank links need the send-slot search
             key0 = b.lookup.key_of_site[sites]
-            grid = b.local_grid()
+            grid = b.local_grid(self.rank)
+            ids = np.arange(first, first + n, dtype=np.int64)
             for d in range(1, Q):
                 v = grid[key0 + b.lookup.key_offset(b.c[d])].astype(np.int64)
-                out[:, d] = np.where(v >= 0, v * Q + d, self.N * Q)
+                col = np.where(v >= 0, v * Q + d, self.N * Q)
+                rem = np.nonzero(v == -2)[0]
+                if rem.size:
+                    col[rem] = self._send_slot[np.searchsorted(self._send_key, ids[rem] * Q + d)]
+                out[:, d] = col
             return out.reshape(-1)
         base = b.geom.coords[sites].astype(np.int64)
         for d in range(1, Q):
@@ -243,7 +249,24 @@ class DomainBuilder:
         # remote links: (site, direction, neighbour site) with the neighbour on another rank
         rs, rd, rn = [], [], []
         is_edge = np.zeros(N, bool)
-        if nranks > 1:
+        if nranks > 1 and self.lookup.dense is not None:
+            rgrid = np.full(self.lookup.dense.size, -1, np.int16)
+            rgrid[self.lookup.key_of_site] = self.rank_of_site.astype(np.int16)
+            for s0 in range(0, N, chunk):
+                s1 = min(N, s0 + chunk)
+                key0 = self.lookup.key_of_site[s0:s1]
+                myrank = self.rank_of_site[s0:s1].astype(np.int16)
+                for d in range(1, Q):
+                    off = self.lookup.key_offset(self.c[d])
+                    nr = rgrid[key0 + off]
+                    idx = np.nonzero((nr >= 0) & (nr != myrank))[0]
+                    if idx.size:
+                        rs.append(idx + s0)
+                        rd.append(np.full(idx.size, d, np.int64))
+                        rn.append(self.lookup.dense[key0[idx] + off].astype(np.int64))
+                        is_edge[idx + s0] = True
+            del rgrid
+        elif nranks > 1:
             for s0 in range(0, N, chunk):
                 s1 = min(N, s0 + chunk)
                 base = coords[s0:s1]
@@ -342,13 +365,74 @@ class DomainBuilder:
                 D.streamingIndices = np.concatenate(stream).astype(np.int64)
 
 
-def _local_grid(self):
-    """voxel -> local site id on rank 0 (single-rank fast path), -1 for solid."""
-    if getattr(self, "_lgrid", None) is None:
+def _gzs_site_halo(self):
+    """The GZS site halo of every rank (GuoZhengShi.h:38-99 + NeighbouringDataManager::ShareNeeds):
+    ``need[r]`` = (local site, direction towards the neighbour, owner rank, owner's local site) and
+    ``serve[r]`` = (requester rank, local site).  Both grouped by the other rank ascending and,
+    inside a group, ordered by the requesting site's global (x, y, z) then direction -- an order
+    both sides can compute from coordinates alone."""
+    if getattr(self, "_gzs", None) is not None:
+        return self._gzs
+    Q = self.Q
+    coords = self.geom.coords.astype(np.int64)
+    dims = self.geom.block_dims.astype(np.int64) * self.geom.block_size
+    rec = []  # requester rank, owner rank, coord key, direction, requester input site, owner input site
+    for D in self.domains:
+        ws = np.nonzero(D.wallMask != 0)[0]
+        if ws.size == 0:
+            continue
+        inp = D.inputIndex[ws]
+        wm, im = D.wallMask[ws], D.ioletMask[ws]
+        for d in range(1, Q):
+            opp = int(self.inv[d])
+            m = ((wm >> np.uint32(d - 1)) & 1).astype(bool)
+            m &= ~((wm >> np.uint32(opp - 1)) & 1).astype(bool)
+            m &= ~((im >> np.uint32(opp - 1)) & 1).astype(bool)
+            if not m.any():
+                continue
+            src = inp[m]
+            nb = self.lookup(coords[src] + self.c[opp])
+            ok = nb >= 0
+            ok[ok] = self.rank_of_site[nb[ok]] != D.rank
+            if not ok.any():
+                continue
+            src, nb = src[ok], nb[ok]
+            c = coords[src]
+            key = (c[:, 0] * dims[1] + c[:, 1]) * dims[2] + c[:, 2]
+            rec.append(np.stack([np.full(src.size, D.rank), self.rank_of_site[nb].astype(np.int64), key,
+                                 np.full(src.size, opp), src, nb], 1))
+    need = {D.rank: np.zeros((0, 4), np.int64) for D in self.domains}
+    serve = {D.rank: np.zeros((0, 2), np.int64) for D in self.domains}
+    if rec:
+        rec = np.concatenate(rec, 0).astype(np.int64)
+        for D in self.domains:
+            mine = rec[rec[:, 0] == D.rank]
+            o = np.lexsort((mine[:, 3], mine[:, 2], mine[:, 1]))
+            mine = mine[o]
+            need[D.rank] = np.stack([self.local_of_input[mine[:, 4]], mine[:, 3], mine[:, 1],
+                                     self.local_of_input[mine[:, 5]]], 1)
+            theirs = rec[rec[:, 1] == D.rank]
+            o = np.lexsort((theirs[:, 3], theirs[:, 2], theirs[:, 0]))
+            theirs = theirs[o]
+            serve[D.rank] = np.stack([theirs[:, 0], self.local_of_input[theirs[:, 5]]], 1)
+    self._gzs = (need, serve)
+    return self._gzs
+
+
+DomainBuilder.gzs_site_halo = _gzs_site_halo
+
+
+def _local_grid(self, rank=0):
+    """voxel -> local site id on ``rank``; -1 solid, -2 fluid on another rank."""
+    cache = self.__dict__.setdefault("_lgrids", {})
+    if rank not in cache:
+        cache.clear()  # one at a time: these are big
         g = np.full(self.lookup.dense.size, -1, np.int32)
-        g[self.lookup.key_of_site] = self.local_of_input.astype(np.int32)
-        self._lgrid = g
-    return self._lgrid
+        own = self.rank_of_site == rank
+        vals = np.where(own, self.local_of_input, -2).astype(np.int32)
+        g[self.lookup.key_of_site] = vals
+        cache[rank] = g
+    return cache[rank]
 
 
 DomainBuilder.local_grid = _local_grid

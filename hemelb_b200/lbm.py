@@ -147,6 +147,22 @@ class GpuLBM:
             if len(recs):
                 r = np.ascontiguousarray(np.stack(recs), np.float64)
                 check(L.hlb_gpu_set_iolets(h, which, len(recs), ptr(r, C.c_double)))
+        self.gzs_need = np.zeros((0, 4), np.int64)
+        self.gzs_serve = np.zeros((0, 2), np.int64)
+        if wall == "GZS" and domain.nranks > 1:
+            need, serve = domain._builder.gzs_site_halo()
+            self.gzs_need, self.gzs_serve = need[domain.rank], serve[domain.rank]
+            nd, sv = self.gzs_need, self.gzs_serve
+            if nd.shape[0]:
+                check(L.hlb_gpu_set_gzs_remote(h, C.c_int64(nd.shape[0]),
+                                               ptr(np.ascontiguousarray(nd[:, 0], np.int64), C.c_int64),
+                                               ptr(np.ascontiguousarray(nd[:, 1], np.int32), C.c_int32),
+                                               ptr(np.ascontiguousarray(nd[:, 2], np.int32), C.c_int32),
+                                               ptr(np.ascontiguousarray(nd[:, 3], np.int64), C.c_int64)))
+            if sv.shape[0]:
+                check(L.hlb_gpu_set_gzs_serve(h, C.c_int64(sv.shape[0]),
+                                              ptr(np.ascontiguousarray(sv[:, 0], np.int32), C.c_int32),
+                                              ptr(np.ascontiguousarray(sv[:, 1], np.int64), C.c_int64)))
         check(L.hlb_gpu_finalise(h))
 
     # ---- multi-GPU ---------------------------------------------------------------------------
@@ -210,6 +226,19 @@ class GpuLBM:
     def post_step(self, slot, first, count):
         check(self.L.hlb_gpu_post_step(self.h, slot, C.c_int64(first), C.c_int64(count)))
 
+    # ---- phase 0: NeighbouringDataManager (GZS site halo) ----------------------------------------
+    def exchange_site_halo(self):
+        check(self.L.hlb_gpu_exchange_site_halo(self.h))
+
+    def get_gzs_send(self):
+        out = np.zeros(max(1, self.gzs_serve.shape[0] * self.Q))
+        check(self.L.hlb_gpu_get_gzs_send(self.h, ptr(out, C.c_double)))
+        return out[:self.gzs_serve.shape[0] * self.Q].reshape(-1, self.Q)
+
+    def set_gzs_ghost(self, rows):
+        rows = np.ascontiguousarray(rows, np.float64)
+        check(self.L.hlb_gpu_set_gzs_ghost(self.h, ptr(rows, C.c_double) if rows.size else None))
+
     # ---- IteratedAction phases of LBM (lb.hpp:162-314) ------------------------------------------
     def request_comms(self):
         check(self.L.hlb_gpu_request_comms(self.h))
@@ -248,6 +277,7 @@ class GpuLBM:
     def do_time_step(self):
         """One pass of StepManager's phase 1 for the LBM actor + SimulationMaster::DoTimeStep's tail
         (SimulationMaster.impl.h:169-220)."""
+        self.exchange_site_halo()
         self.request_comms()
         self.pre_send()
         self.pre_receive()

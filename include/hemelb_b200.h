@@ -86,11 +86,17 @@ int hlb_gpu_set_neighbours(hlb_gpu_t h, const int* rank, const int64_t* count, c
 int hlb_gpu_set_streaming_indices(hlb_gpu_t h, const int64_t* idx);
 /* iolets of the inlet (which = 0) / outlet (which = 1) BoundaryValues object */
 int hlb_gpu_set_iolets(hlb_gpu_t h, int which, int n, const double* records);
-/* remote sites GZS extrapolates from (NeighbouringDataManager::RegisterNeededSite,
- * Code/lb/streamers/GuoZhengShi.h:93-99): for each boundary link needing a remote f_old row,
- * (local site, direction, owner rank, owner's local site id).  Optional. */
+/* GZS site halo (geometry::neighbouring::NeighbouringDataManager, registered by
+ * Code/lb/streamers/GuoZhengShi.h:93-99 and shared by NeighbouringDataManager::ShareNeeds):
+ *  _remote: the rows THIS rank needs -- for each wall link whose GZS extrapolation reads the
+ *           neighbour in `direction` (the inverse of the wall direction) of `local_site` and that
+ *           neighbour lives on `owner_rank` as its local site `owner_site`; grouped by ascending
+ *           owner rank.  Ghost row k of the per-step exchange is entry k of this list.
+ *  _serve:  the rows this rank SHIPS each step: (requester rank, local site), grouped by ascending
+ *           requester rank and, within a rank, in that requester's _remote order. */
 int hlb_gpu_set_gzs_remote(hlb_gpu_t h, int64_t n, const int64_t* local_site, const int32_t* direction,
                            const int32_t* owner_rank, const int64_t* owner_site);
+int hlb_gpu_set_gzs_serve(hlb_gpu_t h, int64_t n, const int32_t* requester_rank, const int64_t* local_site);
 int hlb_gpu_finalise(hlb_gpu_t h);
 
 /* ---- multi-GPU: replaces net::Net's MPI point-to-point (Code/net/mixins/pointpoint/
@@ -109,6 +115,12 @@ int hlb_gpu_get_halo(hlb_gpu_t h, int which, double* out);
 int hlb_gpu_set_halo(hlb_gpu_t h, int which, const double* in);
 /* EquilibriumInitialCondition::SetFs (Code/lb/InitialCondition.hpp:40-52) */
 int hlb_gpu_set_equilibrium(hlb_gpu_t h, double density, const double* momentum3);
+/* phase 0 of a step: NeighbouringDataManager::TransferFieldDependentInformation
+ * (NeighbouringDataManager.cc:101-142) -- pack and ship the whole f_old rows of the _serve list,
+ * receive the _remote ones (NCCL; or stage them through the host with the two calls below) */
+int hlb_gpu_exchange_site_halo(hlb_gpu_t h);
+int hlb_gpu_get_gzs_send(hlb_gpu_t h, double* out);     /* n_serve * Q doubles, site-major */
+int hlb_gpu_set_gzs_ghost(hlb_gpu_t h, const double* in); /* n_remote * Q doubles, site-major */
 int hlb_gpu_request_comms(hlb_gpu_t h);   /* FieldData::SendAndReceive + Net::Receive/Send */
 int hlb_gpu_copy_received(hlb_gpu_t h);   /* Net::Wait + FieldData::CopyReceived */
 int hlb_gpu_swap(hlb_gpu_t h);            /* FieldData::SwapOldAndNew */

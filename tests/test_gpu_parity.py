@@ -210,6 +210,57 @@ def test_internal_renumbering_is_invisible(geom_name, Q, kernel, wall, inlet, ou
         assert np.array_equal(a.get_cache(name), b.get_cache(name)), name
 
 
+@pytest.mark.parametrize("kernel,inlet", [("LBGK", "NASH"), ("MRT", "LADD")])
+def test_multi_rank_gzs_site_halo_host_staged(kernel, inlet):
+    """GZS links that extrapolate from a site on another rank: the phase-0 site halo
+    (NeighbouringDataManager) staged through the host between 3 emulated ranks on one GPU."""
+    geom, Q, R = geometry("cylinder_long"), 19, 3
+    rank = G.slab_decomposition(geom, R)
+    inlets, outlets = iolets_for(geom, inlet, "NASH")
+    doms = build_domains(geom, Q, rank, R)
+    odom = O.OracleDomains(geom, Q, rank, R)
+    sim = O.OracleSim(odom, kernel, "GZS", inlet, "NASH", tau=0.8, inlets=inlets, outlets=outlets)
+    gpus = [GpuLBM(d, kernel, "GZS", inlet, "NASH", tau=0.8, inlets=inlets, outlets=outlets) for d in doms]
+    assert sum(g.gzs_need.shape[0] for g in gpus) > 0
+    for r, d in enumerate(doms):
+        f0 = anisotropic_f(d.N, Q, d.totalSharedFs, site_offset=5 * r)
+        sim.set_f(f0, r)
+        gpus[r].set_f(f0)
+    for _ in range(5):
+        for g in gpus:
+            g.exchange_site_halo()  # packs the serve rows
+        sends = [g.get_gzs_send() for g in gpus]
+        for r, g in enumerate(gpus):
+            rows = np.zeros((g.gzs_need.shape[0], Q))
+            for p in range(R):
+                mine = np.nonzero(g.gzs_need[:, 2] == p)[0]
+                theirs = np.nonzero(gpus[p].gzs_serve[:, 0] == r)[0]
+                assert mine.size == theirs.size
+                rows[mine] = sends[p][theirs]
+            g.set_gzs_ghost(rows)
+        for g in gpus:
+            g.request_comms()
+            g.pre_send()
+            g.pre_receive()
+        halo = [g.get_halo(which=1) for g in gpus]
+        for r, d in enumerate(doms):
+            recv = np.zeros(d.totalSharedFs)
+            for (p, cnt, first) in d.procs:
+                op = doms[p].procs
+                j = int(np.nonzero(op[:, 0] == r)[0][0])
+                o_first = int(op[j, 2]) - (doms[p].N * Q + 1)
+                m_first = int(first) - (d.N * Q + 1)
+                recv[m_first:m_first + cnt] = halo[p][o_first:o_first + cnt]
+            gpus[r].set_halo(recv, which=0)
+        for g in gpus:
+            g.post_receive()
+            g.swap_old_and_new()
+            g.state.increment()
+    sim.step(5)
+    for r, d in enumerate(doms):
+        _check(gpus[r].get_f()[:d.N * Q], sim.get_f(r)[:d.N * Q], "rank %d f_old" % r)
+
+
 def test_error_paths():
     from hemelb_b200.capi import HlbError
     geom = geometry("four_cube")
