@@ -208,7 +208,7 @@ class IoletPlane:
     radius: float
 
 
-def voxelise(shape, phi, iolets, block_size=8, normal_fn=None, chunk=None) -> Geometry:
+def voxelise(shape, phi, iolets, block_size=8, normal_fn=None, chunk=None, mask=None, phi_local=None, _site_hook=None) -> Geometry:
     """Voxelise the region ``phi(p) < 0`` clipped by the iolet planes.
 
     ``phi`` maps an (M,3) float64 array of positions to signed distance-like values (negative =
@@ -237,9 +237,14 @@ def voxelise(shape, phi, iolets, block_size=8, normal_fn=None, chunk=None) -> Ge
         c, _ = clipped(p)
         return (phi(p) < 0) & ~c
 
-    # fluid mask, slab by slab to bound memory
+    # fluid mask, slab by slab to bound memory (or a precomputed candidate mask refined by the clips)
     coords = []
     nx = int(shape[0])
+    if mask is not None:
+        c = np.argwhere(mask).astype(np.float64)
+        cl, _ = clipped(c)
+        coords.append(c[~cl].astype(np.int32))
+        nx = 0
     step = chunk or max(1, int(4e6 // max(1, int(shape[1] * shape[2]))))
     yy, zz = np.meshgrid(np.arange(shape[1]), np.arange(shape[2]), indexing="ij")
     for x0 in range(0, nx, step):
@@ -264,6 +269,11 @@ def voxelise(shape, phi, iolets, block_size=8, normal_fn=None, chunk=None) -> Ge
     biolet = np.full((Nb, 26), -1, np.int32)
     bdist = np.full((Nb, 26), -1.0, np.float32)
     p0 = coords[bsite].astype(np.float64)
+    if _site_hook is not None:
+        _site_hook["sites"] = p0
+    if phi_local is None:
+        def phi_local(p, which):
+            return phi(p)
     for l, c in enumerate(NEIGHBOURHOOD):
         cut = ~nb_fluid[bsite, l]
         if not cut.any():
@@ -274,14 +284,15 @@ def voxelise(shape, phi, iolets, block_size=8, normal_fn=None, chunk=None) -> Ge
         b = a + cvec
         # wall crossing by bisection (phi(a) < 0 always)
         t_wall = np.full(idx.size, np.inf)
-        outside = phi(b) >= 0
+        outside = phi_local(b, idx) >= 0
         if outside.any():
             lo = np.zeros(outside.sum())
             hi = np.ones(outside.sum())
             aa = a[outside]
-            for _ in range(40):
+            io = idx[outside]
+            for _ in range(30):
                 mid = 0.5 * (lo + hi)
-                inside = phi(aa + mid[:, None] * cvec) < 0
+                inside = phi_local(aa + mid[:, None] * cvec, io) < 0
                 lo = np.where(inside, mid, lo)
                 hi = np.where(inside, hi, mid)
             t_wall[outside] = hi
@@ -309,10 +320,11 @@ def voxelise(shape, phi, iolets, block_size=8, normal_fn=None, chunk=None) -> Ge
     if normal_fn is None:
         def normal_fn(p):
             g = np.empty_like(p)
+            ar = np.arange(p.shape[0])
             for k in range(3):
                 e = np.zeros(3)
                 e[k] = 0.25
-                g[:, k] = phi(p + e) - phi(p - e)
+                g[:, k] = phi_local(p + e, ar) - phi_local(p - e, ar)
             n = np.linalg.norm(g, axis=1)
             n[n == 0] = 1.0
             return g / n[:, None]
@@ -457,13 +469,40 @@ def capsule_tree(generations: int, root_radius: float, root_length: float, seed:
     AB = Bp - A
     L2 = (AB * AB).sum(1)
 
+    def seg_dist(p, k):
+        d = p - A[k]
+        t = np.clip((d @ AB[k]) / L2[k], 0.0, 1.0)
+        return np.linalg.norm(d - t[:, None] * AB[k], axis=1) - Rr[k]
+
     def phi(p):
         out = np.full(p.shape[0], np.inf)
         for k in range(A.shape[0]):
-            d = p - A[k]
-            t = np.clip((d @ AB[k]) / L2[k], 0.0, 1.0)
-            dist = np.linalg.norm(d - t[:, None] * AB[k], axis=1) - Rr[k]
-            np.minimum(out, dist, out=out)
+            np.minimum(out, seg_dist(p, k), out=out)
+        return out
+
+    # rasterise each capsule inside its own bounding box
+    mask = np.zeros(tuple(int(x) for x in shape), bool)
+    boxes = []
+    for k in range(A.shape[0]):
+        lo_k = np.maximum(np.floor(np.minimum(A[k], Bp[k]) - Rr[k] - 2).astype(int), 0)
+        hi_k = np.minimum(np.ceil(np.maximum(A[k], Bp[k]) + Rr[k] + 2).astype(int) + 1, shape)
+        boxes.append((lo_k, hi_k))
+        gx, gy, gz = np.meshgrid(np.arange(lo_k[0], hi_k[0]), np.arange(lo_k[1], hi_k[1]), np.arange(lo_k[2], hi_k[2]),
+                                 indexing="ij")
+        pts = np.stack([gx.ravel(), gy.ravel(), gz.ravel()], 1).astype(np.float64)
+        inside = seg_dist(pts, k) < 0
+        mask[lo_k[0]:hi_k[0], lo_k[1]:hi_k[1], lo_k[2]:hi_k[2]] |= inside.reshape(gx.shape)
+
+    cand_cache = {}
+
+    def phi_local(p, which):
+        # min over the capsules whose box holds the boundary site (set up lazily per call pattern)
+        out = np.full(p.shape[0], np.inf)
+        site = cand_cache["sites"][which]
+        for k, (lo_k, hi_k) in enumerate(boxes):
+            m = ((site >= lo_k - 1) & (site < hi_k + 1)).all(1)
+            if m.any():
+                out[m] = np.minimum(out[m], seg_dist(p[m], k))
         return out
 
     inlets, outlets = [], []
@@ -473,7 +512,7 @@ def capsule_tree(generations: int, root_radius: float, root_length: float, seed:
         if s[3]:
             dk = AB[k] / np.sqrt(L2[k])
             outlets.append(IoletPlane(CUT_OUTLET, len(outlets), Bp[k] - dk * 0.25, -dk, Rr[k] + 2))
-    g = voxelise(shape, phi, inlets + outlets, block_size)
+    g = voxelise(shape, phi, inlets + outlets, block_size, mask=mask, phi_local=phi_local, _site_hook=cand_cache)
     g.meta.update(kind="tree", generations=generations, inlets=inlets, outlets=outlets, segments=len(segs))
     return g
 
