@@ -35,6 +35,20 @@ BYTES_PER_SITE = 20 * Q  # 2*Q*8 B distributions + Q*4 B neighbour indices (SURV
 TAU = 0.8
 
 
+def measured_traffic(bulk_sites_per_launch):
+    """DRAM bytes per launch of the bulk kernel from the committed ncu --set full capture, if that
+    capture was taken on this very launch shape; else None."""
+    p = os.path.join(ROOT, "profiles", "r01_bulk_fullsize_traffic.json")
+    try:
+        with open(p) as fh:
+            t = json.load(fh)
+        if int(t["sites_per_launch"]) == int(bulk_sites_per_launch):
+            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -76,13 +90,38 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def build_workload(radius, length, rank, nranks, block_size=8):
-    """Geometry + this rank's Domain tables.  N > 1: z-slabs of a cylinder nranks times longer; each
-    rank voxelises only its own slab plus one halo layer either side (global coordinates)."""
-    from hemelb_b200 import geometry as G
-    from hemelb_b200.domain import DomainBuilder
+def cylinder_iolets(geom_meta, radius):
     from hemelb_b200.capi import iolet_record
     from hemelb_b200.lbm import prepare_boundary_objects
+    inl, outl = geom_meta["inlets"][0], geom_meta["outlets"][0]
+    inlets = [iolet_record(0, tuple(inl.normal), tuple(inl.position), radius=radius, density_mean=1.0005,
+                           density_amp=0.0, period=1000.0)]
+    outlets = [iolet_record(0, tuple(outl.normal), tuple(outl.position), radius=radius, density_mean=0.9995,
+                            density_amp=0.0, period=1000.0)]
+    prepare_boundary_objects(inlets, outlets)
+    return inlets, outlets
+
+
+def build_workload(radius, length, rank, nranks, block_size=8, device=0):
+    """This rank's Domain tables, built on the GPU straight from the cylinder's analytic shape
+    (hlb_dom_*: voxelisation, site order, neighbourIndices, halo tables).  N > 1: z-slabs of a
+    cylinder nranks times longer; each rank voxelises only its own slab plus one voxel of rim."""
+    from hemelb_b200.devdomain import DeviceDomain, cylinder_shape
+    total_len = length * nranks
+    caps, iolets, shape = cylinder_shape(radius, total_len)
+    partition = None
+    if nranks > 1:
+        margin, per, big = 2, total_len // nranks, 2 ** 60
+        partition = ("slabs", 2, [-big] + [margin + r * per for r in range(1, nranks)] + [big])
+    dom = DeviceDomain.from_shape(caps, iolets, shape, Q, block_size, partition, rank, nranks, device)
+    inlets, outlets = cylinder_iolets(dom.meta, radius)
+    return dom, inlets, outlets
+
+
+def build_workload_host(radius, length, rank, nranks, block_size=8):
+    """The same workload through the host (numpy) voxeliser and Domain builder (--host-tables)."""
+    from hemelb_b200 import geometry as G
+    from hemelb_b200.domain import DomainBuilder
     total_len = length * nranks
     if nranks == 1:
         geom = G.cylinder_extruded(radius, total_len, block_size)
@@ -90,14 +129,8 @@ def build_workload(radius, length, rank, nranks, block_size=8):
     else:
         geom, rank_of_site = G.cylinder_slab(radius, total_len, nranks, rank, block_size)
     dom = DomainBuilder(geom, Q, rank_of_site, nranks).domains[rank]
-    meta = geom.meta
-    inl, outl = meta["inlets"][0], meta["outlets"][0]
-    inlets = [iolet_record(0, tuple(inl.normal), tuple(inl.position), radius=radius, density_mean=1.0005,
-                           density_amp=0.0, period=1000.0)]
-    outlets = [iolet_record(0, tuple(outl.normal), tuple(outl.position), radius=radius, density_mean=0.9995,
-                            density_amp=0.0, period=1000.0)]
-    prepare_boundary_objects(inlets, outlets)
-    return geom, dom, inlets, outlets
+    inlets, outlets = cylinder_iolets(geom.meta, radius)
+    return dom, inlets, outlets
 
 
 def cpu_reference_run(steps, warmup, target_seconds=12.0, radius=40.0, length=320):
@@ -161,6 +194,7 @@ def main():
     ap.add_argument("--length", type=int, default=1500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reorder", action="store_true")
+    ap.add_argument("--host-tables", action="store_true", help="voxelise and build the Domain tables on the host (numpy)")
     ap.add_argument("--block-size", type=int, default=8, help="sites per block side of the synthetic .gmy (HemeLB default 8)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -192,9 +226,14 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     t_setup = time.time()
-    geom, dom, inlets, outlets = build_workload(args.radius, args.length, rank, world, args.block_size)
-    gpu = GpuLBM(dom, "LBGK", "BFL", "NASH", "NASH", tau=TAU, inlets=inlets, outlets=outlets, device=local_rank,
-                 reorder=not args.no_reorder)
+    if args.host_tables:
+        dom, inlets, outlets = build_workload_host(args.radius, args.length, rank, world, args.block_size)
+        gpu = GpuLBM(dom, "LBGK", "BFL", "NASH", "NASH", tau=TAU, inlets=inlets, outlets=outlets, device=local_rank,
+                     reorder=not args.no_reorder)
+    else:
+        dom, inlets, outlets = build_workload(args.radius, args.length, rank, world, args.block_size, local_rank)
+        gpu = GpuLBM.from_device_domain(dom, "LBGK", "BFL", "NASH", "NASH", tau=TAU, inlets=inlets, outlets=outlets,
+                                        reorder=not args.no_reorder)
     if world > 1:
         import torch
         uid = [GpuLBM.comm_unique_id() if rank == 0 else None]
@@ -264,7 +303,9 @@ def main():
         "sites": {"global": n_sites_global, "rank0": n_sites_local, "rank0_by_type_mid": [int(x) for x in dom.mid],
                   "rank0_by_type_edge": [int(x) for x in dom.edge], "halo_doubles_rank0": int(dom.totalSharedFs)},
         "roofline": {"bound": "hbm", "achieved": bulk_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": bulk_gbs / peak if peak else None, "traffic": None,
+                     "frac": bulk_gbs / peak if peak else None,
+                     "traffic": measured_traffic(int(dom.mid[0])), "traffic_unit": "bytes per launch (ncu dram read+write)",
+                     "algorithmic_bytes_per_launch": int(dom.mid[0]) * BYTES_PER_SITE,
                      "kernel": "collide_stream_kernel<19,LBGK,none,none> (mid-fluid range)",
                      "bytes_per_site": BYTES_PER_SITE, "peak_kind": peak_kind + " HBM copy (burst)",
                      "kernel_share_of_step": bulk_ms / ms if ms else None,
@@ -274,6 +315,7 @@ def main():
                 "path": "hlb_gpu_set_step_scalars + request_comms/stream_and_collide x12/edge_done/copy_received/"
                         "post_step x12/swap + hlb_gpu_monitor per step, from Python over ctypes"},
         "gpu_launches": int(launches), "clocks": clocks, "setup_seconds": t_setup,
+        "tables": "host (numpy)" if args.host_tables else "device (hlb_dom_*), %.3f s of kernels" % dom.build_seconds,
         "monitor": mon,
     }
     if not args.no_cpu_baseline and world == 1:

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "../../include/hemelb_b200.h"
+#include "engine_internal.h"
 #include "kernels.cuh"
 
 namespace hlb {
@@ -818,6 +819,35 @@ int one_step(hlb_gpu_t h) {
 }
 
 }  // namespace
+
+// ---- internal seam for the device-side Domain builder (engine_internal.h)
+int hlb_internal_fail(const char* msg) { return fail(msg); }
+
+int hlb_gpu_internal_raw(hlb_gpu_t h, hlb_gpu_raw* out) {
+  if (!h || !out) return fail("null argument");
+  if (h->finalised) return fail("handle already finalised");
+  CU(cudaSetDevice(h->cfg.device));
+  if (h->cfg.reorder && !h->coordsAll) CU(cudaMalloc(&h->coordsAll, sizeof(int32_t) * 3 * h->stride));
+  out->nbr = h->nbr;
+  out->coordsAll = h->coordsAll;
+  out->stride = h->stride;
+  out->hWall = h->hWall.data();
+  out->hIolet = h->hIolet.data();
+  out->hIoletId = h->hIoletId.data();
+  out->hCut = h->hCut.data();
+  out->hNormal = h->hNormal.data();
+  out->hCoords = h->hCoords.data();
+  out->bStride = h->bStride;
+  out->NB = h->NB;
+  return 0;
+}
+
+int hlb_gpu_internal_mark_installed(hlb_gpu_t h) {
+  if (!h) return fail("null argument");
+  h->haveNbr = h->haveSiteData = h->haveCut = h->haveNormal = h->haveCoords = true;
+  if (h->cfg.reorder) h->coordsCovered = h->N;
+  return 0;
+}
 
 extern "C" {
 

@@ -431,10 +431,10 @@ def cylinder_extruded(radius: float, length: int, block_size: int = 8, margin: i
     return g.gmy_sort()
 
 
-def capsule_tree(generations: int, root_radius: float, root_length: float, seed: int = 20261017,
-                 half_angle_deg: float = 35.0, block_size: int = 8, margin: int = 3):
-    """configs[2]: a bifurcating tree of cylinders obeying Murray's law (r_child = r / 2^(1/3)),
-    one inlet at the root and one outlet per leaf branch."""
+def tree_segments(generations: int, root_radius: float, root_length: float, seed: int = 20261017,
+                  half_angle_deg: float = 35.0, margin: int = 3):
+    """Capsule end points / radii of the bifurcating tree (Murray's law, r_child = r / 2^(1/3)),
+    shifted into a lattice with ``margin`` voxels of clearance: (A, B, R, is_leaf, voxel shape)."""
     rng = np.random.default_rng(seed)
     segs = []  # (a, b, r, is_leaf)
 
@@ -466,6 +466,16 @@ def capsule_tree(generations: int, root_radius: float, root_length: float, seed:
     A = np.array([s[0] + shift for s in segs])
     Bp = np.array([s[1] + shift for s in segs])
     Rr = np.array([s[2] for s in segs])
+    leaf = np.array([s[3] for s in segs], bool)
+    return A, Bp, Rr, leaf, shape
+
+
+def capsule_tree(generations: int, root_radius: float, root_length: float, seed: int = 20261017,
+                 half_angle_deg: float = 35.0, block_size: int = 8, margin: int = 3):
+    """configs[2]: a bifurcating tree of cylinders obeying Murray's law (r_child = r / 2^(1/3)),
+    one inlet at the root and one outlet per leaf branch."""
+    A, Bp, Rr, leaf, shape = tree_segments(generations, root_radius, root_length, seed, half_angle_deg, margin)
+    segs = [(A[k], Bp[k], Rr[k], bool(leaf[k])) for k in range(A.shape[0])]
     AB = Bp - A
     L2 = (AB * AB).sum(1)
 
@@ -627,20 +637,14 @@ def morton(ijk: np.ndarray) -> np.ndarray:
     return (_spread(ijk[:, 0]) << np.uint64(2)) ^ (_spread(ijk[:, 1]) << np.uint64(1)) ^ _spread(ijk[:, 2])
 
 
-def basic_decomposition(geom: Geometry, nranks: int) -> np.ndarray:
-    """Site -> rank by the reference's ``BasicDecomposition`` (whole blocks, recursive bisection of
-    the Morton-ordered cumulative fluid-site counts; ``BasicDecomposition.cc:21-96``)."""
-    B = geom.block_size
-    bc = (geom.coords // B).astype(np.int64)
-    bd = geom.block_dims.astype(np.int64)
-    gmy_idx = (bc[:, 0] * bd[1] + bc[:, 1]) * bd[2] + bc[:, 2]
-    uniq, counts = np.unique(gmy_idx, return_counts=True)
-    ijk = np.stack([uniq // (bd[1] * bd[2]), (uniq // bd[2]) % bd[1], uniq % bd[2]], 1)
+def basic_decomposition_blocks(ijk: np.ndarray, counts: np.ndarray, nranks: int) -> np.ndarray:
+    """Rank of each non-empty block by the reference's ``BasicDecomposition``: recursive bisection
+    of the Morton-ordered cumulative fluid-site counts (``BasicDecomposition.cc:21-96``)."""
     order = np.argsort(morton(ijk), kind="stable")
     counts_m = counts[order]
     if counts_m.size < nranks:
         raise ValueError("More ranks than blocks")
-    cum = np.concatenate([[0], np.cumsum(counts_m)]).astype(np.uint64)
+    cum = np.concatenate([[0], np.cumsum(counts_m.astype(np.int64))]).astype(np.uint64)
     rank_for_block = np.zeros(counts_m.size, np.int32)
 
     def assign(cb, ce, rb, re, n):
@@ -660,8 +664,20 @@ def basic_decomposition(geom: Geometry, nranks: int) -> np.ndarray:
         rank_for_block[rm:re] += n_lo
 
     assign(0, cum.size - 1, 0, rank_for_block.size, nranks)
-    block_rank = np.empty(uniq.size, np.int32)
+    block_rank = np.empty(counts_m.size, np.int32)
     block_rank[order] = rank_for_block
+    return block_rank
+
+
+def basic_decomposition(geom: Geometry, nranks: int) -> np.ndarray:
+    """Site -> rank by the reference's ``BasicDecomposition`` (whole blocks)."""
+    B = geom.block_size
+    bc = (geom.coords // B).astype(np.int64)
+    bd = geom.block_dims.astype(np.int64)
+    gmy_idx = (bc[:, 0] * bd[1] + bc[:, 1]) * bd[2] + bc[:, 2]
+    uniq, counts = np.unique(gmy_idx, return_counts=True)
+    ijk = np.stack([uniq // (bd[1] * bd[2]), (uniq // bd[2]) % bd[1], uniq % bd[2]], 1)
+    block_rank = basic_decomposition_blocks(ijk, counts, nranks)
     return block_rank[np.searchsorted(uniq, gmy_idx)].astype(np.int32)
 
 

@@ -143,10 +143,7 @@ class GpuLBM:
                                            ptr(np.ascontiguousarray(pr[:, 2], np.int64), C.c_int64)))
             check(L.hlb_gpu_set_streaming_indices(h, ptr(np.ascontiguousarray(domain.streamingIndices, np.int64),
                                                          C.c_int64)))
-        for which, recs in ((0, inlets), (1, outlets)):
-            if len(recs):
-                r = np.ascontiguousarray(np.stack(recs), np.float64)
-                check(L.hlb_gpu_set_iolets(h, which, len(recs), ptr(r, C.c_double)))
+        self._set_iolets(inlets, outlets)
         self.gzs_need = np.zeros((0, 4), np.int64)
         self.gzs_serve = np.zeros((0, 2), np.int64)
         if wall == "GZS" and domain.nranks > 1:
@@ -164,6 +161,44 @@ class GpuLBM:
                                               ptr(np.ascontiguousarray(sv[:, 0], np.int32), C.c_int32),
                                               ptr(np.ascontiguousarray(sv[:, 1], np.int64), C.c_int64)))
         check(L.hlb_gpu_finalise(h))
+
+    def _set_iolets(self, inlets, outlets):
+        for which, recs in ((0, inlets), (1, outlets)):
+            if len(recs):
+                r = np.ascontiguousarray(np.stack(recs), np.float64)
+                check(self.L.hlb_gpu_set_iolets(self.h, which, len(recs), ptr(r, C.c_double)))
+
+    @classmethod
+    def from_device_domain(cls, dd, kernel="LBGK", wall="SBB", inlet="NASH", outlet="NASH", tau=0.8, inlets=(),
+                           outlets=(), reorder=True):
+        """The engine for a ``devdomain.DeviceDomain``: the tables move device-to-device
+        (``hlb_gpu_create_from_domain``); nothing of size N crosses the host."""
+        self = cls.__new__(cls)
+        self.L = lib()
+        self.domain = dd
+        self.Q, self.N, self.S = dd.Q, dd.N, dd.totalSharedFs
+        self.state = SimulationState()
+        self.inlet_values = BoundaryValues(inlets, self.state)
+        self.outlet_values = BoundaryValues(outlets, self.state)
+        self.cache_mask = 0
+        cfg = HlbConfig()
+        cfg.kernel = capi.KERNELS[kernel]
+        cfg.wall = capi.WALLS[wall]
+        cfg.inlet = capi.IOLETS[inlet]
+        cfg.outlet = capi.IOLETS[outlet]
+        cfg.tau = tau
+        cfg.n_inlets = len(inlets)
+        cfg.n_outlets = len(outlets)
+        cfg.reorder = 1 if reorder else 0
+        self.cfg = cfg
+        h = C.c_void_p()
+        check(self.L.hlb_gpu_create_from_domain(dd.d, C.byref(cfg), C.byref(h)))
+        self.h = h
+        self._set_iolets(inlets, outlets)
+        self.gzs_need = np.zeros((0, 4), np.int64)
+        self.gzs_serve = np.zeros((0, 2), np.int64)
+        check(self.L.hlb_gpu_finalise(h))
+        return self
 
     # ---- multi-GPU ---------------------------------------------------------------------------
     @staticmethod

@@ -163,6 +163,75 @@ int hlb_gpu_launch_count(hlb_gpu_t h, int64_t* n);
 /* the device-resident tables, converted back to reference form (for parity tests) */
 int hlb_gpu_get_neighbour_indices(hlb_gpu_t h, int64_t* idx);
 
+/* ==== device-side geometry::Domain construction ==================================================
+ * Replaces, for one rank, the host loops of geometry::Domain (Code/geometry/Domain.cc:69-357 site
+ * order and collision-type buckets, :425-505 neighbourIndices, :247-285 neighbouringProcs,
+ * :507-580 halo slots and streamingIndicesForReceivedDistributions) fed by GeometryReader
+ * (Code/geometry/GeometryReader.cc:556-652).  Every table it produces is bit-identical to the
+ * reference's; it can be read back in reference form (parity tests) or handed to an engine handle
+ * device-to-device (hlb_gpu_create_from_domain), so the N*Q int64 table never visits the host.
+ * Two site sources: an explicit .gmy-level site list, or an analytic union of capsules clipped by
+ * flat iolet caps voxelised on the device (synthetic geometries; the link model of
+ * doc/dev/file-formats/geometry.md: per-link cut type / iolet id / float32 distance, wall normal). */
+typedef struct hlb_dom_handle* hlb_dom_t;
+
+typedef struct {
+  int lattice;            /* 15, 19 or 27 */
+  int block_size;         /* sites per block side (.gmy header), <= 8 */
+  int64_t block_dims[3];  /* blocks per axis (.gmy header) */
+  int rank, nranks;       /* the rank whose Domain is built */
+  int device;             /* CUDA ordinal */
+} hlb_dom_config;
+
+int hlb_dom_create(const hlb_dom_config* cfg, hlb_dom_t* out);
+int hlb_dom_destroy(hlb_dom_t d);
+/* source A: fluid sites as GeometryReader delivers them.  coords: n_sites x 3 global voxel
+ * coordinates (any order; only this rank's sites and their lattice neighbours are needed);
+ * rank_of_site: n_sites (NULL = all on rank 0) -- the decomposition's answer, ParMETIS or basic;
+ * cut-link records for the sites that have any: record_site[n_records] indexes coords, link arrays
+ * are n_records x 26 in the file's neighbour order (Code/io/formats/geometry.h:120-156). */
+int hlb_dom_set_sites(hlb_dom_t d, int64_t n_sites, const int32_t* coords, const int32_t* rank_of_site,
+                      int64_t n_records, const int64_t* record_site, const uint8_t* link_type,
+                      const int32_t* link_iolet, const float* link_dist, const uint8_t* normal_available,
+                      const float* normal);
+/* source B: union of capsules {a[3], b[3], radius} (7 doubles each) clipped by iolet caps
+ * {kind (2 inlet / 3 outlet), index, position[3], normal[3] (into the fluid), radius} (9 doubles
+ * each), in voxel units of the block lattice. */
+int hlb_dom_set_shape(hlb_dom_t d, int n_capsules, const double* capsules, int n_iolets, const double* iolets);
+/* site -> rank rule for source B: slabs along an axis (rank r owns first_coord[r] <= x < first_coord
+ * [r+1]; nranks + 1 ascending values; cuts through blocks like a ParMETIS site partition), or
+ * whole blocks (rank_of_block[prod(block_dims)], .gmy block order; what BasicDecomposition,
+ * Code/geometry/decomposition/BasicDecomposition.cc:21-96, produces) */
+int hlb_dom_set_partition_slabs(hlb_dom_t d, int axis, const int64_t* first_coord);
+int hlb_dom_set_partition_blocks(hlb_dom_t d, const int32_t* rank_of_block);
+/* source B: fluid sites per block over a box of blocks [lo, hi) (the input of BasicDecomposition);
+ * counts is x-major / z-fastest over the box */
+int hlb_dom_count_block_sites(hlb_dom_t d, const int64_t* lo, const int64_t* hi, int32_t* counts);
+int hlb_dom_build(hlb_dom_t d);
+int hlb_dom_build_seconds(hlb_dom_t d, double* seconds);  /* device time of the last build */
+/* ---- the tables, reference form */
+int hlb_dom_get_counts(hlb_dom_t d, int64_t* n_sites, int64_t* mid6, int64_t* edge6, int64_t* total_shared_fs,
+                       int* n_neighbours);
+int hlb_dom_get_neighbours(hlb_dom_t d, int* rank, int64_t* count, int64_t* first);
+int hlb_dom_get_streaming_indices(hlb_dom_t d, int64_t* idx);
+int hlb_dom_get_neighbour_indices(hlb_dom_t d, int64_t first_site, int64_t n, int64_t* idx);
+int hlb_dom_get_site_coords(hlb_dom_t d, int64_t first_site, int64_t n, int64_t* coords);  /* n x 3 */
+int hlb_dom_get_input_index(hlb_dom_t d, int64_t first_site, int64_t n, int64_t* idx);     /* source A */
+/* the boundary-typed sites (local ids [mid[0], sum(mid)) then [sum(mid)+edge[0], N)), site-major:
+ * SiteData masks + iolet id, distanceToWall (Q-1 per site, -1 where uncut), wallNormalAtSite
+ * (3 per site, +inf where the file has none) */
+int hlb_dom_get_boundary_tables(hlb_dom_t d, uint32_t* wall_mask, uint32_t* iolet_mask, int32_t* iolet_id,
+                                double* dist, double* normal);
+/* source B: the voxelised geometry in .gmy terms (sites in traversal order; one record per site
+ * with a non-fluid 26-neighbour), e.g. to write a .gmy the reference can read */
+int hlb_dom_get_geometry_sizes(hlb_dom_t d, int64_t* n_sites, int64_t* n_records);
+int hlb_dom_get_geometry(hlb_dom_t d, int32_t* coords, int64_t* record_site, uint8_t* link_type, int32_t* link_iolet,
+                         float* link_dist, uint8_t* normal_available, float* normal);
+/* hlb_gpu_create + every hlb_gpu_set_* table call, device-to-device.  `policy` supplies kernel,
+ * wall, inlet, outlet, tau, n_inlets, n_outlets, reorder; sizes, ranks and device come from the
+ * built domain.  Still to do on the handle: hlb_gpu_set_iolets, hlb_gpu_finalise. */
+int hlb_gpu_create_from_domain(hlb_dom_t d, const hlb_gpu_config* policy, hlb_gpu_t* out);
+
 #ifdef __cplusplus
 }
 #endif

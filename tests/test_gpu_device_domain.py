@@ -1,0 +1,207 @@
+"""Device-side geometry::Domain construction (hlb_dom_*): every table bit-identical to the host
+builder (itself pinned bit-for-bit to the oracle's literal restatement of Code/geometry/Domain.cc
+in tests/test_domain_tables.py) and to the oracle directly; the device voxeliser against the host
+one; and the engine fed device-to-device against the oracle."""
+import numpy as np
+import pytest
+
+import oracle as O
+from hemelb_b200 import geometry as G
+from hemelb_b200.devdomain import (DeviceDomain, basic_decomposition_of_counts, cylinder_shape, tree_shape)
+from hemelb_b200.domain import build_domains
+from hemelb_b200.lbm import GpuLBM
+from tests.cases import anisotropic_f, geometry, iolets_for
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("N", "totalSharedFs", "counts", "neighbourIndices", "wallMask", "ioletMask", "ioletId", "distanceToWall",
+        "globalCoords", "streamingIndices", "procs")
+
+
+def _same(dev: DeviceDomain, host, what):
+    a, b = dev.tables(), host.tables()
+    for k in KEYS:
+        va, vb = np.asarray(a[k]), np.asarray(b[k])
+        assert va.shape == vb.shape and np.array_equal(va, vb), (what, k)
+    # wall normals: the engine only reads them for boundary-typed sites
+    bs = dev.boundary_sites()
+    na, nb = a["wallNormal"].reshape(-1, 3)[bs], b["wallNormal"].reshape(-1, 3)[bs]
+    assert np.array_equal(na, nb), (what, "wallNormal")
+
+
+@pytest.mark.parametrize("name", ["four_cube", "cylinder", "tree", "sac"])
+@pytest.mark.parametrize("Q", (15, 19, 27))
+def test_explicit_source_tables_bit_exact(name, Q):
+    geom = geometry(name)
+    cases = [(None, 1), (G.slab_decomposition(geom, 2, axis=2), 2), (G.slab_decomposition(geom, 3, axis=0), 3)]
+    if name != "four_cube":
+        cases.append((G.basic_decomposition(geom, 5), 5))
+    for ros, R in cases:
+        host = build_domains(geom, Q, ros, R)
+        for r in range(R):
+            dev = DeviceDomain.from_geometry(geom, Q, ros, r, R)
+            _same(dev, host[r], (name, Q, R, r))
+            assert np.array_equal(dev.input_index(), host[r].inputIndex)
+            dev.close()
+
+
+def test_explicit_source_against_oracle_directly():
+    geom, Q, R = geometry("tree"), 19, 4
+    ros = G.basic_decomposition(geom, R)
+    od = O.OracleDomains(geom, Q, ros, R)
+    for r in range(R):
+        dev = DeviceDomain.from_geometry(geom, Q, ros, r, R)
+        a, b = od.tables(r), dev.tables()
+        for k in ("neighbourIndices", "streamingIndices", "globalCoords", "wallMask", "ioletMask", "ioletId",
+                  "distanceToWall"):
+            assert np.array_equal(np.asarray(a[k]).reshape(-1), np.asarray(b[k]).reshape(-1)), (r, k)
+        assert np.array_equal(np.asarray(a["counts"]), b["counts"])
+        dev.close()
+
+
+def test_explicit_source_halo_only_upload():
+    """A rank only needs its own sites and their lattice neighbours (what cylinder_slab ships)."""
+    R, Q = 3, 19
+    full = G.cylinder_extruded(6.3, 60)
+    per = 60 // R
+    ros_full = np.minimum((full.coords[:, 2].astype(np.int64) - 2) // per, R - 1).astype(np.int32)
+    host = build_domains(full, Q, ros_full, R)
+    for r in range(R):
+        sub, ros = G.cylinder_slab(6.3, 60, R, r)
+        dev = DeviceDomain.from_geometry(sub, Q, ros, r, R)
+        _same(dev, host[r], ("slab", r))
+        dev.close()
+
+
+def _shape(name):
+    if name == "cylinder":
+        return cylinder_shape(5.3, 20)
+    return tree_shape(3, 5.0, 16.0)
+
+
+@pytest.mark.parametrize("name", ["cylinder", "tree"])
+def test_device_voxeliser_matches_host_voxeliser(name):
+    caps, iolets, shape = _shape(name)
+    dev = DeviceDomain.from_shape(caps, iolets, shape, 19)
+    g = dev.geometry()
+    h = geometry(name)
+    assert np.array_equal(g.block_dims, h.block_dims)
+    assert np.array_equal(g.coords, h.coords)  # same fluid sites, .gmy order
+    assert np.array_equal(g.bsite, h.bsite)
+    assert np.array_equal(g.btype, h.btype) and np.array_equal(g.biolet, h.biolet)
+    assert np.array_equal(g.bnavail, h.bnavail)
+    # cut distances: both bisect to 2^-30, float32-rounded; the host's phi sums in another order
+    assert np.abs(g.bdist.astype(np.float64) - h.bdist.astype(np.float64)).max() <= 2e-6
+    # normals: exact radial direction on the device; the host tree uses a finite difference of phi
+    # (so they differ where two capsules meet: compare away from the junction kinks)
+    dn = np.abs(g.bnormal.astype(np.float64) - h.bnormal.astype(np.float64)).max(1)
+    assert dn.max() <= 1e-6 if name == "cylinder" else np.quantile(dn, 0.8) <= 2e-2
+
+
+@pytest.mark.parametrize("name", ["cylinder", "tree"])
+@pytest.mark.parametrize("Q", (15, 19, 27))
+def test_analytic_source_tables_bit_exact(name, Q):
+    """Tables built straight from the shape == host builder on the downloaded voxelisation."""
+    caps, iolets, shape = _shape(name)
+    dev = DeviceDomain.from_shape(caps, iolets, shape, Q)
+    g = dev.geometry()
+    _same(dev, build_domains(g, Q)[0], (name, Q, "single"))
+    # slabs along z through blocks
+    R = 3
+    z = g.coords[:, 2].astype(np.int64)
+    cuts = [int(np.quantile(z, k / R)) for k in range(1, R)]
+    first = np.array([np.iinfo(np.int64).min // 2] + cuts + [np.iinfo(np.int64).max // 2], np.int64)
+    ros = (np.searchsorted(first, z, side="right") - 1).astype(np.int32)
+    host = build_domains(g, Q, ros, R)
+    for r in range(R):
+        d = DeviceDomain.from_shape(caps, iolets, shape, Q, partition=("slabs", 2, first), rank=r, nranks=R)
+        _same(d, host[r], (name, Q, "slabs", r))
+        d.close()
+    # whole blocks by BasicDecomposition of the device's own per-block counts
+    R = 4
+    counts = dev.count_block_sites()
+    assert counts.sum() == g.n_sites
+    rob = basic_decomposition_of_counts(counts, R)
+    ros = G.basic_decomposition(g, R)
+    bd = g.block_dims.astype(np.int64)
+    bc = (g.coords // g.block_size).astype(np.int64)
+    assert np.array_equal(rob[(bc[:, 0] * bd[1] + bc[:, 1]) * bd[2] + bc[:, 2]], ros)
+    host = build_domains(g, Q, ros, R)
+    for r in range(R):
+        d = DeviceDomain.from_shape(caps, iolets, shape, Q, partition=("blocks", rob), rank=r, nranks=R)
+        _same(d, host[r], (name, Q, "blocks", r))
+        d.close()
+    dev.close()
+
+
+@pytest.mark.parametrize("source", ["explicit", "analytic"])
+@pytest.mark.parametrize("Q,kernel,wall,inlet,outlet", [
+    (19, "LBGK", "BFL", "NASH", "NASH"), (19, "MRT", "GZS", "LADD", "NASH"), (27, "TRT", "BFL", "NASH", "NASH"),
+    (15, "LBGK", "SBB", "LADD", "LADD")])
+def test_engine_from_device_domain_matches_oracle(source, Q, kernel, wall, inlet, outlet):
+    if source == "explicit":
+        geom = geometry("tree")
+        dev = DeviceDomain.from_geometry(geom, Q)
+    else:
+        caps, iolets, shape = tree_shape(3, 5.0, 16.0)
+        dev = DeviceDomain.from_shape(caps, iolets, shape, Q)
+        geom = dev.geometry()
+    inlets, outlets = iolets_for(geom, inlet, outlet)
+    gpu = GpuLBM.from_device_domain(dev, kernel, wall, inlet, outlet, tau=0.8, inlets=inlets, outlets=outlets)
+    sim = O.OracleSim(O.OracleDomains(geom, Q), kernel, wall, inlet, outlet, tau=0.8, inlets=inlets, outlets=outlets)
+    # the engine's table read-back (reference form, through the internal renumbering)
+    assert np.array_equal(gpu.get_neighbour_indices(), build_domains(geom, Q)[0].neighbour_indices())
+    f0 = anisotropic_f(dev.N, Q, 0)
+    gpu.set_f(f0)
+    sim.set_f(f0)
+    gpu.set_cache_mask(255)
+    sim.set_cache_mask(255)
+    gpu.step(10)
+    sim.step(10)
+    assert np.array_equal(gpu.get_f()[:dev.N * Q], sim.get_f()[:dev.N * Q])
+    for name in ("density", "velocity", "wall_shear_stress", "traction"):
+        assert np.array_equal(gpu.get_cache(name), sim.get_cache(name)), name
+
+
+def test_two_rank_engine_from_device_domain_host_staged_halo():
+    """Two ranks built on the device from the shape, halo moved through the host: identical to the
+    oracle's two emulated ranks."""
+    Q, R = 19, 2
+    caps, iolets, shape = cylinder_shape(5.3, 20)
+    whole = DeviceDomain.from_shape(caps, iolets, shape, Q)
+    geom = whole.geometry()
+    cut = 2 + 10
+    first = np.array([-2**60, cut, 2**60], np.int64)
+    ros = (geom.coords[:, 2] >= cut).astype(np.int32)
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    doms = [DeviceDomain.from_shape(caps, iolets, shape, Q, partition=("slabs", 2, first), rank=r, nranks=R)
+            for r in range(R)]
+    gpus = [GpuLBM.from_device_domain(d, "LBGK", "BFL", tau=0.8, inlets=inlets, outlets=outlets) for d in doms]
+    sim = O.OracleSim(O.OracleDomains(geom, Q, ros, R), "LBGK", "BFL", tau=0.8, inlets=inlets, outlets=outlets)
+    for r, (d, g) in enumerate(zip(doms, gpus)):
+        f0 = anisotropic_f(d.N, Q, d.totalSharedFs, site_offset=1000 * r)
+        g.set_f(f0)
+        sim.set_f(f0, r)
+    for _ in range(6):
+        for g in gpus:
+            g.request_comms()
+            g.pre_send()
+            g.pre_receive()
+        halos = [g.get_halo(1) for g in gpus]
+        # slice k of rank a towards b pairs with b's slice towards a (same offsets both sides)
+        for a, (d, g) in enumerate(zip(doms, gpus)):
+            recv = np.zeros(d.totalSharedFs)
+            for (p, cnt, fst) in d.procs:
+                o = int(fst) - (d.N * Q + 1)
+                back = doms[p].procs
+                j = int(np.nonzero(back[:, 0] == a)[0][0])
+                po = int(back[j, 2]) - (doms[p].N * Q + 1)
+                recv[o:o + cnt] = halos[p][po:po + cnt]
+            g.set_halo(recv, 0)
+        for g in gpus:
+            g.post_receive()
+            g.swap_old_and_new()
+            g.state.increment()
+        sim.step(1)
+    for r, (d, g) in enumerate(zip(doms, gpus)):
+        assert np.array_equal(g.get_f()[:d.N * Q], sim.get_f(r)[:d.N * Q]), r
