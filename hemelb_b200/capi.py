@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhemelb_b200.so")
+LIB_PATH = os.environ.get("HLB_LIB", os.path.join(HERE, "libhemelb_b200.so"))  # HLB_LIB: an experimental build
 
 KERNELS = {"LBGK": 0, "MRT": 1, "TRT": 2}
 WALLS = {"SBB": 0, "SIMPLEBOUNCEBACK": 0, "BFL": 1, "GZS": 2}

@@ -706,6 +706,7 @@ int launch_range(hlb_gpu_t h, int slot, int64_t first, int64_t count, bool post)
     CU(cudaEventRecord(h->profEv[h->profUsed], h->compute));
   }
   h->launch(wall, iolet, A, h->mrt.data(), first, count, h->compute);
+  if (wall == W_GZS) h->launches++;  // the per-link kernel behind the per-site one
   if (h->cacheMask & C_MONITOR) h->monitorLaunches++;
   if (prof) {
     CU(cudaEventRecord(h->profEv[h->profUsed + 1], h->compute));

@@ -17,6 +17,8 @@ void launch_collide_stream(int wall, int iolet, const StepArgs& A, const void* m
 #define HLB_CASE(W, I)                                                              \
   if (wall == W && iolet == I) {                                                    \
     collide_stream_kernel<Q, KERNEL, W, I><<<grid, block, 0, s>>>(A, M, first, count); \
+    if constexpr (W == W_GZS)                                                       \
+      gzs_links_kernel<Q, KERNEL, I><<<(unsigned)((count + kGzsTile - 1) / kGzsTile), kGzsThreads, 0, s>>>(A, M, first, count); \
     return;                                                                         \
   }
   HLB_CASE(W_NONE, I_NONE)

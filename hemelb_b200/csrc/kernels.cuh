@@ -346,81 +346,266 @@ __device__ __forceinline__ void parabolic_velocity(const IoletDev& io, const dou
 }
 
 // ---------------------------------------------------------------------------------- GZS wall link
-// GuoZhengShi.h:123-284 for wall direction iPrime of one site.  Kept out of line with run-time
-// direction: it re-runs a whole collision per wall link and would explode the unrolled site loop.
+// GuoZhengShi.h:123-284.  Every wall link re-runs a whole collision on an extrapolated wall node,
+// of which only ONE post-collision population is kept.  So the links do not ride in the per-site
+// thread (that serialises up to Q-1 collisions behind one another): gzs_links_kernel gives every
+// (site, wall direction) pair its own thread, recomputes the site's hydrodynamic variables from
+// f_old, and evaluates just the component it streams -- the same operations, in the same order,
+// as the reference performs for that component.
+
+// What one wall link needs of the wall node's f_neq (GuoZhengShi.h:228-262): the site's own f_neq,
+// blended with the fluid neighbour's when the link extrapolates.  Evaluated per component, on
+// demand: LBGK needs one component, TRT a pair, MRT all of them.
+template <int Q> struct GzsNode {
+  const double (*sf)[128];  // the tile's staged f_old rows, [direction][site in tile]
+  int t;
+  double rho, density_1, mm, m[3];
+  bool blend;
+  double q;
+  const double* nrow;  // neighbour's f_old row
+  int64_t nstep;
+  double nrho, ndensity_1, nmm, nm[3];
+  template <int J> __device__ __forceinline__ double fneq() const {
+    double v = sf[J][t] - feq_i<Q>(J, rho, density_1, mm, m);
+    if (blend) v = q * v + (1. - q) * (nrow[J * nstep] - feq_i<Q>(J, nrho, ndensity_1, nmm, nm));
+    return v;
+  }
+};
+
+// component D of kernel.Collide on the wall node (or, for the SBB fall-back, on the site itself):
+// base = f[D] of that node
+template <int Q, int KERNEL, int D>
+__device__ __forceinline__ double gzs_component(const StepArgs& A, const MrtArgs<Q>& M, const GzsNode<Q>& N, bool sbb,
+                                                double wdensity_1, double wmm, const double (&mw)[3],
+                                                const double (&fneqW)[Q],
+                                                const double (&mneq)[mrt_k<Q>() > 0 ? mrt_k<Q>() : 1]) {
+  // fneqW / mneq are filled for MRT only (once per link, before the per-direction dispatch, so
+  // that divergent warps do not repeat the projection); the other kernels evaluate the
+  // components they touch
+  const double fn = KERNEL == K_MRT ? fneqW[D] : N.template fneq<D>();
+  const double base = sbb ? N.sf[D][N.t] : feq_i<Q>(D, N.rho, wdensity_1, wmm, mw) + fn;
+  if constexpr (KERNEL == K_LBGK) {
+    return base + fn * A.omega;
+  } else if constexpr (KERNEL == K_MRT) {
+    double collision = 0.;  // MRT.h:88-105
+#pragma unroll
+    for (int k = 0; k < mrt_k<Q>(); ++k)
+      if (mrt_m<Q>(k, D) != 0) collision += M.SMn[k][D] * mneq[k];
+    return base - collision;
+  } else {
+    constexpr int a = (D & 1) ? D : D - 1, b = a + 1;
+    const double fa = D == a ? fn : N.template fneq<a>(), fb = D == b ? fn : N.template fneq<b>();
+    const double sym = 0.5 * A.omega * (fa + fb);
+    const double asym = 0.5 * A.omegaMinus * (fa - fb);
+    return D == a ? base + sym + asym : base + sym - asym;
+  }
+}
+
+// compile-time walk over the directions: the one that equals `o` evaluates its component
+template <int Q, int KERNEL, int D>
+__device__ __forceinline__ void gzs_pick(const StepArgs& A, const MrtArgs<Q>& M, const GzsNode<Q>& N, int o, bool sbb,
+                                         double wdensity_1, double wmm, const double (&mw)[3],
+                                         const double (&fneqW)[Q],
+                                         const double (&mneq)[mrt_k<Q>() > 0 ? mrt_k<Q>() : 1], double& out) {
+  if constexpr (D < Q) {
+    if (D == o) out = gzs_component<Q, KERNEL, D>(A, M, N, sbb, wdensity_1, wmm, mw, fneqW, mneq);
+    gzs_pick<Q, KERNEL, D + 1>(A, M, N, o, sbb, wdensity_1, wmm, mw, fneqW, mneq, out);
+  }
+}
+
+// all components at once (MRT)
+template <int Q, int J = 0>
+__device__ __forceinline__ void gzs_fill(const GzsNode<Q>& N, double (&fneqW)[Q]) {
+  if constexpr (J < Q) {
+    fneqW[J] = N.template fneq<J>();
+    gzs_fill<Q, J + 1>(N, fneqW);
+  }
+}
+
+// One CTA owns a tile of kGzsTile consecutive sites of the launch: their f_old rows are staged
+// through shared memory once, the tile's wall links are compacted into a list (so warps are full
+// whatever the wall orientation), and the threads walk the list.
+constexpr int kGzsTile = 128;  // (GzsNode::sf is typed on it)
+constexpr int kGzsThreads = 256;
+
 template <int Q, int KERNEL, int IOLET>
-__device__ __noinline__ void gzs_link(const StepArgs& A, const MrtArgs<Q>& M, int64_t site, int64_t b, int iPrime,
-                                      uint32_t wallMask, uint32_t ioletMask, double rho, const double (&m)[3],
-                                      const double* fneqIn, const double* fpostIn) {
-  const int i = inv_dir(iPrime);
-  const double q = (double)A.cutDist[(int64_t)(iPrime - 1) * A.bStride + b];
-  double mw[3];
+__global__ void __launch_bounds__(kGzsThreads, 2) gzs_links_kernel(const StepArgs A, const MrtArgs<Q> M, int64_t first,
+                                                               int64_t count) {
+  constexpr int T = kGzsTile;
+  __shared__ double sf[Q][T];
+  __shared__ double srho[T], smom[3][T];
+  __shared__ int64_t ssite[T];
+  __shared__ int32_t sb[T];
+  __shared__ uint32_t swall[T], siolet[T];
+  __shared__ uint16_t slink[T * (Q - 1)];
+  __shared__ int soff[(Q - 1) * (T / 32) + 1];
+  const int tx = threadIdx.x;
+  const int64_t tile0 = (int64_t)blockIdx.x * T;
+  const int nT = (int)((count - tile0) < T ? (count - tile0) : T);
+  if (tx < T) {
+    uint32_t wall = 0, iol = 0;
+    if (tx < nT) {
+      const int64_t site = A.siteList ? (int64_t)A.siteList[tile0 + tx] : first + tile0 + tx;
+      const int64_t b = bidx(A, site);
+      ssite[tx] = site;
+      sb[tx] = (int32_t)b;
+      wall = A.wallMask[b];
+      if constexpr (IOLET != I_NONE) iol = A.ioletMask[b];
+    }
+    swall[tx] = wall;
+    siolet[tx] = iol;
+  }
+  __syncthreads();
+  for (int e = tx; e < Q * T; e += kGzsThreads) {
+    const int d = e / T, t = e % T;
+    if (t < nT) sf[d][t] = A.fOld[(int64_t)d * A.stride + ssite[t]];
+  }
+  __syncthreads();
+  // per site: density and momentum; its GZS links = wall links that are not iolet links
+  // (the iolet link takes precedence, StreamerTypeFactory.h:65-79)
+  uint32_t links = 0;
+  if (tx < nT) {
+    double f[Q];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) mw[k] = m[k] * (1. - 1. / q);
-  double fneqW[Q];
+    for (int d = 0; d < Q; ++d) f[d] = sf[d][tx];
+    double rho, m[3];
+    density_momentum<Q>(f, rho, m);
+    srho[tx] = rho;
+    smom[0][tx] = m[0];
+    smom[1][tx] = m[1];
+    smom[2][tx] = m[2];
+    links = swall[tx] & ~siolet[tx];
+  }
+  // the tile's link list, direction-major (so a warp works on one direction and the per-direction
+  // specialisations below do not diverge): position = links of earlier directions + earlier sites
+  constexpr int SW = T / 32;  // warps that hold sites
+  const int warp = tx >> 5, lane = tx & 31;
+  if (warp < SW) {
 #pragma unroll
-  for (int j = 0; j < Q; ++j) fneqW[j] = fneqIn[j];
-  bool sbb = false;
-  if (q < 0.75) {
-    const bool hasIoletI = (ioletMask >> (i - 1)) & 1u;
-    const bool hasWallI = (wallMask >> (i - 1)) & 1u;
-    if (IOLET != I_NONE && hasIoletI) {
-      const IoletDev& io = A.iolets[A.ioletId[b]];
-      if (io.kind != 1) {
-        sbb = true;
-      } else {
-        double np[3], nv[3];
-        np[0] = (double)A.coords[b] + (double)Lat<Q>::cx(i);
-        np[1] = (double)A.coords[A.bStride + b] + (double)Lat<Q>::cy(i);
-        np[2] = (double)A.coords[2 * A.bStride + b] + (double)Lat<Q>::cz(i);
-        parabolic_velocity(io, np, A.timeStep, nv);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const double second = nv[k] * (q - 1) / (q + 1);
-          mw[k] = q * mw[k] + (1. - q) * rho * second;
-        }
-      }
-    } else if (hasWallI) {
-      sbb = true;
-    } else {
-      // neighbour site's f_old: local plane read, or the phase-0 ghost row of a remote site
-      double nf[Q];
-      const int32_t n = A.gzsNeighbour[(int64_t)(i - 1) * A.bStride + b];
-      if (n >= 0) {
-#pragma unroll
-        for (int j = 0; j < Q; ++j) nf[j] = A.fOld[(int64_t)j * A.stride + n];
-      } else {
-        const int64_t g = -(int64_t)n - 1;
-#pragma unroll
-        for (int j = 0; j < Q; ++j) nf[j] = A.gzsGhost[g * Q + j];
-      }
-      double nrho, nm[3], nu[3], nfeq[Q];
-      density_momentum<Q>(nf, nrho, nm);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) nu[k] = nm[k] / nrho;
-      feq_all<Q>(nrho, nm, nfeq);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const double second = nu[k] * (q - 1) / (q + 1);
-        mw[k] = q * mw[k] + (1. - q) * rho * second;
-      }
-#pragma unroll
-      for (int j = 0; j < Q; ++j) fneqW[j] = q * fneqW[j] + (1. - q) * (nf[j] - nfeq[j]);
+    for (int d = 1; d < Q; ++d) {
+      const unsigned ballot = __ballot_sync(0xffffffffu, (links >> (d - 1)) & 1u);
+      if (lane == 0) soff[(d - 1) * SW + warp] = __popc(ballot);
     }
   }
-  double out;
-  if (sbb) {
-    out = fpostIn[iPrime];
-  } else {
-    double fW[Q], feqW[Q], fpostW[Q];
-    feq_all<Q>(rho, mw, feqW);
-#pragma unroll
-    for (int j = 0; j < Q; ++j) fW[j] = feqW[j] + fneqW[j];
-    // (the reference leaves m_neq of this HydroVars unset for MRT; we project its f_neq)
-    collide<Q, KERNEL>(A, M, fW, fneqW, fpostW);
-    out = fpostW[i];
+  __syncthreads();
+  if (tx == 0) {
+    int acc = 0;
+    for (int e = 0; e < (Q - 1) * SW; ++e) {
+      const int c = soff[e];
+      soff[e] = acc;
+      acc += c;
+    }
+    soff[(Q - 1) * SW] = acc;
   }
-  A.fNew[(int64_t)i * A.stride + site] = out;
+  __syncthreads();
+  const int total = soff[(Q - 1) * SW];
+  if (warp < SW) {
+#pragma unroll
+    for (int d = 1; d < Q; ++d) {
+      const bool bit = (links >> (d - 1)) & 1u;
+      const unsigned ballot = __ballot_sync(0xffffffffu, bit);
+      if (bit) slink[soff[(d - 1) * SW + warp] + __popc(ballot & ((1u << lane) - 1u))] = (uint16_t)(tx | (d << 8));
+    }
+  }
+  __syncthreads();
+
+  for (int k = tx; k < total; k += kGzsThreads) {
+    const int t = slink[k] & 255;
+    const int iPrime = slink[k] >> 8;  // the direction that hits the wall
+    const int i = inv_dir(iPrime);
+    const int64_t site = ssite[t];
+    const int64_t b = sb[t];
+    const uint32_t wallMask = swall[t], ioletMask = siolet[t];
+    GzsNode<Q> N;
+    N.sf = sf;
+    N.t = t;
+    N.rho = srho[t];
+    N.m[0] = smom[0][t];
+    N.m[1] = smom[1][t];
+    N.m[2] = smom[2][t];
+    N.density_1 = 1. / N.rho;
+    N.mm = N.m[0] * N.m[0] + N.m[1] * N.m[1] + N.m[2] * N.m[2];
+    N.blend = false;
+    N.nrow = A.fOld;
+    N.nstep = 0;
+    N.nrho = N.ndensity_1 = 1.;
+    N.nmm = 0.;
+    N.nm[0] = N.nm[1] = N.nm[2] = 0.;
+    const double rho = N.rho;
+    const double q = (double)A.cutDist[(int64_t)(iPrime - 1) * A.bStride + b];
+    N.q = q;
+    double mw[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) mw[c] = N.m[c] * (1. - 1. / q);
+    bool sbb = false;
+    if (q < 0.75) {
+      const bool hasIoletI = (ioletMask >> (i - 1)) & 1u;
+      const bool hasWallI = (wallMask >> (i - 1)) & 1u;
+      if (IOLET != I_NONE && hasIoletI) {
+        const IoletDev& io = A.iolets[A.ioletId[b]];
+        if (io.kind != 1) {
+          sbb = true;
+        } else {
+          double np[3], nv[3];
+          np[0] = (double)A.coords[b] + (double)Lat<Q>::cx(i);
+          np[1] = (double)A.coords[A.bStride + b] + (double)Lat<Q>::cy(i);
+          np[2] = (double)A.coords[2 * A.bStride + b] + (double)Lat<Q>::cz(i);
+          parabolic_velocity(io, np, A.timeStep, nv);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const double second = nv[c] * (q - 1) / (q + 1);
+            mw[c] = q * mw[c] + (1. - q) * rho * second;
+          }
+        }
+      } else if (hasWallI) {
+        sbb = true;
+      } else {
+        // neighbour site's f_old: local plane read, or the phase-0 ghost row of a remote site
+        // (read again, from L1, by the components that blend it in)
+        const int32_t n = A.gzsNeighbour[(int64_t)(i - 1) * A.bStride + b];
+        N.nrow = n >= 0 ? A.fOld + n : A.gzsGhost + (-(int64_t)n - 1) * Q;
+        N.nstep = n >= 0 ? A.stride : 1;
+        double nrho = 0.0, nm[3] = {0.0, 0.0, 0.0}, nu[3];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {  // Lattice.h:181-191, as density_momentum()
+          const double v = N.nrow[j * N.nstep];
+          nrho += v;
+          if (Lat<Q>::cx(j) != 0) nm[0] += cmul(Lat<Q>::cx(j), v);
+          if (Lat<Q>::cy(j) != 0) nm[1] += cmul(Lat<Q>::cy(j), v);
+          if (Lat<Q>::cz(j) != 0) nm[2] += cmul(Lat<Q>::cz(j), v);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) nu[c] = nm[c] / nrho;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const double second = nu[c] * (q - 1) / (q + 1);
+          mw[c] = q * mw[c] + (1. - q) * rho * second;
+        }
+        N.blend = true;
+        N.nrho = nrho;
+        N.ndensity_1 = 1. / nrho;
+        N.nmm = nm[0] * nm[0] + nm[1] * nm[1] + nm[2] * nm[2];
+        N.nm[0] = nm[0];
+        N.nm[1] = nm[1];
+        N.nm[2] = nm[2];
+      }
+    }
+    // (the reference leaves m_neq of the wall node's HydroVars unset for MRT; we project its f_neq)
+    double fneqW[Q];
+    double mneq[mrt_k<Q>() > 0 ? mrt_k<Q>() : 1];
+    fneqW[0] = mneq[0] = 0.;
+    if constexpr (KERNEL == K_MRT) {
+      gzs_fill<Q>(N, fneqW);
+      mrt_project<Q>(fneqW, mneq);
+    }
+    // SBB: component iPrime of the site's own collision; else component i of the wall node's
+    const int o = sbb ? iPrime : i;
+    const double wdensity_1 = 1. / rho;
+    const double wmm = mw[0] * mw[0] + mw[1] * mw[1] + mw[2] * mw[2];
+    double out = 0.;
+    gzs_pick<Q, KERNEL, 1>(A, M, N, o, sbb, wdensity_1, wmm, mw, fneqW, mneq, out);
+    A.fNew[(int64_t)i * A.stride + site] = out;
+  }
 }
 
 // ---------------------------------------------------------------------------------- the site kernel
@@ -540,9 +725,8 @@ __global__ void __launch_bounds__(256) collide_stream_kernel(const StepArgs A, c
         if (invWall || q < 0.5) v = fpost[d];
         else v = (fpost[d] + (2.0 * q - 1) * fpost[id]) / (2.0 * q);
         A.fNew[(int64_t)id * A.stride + site] = v;
-      } else if constexpr (WALL == W_GZS) {
-        gzs_link<Q, KERNEL, IOLET>(A, M, site, b, d, wallMask, ioletMask, rho, m, fneq, fpost);
       }
+      // W_GZS: gzs_links_kernel owns this population
     } else {
       A.fNew[target[d]] = fpost[d];  // BulkStreamer.h:31-39
     }
