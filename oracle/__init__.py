@@ -78,6 +78,11 @@ def ref_lib(sse3: bool = False):
             L.href_tau.restype = C.c_double
             L.href_sim_get_tau.restype = C.c_double
             L.href_cosine_density.restype = C.c_double
+            if hasattr(L, "href_xtr_open"):
+                L.href_xtr_open.restype = C.c_void_p
+                L.href_xtr_last_error.restype = C.c_char_p
+                L.href_xtr_string_length.restype = C.c_uint64
+                L.href_xtr_field_header_length.restype = C.c_uint64
             _refs[sse3] = L
     return _refs[sse3]
 
@@ -299,3 +304,41 @@ class RefSim(_SimCommon):
             self.L.href_sim_destroy(self.h)
         except Exception:
             pass
+
+    # ---- extraction / checkpoint through the reference's own sources (oracle/ref_xtr.h)
+    def xtr_open(self, path, fields, selector="whole", sel_params=(), frequency=1, single_timestep_files=False,
+                 dt=1e-4, dx=1e-4, origin=(0.0, 0.0, 0.0), fluid_density=1000.0, reference_pressure=0.0):
+        """fields: oracle.xtr.Field list.  Constructs one LocalPropertyOutput per emulated rank (writes
+        the header and the .off file); returns a session for xtr_write."""
+        from . import xtr as X
+        names = (C.c_char_p * len(fields))(*[f.name.encode() for f in fields])
+        src = np.array([X.SOURCES.index(f.source) for f in fields], np.int32)
+        tc = np.array([f.typecode for f in fields], np.int32)
+        noff = np.array([len(f.offsets) for f in fields], np.int32)
+        offs = np.array([o for f in fields for o in f.offsets] + [0.0], np.float64)
+        sel = np.zeros(8, np.float32)
+        sel[:len(sel_params)] = sel_params
+        org = np.ascontiguousarray(origin, np.float64)
+        kind = X.SELECTORS[selector]
+        h = self.L.href_xtr_open(self.h, str(path).encode(), C.c_uint64(frequency), int(single_timestep_files), kind,
+                                 _ptr(sel, C.c_float), len(fields), names, _ptr(src, C.c_int), _ptr(tc, C.c_int),
+                                 _ptr(noff, C.c_int), _d(offs), C.c_double(dt), C.c_double(dx), _d(org),
+                                 C.c_double(fluid_density), C.c_double(reference_pressure))
+        if not h:
+            raise RuntimeError(self.L.href_xtr_last_error().decode())
+        return C.c_void_p(h)
+
+    def xtr_write(self, session, timestep, total_steps=1000):
+        if self.L.href_xtr_write(session, C.c_uint64(timestep), C.c_uint64(total_steps)):
+            raise RuntimeError(self.L.href_xtr_last_error().decode())
+
+    def xtr_close(self, session):
+        self.L.href_xtr_close(session)
+
+    def load_checkpoint(self, xtr_path, off_path=None, target=None):
+        t = C.c_uint64(0)
+        rc = self.L.href_load_checkpoint(self.h, str(xtr_path).encode(), (str(off_path) if off_path else "").encode(),
+                                         C.c_int64(-1 if target is None else target), C.byref(t))
+        if rc:
+            raise RuntimeError(self.L.href_xtr_last_error().decode())
+        return int(t.value)

@@ -672,3 +672,6 @@ void href_sim_step(void* sp, int n) {
 }
 
 }  // extern "C"
+
+// extraction (.xtr / .off) and checkpoint reading through the reference's own sources
+#include "ref_xtr.h"

@@ -46,6 +46,20 @@ namespace hemelb::geometry {
     proc_t GetLocalRank() const { return localRank; }
     proc_t GetProcIdFromGlobalCoords(const util::Vector3D<site_t>& c) const { return procOf(c); }
     site_t GetContiguousSiteId(const util::Vector3D<site_t>& c) const { return contigOf(c); }
+    // extraction / checkpoint sources (LbDataSourceIterator.cc:92-112, LocalDistributionInput.cc:133-146)
+    bool GetContiguousSiteId(const util::Vector3D<site_t>& c, proc_t& rank, site_t& index) const {
+      rank = procOf(c);
+      if (rank == SITE_OR_BLOCK_SOLID) return false;
+      index = contigOf(c);
+      return true;
+    }
+    bool IsValidLatticeSite(const util::Vector3D<site_t>& c) const {
+      for (int k = 0; k < 3; ++k) if (c[k] < 0 || c[k] >= latticeExtent[k]) return false;
+      return true;
+    }
+    util::Vector3D<site_t> latticeExtent{site_t(1) << 40, site_t(1) << 40, site_t(1) << 40};
+    struct LatticeInfoView { unsigned n; unsigned GetNumVectors() const { return n; } };
+    LatticeInfoView GetLatticeInfo() const { return LatticeInfoView{(unsigned)numVectors}; }
     site_t GetGlobalNoncontiguousSiteIdFromGlobalCoords(const util::Vector3D<site_t>& c) const { return globalIdOf(c); }
     neighbouring::NeighbouringDomain ndom;
     neighbouring::NeighbouringDomain& GetNeighbouringData() { return ndom; }
