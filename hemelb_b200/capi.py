@@ -37,6 +37,10 @@ SYMBOLS = [
     "hlb_dom_get_counts", "hlb_dom_get_neighbours", "hlb_dom_get_streaming_indices", "hlb_dom_get_neighbour_indices",
     "hlb_dom_get_site_coords", "hlb_dom_get_input_index", "hlb_dom_get_boundary_tables", "hlb_dom_get_geometry_sizes",
     "hlb_dom_get_geometry", "hlb_gpu_create_from_domain",
+    # property extraction and checkpoints
+    "hlb_xtr_create", "hlb_xtr_create_from_domain", "hlb_xtr_destroy", "hlb_xtr_sizes", "hlb_xtr_required_caches",
+    "hlb_xtr_header", "hlb_xtr_encode", "hlb_xtr_pinned_buffer", "hlb_xtr_last_encode_ms",
+    "hlb_gpu_load_distributions", "hlb_gpu_load_distributions_from_domain",
 ]
 
 

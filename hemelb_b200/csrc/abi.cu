@@ -850,6 +850,35 @@ int hlb_gpu_internal_mark_installed(hlb_gpu_t h) {
   return 0;
 }
 
+int hlb_gpu_internal_view(hlb_gpu_t h, hlb_gpu_view* out) {
+  if (!h || !out) return fail("null argument");
+  if (!h->finalised) return fail("handle not finalised");
+  out->Q = h->Q;
+  out->device = h->cfg.device;
+  out->rank = h->cfg.rank;
+  out->nranks = h->cfg.nranks;
+  out->N = h->N;
+  out->stride = h->stride;
+  out->midBulk = h->midBulk;
+  out->midTotal = h->midTotal;
+  out->edgeBulk = h->edgeBulk;
+  out->bStride = h->bStride;
+  out->f[0] = h->f[h->cur];
+  out->f[1] = h->f[h->cur ^ 1];
+  out->perm = h->perm;
+  out->wallMask = h->wallMask;
+  out->wallNormal = h->wallNormal;
+  for (int i = 0; i < 8; ++i) out->cache[i] = h->cache[i];
+  out->computeStream = (void*)h->compute;
+  return 0;
+}
+
+int hlb_gpu_internal_count_launch(hlb_gpu_t h, int64_t n) {
+  if (!h) return fail("null argument");
+  h->launches += n;
+  return 0;
+}
+
 extern "C" {
 
 const char* hlb_gpu_last_error(void) { return g_err.c_str(); }

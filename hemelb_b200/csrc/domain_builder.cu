@@ -1274,6 +1274,17 @@ int hlb_dom_get_neighbour_indices(hlb_dom_t d, int64_t first, int64_t n, int64_t
   return 0;
 }
 
+}  // extern "C"
+int hlb_dom_internal_coords(hlb_dom_handle* d, const int32_t** planes, int64_t* n_sites, int* device) {
+  if (!d || !planes || !n_sites) return fail("null argument");
+  if (!d->built) return fail("domain not built");
+  *planes = d->coordsLocal;
+  *n_sites = d->N;
+  if (device) *device = d->cfg.device;
+  return 0;
+}
+extern "C" {
+
 int hlb_dom_get_site_coords(hlb_dom_t d, int64_t first, int64_t n, int64_t* coords) {
   if (!d || !coords) return fail("null argument");
   if (!d->built) return fail("domain not built");

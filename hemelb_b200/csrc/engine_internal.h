@@ -28,3 +28,22 @@ int hlb_gpu_internal_raw(hlb_gpu_t h, hlb_gpu_raw* out);
 int hlb_gpu_internal_mark_installed(hlb_gpu_t h);
 // error text shared with hlb_gpu_last_error()
 int hlb_internal_fail(const char* msg);
+
+// Read/write view of a FINALISED engine handle for the extraction / checkpoint kernels
+// (extraction.cu): where the distributions, caches and boundary tables live on the device.
+struct hlb_gpu_view {
+  int Q, device, rank, nranks;
+  int64_t N, stride, midBulk, midTotal, edgeBulk, bStride;
+  double* f[2];               // f[0] = current f_old, f[1] = current f_new (SoA, `stride`)
+  const uint32_t* perm;       // reference site -> internal site, or null (identity)
+  const uint32_t* wallMask;   // by boundary ordinal of the INTERNAL site
+  const double* wallNormal;   // 3 planes of bStride
+  double* cache[8];           // MacroscopicPropertyCache arrays (reference site-major), null if never requested
+  void* computeStream;        // cudaStream_t
+};
+int hlb_gpu_internal_view(hlb_gpu_t h, hlb_gpu_view* out);
+int hlb_gpu_internal_count_launch(hlb_gpu_t h, int64_t n);
+
+// device-resident site coordinates of a built Domain: 3 planes of N int32, reference site order
+struct hlb_dom_handle;
+int hlb_dom_internal_coords(hlb_dom_handle* d, const int32_t** planes, int64_t* n_sites, int* device);

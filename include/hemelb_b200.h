@@ -232,6 +232,75 @@ int hlb_dom_get_geometry(hlb_dom_t d, int32_t* coords, int64_t* record_site, uin
  * built domain.  Still to do on the handle: hlb_gpu_set_iolets, hlb_gpu_finalise. */
 int hlb_gpu_create_from_domain(hlb_dom_t d, const hlb_gpu_config* policy, hlb_gpu_t* out);
 
+/* ==== property extraction (.xtr) and checkpoints ==================================================
+ * Replaces, for one rank, the per-site loops of extraction::LocalPropertyOutput::Write
+ * (Code/extraction/LocalPropertyOutput.cc:262-367) over extraction::LbDataSourceIterator
+ * (Code/extraction/LbDataSourceIterator.cc:36-87: property cache -> physical units through
+ * util::UnitConverter) and the geometry selectors (Code/extraction/*GeometrySelector.cc), and the
+ * record decoding of extraction::LocalDistributionInput::LoadDistribution
+ * (Code/extraction/LocalDistributionInput.cc:107-165).  The bytes are the reference's file format
+ * (doc/dev/file-formats/extraction.md, version 5, XDR big-endian) exactly.  File offsets across
+ * ranks (the Scan/AllReduce of LocalPropertyOutput.cc:96-110), the .off file and the actual
+ * MPI-IO / POSIX writes stay with the host (hemelb_b200/extraction.py; in a HemeLB build the
+ * unchanged LocalPropertyOutput constructor) -- the handle produces the header and this rank's
+ * record bytes. */
+typedef struct hlb_xtr_handle* hlb_xtr_t;
+/* extraction::source::Type (Code/extraction/OutputField.h:18-40) */
+enum {
+  HLB_XTR_PRESSURE = 0, HLB_XTR_VELOCITY = 1, HLB_XTR_SHEARSTRESS = 2, HLB_XTR_VONMISESSTRESS = 3,
+  HLB_XTR_SHEARRATE = 4, HLB_XTR_STRESSTENSOR = 5, HLB_XTR_TRACTION = 6,
+  HLB_XTR_TANGENTIALPROJECTIONTRACTION = 7, HLB_XTR_DISTRIBUTIONS = 8, HLB_XTR_MPIRANK = 9
+};
+/* io::formats::extraction::TypeCode (Code/io/formats/extraction.h:25-32) */
+enum { HLB_XTR_FLOAT = 0, HLB_XTR_DOUBLE = 1, HLB_XTR_INT32 = 2, HLB_XTR_UINT32 = 3, HLB_XTR_INT64 = 4, HLB_XTR_UINT64 = 5 };
+/* GeometrySelector subclasses; selector_params: plane {point[3], normal[3], radius (<= 0: infinite)},
+ * line {endpoint1[3], endpoint2[3]}, surface point {point[3]} -- physical units, float as the reference */
+enum { HLB_XTR_WHOLE = 0, HLB_XTR_SURFACE = 1, HLB_XTR_PLANE = 2, HLB_XTR_LINE = 3, HLB_XTR_SURFACEPOINT = 4 };
+
+typedef struct {          /* extraction::OutputField (Code/extraction/OutputField.h:105-112) */
+  const char* name;
+  int source;             /* HLB_XTR_PRESSURE ... */
+  int typecode;           /* HLB_XTR_FLOAT ... */
+  uint32_t n_offsets;     /* 0, 1 or the field length; only Pressure subtracts offsets[0] from the data
+                             (LocalPropertyOutput.cc:308-310), the rest is header information */
+  const double* offsets;
+} hlb_xtr_field;
+
+typedef struct {          /* extraction::PropertyOutputFile + the util::UnitConverter constructor arguments */
+  int selector;           /* HLB_XTR_WHOLE ... */
+  float selector_params[7];
+  int n_fields;           /* <= 16 */
+  const hlb_xtr_field* fields;
+  double time_step, voxel_size, origin[3], fluid_density, reference_pressure;
+} hlb_xtr_spec;
+
+/* evaluates the selector for every local site on the device (CountWrittenSitesOnRank,
+ * LocalPropertyOutput.cc:133-145) and keeps the included-site list.  site_coords:
+ * Domain::globalSiteCoords, n_sites x 3 int64 (borrowed for the call).  `h` must be finalised. */
+int hlb_xtr_create(hlb_gpu_t h, const hlb_xtr_spec* spec, const int64_t* site_coords, hlb_xtr_t* out);
+/* same with the coordinates of a device-built Domain (no host copy) */
+int hlb_xtr_create_from_domain(hlb_gpu_t h, hlb_dom_t d, const hlb_xtr_spec* spec, hlb_xtr_t* out);
+int hlb_xtr_destroy(hlb_xtr_t x);
+/* local_site_count; bytes per site record (CalcSiteWriteLen); MainHeaderLength + field header length */
+int hlb_xtr_sizes(hlb_xtr_t x, uint64_t* local_site_count, uint64_t* site_length, uint64_t* header_length);
+/* PropertyActor::SetRequiredProperties (Code/extraction/PropertyActor.cc:22-75): HLB_CACHE_* the fields need */
+int hlb_xtr_required_caches(hlb_xtr_t x, uint32_t* cache_mask);
+/* LocalPropertyOutput::PrepareHeader (LocalPropertyOutput.cc:178-213): main header + field headers */
+int hlb_xtr_header(hlb_xtr_t x, uint64_t global_site_count, void* buf, uint64_t capacity);
+/* the record bytes of included sites [first_site, first_site + n_sites) of the current state (property
+ * caches of the last step, f_old), encoded on the device and copied to host_buf (pageable or pinned).
+ * Slices let a large checkpoint stream through a bounded buffer. */
+int hlb_xtr_encode(hlb_xtr_t x, uint64_t first_site, uint64_t n_sites, void* host_buf, uint64_t capacity);
+/* a pinned host buffer owned by the handle (grown on demand) for hlb_xtr_encode to land in */
+int hlb_xtr_pinned_buffer(hlb_xtr_t x, uint64_t bytes, void** ptr);
+/* device time of the last hlb_xtr_encode's kernel (CUDA events on the engine's stream) */
+int hlb_xtr_last_encode_ms(hlb_xtr_t x, float* ms);
+/* checkpoint: this rank's slice of one time step of a distributions-only double extraction file
+ * (without the IO rank's leading 8-byte time stamp).  Checks every record's grid position against the
+ * local site at that index and sets f_old = f_new = the stored values. */
+int hlb_gpu_load_distributions(hlb_gpu_t h, const void* records, uint64_t n_bytes, const int64_t* site_coords);
+int hlb_gpu_load_distributions_from_domain(hlb_gpu_t h, hlb_dom_t d, const void* records, uint64_t n_bytes);
+
 #ifdef __cplusplus
 }
 #endif

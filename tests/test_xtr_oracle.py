@@ -92,7 +92,7 @@ def selector_cases(geom_name):
         ("whole", ()), ("surface", ()),
         ("plane", (*c, 0.0, 0.0, 1.0, 0.0)), ("plane", (*c, 0.3, -0.2, 1.0, 3.2 * dxs)),
         ("line", (*(c - dxs * np.array([0, 0, 30.0])), *(c + dxs * np.array([1.0, 0.5, 30.0])))),
-        ("surfacepoint", tuple(o + dxs * np.array([1.2, 2.1, 2.0]))),
+        ("surfacepoint", None),  # filled in by the test: next to an actual wall site
     ]
 
 
@@ -106,6 +106,9 @@ def test_files_identical_to_reference(tmp_path, geom_name, Q, R):
     conv = X.UnitConverter(DT, DX, ORIGIN, RHO, 80.0)
     data = rank_data(ref, T, Q)
     for k, (sel, params) in enumerate(selector_cases(geom_name)):
+        if params is None:
+            w = np.flatnonzero(T[-1]["wallMask"])[5]
+            params = tuple(np.array(ORIGIN) + DX * (T[-1]["globalCoords"].reshape(-1, 3)[w] + np.array([0.3, -0.2, 0.4])))
         path = tmp_path / ("out%d.xtr" % k)
         s = ref.xtr_open(path, ALL_FIELDS, sel, params, frequency=5, dt=DT, dx=DX, origin=ORIGIN, fluid_density=RHO,
                          reference_pressure=80.0)
@@ -119,7 +122,7 @@ def test_files_identical_to_reference(tmp_path, geom_name, Q, R):
         assert len(got) == len(want), (sel, po.local_counts)
         assert got == want, sel
         assert (tmp_path / ("out%d.off" % k)).read_bytes() == po.offset_file()
-        if sel in ("plane", "line", "surface"):
+        if sel != "whole":
             assert 0 < po.global_count < sum(t["N"] for t in T), sel
 
 
