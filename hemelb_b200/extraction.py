@@ -129,6 +129,17 @@ def extraction_to_offset(path: str) -> str:
     return path[:i] + ".off"
 
 
+def write_layout(comms, local_site_count: int, site_len: int, header_length: int) -> dict:
+    """Where each rank writes (LocalPropertyOutput.cc:96-110): only the IO rank writes the 8-byte
+    time stamp; every rank's start = header + exclusive prefix sum of the local lengths."""
+    global_site_count = comms.allreduce_sum(local_site_count)                                    # :99
+    local_len = local_site_count * site_len + (8 if comms.rank == IO_RANK else 0)                # :104
+    global_len = site_len * global_site_count + 8                                                # :106
+    local_write_end = comms.scan_sum(local_len) + header_length                                  # :109
+    return dict(global_site_count=global_site_count, local_data_write_length=local_len,
+                global_data_write_length=global_len, local_write_start=local_write_end - local_len)
+
+
 def _create_handle(lbm, spec: PropertyOutputFile, units: Units):
     L = lib()
     fields = (XtrField * max(1, len(spec.fields)))()
@@ -185,11 +196,8 @@ class GpuLocalPropertyOutput:
         check(self.L.hlb_xtr_sizes(self.x, C.byref(n), C.byref(sl), C.byref(hl)))
         self.local_site_count, self.site_len, self.header_length = int(n.value), int(sl.value), int(hl.value)
         c = self.comms
-        self.global_site_count = c.allreduce_sum(self.local_site_count)                       # :99
-        self.local_data_write_length = self.local_site_count * self.site_len + (8 if c.rank == IO_RANK else 0)  # :104
-        self.global_data_write_length = self.site_len * self.global_site_count + 8             # :106
-        local_write_end = c.scan_sum(self.local_data_write_length) + self.header_length        # :109
-        self.local_write_start = local_write_end - self.local_data_write_length
+        for k, v in write_layout(c, self.local_site_count, self.site_len, self.header_length).items():
+            setattr(self, k, v)
         self.header_data = b""
         if c.rank == IO_RANK:
             buf = (C.c_char * self.header_length)()
