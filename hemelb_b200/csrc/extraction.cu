@@ -205,7 +205,16 @@ __global__ void __launch_bounds__(kTileSites) xtr_encode_kernel(EncodeArgs A, ui
         }
         case 8: {  // Distributions: f_old of the site
           const int64_t i = A.perm ? (int64_t)A.perm[s] : s;
-          for (int d = 0; d < A.Q; ++d) w = put_value(rec, w, F.typecode, A.f[(int64_t)d * A.stride + i], false, 0);
+          // nine independent loads in flight per thread, then their conversions (Q = 15 / 19 / 27)
+          for (int d0 = 0; d0 < A.Q; d0 += 9) {
+            double v[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j)
+              v[j] = d0 + j < A.Q ? __ldcs(A.f + (int64_t)(d0 + j) * A.stride + i) : 0.0;
+#pragma unroll
+            for (int j = 0; j < 9; ++j)
+              if (d0 + j < A.Q) w = put_value(rec, w, F.typecode, v[j], false, 0);
+          }
           break;
         }
         default:

@@ -16,6 +16,10 @@
 #include <cfloat>
 #include "lattice.cuh"
 
+#ifndef HLB_MRT_MIN_CTAS
+#define HLB_MRT_MIN_CTAS 2
+#endif
+
 namespace hlb {
 
 enum KernelKind { K_LBGK = 0, K_MRT = 1, K_TRT = 2 };
@@ -609,8 +613,9 @@ __global__ void __launch_bounds__(kGzsThreads, 2) gzs_links_kernel(const StepArg
 }
 
 // ---------------------------------------------------------------------------------- the site kernel
+// two resident CTAs per SM (<= 128 registers) wherever the arrays allow it: Q <= 19
 template <int Q, int KERNEL, int WALL, int IOLET>
-__global__ void __launch_bounds__(256) collide_stream_kernel(const StepArgs A, const MrtArgs<Q> M, int64_t first, int64_t count) {
+__global__ void __launch_bounds__(256, (Q <= 19 && (KERNEL != K_MRT || HLB_MRT_MIN_CTAS == 2)) ? 2 : 1) collide_stream_kernel(const StepArgs A, const MrtArgs<Q> M, int64_t first, int64_t count) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= count) return;
   const int64_t site = A.siteList ? (int64_t)A.siteList[tid] : first + tid;
@@ -620,6 +625,21 @@ __global__ void __launch_bounds__(256) collide_stream_kernel(const StepArgs A, c
   double f[Q];
 #pragma unroll
   for (int d = 0; d < Q; ++d) f[d] = __ldcs(A.fOld + (int64_t)d * A.stride + site);
+  // boundary tables: issued with the distribution loads, not after the collision.  The BFL cut
+  // distances are fetched for every direction (plane-major, coalesced; the sectors are shared with
+  // the neighbouring wall sites and would be read anyway) so that no load waits for the wall mask.
+  uint32_t wallMask = 0, ioletMask = 0;
+  int64_t b = 0;
+  float cut[WALL == W_BFL ? Q : 1];
+  if constexpr (HAS_WALL || HAS_IOLET) {
+    b = bidx(A, site);
+    if constexpr (HAS_WALL) wallMask = __ldg(A.wallMask + b);
+    if constexpr (HAS_IOLET) ioletMask = __ldg(A.ioletMask + b);
+    if constexpr (WALL == W_BFL) {
+#pragma unroll
+      for (int d = 1; d < Q; ++d) cut[d] = __ldg(A.cutDist + (int64_t)(d - 1) * A.bStride + b);
+    }
+  }
   uint32_t target[Q];
   target[0] = (uint32_t)site;
   if (A.nbrFlags) {
@@ -651,14 +671,6 @@ __global__ void __launch_bounds__(256) collide_stream_kernel(const StepArgs A, c
     for (int d = 0; d < Q; ++d) fneq[d] = f[d] - feq_i<Q>(d, rho, density_1, mm, m);
   }
   collide<Q, KERNEL>(A, M, f, fneq, fpost);
-
-  uint32_t wallMask = 0, ioletMask = 0;
-  int64_t b = 0;
-  if constexpr (HAS_WALL || HAS_IOLET) {
-    b = bidx(A, site);
-    if constexpr (HAS_WALL) wallMask = A.wallMask[b];
-    if constexpr (HAS_IOLET) ioletMask = A.ioletMask[b];
-  }
 
   // per-site iolet quantities (NashZerothOrderPressure.h:27-60 / LaddIolet.h:29-66)
   double ghostRho = 0, ghostM[3] = {0, 0, 0}, ghostD1 = 0, ghostMM = 0;
@@ -719,7 +731,7 @@ __global__ void __launch_bounds__(256) collide_stream_kernel(const StepArgs A, c
       if constexpr (WALL == W_SBB) {  // SimpleBounceBack.h:23-42
         A.fNew[(int64_t)id * A.stride + site] = fpost[d];
       } else if constexpr (WALL == W_BFL) {  // BouzidiFirdaousLallemand.h:41-70
-        const double q = (double)A.cutDist[(int64_t)(d - 1) * A.bStride + b];
+        const double q = (double)cut[d];
         const bool invWall = (wallMask >> (id - 1)) & 1u;
         double v;
         if (invWall || q < 0.5) v = fpost[d];
