@@ -263,8 +263,16 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = gpu.launch_count()
-    ms, bulk_ms, bulk_sites = gpu.time_steps_detail(args.steps)
+    ms = gpu.time_steps(args.steps)   # the product schedule: boundary ranges beside the bulk kernel
     launches = gpu.launch_count() - l0
+    barrier()
+    # second timed region, same K steps, every kernel back to back on one stream: the dominant
+    # kernel's own launch duration (CUDA events around each of its launches) for the roofline
+    gpu.set_overlap(False)
+    gpu.step(2)
+    barrier()
+    serial_ms, bulk_ms, bulk_sites = gpu.time_steps_detail(args.steps)
+    gpu.set_overlap(True)
     barrier()
     clocks = sampler.stop()
     if dist is not None:
@@ -308,7 +316,10 @@ def main():
                      "algorithmic_bytes_per_launch": int(dom.mid[0]) * BYTES_PER_SITE,
                      "kernel": "collide_stream_kernel<19,LBGK,none,none> (mid-fluid range)",
                      "bytes_per_site": BYTES_PER_SITE, "peak_kind": peak_kind + " HBM copy (burst)",
-                     "kernel_share_of_step": bulk_ms / ms if ms else None,
+                     "kernel_share_of_step": bulk_ms / serial_ms if serial_ms else None,
+                     "timed_in": "a second K-step region with the boundary ranges serialised behind the bulk kernel "
+                                 "(hlb_gpu_set_overlap(0)); `value` is the overlapped schedule",
+                     "serial_ms_per_step": serial_ms / args.steps,
                      "whole_step_frac": (mlups * 1e6 * BYTES_PER_SITE / 1e9 / world) / peak},
         "e2e": {"value": e2e_mlups, "unit": "MLUPS", "h2d_bytes_per_step": 8 * (len(inlets) + len(outlets)),
                 "d2h_bytes_per_step": 32,

@@ -116,8 +116,12 @@ struct hlb_gpu_handle {
   int Q = 0;
   int64_t N = 0, stride = 0, S = 0, fLen = 0;
   int64_t mid[6], edge[6], midTotal = 0, midBulk = 0, edgeBulk = 0, NB = 0, bStride = 0;
-  cudaStream_t compute = nullptr, comm = nullptr;
-  cudaEvent_t evEdge = nullptr, evComm = nullptr, evT0 = nullptr, evT1 = nullptr;
+  cudaStream_t compute = nullptr, comm = nullptr, aux = nullptr;
+  cudaEvent_t evEdge = nullptr, evComm = nullptr, evT0 = nullptr, evT1 = nullptr, evFork = nullptr, evJoin = nullptr;
+  // mid-domain boundary ranges run on `aux` beside the mid-fluid (bulk) kernel: they read f_old and
+  // write disjoint (site, direction) slots of f_new, so the only ordering needed is "after what
+  // preceded the bulk launch" (evFork) and "before anything that follows the streaming" (join_aux)
+  bool overlap = true, forkValid = false, auxPending = false;
   double* f[2] = {nullptr, nullptr};
   int cur = 0;
   uint32_t* nbr = nullptr;
@@ -200,6 +204,17 @@ int ensure_staging(hlb_gpu_t h, size_t bytes) {
   h->stagingBytes = 0;
   CU(cudaMalloc(&h->staging, bytes));
   h->stagingBytes = bytes;
+  return 0;
+}
+
+// make `compute` wait for the boundary kernels that were put on `aux`
+int join_aux(hlb_gpu_t h) {
+  if (h->auxPending) {
+    CU(cudaEventRecord(h->evJoin, h->aux));
+    CU(cudaStreamWaitEvent(h->compute, h->evJoin, 0));
+    h->auxPending = false;
+  }
+  h->forkValid = false;
   return 0;
 }
 
@@ -664,6 +679,21 @@ int launch_range(hlb_gpu_t h, int slot, int64_t first, int64_t count, bool post)
   int whole = -1;
   for (int k = 0; k < 12; ++k)
     if (first == h->rangeFirst[k] && first + count == h->rangeFirst[k + 1]) whole = k;
+  // which stream: whole mid-domain boundary ranges go beside the bulk kernel (see `aux`)
+  cudaStream_t st = h->compute;
+  const bool midWhole = !post && h->overlap && whole >= 0 && whole < 6;
+  if (midWhole && slot == 0) {
+    if (!h->auxPending) {
+      CU(cudaEventRecord(h->evFork, h->compute));
+      h->forkValid = true;
+    }
+  } else if (midWhole && h->forkValid) {
+    st = h->aux;
+    if (!h->auxPending) CU(cudaStreamWaitEvent(h->aux, h->evFork, 0));
+    h->auxPending = true;
+  } else if (join_aux(h)) {
+    return 1;
+  }
   if (whole >= 0 && h->nbrFlags && !post) {
     A.nbrFlags = h->nbrFlags;
     A.nbrBase = h->nbrBase;
@@ -705,7 +735,7 @@ int launch_range(hlb_gpu_t h, int slot, int64_t first, int64_t count, bool post)
     }
     CU(cudaEventRecord(h->profEv[h->profUsed], h->compute));
   }
-  h->launch(wall, iolet, A, h->mrt.data(), first, count, h->compute);
+  h->launch(wall, iolet, A, h->mrt.data(), first, count, st);
   if (wall == W_GZS) h->launches++;  // the per-link kernel behind the per-site one
   if (h->cacheMask & C_MONITOR) h->monitorLaunches++;
   if (prof) {
@@ -745,10 +775,12 @@ int post_comms(hlb_gpu_t h) {
 int upload_densities(hlb_gpu_t h, int which, const double* d) {
   const int n = which ? h->cfg.n_outlets : h->cfg.n_inlets;
   if (n == 0) return 0;
+  if (join_aux(h)) return 1;
   if (!d) return fail("iolet densities missing");
   // ring of pinned slots: a slot is reused only after the stream drained (every kPinnedSlots steps)
   const int slot = (int)(h->pinnedCursor[which]++ % kPinnedSlots);
-  if (slot == 0 && h->pinnedCursor[which] > 1) CU(cudaStreamSynchronize(h->compute));
+  if (slot == 0 && h->pinnedCursor[which] > 1) if (join_aux(h)) return 1;
+  CU(cudaStreamSynchronize(h->compute));
   double* src = h->ioletDensityPinned[which] + (size_t)slot * n;
   std::memcpy(src, d, sizeof(double) * n);
   CU(cudaMemcpyAsync(h->ioletDensityDev[which], src, sizeof(double) * n, cudaMemcpyHostToDevice, h->compute));
@@ -760,6 +792,7 @@ int upload_densities(hlb_gpu_t h, int which, const double* d) {
 // that other ranks' GZS links extrapolate from.
 int exchange_site_halo(hlb_gpu_t h) {
   if (h->nGzsNeed == 0 && h->nGzsServe == 0) return 0;
+  if (join_aux(h)) return 1;
   const int Q = h->Q;
   if (h->nGzsServe) {
     gzs_pack_kernel<<<blocks_for(h->nGzsServe * Q), 256, 0, h->compute>>>(h->f[h->cur], h->gzsServeDev, h->nGzsServe, Q,
@@ -853,6 +886,7 @@ int hlb_gpu_internal_mark_installed(hlb_gpu_t h) {
 int hlb_gpu_internal_view(hlb_gpu_t h, hlb_gpu_view* out) {
   if (!h || !out) return fail("null argument");
   if (!h->finalised) return fail("handle not finalised");
+  if (join_aux(h)) return 1;
   out->Q = h->Q;
   out->device = h->cfg.device;
   out->rank = h->cfg.rank;
@@ -935,6 +969,15 @@ int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
   if (h->fLen >= ((int64_t)1 << 32)) { delete h; return fail("too many sites for 32-bit streaming indices on one GPU"); }
   CU(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&h->comm, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;  // (numerically lowest = highest priority)
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, hi));
+    const char* e = getenv("HLB_OVERLAP");
+    h->overlap = !(e && e[0] == '0');
+  }
+  CU(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&h->evEdge, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&h->evComm, cudaEventDisableTiming));
   CU(cudaEventCreate(&h->evT0));
@@ -1026,6 +1069,9 @@ int hlb_gpu_destroy(hlb_gpu_t h) {
   cudaEventDestroy(h->evT0);
   cudaEventDestroy(h->evT1);
   cudaStreamDestroy(h->compute);
+  if (h->aux) cudaStreamDestroy(h->aux);
+  if (h->evFork) cudaEventDestroy(h->evFork);
+  if (h->evJoin) cudaEventDestroy(h->evJoin);
   cudaStreamDestroy(h->comm);
   delete h;
   return 0;
@@ -1360,6 +1406,7 @@ int hlb_gpu_set_f(hlb_gpu_t h, int which, const double* f) {
   if (!h || !f) return fail("null argument");
   if (!h->finalised) return fail("hlb_gpu_set_f before hlb_gpu_finalise");
   CU(cudaSetDevice(h->cfg.device));
+  if (join_aux(h)) return 1;
   CU(cudaStreamSynchronize(h->compute));
   double* dst = h->f[which ? h->cur ^ 1 : h->cur];
   const int Q = h->Q;
@@ -1378,6 +1425,7 @@ int hlb_gpu_set_f(hlb_gpu_t h, int which, const double* f) {
 int hlb_gpu_get_f(hlb_gpu_t h, int which, double* f) {
   if (!h || !f) return fail("null argument");
   CU(cudaSetDevice(h->cfg.device));
+  if (join_aux(h)) return 1;
   CU(cudaStreamSynchronize(h->compute));
   CU(cudaStreamSynchronize(h->comm));
   const double* src = h->f[which ? h->cur ^ 1 : h->cur];
@@ -1396,6 +1444,7 @@ int hlb_gpu_get_f(hlb_gpu_t h, int which, double* f) {
 int hlb_gpu_get_halo(hlb_gpu_t h, int which, double* out) {
   if (!h || (!out && h->S)) return fail("null argument");
   CU(cudaSetDevice(h->cfg.device));
+  if (join_aux(h)) return 1;
   CU(cudaStreamSynchronize(h->compute));
   const double* src = h->f[which ? h->cur ^ 1 : h->cur] + (int64_t)h->Q * h->stride + 1;
   if (h->S) CU(cudaMemcpy(out, src, sizeof(double) * h->S, cudaMemcpyDeviceToHost));
@@ -1405,6 +1454,7 @@ int hlb_gpu_get_halo(hlb_gpu_t h, int which, double* out) {
 int hlb_gpu_set_halo(hlb_gpu_t h, int which, const double* in) {
   if (!h || (!in && h->S)) return fail("null argument");
   CU(cudaSetDevice(h->cfg.device));
+  if (join_aux(h)) return 1;
   CU(cudaStreamSynchronize(h->compute));
   double* dst = h->f[which ? h->cur ^ 1 : h->cur] + (int64_t)h->Q * h->stride + 1;
   if (h->S) CU(cudaMemcpy(dst, in, sizeof(double) * h->S, cudaMemcpyHostToDevice));
@@ -1472,6 +1522,7 @@ int hlb_gpu_exchange_site_halo(hlb_gpu_t h) {
 int hlb_gpu_get_gzs_send(hlb_gpu_t h, double* out) {
   if (!h || (!out && h->nGzsServe)) return fail("null argument");
   CU(cudaSetDevice(h->cfg.device));
+  if (join_aux(h)) return 1;
   CU(cudaStreamSynchronize(h->compute));
   if (h->nGzsServe) CU(cudaMemcpy(out, h->gzsSendBuf, sizeof(double) * h->Q * h->nGzsServe, cudaMemcpyDeviceToHost));
   return 0;
@@ -1480,6 +1531,7 @@ int hlb_gpu_get_gzs_send(hlb_gpu_t h, double* out) {
 int hlb_gpu_set_gzs_ghost(hlb_gpu_t h, const double* in) {
   if (!h || (!in && h->nGzsNeed)) return fail("null argument");
   CU(cudaSetDevice(h->cfg.device));
+  if (join_aux(h)) return 1;
   CU(cudaStreamSynchronize(h->compute));
   if (h->nGzsNeed) CU(cudaMemcpy(h->gzsGhost, in, sizeof(double) * h->Q * h->nGzsNeed, cudaMemcpyHostToDevice));
   return 0;
@@ -1507,6 +1559,7 @@ int hlb_gpu_copy_received(hlb_gpu_t h) {
   if (!h) return fail("null argument");
   if (!h->finalised) return fail("handle not finalised");
   CU(cudaSetDevice(h->cfg.device));
+  if (join_aux(h)) return 1;  // everything streamed before the received populations land
   if (h->edgePending) {  // caller never marked the end of PreSend: post now (no overlap)
     h->edgePending = false;
     if (post_comms(h)) return 1;
@@ -1529,6 +1582,7 @@ int hlb_gpu_copy_received(hlb_gpu_t h) {
 
 int hlb_gpu_swap(hlb_gpu_t h) {
   if (!h) return fail("null argument");
+  if (join_aux(h)) return 1;
   h->cur ^= 1;
   return 0;
 }
@@ -1540,7 +1594,8 @@ int hlb_gpu_get_cache(hlb_gpu_t h, uint32_t which, double* out) {
   for (int i = 0; i < 8; ++i)
     if (which == (1u << i)) {
       if (!h->cache[i]) return fail("cache was never requested");
-      CU(cudaStreamSynchronize(h->compute));
+      if (join_aux(h)) return 1;
+  CU(cudaStreamSynchronize(h->compute));
       CU(cudaMemcpy(out, h->cache[i], sizeof(double) * per[i] * h->N, cudaMemcpyDeviceToHost));
       return 0;
     }
@@ -1556,6 +1611,13 @@ int hlb_gpu_step(hlb_gpu_t h, int nsteps) {
   return 0;
 }
 
+int hlb_gpu_set_overlap(hlb_gpu_t h, int enabled) {
+  if (!h) return fail("null argument");
+  if (join_aux(h)) return 1;
+  h->overlap = enabled != 0;
+  return 0;
+}
+
 int hlb_gpu_get_time_step(hlb_gpu_t h, uint64_t* t) {
   if (!h || !t) return fail("null argument");
   *t = h->timeStep;
@@ -1565,6 +1627,7 @@ int hlb_gpu_get_time_step(hlb_gpu_t h, uint64_t* t) {
 int hlb_gpu_sync(hlb_gpu_t h) {
   if (!h) return fail("null argument");
   CU(cudaSetDevice(h->cfg.device));
+  if (join_aux(h)) return 1;
   CU(cudaStreamSynchronize(h->compute));
   CU(cudaStreamSynchronize(h->comm));
   return 0;
@@ -1573,6 +1636,7 @@ int hlb_gpu_sync(hlb_gpu_t h) {
 int hlb_gpu_time_steps(hlb_gpu_t h, int nsteps, float* ms) {
   if (!h || !ms) return fail("null argument");
   CU(cudaSetDevice(h->cfg.device));
+  if (join_aux(h)) return 1;
   CU(cudaStreamSynchronize(h->compute));
   CU(cudaStreamSynchronize(h->comm));
   CU(cudaEventRecord(h->evT0, h->compute));
@@ -1607,6 +1671,7 @@ int hlb_gpu_time_steps_detail(hlb_gpu_t h, int nsteps, float* total_ms, float* b
 int hlb_gpu_monitor(hlb_gpu_t h, double* out4) {
   if (!h || !out4) return fail("null argument");
   CU(cudaSetDevice(h->cfg.device));
+  if (join_aux(h)) return 1;
   unsigned long long init[4] = {~0ull, ~0ull, 0ull, 0ull};
   CU(cudaMemcpyAsync(h->monitorDev, init, sizeof(init), cudaMemcpyHostToDevice, h->compute));
   if (h->monitorFused && h->monitorLaunches > 0) {
@@ -1628,6 +1693,7 @@ int hlb_gpu_monitor(hlb_gpu_t h, double* out4) {
   h->launches++;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(out4, h->monitorDev + 4, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->compute));
+  if (join_aux(h)) return 1;
   CU(cudaStreamSynchronize(h->compute));
   return 0;
 }

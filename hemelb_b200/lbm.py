@@ -355,6 +355,10 @@ class GpuLBM:
     def sync(self):
         check(self.L.hlb_gpu_sync(self.h))
 
+    def set_overlap(self, enabled: bool):
+        """Boundary ranges beside the bulk kernel on a second stream (default on); results identical."""
+        check(self.L.hlb_gpu_set_overlap(self.h, 1 if enabled else 0))
+
     def monitor(self):
         out = np.zeros(4)
         check(self.L.hlb_gpu_monitor(self.h, ptr(out, C.c_double)))

@@ -147,6 +147,13 @@ int hlb_gpu_get_cache(hlb_gpu_t h, uint32_t which, double* out);
  *      cosine iolet densities evaluated on the host as InOutLetCosine::GetDensity does */
 int hlb_gpu_step(hlb_gpu_t h, int nsteps);
 int hlb_gpu_get_time_step(hlb_gpu_t h, uint64_t* t);
+/* scheduling knob (default on; HLB_OVERLAP=0 in the environment turns it off at create): launch the
+ * whole mid-domain wall / inlet / outlet ranges of LBM::PreReceive on a second, higher-priority
+ * stream beside the mid-fluid kernel.  They read f_old and write disjoint slots of f_new, so the
+ * result is bit-identical either way; everything that follows the streaming (CopyReceived,
+ * PostStep, swap, read-backs) waits for both streams.  Off = every kernel back to back on one
+ * stream (what per-kernel timing wants). */
+int hlb_gpu_set_overlap(hlb_gpu_t h, int enabled);
 int hlb_gpu_sync(hlb_gpu_t h);
 /* CUDA-event timing of nsteps whole steps on the engine's own streams (ms) */
 int hlb_gpu_time_steps(hlb_gpu_t h, int nsteps, float* ms);
