@@ -10,8 +10,9 @@ template <int Q, int KERNEL>
 void launch_collide_stream(int wall, int iolet, const StepArgs& A, const void* mrt, int64_t first, int64_t count,
                            void* stream) {
   if (count <= 0) return;
-  const dim3 block(256);
-  const dim3 grid((unsigned)((count + 255) / 256));
+  constexpr int T = site_threads<Q>();
+  const dim3 block(T);
+  const dim3 grid((unsigned)((count + T - 1) / T));
   cudaStream_t s = (cudaStream_t)stream;
   const MrtArgs<Q>& M = *(const MrtArgs<Q>*)mrt;
 #define HLB_CASE(W, I)                                                              \

@@ -16,8 +16,11 @@
 #include <cfloat>
 #include "lattice.cuh"
 
-#ifndef HLB_MRT_MIN_CTAS
-#define HLB_MRT_MIN_CTAS 2
+#ifndef HLB_Q27_THREADS
+#define HLB_Q27_THREADS 128
+#endif
+#ifndef HLB_Q27_MIN_CTAS
+#define HLB_Q27_MIN_CTAS 3
 #endif
 
 namespace hlb {
@@ -88,6 +91,9 @@ struct StepArgs {
   // fused monitors (C_MONITOR): {min f, min rho, max rho, max u^2} as order-preserving u64 keys
   unsigned long long* __restrict__ monitorSlots;
 };
+
+template <int Q> constexpr int site_threads() { return Q > 19 ? HLB_Q27_THREADS : 256; }
+template <int Q> constexpr int site_min_ctas() { return Q > 19 ? HLB_Q27_MIN_CTAS : 2; }
 
 template <int Q> struct MrtArgs {
   double SMn[mrt_k<Q>() > 0 ? mrt_k<Q>() : 1][Q];  // collisionMatrixDiagonals[k] * normalisedReducedMomentBasis[k][d]
@@ -613,9 +619,10 @@ __global__ void __launch_bounds__(kGzsThreads, 2) gzs_links_kernel(const StepArg
 }
 
 // ---------------------------------------------------------------------------------- the site kernel
-// two resident CTAs per SM (<= 128 registers) wherever the arrays allow it: Q <= 19
+// Q <= 19: 256-thread CTAs, two resident per SM (<= 128 registers).  D3Q27 needs ~190 registers:
+// 128-thread CTAs, three resident (<= 168 registers; 12 warps per SM instead of 8).
 template <int Q, int KERNEL, int WALL, int IOLET>
-__global__ void __launch_bounds__(256, (Q <= 19 && (KERNEL != K_MRT || HLB_MRT_MIN_CTAS == 2)) ? 2 : 1) collide_stream_kernel(const StepArgs A, const MrtArgs<Q> M, int64_t first, int64_t count) {
+__global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) collide_stream_kernel(const StepArgs A, const MrtArgs<Q> M, int64_t first, int64_t count) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= count) return;
   const int64_t site = A.siteList ? (int64_t)A.siteList[tid] : first + tid;
@@ -669,6 +676,17 @@ __global__ void __launch_bounds__(256, (Q <= 19 && (KERNEL != K_MRT || HLB_MRT_M
     const double mm = m[0] * m[0] + m[1] * m[1] + m[2] * m[2];
 #pragma unroll
     for (int d = 0; d < Q; ++d) fneq[d] = f[d] - feq_i<Q>(d, rho, density_1, mm, m);
+  }
+  // Where the (rare) moment extraction / monitor block sits decides which Q-arrays are live across
+  // the pushes.  Before the collision: f and f_neq die as f_post is formed (MRT, whose collision
+  // needs many temporaries, and D3Q27: 30-60 fewer registers).  After the pushes: the index and cut
+  // distance registers are free by then (LBGK / TRT on Q <= 19 fit 128 registers that way).
+  constexpr bool CACHES_FIRST = KERNEL == K_MRT || Q > 19;
+  if constexpr (CACHES_FIRST) {
+    if (A.cacheMask) {
+      if (A.cacheMask & 255u) update_caches<Q, KERNEL>(A, site, HAS_WALL || HAS_IOLET, rho, u, fneq);
+      if (A.cacheMask & C_MONITOR) fused_monitor<Q>(A, tid, f, rho, m);
+    }
   }
   collide<Q, KERNEL>(A, M, f, fneq, fpost);
 
@@ -744,9 +762,11 @@ __global__ void __launch_bounds__(256, (Q <= 19 && (KERNEL != K_MRT || HLB_MRT_M
     }
   }
 
-  if (A.cacheMask) {
-    if (A.cacheMask & 255u) update_caches<Q, KERNEL>(A, site, HAS_WALL || HAS_IOLET, rho, u, fneq);
-    if (A.cacheMask & C_MONITOR) fused_monitor<Q>(A, tid, f, rho, m);
+  if constexpr (!CACHES_FIRST) {
+    if (A.cacheMask) {
+      if (A.cacheMask & 255u) update_caches<Q, KERNEL>(A, site, HAS_WALL || HAS_IOLET, rho, u, fneq);
+      if (A.cacheMask & C_MONITOR) fused_monitor<Q>(A, tid, f, rho, m);
+    }
   }
 }
 
