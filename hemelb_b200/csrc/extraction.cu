@@ -467,6 +467,8 @@ int build_site_list(hlb_xtr_handle* x, const hlb_xtr_spec* spec, const int32_t* 
   SelectorDev S;
   std::memset(&S, 0, sizeof(S));
   S.kind = spec->selector;
+  const bool normalised = S.kind == HLB_XTR_PLANE_NORMALISED;
+  if (normalised) S.kind = HLB_XTR_PLANE;
   if (S.kind < 0 || S.kind > 4) return fail("unknown geometry selector");
   for (int k = 0; k < 7; ++k) S.p[k] = spec->selector_params[k];
   S.voxel = spec->voxel_size;
@@ -477,7 +479,7 @@ int build_site_list(hlb_xtr_handle* x, const hlb_xtr_spec* spec, const int32_t* 
     float acc = 0.f;
     for (int k = 0; k < 3; ++k) acc = acc + nrm[k] * nrm[k];
     const float mag = std::sqrt(acc);
-    for (int k = 0; k < 3; ++k) S.normal[k] = nrm[k] / mag;
+    for (int k = 0; k < 3; ++k) S.normal[k] = normalised ? nrm[k] : nrm[k] / mag;
   }
   if (S.kind == 3) {  // lineVector = endpoint2 - endpoint1, lineLength = |lineVector|
     float acc = 0.f;

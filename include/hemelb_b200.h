@@ -262,7 +262,13 @@ enum {
 enum { HLB_XTR_FLOAT = 0, HLB_XTR_DOUBLE = 1, HLB_XTR_INT32 = 2, HLB_XTR_UINT32 = 3, HLB_XTR_INT64 = 4, HLB_XTR_UINT64 = 5 };
 /* GeometrySelector subclasses; selector_params: plane {point[3], normal[3], radius (<= 0: infinite)},
  * line {endpoint1[3], endpoint2[3]}, surface point {point[3]} -- physical units, float as the reference */
-enum { HLB_XTR_WHOLE = 0, HLB_XTR_SURFACE = 1, HLB_XTR_PLANE = 2, HLB_XTR_LINE = 3, HLB_XTR_SURFACEPOINT = 4 };
+enum {
+  HLB_XTR_WHOLE = 0, HLB_XTR_SURFACE = 1, HLB_XTR_PLANE = 2, HLB_XTR_LINE = 3, HLB_XTR_SURFACEPOINT = 4,
+  /* plane whose normal is used as given: what PlaneGeometrySelector::GetNormal() returns (the
+   * constructor normalised it already, PlaneGeometrySelector.cc:12-29); HLB_XTR_PLANE takes the
+   * configured normal and normalises it exactly as that constructor does */
+  HLB_XTR_PLANE_NORMALISED = 5
+};
 
 typedef struct {          /* extraction::OutputField (Code/extraction/OutputField.h:105-112) */
   const char* name;
