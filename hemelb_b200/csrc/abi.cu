@@ -516,7 +516,9 @@ int ensure_caches(hlb_gpu_t h, uint32_t mask) {
     if ((mask >> i) & 1u)
       if (!h->cache[i]) {
         CU(cudaMalloc(&h->cache[i], sizeof(double) * per[i] * std::max<int64_t>(h->N, 1)));
-        CU(cudaMemset(h->cache[i], 0, sizeof(double) * per[i] * std::max<int64_t>(h->N, 1)));
+        // on the engine's own stream: a null-stream memset is not ordered against `compute`
+        // (non-blocking stream) and could still be clearing the array while the step writes it
+        CU(cudaMemsetAsync(h->cache[i], 0, sizeof(double) * per[i] * std::max<int64_t>(h->N, 1), h->compute));
       }
   return 0;
 }
