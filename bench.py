@@ -272,14 +272,14 @@ def main():
     gpu.step(2)
     barrier()
     serial_ms, bulk_ms, bulk_sites = gpu.time_steps_detail(args.steps)
-    gpu.set_overlap(True)
+    gpu.set_overlap(gpu.default_overlap)
     barrier()
     clocks = sampler.stop()
     if dist is not None:
         import torch
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, serial_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, serial_ms = float(t[0].item()), float(t[1].item())
     mlups = n_sites_global * args.steps / (ms * 1e-3) / 1e6
 
     # ---- end to end through the phase API with host scalars every step

@@ -83,7 +83,7 @@ def main():
         gpu.step(2)
         gpu.sync()
         serial_ms, bulk_ms, bulk_sites = gpu.time_steps_detail(args.steps)
-        gpu.set_overlap(True)
+        gpu.set_overlap(gpu.default_overlap)
         mon = gpu.monitor()
         B = 20 * Q
         mlups = dom.N * args.steps / (ms * 1e-3) / 1e6

@@ -120,7 +120,7 @@ def main():
     gpu.step(2)
     barrier()
     serial_ms, bulk_ms, bulk_sites = gpu.time_steps_detail(args.steps)
-    gpu.set_overlap(True)
+    gpu.set_overlap(gpu.default_overlap)
     barrier()
     mon = gpu.monitor()
     per_rank = [dom.N]
@@ -128,9 +128,9 @@ def main():
     nbrs = [int(dom.procs.shape[0])]
     if dist is not None:
         import torch
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, serial_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, serial_ms = float(t[0].item()), float(t[1].item())
         g = [None] * world
         dist.all_gather_object(g, (dom.N, int(dom.totalSharedFs), int(dom.procs.shape[0]), float(mon["min_f"])))
         per_rank, halo, nbrs = [x[0] for x in g], [x[1] for x in g], [x[2] for x in g]

@@ -975,8 +975,11 @@ int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
     int lo = 0, hi = 0;  // (numerically lowest = highest priority)
     CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CU(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, hi));
+    // measured (profiles/README.md): +0.6 % on a 1e8-site single-GPU step and +4..16 % on small
+    // ones, but -0.9 % on the 2-GPU tree where NCCL traffic shares the machine -> default on for
+    // a single rank only; HLB_OVERLAP=0/1 or hlb_gpu_set_overlap override
     const char* e = getenv("HLB_OVERLAP");
-    h->overlap = !(e && e[0] == '0');
+    h->overlap = e ? (e[0] != '0') : (cfg->nranks <= 1);
   }
   CU(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));

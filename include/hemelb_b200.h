@@ -147,7 +147,8 @@ int hlb_gpu_get_cache(hlb_gpu_t h, uint32_t which, double* out);
  *      cosine iolet densities evaluated on the host as InOutLetCosine::GetDensity does */
 int hlb_gpu_step(hlb_gpu_t h, int nsteps);
 int hlb_gpu_get_time_step(hlb_gpu_t h, uint64_t* t);
-/* scheduling knob (default on; HLB_OVERLAP=0 in the environment turns it off at create): launch the
+/* scheduling knob (default: on for a single rank, off when nranks > 1; HLB_OVERLAP=0/1 in the
+ * environment overrides the default at create): launch the
  * whole mid-domain wall / inlet / outlet ranges of LBM::PreReceive on a second, higher-priority
  * stream beside the mid-fluid kernel.  They read f_old and write disjoint slots of f_new, so the
  * result is bit-identical either way; everything that follows the streaming (CopyReceived,
