@@ -272,7 +272,7 @@ def main():
     gpu.step(2)
     barrier()
     serial_ms, bulk_ms, bulk_sites = gpu.time_steps_detail(args.steps)
-    gpu.set_overlap(gpu.default_overlap)
+    gpu.set_overlap(True)
     barrier()
     clocks = sampler.stop()
     if dist is not None:

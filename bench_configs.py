@@ -77,13 +77,13 @@ def main():
         setup = time.time() - t0
         gpu.step(args.warmup)
         gpu.sync()
-        ms = gpu.time_steps(args.steps)  # product schedule (boundary ranges beside the bulk kernel)
+        ms, fused_ms, fused_sites = gpu.time_steps_detail(args.steps)  # product schedule: fused mid-domain kernel
         gpu.sync()
         gpu.set_overlap(False)           # second region, kernels back to back: the bulk kernel's own duration
         gpu.step(2)
         gpu.sync()
         serial_ms, bulk_ms, bulk_sites = gpu.time_steps_detail(args.steps)
-        gpu.set_overlap(gpu.default_overlap)
+        gpu.set_overlap(True)
         mon = gpu.monitor()
         B = 20 * Q
         mlups = dom.N * args.steps / (ms * 1e-3) / 1e6
@@ -96,6 +96,8 @@ def main():
                 "whole_step_frac_of_hbm_roofline": mlups * 1e6 * B / 1e9 / peak,
                 "bulk_kernel_GBps": bulk_sites * B / 1e9 / (bulk_ms * 1e-3) if bulk_ms else None,
                 "bulk_kernel_frac": (bulk_sites * B / 1e9 / (bulk_ms * 1e-3)) / peak if bulk_ms else None,
+                "fused_mid_kernel": bool(fused_sites > bulk_sites),
+                "fused_kernel_frac": (fused_sites * B / 1e9 / (fused_ms * 1e-3)) / peak if fused_sites > bulk_sites else None,
                 "bulk_share_of_step": bulk_ms / serial_ms if serial_ms else None,
                 "serial_ms_per_step": serial_ms / args.steps,
                 "uncounted_boundary_bytes_per_step": 16 * nb + 8 * wall_links,

@@ -114,13 +114,13 @@ def main():
 
     gpu.step(max(args.warmup, 3))
     barrier()
-    ms = gpu.time_steps(args.steps)  # product schedule (boundary ranges beside the bulk kernel)
+    ms, fused_ms, fused_sites = gpu.time_steps_detail(args.steps)  # product schedule: fused mid-domain kernel
     barrier()
     gpu.set_overlap(False)           # second region, kernels back to back: the bulk kernel's own duration
     gpu.step(2)
     barrier()
     serial_ms, bulk_ms, bulk_sites = gpu.time_steps_detail(args.steps)
-    gpu.set_overlap(gpu.default_overlap)
+    gpu.set_overlap(True)
     barrier()
     mon = gpu.monitor()
     per_rank = [dom.N]
@@ -152,6 +152,8 @@ def main():
             "MLUPS": mlups, "ms_per_step": ms / args.steps, "bytes_per_site": B,
             "whole_step_frac_of_hbm_roofline": mlups * 1e6 * B / 1e9 / peak / world,
             "rank0_bulk_kernel_frac": (bulk_sites * B / 1e9 / (bulk_ms * 1e-3)) / peak if bulk_ms else None,
+            "fused_mid_kernel": bool(fused_sites > bulk_sites),
+            "rank0_fused_kernel_frac": (fused_sites * B / 1e9 / (fused_ms * 1e-3)) / peak if fused_sites > bulk_sites else None,
             "rank0_bulk_share_of_step": bulk_ms / serial_ms if serial_ms else None, "serial_ms_per_step": serial_ms / args.steps,
             "rank0_boundary_fraction": nb / max(dom.N, 1), "n_outlets": len(outs),
             "lattice_blocks": [int(x) for x in bd],

@@ -29,7 +29,9 @@
 namespace hlb {
 // per-(lattice, kernel) launchers, defined in cs_q*_*.cu
 #define HLB_DECL(Q, K) \
-  extern template void launch_collide_stream<Q, K>(int, int, const StepArgs&, const void*, int64_t, int64_t, void*);
+  extern template void launch_collide_stream<Q, K>(int, int, const StepArgs&, const void*, int64_t, int64_t, void*); \
+  extern template bool launch_fused_mid<Q, K>(int, int, int, const StepArgs&, const void*, const IoletDev*,          \
+                                              const double*, const MidItem*, int64_t, void*);
 HLB_DECL(15, K_LBGK) HLB_DECL(15, K_MRT) HLB_DECL(15, K_TRT)
 HLB_DECL(19, K_LBGK) HLB_DECL(19, K_MRT) HLB_DECL(19, K_TRT)
 HLB_DECL(27, K_LBGK) HLB_DECL(27, K_TRT)
@@ -143,6 +145,13 @@ struct hlb_gpu_handle {
   uint64_t timeStep = 1;  // SimulationState.cc:16
   std::vector<char> mrt;
   LaunchFn launch = nullptr;
+  FusedLaunchFn launchFused = nullptr;
+  // fused mid-domain launch (kernels.cuh, fused_mid_kernel): the work items of the six mid ranges
+  // merged by lattice position; whole-range mid launches are deferred and flushed as one kernel
+  MidItem* midItems = nullptr;
+  int64_t nMidItems = 0;
+  uint32_t allMidMask = 0, pendingMid = 0;
+  bool fuse = true, inFlush = false, fuseDefault = true, overlapDefault = true;
   double omegaMinus = 0;
   // host staging of the boundary tables until finalise
   std::vector<uint32_t> hWall, hIolet;
@@ -207,8 +216,11 @@ int ensure_staging(hlb_gpu_t h, size_t bytes) {
   return 0;
 }
 
+int flush_mid(hlb_gpu_t h);
+
 // make `compute` wait for the boundary kernels that were put on `aux`
 int join_aux(hlb_gpu_t h) {
+  if (h->pendingMid && flush_mid(h)) return 1;
   if (h->auxPending) {
     CU(cudaEventRecord(h->evJoin, h->aux));
     CU(cudaStreamWaitEvent(h->compute, h->evJoin, 0));
@@ -546,6 +558,8 @@ void fill_mrt(hlb_gpu_t h) {
 // Renumber the sites inside each of the 12 ranges by (x, y, z): long z-runs.  Everything indexed by
 // site moves with it: the neighbour table (positions and values), the streaming indices of the
 // received distributions and the staged boundary tables.  Halo slots and range bounds do not move.
+int build_mid_items(hlb_gpu_t h, const int lo[3], int64_t Ly, int64_t Lz);
+
 int build_permutation(hlb_gpu_t h) {
   const int Q = h->Q;
   const int64_t N = h->N;
@@ -634,6 +648,58 @@ int build_permutation(hlb_gpu_t h) {
     move(h->hNormal, 3);
     move(h->hCoords, 3);
   }
+  return build_mid_items(h, lo, Ly, Lz);
+}
+
+// (x, y, z) key of the first site of each work item (internal id -> reference id -> coordinates)
+__global__ void mid_item_keys_kernel(const MidItem* __restrict__ items, int64_t n, const uint32_t* __restrict__ iperm,
+                                     const int32_t* __restrict__ coords, int64_t stride, int lox, int loy, int loz,
+                                     int64_t Ly, int64_t Lz, uint64_t* __restrict__ keys) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int64_t s = iperm[items[j].first];
+  const int64_t x = coords[s] - lox, y = coords[stride + s] - loy, z = coords[2 * stride + s] - loz;
+  keys[j] = (uint64_t)((x * Ly + y) * Lz + z);
+}
+
+// work items of the fused mid-domain kernel: every mid range cut into pieces of <= T sites, all
+// pieces ordered by the lattice position of their first site (needs the renumbered order, in which
+// every range is sorted by that same key)
+int build_mid_items(hlb_gpu_t h, const int lo[3], int64_t Ly, int64_t Lz) {
+  if (!(h->cfg.kernel == HLB_KERNEL_MRT || h->Q > 19)) return 0;  // no fused kernel for the rest
+  const int T = h->Q > 19 ? HLB_Q27_THREADS : 256;
+  std::vector<MidItem> items;
+  h->allMidMask = 0;
+  for (int t = 0; t < 6; ++t) {
+    if (h->mid[t] > 0) h->allMidMask |= 1u << t;
+    for (int64_t o = 0; o < h->mid[t]; o += T) {
+      MidItem it;
+      it.first = (uint32_t)(h->rangeFirst[t] + o);
+      it.countSlot = (uint32_t)std::min<int64_t>(T, h->mid[t] - o) | ((uint32_t)t << 16);
+      items.push_back(it);
+    }
+  }
+  const int64_t n = (int64_t)items.size();
+  h->nMidItems = n;
+  if (n == 0) return 0;
+  MidItem* dItems = nullptr;
+  uint64_t* dKeys = nullptr;
+  CU(cudaMalloc(&dItems, sizeof(MidItem) * n));
+  CU(cudaMalloc(&dKeys, sizeof(uint64_t) * n));
+  CU(cudaMemcpy(dItems, items.data(), sizeof(MidItem) * n, cudaMemcpyHostToDevice));
+  mid_item_keys_kernel<<<blocks_for(n), 256>>>(dItems, n, h->iperm, h->coordsAll, h->stride, lo[0], lo[1], lo[2], Ly, Lz,
+                                               dKeys);
+  CU(cudaGetLastError());
+  std::vector<uint64_t> keys(n);
+  CU(cudaMemcpy(keys.data(), dKeys, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
+  cudaFree(dKeys);
+  std::vector<int64_t> order(n);
+  for (int64_t j = 0; j < n; ++j) order[j] = j;
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return keys[a] < keys[b]; });
+  std::vector<MidItem> sorted(n);
+  for (int64_t j = 0; j < n; ++j) sorted[j] = items[order[j]];
+  CU(cudaMemcpy(dItems, sorted.data(), sizeof(MidItem) * n, cudaMemcpyHostToDevice));
+  h->midItems = dItems;
   return 0;
 }
 
@@ -681,6 +747,16 @@ int launch_range(hlb_gpu_t h, int slot, int64_t first, int64_t count, bool post)
   int whole = -1;
   for (int k = 0; k < 12; ++k)
     if (first == h->rangeFirst[k] && first + count == h->rangeFirst[k + 1]) whole = k;
+  // whole mid-domain ranges are deferred: when all of them have been asked for they leave as ONE
+  // fused launch (flush_mid), at the next call that is not such a request
+  if (!post && h->fuse && h->midItems && whole >= 0 && whole < 6 && !h->inFlush) {
+    if (h->pendingMid & (1u << whole)) {
+      if (flush_mid(h)) return 1;
+    }
+    h->pendingMid |= 1u << whole;
+    return 0;
+  }
+  if (h->pendingMid && !h->inFlush && flush_mid(h)) return 1;
   // which stream: whole mid-domain boundary ranges go beside the bulk kernel (see `aux`)
   cudaStream_t st = h->compute;
   const bool midWhole = !post && h->overlap && whole >= 0 && whole < 6;
@@ -748,6 +824,43 @@ int launch_range(hlb_gpu_t h, int slot, int64_t first, int64_t count, bool post)
   h->launches++;
   CU(cudaGetLastError());
   return 0;
+}
+
+int flush_mid(hlb_gpu_t h) {
+  const uint32_t pending = h->pendingMid;
+  h->pendingMid = 0;
+  if (!pending) return 0;
+  if (pending == h->allMidMask) {
+    StepArgs A = make_args(h, 1);
+    const bool prof = h->profileBulk;
+    if (prof) {
+      while (h->profEv.size() < h->profUsed + 2) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        h->profEv.push_back(e);
+      }
+      CU(cudaEventRecord(h->profEv[h->profUsed], h->compute));
+    }
+    if (h->launchFused(h->cfg.wall, h->cfg.inlet, h->cfg.outlet, A, h->mrt.data(), h->ioletsDev[0],
+                       h->ioletDensityDev[0], h->midItems, h->nMidItems, h->compute)) {
+      h->launches++;
+      if (h->cacheMask & C_MONITOR) h->monitorLaunches++;
+      if (prof) {
+        CU(cudaEventRecord(h->profEv[h->profUsed + 1], h->compute));
+        h->profUsed += 2;
+        h->profSites += h->midTotal;
+      }
+      CU(cudaGetLastError());
+      return 0;
+    }
+  }
+  // not every mid range was requested, or this policy bundle has no fused kernel: one by one
+  h->inFlush = true;
+  int rc = 0;
+  for (int t = 0; t < 6 && !rc; ++t)
+    if (pending & (1u << t)) rc = launch_range(h, t, h->rangeFirst[t], h->mid[t], false);
+  h->inFlush = false;
+  return rc;
 }
 
 int post_comms(hlb_gpu_t h) {
@@ -978,8 +1091,12 @@ int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
     // measured (profiles/README.md): +0.6 % on a 1e8-site single-GPU step and +4..16 % on small
     // ones, but -0.9 % on the 2-GPU tree where NCCL traffic shares the machine -> default on for
     // a single rank only; HLB_OVERLAP=0/1 or hlb_gpu_set_overlap override
+    const char* ef = getenv("HLB_FUSE");
+    h->fuse = !(ef && ef[0] == '0');
     const char* e = getenv("HLB_OVERLAP");
     h->overlap = e ? (e[0] != '0') : (cfg->nranks <= 1);
+    h->overlapDefault = h->overlap;
+    h->fuseDefault = h->fuse;
   }
   CU(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
@@ -1020,6 +1137,7 @@ int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
 #define HLB_PICK(QQ, KK, KE)                                      \
   if (Q == QQ && cfg->kernel == KK) {                             \
     h->launch = &launch_collide_stream<QQ, KE>;                   \
+    h->launchFused = &launch_fused_mid<QQ, KE>;                   \
     fill_mrt<QQ>(h);                                              \
   }
   HLB_PICK(15, 0, K_LBGK) HLB_PICK(15, 1, K_MRT) HLB_PICK(15, 2, K_TRT)
@@ -1075,6 +1193,7 @@ int hlb_gpu_destroy(hlb_gpu_t h) {
   cudaEventDestroy(h->evT1);
   cudaStreamDestroy(h->compute);
   if (h->aux) cudaStreamDestroy(h->aux);
+  if (h->midItems) cudaFree(h->midItems);
   if (h->evFork) cudaEventDestroy(h->evFork);
   if (h->evJoin) cudaEventDestroy(h->evJoin);
   cudaStreamDestroy(h->comm);
@@ -1619,7 +1738,8 @@ int hlb_gpu_step(hlb_gpu_t h, int nsteps) {
 int hlb_gpu_set_overlap(hlb_gpu_t h, int enabled) {
   if (!h) return fail("null argument");
   if (join_aux(h)) return 1;
-  h->overlap = enabled != 0;
+  h->overlap = enabled ? h->overlapDefault : false;
+  h->fuse = enabled ? h->fuseDefault : false;
   return 0;
 }
 

@@ -621,11 +621,11 @@ __global__ void __launch_bounds__(kGzsThreads, 2) gzs_links_kernel(const StepArg
 // ---------------------------------------------------------------------------------- the site kernel
 // Q <= 19: 256-thread CTAs, two resident per SM (<= 128 registers).  D3Q27 needs ~190 registers:
 // 128-thread CTAs, three resident (<= 168 registers; 12 warps per SM instead of 8).
-template <int Q, int KERNEL, int WALL, int IOLET>
-__global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) collide_stream_kernel(const StepArgs A, const MrtArgs<Q> M, int64_t first, int64_t count) {
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= count) return;
-  const int64_t site = A.siteList ? (int64_t)A.siteList[tid] : first + tid;
+// One site: load, collide, stream, (rarely) extract moments.  `tid` only spreads the monitor atomics.
+template <int Q, int KERNEL, int WALL, int IOLET, bool COMPRESSED_TABLE>
+__device__ __forceinline__ void site_body(const StepArgs& A, const MrtArgs<Q>& M, const int64_t site, const int64_t tid,
+                                          const IoletDev* __restrict__ ioletTable,
+                                          const double* __restrict__ ioletDensityTable) {
   constexpr bool HAS_WALL = WALL != W_NONE;
   constexpr bool HAS_IOLET = IOLET != I_NONE;
 
@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) collide
   }
   uint32_t target[Q];
   target[0] = (uint32_t)site;
-  if (A.nbrFlags) {
+  if (COMPRESSED_TABLE && A.nbrFlags) {
     const int64_t g = A.groupOffset + (tid >> 5);
     const uint32_t flags = __ldg(A.nbrFlags + g);
     const uint32_t lane = (uint32_t)(tid & 31);
@@ -698,9 +698,9 @@ __global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) collide
   if constexpr (HAS_IOLET) {
     if (ioletMask) {
       const int id = A.ioletId[b];
-      io = A.iolets + id;
+      io = ioletTable + id;
       if constexpr (IOLET == I_NASH) {
-        ghostRho = A.ioletDensity[id];
+        ghostRho = ioletDensityTable[id];
         const float nf0 = (float)io->normal[0], nf1 = (float)io->normal[1], nf2 = (float)io->normal[2];
         double dot = 0.0;
         dot += m[0] * (double)nf0;
@@ -770,6 +770,52 @@ __global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) collide
   }
 }
 
+template <int Q, int KERNEL, int WALL, int IOLET>
+__global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) collide_stream_kernel(const StepArgs A, const MrtArgs<Q> M, int64_t first, int64_t count) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= count) return;
+  const int64_t site = A.siteList ? (int64_t)A.siteList[tid] : first + tid;
+  site_body<Q, KERNEL, WALL, IOLET, true>(A, M, site, tid, A.iolets, A.ioletDensity);
+}
+
+// ---------------------------------------------------------------------------------- the fused mid-domain kernel
+// All six mid-domain ranges of LBM::PreReceive in ONE launch.  The ranges are cut into work items
+// of <= site_threads sites; the items of all ranges are merged by the (x, y, z) key of their first
+// site, so the CTA that updates the wall / inlet / outlet sites of a lattice row runs next to (in
+// time) the CTAs that update the row's mid-fluid sites, and the per-range kernel tails disappear.
+// Measured (profiles/README.md): +11..12 % on MRT and D3Q27 steps, whose mid-fluid kernel is not at
+// the HBM limit; -8 % on D3Q19 LBGK, where the stand-alone mid-fluid kernel runs at 98.5 % of the
+// peak and the item-descriptor load in front of every CTA's distribution loads costs more than
+// the fusion gains.  Hence instantiated, and used, for MRT and D3Q27 only (launch_fused_mid).
+struct MidItem {
+  uint32_t first;      // internal site id
+  uint32_t countSlot;  // sites in the item | streamer slot << 16
+};
+
+template <int Q, int KERNEL, int WALL, int INLET, int OUTLET>
+__global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) fused_mid_kernel(
+    const StepArgs A, const MrtArgs<Q> M, const IoletDev* __restrict__ inletIolets,
+    const double* __restrict__ inletDensity, const MidItem* __restrict__ items) {
+  const MidItem it = items[blockIdx.x];
+  const int count = (int)(it.countSlot & 0xffffu), slot = (int)(it.countSlot >> 16);
+  if ((int)threadIdx.x >= count) return;
+  const int64_t site = (int64_t)it.first + threadIdx.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot == 0) {
+    site_body<Q, KERNEL, W_NONE, I_NONE, false>(A, M, site, tid, nullptr, nullptr);
+  } else if (slot == 1) {
+    site_body<Q, KERNEL, WALL, I_NONE, false>(A, M, site, tid, A.iolets, A.ioletDensity);
+  } else if (slot == 2) {
+    site_body<Q, KERNEL, W_NONE, INLET, false>(A, M, site, tid, inletIolets, inletDensity);
+  } else if (slot == 3) {
+    site_body<Q, KERNEL, W_NONE, OUTLET, false>(A, M, site, tid, A.iolets, A.ioletDensity);
+  } else if (slot == 4) {
+    site_body<Q, KERNEL, WALL, INLET, false>(A, M, site, tid, inletIolets, inletDensity);
+  } else {
+    site_body<Q, KERNEL, WALL, OUTLET, false>(A, M, site, tid, A.iolets, A.ioletDensity);
+  }
+}
+
 // PostStep: only BFL does work (BouzidiFirdaousLallemand.h:72-91); runs after all streaming and
 // the halo unpack, one thread per boundary-typed site of the range.
 template <int Q>
@@ -795,10 +841,17 @@ __global__ void __launch_bounds__(256) bfl_post_step_kernel(const StepArgs A, in
 }
 
 // Host-side launch entry, one per (Q, KERNEL) translation unit
+typedef bool (*FusedLaunchFn)(int wall, int inlet, int outlet, const StepArgs& A, const void* mrt,
+                              const IoletDev* inletIolets, const double* inletDensity, const MidItem* items,
+                              int64_t nItems, void* stream);
 typedef void (*LaunchFn)(int wall, int iolet, const StepArgs& A, const void* mrt, int64_t first, int64_t count,
                          void* stream);
 template <int Q, int KERNEL>
 void launch_collide_stream(int wall, int iolet, const StepArgs& A, const void* mrt, int64_t first, int64_t count,
                            void* stream);
+// returns false when the (wall, inlet, outlet) bundle has no fused instantiation
+template <int Q, int KERNEL>
+bool launch_fused_mid(int wall, int inlet, int outlet, const StepArgs& A, const void* mrt, const IoletDev* inletIolets,
+                      const double* inletDensity, const MidItem* items, int64_t nItems, void* stream);
 
 }  // namespace hlb

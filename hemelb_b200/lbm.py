@@ -355,15 +355,9 @@ class GpuLBM:
     def sync(self):
         check(self.L.hlb_gpu_sync(self.h))
 
-    @property
-    def default_overlap(self) -> bool:
-        """The library's default schedule for this handle (hlb_gpu_create): HLB_OVERLAP, else on for a single rank."""
-        import os
-        e = os.environ.get("HLB_OVERLAP")
-        return (e[0] != "0") if e else int(getattr(self.domain, "nranks", 1)) <= 1
-
     def set_overlap(self, enabled: bool):
-        """Boundary ranges beside the bulk kernel on a second stream (default on); results identical."""
+        """True: the product schedule (fused mid-domain kernel / second stream, as created); False: every
+        range its own kernel back to back on one stream.  Results are identical."""
         check(self.L.hlb_gpu_set_overlap(self.h, 1 if enabled else 0))
 
     def monitor(self):
