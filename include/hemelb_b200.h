@@ -147,16 +147,14 @@ int hlb_gpu_get_cache(hlb_gpu_t h, uint32_t which, double* out);
  *      cosine iolet densities evaluated on the host as InOutLetCosine::GetDensity does */
 int hlb_gpu_step(hlb_gpu_t h, int nsteps);
 int hlb_gpu_get_time_step(hlb_gpu_t h, uint64_t* t);
-/* scheduling knob.  Product schedule (enabled = 1, the default): the whole mid-domain ranges that
- * LBM::PreReceive asks for one streamer at a time are deferred and leave as ONE fused kernel whose
- * work items are ordered by lattice position, so the boundary sites of a lattice row are updated
- * next to the row's mid-fluid sites and every 32 B sector of f_new is completed in L2 (see
- * fused_mid_kernel); policy bundles without a fused instantiation (GZS walls) run the boundary
- * ranges on a second stream beside the mid-fluid kernel instead.  The ranges read f_old and write
- * disjoint slots of f_new, so the result is bit-identical in every schedule; whatever follows the
- * streaming (CopyReceived, PostStep, swap, read-backs) waits for all of it.  enabled = 0: every
- * range its own kernel, back to back on one stream (per-kernel timing, A/B comparisons).
- * Environment at create: HLB_FUSE=0 / HLB_OVERLAP=0|1 override the defaults. */
+/* scheduling knob.  Product schedule (enabled = 1, as created): for MRT and D3Q27 bundles the whole
+ * mid-domain ranges that LBM::PreReceive asks for one streamer at a time are deferred and leave as
+ * ONE fused kernel whose work items are ordered by lattice position (fused_mid_kernel, kernels.cuh);
+ * otherwise, on a single rank, the boundary ranges run on a second stream beside the mid-fluid
+ * kernel.  The ranges read f_old and write disjoint slots of f_new, so the result is bit-identical
+ * in every schedule; whatever follows the streaming (CopyReceived, PostStep, swap, read-backs)
+ * waits for all of it.  enabled = 0: every range its own kernel, back to back on one stream
+ * (per-kernel timing, A/B comparisons).  Environment at create: HLB_FUSE=0, HLB_OVERLAP=0|1. */
 int hlb_gpu_set_overlap(hlb_gpu_t h, int enabled);
 int hlb_gpu_sync(hlb_gpu_t h);
 /* CUDA-event timing of nsteps whole steps on the engine's own streams (ms) */
