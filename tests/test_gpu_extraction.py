@@ -330,3 +330,30 @@ def test_error_behaviour(tmp_path):
     g19 = make_gpus(case19)[0]
     with pytest.raises(HlbError, match="contains 15 distributions"):
         GpuLocalDistributionInput(tmp_path / "c.xtr").load_distribution(g19)
+
+
+def test_single_timestep_files_mode(tmp_path):
+    """One file per written step, named as the reference names them (LocalPropertyOutput.cc:77-93,
+    250-258; checked against the compiled reference in tests/test_xtr_oracle.py)."""
+    from hemelb_b200.extraction import GpuLocalPropertyOutput, OutputField, PropertyOutputFile
+    fields = [("Pressure", "pressure", "float", (80.0,)), ("Velocity", "velocity", "float", ())]
+    case = dict(geom="cylinder", Q=19, R=2, wall="BFL", steps=3, fields=fields, selector="surface", params=(), frequency=2)
+    gpus = make_gpus(case)
+    start(case, gpus)
+    sim, T = make_sim("oracle", case)
+    outs = [None] * 2
+
+    def open_(r, comm):
+        spec = PropertyOutputFile(str(tmp_path / "snap_%d.xtr"), 2, "surface", (),
+                                  [OutputField(n, s, t, o) for (n, s, t, o) in fields], single_timestep_files=True)
+        outs[r] = GpuLocalPropertyOutput(gpus[r], spec, units(), comm)
+    run_ranks(2, open_)
+    for t in (4, 5, 120):
+        run_ranks(2, lambda r, comm: outs[r].write(t, 12345))
+    [o.close() for o in outs]
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["snap_    4.xtr", "snap_  120.xtr", "snap_.off"]
+    po = X.PropertyOutput(xfields(fields), "surface", (), X.UnitConverter(DT, DX, ORIGIN, RHO, REF_PRESSURE), 19,
+                          rank_data(sim, T, 19))
+    assert (tmp_path / "snap_    4.xtr").read_bytes() == po.header + po.record(4)
+    assert (tmp_path / "snap_  120.xtr").read_bytes() == po.header + po.record(120)
+    assert (tmp_path / "snap_.off").read_bytes() == po.offset_file()

@@ -188,3 +188,25 @@ def test_checkpoint_rejects_wrong_files(tmp_path):
         ref.load_checkpoint(tmp_path / "p.xtr")
     with pytest.raises(ValueError):
         X.load_checkpoint((tmp_path / "p.xtr").read_bytes(), (tmp_path / "p.off").read_bytes(), Q, [T[0]["globalCoords"]])
+
+
+@needs_ref
+def test_single_timestep_files_mode(tmp_path):
+    """file_timestep_mode = single_timestep_files (LocalPropertyOutput.cc:77-93, 250-258): one
+    file per written step, name = pattern with %d replaced by the step right-aligned in a field of
+    max(3, digits of totalSteps) characters; the .off name drops the %d."""
+    Q = 19
+    ref, T = make_ref("cylinder", Q, 2)
+    fields = [X.Field("Pressure", "pressure", "float", [80.0]), X.Field("Velocity", "velocity", "float")]
+    s = ref.xtr_open(tmp_path / "snap_%d.xtr", fields, "surface", (), frequency=2, single_timestep_files=True, dt=DT, dx=DX,
+                     origin=ORIGIN, fluid_density=RHO, reference_pressure=80.0)
+    ref.xtr_write(s, 4, 12345)
+    ref.xtr_write(s, 5, 12345)
+    ref.xtr_write(s, 120, 12345)
+    ref.xtr_close(s)
+    names = sorted(p.name for p in tmp_path.iterdir())
+    assert names == ["snap_    4.xtr", "snap_  120.xtr", "snap_.off"], names
+    po = X.PropertyOutput(fields, "surface", (), X.UnitConverter(DT, DX, ORIGIN, RHO, 80.0), Q, rank_data(ref, T, Q))
+    assert (tmp_path / "snap_    4.xtr").read_bytes() == po.header + po.record(4)
+    assert (tmp_path / "snap_  120.xtr").read_bytes() == po.header + po.record(120)
+    assert (tmp_path / "snap_.off").read_bytes() == po.offset_file()
