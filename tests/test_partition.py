@@ -1,0 +1,109 @@
+"""The METIS-free weighted k-way block partitioner (hemelb_b200/partition.py): balance
+and cut properties against the reference's BasicDecomposition on the same vertex weights, and that
+its output is a valid input of the Domain builder (emulated multi-rank run == single-rank run)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from hemelb_b200 import geometry as G
+from hemelb_b200 import partition as P
+from hemelb_b200.domain import build_domains
+from tests.cases import anisotropic_f, geometry, iolets_for
+
+
+def collision_types(geom, Q=19):
+    """Collision type 0..5 of every input site (Domain.cc:186-207), from the single-rank tables."""
+    dom = build_domains(geom, Q)[0]
+    t = dom.tables()
+    wall = np.asarray(t["wallMask"]) != 0
+    st = np.asarray(t["siteType"])
+    local = np.where(st == 2, np.where(wall, 4, 2), np.where(st == 3, np.where(wall, 5, 3), np.where(wall, 1, 0)))
+    out = np.empty(geom.n_sites, np.int64)
+    out[np.asarray(t["inputIndex"])] = local
+    return out
+
+
+def test_reference_weight_table():
+    """DecompositionWeights.h.in:25-62 for the default architecture and BFL / GZS walls."""
+    assert P.site_weights("BFL", "NASH", "NASH", "AMDBULLDOZER").tolist() == [4, 8, 16, 16, 16, 16]
+    assert P.site_weights("GZS", "LADD", "NASH", "ISBFILEVELOCITYINLET").tolist() == [4, 28, 48, 16, 48, 16]
+    assert P.site_weights("SBB", "NASH", "NASH", "NEUTRAL").tolist() == [1] * 6
+
+
+def test_face_adjacency():
+    ijk = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [2, 2, 2], [1, 1, 0]])
+    got = {tuple(p) for p in P.face_adjacency(ijk).tolist()}
+    assert got == {(0, 1), (0, 2), (0, 3), (1, 5), (2, 5)}
+
+
+@pytest.mark.parametrize("geom_name,nranks", [("tree", 4), ("tree", 7), ("sac", 3), ("cylinder_long", 5)])
+def test_weighted_kway_properties(geom_name, nranks):
+    geom = geometry(geom_name)
+    types = collision_types(geom)
+    for wall, arch in (("BFL", "B200"), ("GZS", "AMDBULLDOZER")):
+        rank, q = P.partition_geometry(geom, types, wall, "NASH", "NASH", nranks, arch, tolerance=0.05)
+        assert rank.shape == (geom.n_sites,) and rank.min() == 0 and rank.max() == nranks - 1
+        assert q["weighted"]["parts"] == nranks
+        # whole blocks
+        B = geom.block_size
+        key = (geom.coords // B).astype(np.int64) @ np.array([1 << 40, 1 << 20, 1])
+        for k in np.unique(key)[:50]:
+            assert np.unique(rank[key == k]).size == 1
+        # never worse balanced than the reference's count-based bisection on the same weights,
+        # within one block of the tolerance
+        loads = np.bincount(np.unique(key, return_inverse=True)[1],
+                            weights=P.site_weights(wall, "NASH", "NASH", arch)[types])
+        slack = loads.max() / (loads.sum() / nranks)
+        assert q["weighted"]["imbalance"] <= max(q["basic"]["imbalance"], 1.05 + slack) + 1e-12
+        assert q["weighted"]["imbalance"] <= 1.05 + slack
+        # deterministic
+        rank2, _ = P.partition_geometry(geom, types, wall, "NASH", "NASH", nranks, arch, tolerance=0.05)
+        assert np.array_equal(rank, rank2)
+
+
+def test_refinement_does_not_increase_the_cut():
+    geom = geometry("tree")
+    types = collision_types(geom)
+    B = geom.block_size
+    bc = (geom.coords // B).astype(np.int64)
+    bd = geom.block_dims.astype(np.int64)
+    gmy = (bc[:, 0] * bd[1] + bc[:, 1]) * bd[2] + bc[:, 2]
+    uniq, inv = np.unique(gmy, return_inverse=True)
+    ijk = np.stack([uniq // (bd[1] * bd[2]), (uniq // bd[2]) % bd[1], uniq % bd[2]], 1)
+    loads = P.block_loads(inv, types, P.site_weights("BFL", "NASH", "NASH"), uniq.size)
+    for nranks in (2, 4, 8):
+        first = P.weighted_bisection(ijk, loads, nranks)
+        done = P.refine(ijk, loads, first, nranks, tolerance=0.05)
+        q0, q1 = P.quality(ijk, loads, first, nranks), P.quality(ijk, loads, done, nranks)
+        assert q1["edge_cut"] <= q0["edge_cut"] + 1e-9 or q1["imbalance"] < q0["imbalance"]
+        assert q1["parts"] == nranks
+
+
+def test_partition_is_a_valid_domain_input():
+    """Tables built for the partition drive a 4-rank emulated run that equals the single-rank run."""
+    geom = geometry("tree")
+    Q = 19
+    rank, _ = P.partition_geometry(geom, collision_types(geom), "BFL", "NASH", "NASH", 4)
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    one = O.OracleSim(O.OracleDomains(geom, Q), "LBGK", "BFL", tau=0.8, inlets=inlets, outlets=outlets)
+    doms = O.OracleDomains(geom, Q, rank, 4)
+    many = O.OracleSim(doms, "LBGK", "BFL", tau=0.8, inlets=inlets, outlets=outlets)
+    t1 = O.OracleDomains(geom, Q).tables(0)
+    f_input = anisotropic_f(geom.n_sites, Q, 0)[:geom.n_sites * Q].reshape(-1, Q)  # indexed by input site
+    f0 = np.zeros(one.f_size(0))
+    f0[:t1["N"] * Q] = f_input[np.asarray(t1["inputIndex"])].ravel()
+    one.set_f(f0)
+    for r in range(4):
+        t = doms.tables(r)
+        f = np.zeros(many.f_size(r))
+        f[:t["N"] * Q] = f_input[np.asarray(t["inputIndex"])].ravel()
+        many.set_f(f, r)
+    one.step(5)
+    many.step(5)
+    got = np.zeros_like(f_input)
+    for r in range(4):
+        t = doms.tables(r)
+        got[np.asarray(t["inputIndex"])] = many.get_f(r)[:t["N"] * Q].reshape(-1, Q)
+    want = np.zeros_like(f_input)
+    want[np.asarray(t1["inputIndex"])] = one.get_f(0)[:t1["N"] * Q].reshape(-1, Q)
+    assert np.array_equal(got, want)
