@@ -152,6 +152,7 @@ struct hlb_gpu_handle {
   int64_t nMidItems = 0;
   uint32_t allMidMask = 0, pendingMid = 0;
   bool fuse = true, inFlush = false, fuseDefault = true, overlapDefault = true;
+  bool fillHoles = true, fillHolesDefault = true, holesNow = false;
   double omegaMinus = 0;
   // host staging of the boundary tables until finalise
   std::vector<uint32_t> hWall, hIolet;
@@ -666,6 +667,9 @@ __global__ void mid_item_keys_kernel(const MidItem* __restrict__ items, int64_t 
 // pieces ordered by the lattice position of their first site (needs the renumbered order, in which
 // every range is sorted by that same key)
 int build_mid_items(hlb_gpu_t h, const int lo[3], int64_t Ly, int64_t Lz) {
+  h->allMidMask = 0;
+  for (int t = 0; t < 6; ++t)
+    if (h->mid[t] > 0) h->allMidMask |= 1u << t;
   if (!(h->cfg.kernel == HLB_KERNEL_MRT || h->Q > 19)) return 0;  // no fused kernel for the rest
   const int T = h->Q > 19 ? HLB_Q27_THREADS : 256;
   std::vector<MidItem> items;
@@ -749,17 +753,23 @@ int launch_range(hlb_gpu_t h, int slot, int64_t first, int64_t count, bool post)
     if (first == h->rangeFirst[k] && first + count == h->rangeFirst[k + 1]) whole = k;
   // whole mid-domain ranges are deferred: when all of them have been asked for they leave as ONE
   // fused launch (flush_mid), at the next call that is not such a request
-  if (!post && h->fuse && h->midItems && whole >= 0 && whole < 6 && !h->inFlush) {
+  if (!post && ((h->fuse && h->midItems) || (h->fillHoles && h->allMidMask)) && whole >= 0 && whole < 6 && !h->inFlush) {
     if (h->pendingMid & (1u << whole)) {
       if (flush_mid(h)) return 1;
     }
     h->pendingMid |= 1u << whole;
+    // the last of the non-empty mid ranges: nothing more to wait for
+    if (h->pendingMid == h->allMidMask) return flush_mid(h);
     return 0;
   }
   if (h->pendingMid && !h->inFlush && flush_mid(h)) return 1;
   // which stream: whole mid-domain boundary ranges go beside the bulk kernel (see `aux`)
   cudaStream_t st = h->compute;
-  const bool midWhole = !post && h->overlap && whole >= 0 && whole < 6;
+  const bool midWhole = !post && h->overlap && !h->holesNow && whole >= 0 && whole < 6;
+  if (h->holesNow && slot == 0) {
+    A.holeFirst = (uint32_t)h->midBulk;
+    A.holeCount = (uint32_t)(h->midTotal - h->midBulk);
+  }
   if (midWhole && slot == 0) {
     if (!h->auxPending) {
       CU(cudaEventRecord(h->evFork, h->compute));
@@ -830,7 +840,13 @@ int flush_mid(hlb_gpu_t h) {
   const uint32_t pending = h->pendingMid;
   h->pendingMid = 0;
   if (!pending) return 0;
-  if (pending == h->allMidMask) {
+  h->holesNow = false;
+  if (pending == h->allMidMask && !(h->midItems && h->fuse) && h->fillHoles) {
+    // every mid range was asked for and runs below in slot order on one stream: the mid-fluid
+    // kernel may pre-write the slots that the boundary ranges fill after it
+    h->holesNow = true;
+  }
+  if (pending == h->allMidMask && h->midItems && h->fuse) {
     StepArgs A = make_args(h, 1);
     const bool prof = h->profileBulk;
     if (prof) {
@@ -860,6 +876,7 @@ int flush_mid(hlb_gpu_t h) {
   for (int t = 0; t < 6 && !rc; ++t)
     if (pending & (1u << t)) rc = launch_range(h, t, h->rangeFirst[t], h->mid[t], false);
   h->inFlush = false;
+  h->holesNow = false;
   return rc;
 }
 
@@ -1091,12 +1108,15 @@ int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
     // measured (profiles/README.md): +0.6 % on a 1e8-site single-GPU step and +4..16 % on small
     // ones, but -0.9 % on the 2-GPU tree where NCCL traffic shares the machine -> default on for
     // a single rank only; HLB_OVERLAP=0/1 or hlb_gpu_set_overlap override
+    const char* eh = getenv("HLB_FILL_HOLES");
+    h->fillHoles = !(eh && eh[0] == '0');
     const char* ef = getenv("HLB_FUSE");
     h->fuse = !(ef && ef[0] == '0');
     const char* e = getenv("HLB_OVERLAP");
     h->overlap = e ? (e[0] != '0') : (cfg->nranks <= 1);
     h->overlapDefault = h->overlap;
     h->fuseDefault = h->fuse;
+    h->fillHolesDefault = h->fillHoles;
   }
   CU(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
@@ -1423,6 +1443,9 @@ int hlb_gpu_finalise(hlb_gpu_t h) {
   const int Q = h->Q;
   for (int64_t b = 0; b < h->NB; ++b)
     if (h->hIolet[b] && (h->hIoletId[b] < 0)) return fail("iolet site without an iolet id");
+  h->allMidMask = 0;
+  for (int t = 0; t < 6; ++t)
+    if (h->mid[t] > 0) h->allMidMask |= 1u << t;
   if (h->cfg.reorder && h->N > 0) {
     if (h->coordsCovered != h->N)
       return fail("reorder requested but hlb_gpu_set_site_coords did not cover every site exactly once");
@@ -1740,6 +1763,7 @@ int hlb_gpu_set_overlap(hlb_gpu_t h, int enabled) {
   if (join_aux(h)) return 1;
   h->overlap = enabled ? h->overlapDefault : false;
   h->fuse = enabled ? h->fuseDefault : false;
+  h->fillHoles = enabled ? h->fillHolesDefault : false;
   return 0;
 }
 

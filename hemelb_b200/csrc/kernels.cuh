@@ -67,6 +67,11 @@ struct StepArgs {
   const IoletDev* __restrict__ iolets;
   const double* __restrict__ ioletDensity;   // GetBoundaryDensity(id) for this step
   uint64_t timeStep;                         // SimulationState::GetTimeStep() (1-indexed)
+  // mid-fluid launches that are known to be followed by the mid-domain boundary ranges (whole-step
+  // schedule): sites [holeFirst, holeFirst + holeCount) are those boundary sites.  A slot of a
+  // mid-fluid site fed by one of them is pre-written here so that the sector it shares with three
+  // mid-fluid-fed slots leaves L2 whole; the boundary streamer overwrites it afterwards.
+  uint32_t holeFirst, holeCount;
   // LbmParameters
   double tau, omega, stressParameter, omegaMinus;
   // caches (MacroscopicPropertyCache), site-major like the reference
@@ -720,6 +725,16 @@ __device__ __forceinline__ void site_body(const StepArgs& A, const MrtArgs<Q>& M
     }
   }
 
+  if constexpr (!HAS_WALL && !HAS_IOLET) {
+    if (A.holeCount) {
+#pragma unroll
+      for (int d = 1; d < Q; ++d) {
+        // the site that streams into slot d of this site is this site's neighbour in direction inv(d)
+        const uint32_t up = target[inv_dir(d)] - (uint32_t)(inv_dir(d) * A.stride);
+        if (up - A.holeFirst < A.holeCount) A.fNew[(int64_t)d * A.stride + site] = 0.0;
+      }
+    }
+  }
   // stream: iolet link, else wall link, else bulk push (StreamerTypeFactory.h:65-79)
   A.fNew[target[0]] = fpost[0];
 #pragma unroll
