@@ -147,14 +147,16 @@ int hlb_gpu_get_cache(hlb_gpu_t h, uint32_t which, double* out);
  *      cosine iolet densities evaluated on the host as InOutLetCosine::GetDensity does */
 int hlb_gpu_step(hlb_gpu_t h, int nsteps);
 int hlb_gpu_get_time_step(hlb_gpu_t h, uint64_t* t);
-/* scheduling knob.  Product schedule (enabled = 1, as created): for MRT and D3Q27 bundles the whole
- * mid-domain ranges that LBM::PreReceive asks for one streamer at a time are deferred and leave as
- * ONE fused kernel whose work items are ordered by lattice position (fused_mid_kernel, kernels.cuh);
- * otherwise, on a single rank, the boundary ranges run on a second stream beside the mid-fluid
- * kernel.  The ranges read f_old and write disjoint slots of f_new, so the result is bit-identical
- * in every schedule; whatever follows the streaming (CopyReceived, PostStep, swap, read-backs)
- * waits for all of it.  enabled = 0: every range its own kernel, back to back on one stream
- * (per-kernel timing, A/B comparisons).  Environment at create: HLB_FUSE=0, HLB_OVERLAP=0|1. */
+/* scheduling knob.  Product schedule (enabled = 1, as created): whole mid-domain range requests
+ * (LBM::PreReceive asks one streamer at a time) are deferred until the last non-empty one arrived,
+ * then run (a) in slot order with the mid-fluid kernel pre-writing the slots the boundary ranges
+ * fill after it (LBGK / TRT, Q <= 19), or (b) as ONE fused kernel ordered by lattice position (MRT,
+ * D3Q27), or (c) with the boundary ranges on a second stream (other bundles, single rank) -- see
+ * DESIGN.md section 4.  The ranges read f_old and write disjoint slots of f_new, so the result of a
+ * step is bit-identical in every schedule; whatever follows the streaming (CopyReceived, PostStep,
+ * swap, read-backs) waits for all of it.  enabled = 0: every range its own kernel in the
+ * reference's plain write order (A/B comparisons).  Sub-range calls always run plain.
+ * Environment at create: HLB_FILL_HOLES=0, HLB_FUSE=0, HLB_OVERLAP=0|1. */
 int hlb_gpu_set_overlap(hlb_gpu_t h, int enabled);
 int hlb_gpu_sync(hlb_gpu_t h);
 /* CUDA-event timing of nsteps whole steps on the engine's own streams (ms) */
