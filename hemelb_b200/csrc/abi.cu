@@ -1638,6 +1638,7 @@ int hlb_gpu_set_step_scalars(hlb_gpu_t h, uint64_t timeStep, const double* inDen
                              uint32_t cacheMask) {
   if (!h) return fail("null argument");
   CU(cudaSetDevice(h->cfg.device));
+  if (join_aux(h)) return 1;  // deferred launches belong to the step whose scalars are still set
   h->timeStep = timeStep;
   if (ensure_caches(h, cacheMask)) return 1;
   h->cacheMask = cacheMask;
