@@ -45,6 +45,9 @@ def main():
     ap.add_argument("--inlet", default="NASH")
     ap.add_argument("--outlet", default="NASH")
     ap.add_argument("--lattice", type=int, default=19)
+    ap.add_argument("--decomposition", default="basic", choices=["basic", "weighted"],
+                    help="basic: the reference's BasicDecomposition over Morton blocks; weighted: the METIS-free "
+                         "weighted k-way block partition (hemelb_b200/partition.py)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -70,18 +73,29 @@ def main():
     bd = dom.block_dims
     # per-block fluid counts: each rank counts an x-slab of blocks
     xs = [int(bd[0]) * r // world for r in range(world + 1)]
-    mine = dom.count_block_sites([xs[rank], 0, 0], [xs[rank + 1], int(bd[1]), int(bd[2])])
+    weighted = args.decomposition == "weighted" and world > 1
+    if weighted:
+        mine = np.stack(dom.count_block_sites_typed([xs[rank], 0, 0], [xs[rank + 1], int(bd[1]), int(bd[2])]))
+    else:
+        mine = dom.count_block_sites([xs[rank], 0, 0], [xs[rank + 1], int(bd[1]), int(bd[2])])
     if dist is not None:
         import torch
         parts = [None] * world
         dist.all_gather_object(parts, mine)
-        counts = np.concatenate(parts, 0)
+        counts = np.concatenate(parts, 1 if weighted else 0)
     else:
         counts = mine
+    boundary_counts = None
+    if weighted:
+        counts, boundary_counts = counts[0], counts[1]
     t_count = time.time() - t0
     n_global = int(counts.sum())
     if world > 1:
-        rob = basic_decomposition_of_counts(counts, world)
+        if weighted:
+            from hemelb_b200.devdomain import weighted_decomposition_of_counts
+            rob = weighted_decomposition_of_counts(counts, boundary_counts, world, args.wall)
+        else:
+            rob = basic_decomposition_of_counts(counts, world)
         dom.set_partition(("blocks", rob))
     t1 = time.time()
     dom.build()
@@ -148,7 +162,8 @@ def main():
                       % (args.generations, r0, l0, Q, args.kernel, args.wall, args.inlet, args.outlet),
             "n_gpus": world, "sites": sum(per_rank), "sites_counted": n_global, "sites_per_rank": per_rank,
             "halo_doubles_per_rank": halo, "neighbours_per_rank": nbrs,
-            "decomposition": "BasicDecomposition over Morton-ordered blocks" if world > 1 else "single rank",
+            "decomposition": ("weighted k-way over blocks (hemelb_b200/partition.py)" if args.decomposition == "weighted"
+                              else "BasicDecomposition over Morton-ordered blocks") if world > 1 else "single rank",
             "MLUPS": mlups, "ms_per_step": ms / args.steps, "bytes_per_site": B,
             "whole_step_frac_of_hbm_roofline": mlups * 1e6 * B / 1e9 / peak / world,
             "rank0_bulk_kernel_frac": (fused_sites * B / 1e9 / (fused_ms * 1e-3)) / peak if fused_ms else None,

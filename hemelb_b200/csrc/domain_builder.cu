@@ -248,7 +248,9 @@ __host__ __device__ inline uint64_t morton3(int64_t x, int64_t y, int64_t z) {
 // block (any owner); else: grid code of every fluid voxel inside the window + own sites per block
 template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(512) classify_blocks_kernel(Shape S, Part P, Win W, Box3 box, int32_t* __restrict__ grid,
-                                                             int32_t* __restrict__ blockCount) {
+                                                             int32_t* __restrict__ blockCount,
+                                                             int32_t* __restrict__ boundaryCount = nullptr,
+                                                             const LatticeTab* __restrict__ lat = nullptr) {
   __shared__ int cand[kMaxBlockCand];
   __shared__ int nCandS;
   const int B = P.B;
@@ -261,7 +263,8 @@ __global__ void __launch_bounds__(512) classify_blocks_kernel(Shape S, Part P, W
   __syncthreads();
   const double h = 0.5 * (B - 1);
   const double cxx = bx * B + h, cyy = by * B + h, czz = bz * B + h;
-  const double reach = 1.7320508075688772 * h + 0.5;
+  // (+ one voxel of rim when the lattice neighbours of the block's sites are classified too)
+  const double reach = 1.7320508075688772 * (h + (COUNT_ONLY && boundaryCount ? 1.0 : 0.0)) + 0.5;
   for (int k = t; k < S.nCaps; k += blockDim.x)
     if (capsule_phi(S.caps[k], cxx, cyy, czz) < reach) {
       const int i = atomicAdd(&nCandS, 1);
@@ -270,7 +273,10 @@ __global__ void __launch_bounds__(512) classify_blocks_kernel(Shape S, Part P, W
   __syncthreads();
   int nCand = nCandS;
   if (nCand == 0) {
-    if (t == 0) blockCount[bi] = 0;
+    if (t == 0) {
+      blockCount[bi] = 0;
+      if (COUNT_ONLY && boundaryCount) boundaryCount[bi] = 0;
+    }
     return;
   }
   if (nCand > kMaxBlockCand) nCand = -1;
@@ -291,6 +297,22 @@ __global__ void __launch_bounds__(512) classify_blocks_kernel(Shape S, Part P, W
   }
   const int c = __syncthreads_count(flag);
   if (t == 0) blockCount[bi] = c;
+  if constexpr (COUNT_ONLY) {
+    if (boundaryCount) {
+      // boundary-typed = some lattice link leaves the fluid (wall or iolet cut): Domain.cc:186-207
+      bool cut = false;
+      if (flag) {
+        const int64_t x = bx * B + t / (B * B), y = by * B + (t / B) % B, z = bz * B + t % B;
+        for (int d = 1; d < lat->Q && !cut; ++d) {
+          const double nx = (double)(x + lat->c[d][0]), ny = (double)(y + lat->c[d][1]), nz = (double)(z + lat->c[d][2]);
+          const bool inL = nx >= 0 && ny >= 0 && nz >= 0 && nx < P.bd[0] * B && ny < P.bd[1] * B && nz < P.bd[2] * B;
+          cut = !(inL && shape_phi(S, cand, nCand, nx, ny, nz) < 0.0 && clipped(S, nx, ny, nz) < 0);
+        }
+      }
+      const int cb = __syncthreads_count(cut);
+      if (t == 0) boundaryCount[bi] = cb;
+    }
+  }
 }
 
 // explicit source: drop every uploaded site inside the window into the grid (its input index) and
@@ -945,7 +967,19 @@ int hlb_dom_set_partition_blocks(hlb_dom_t d, const int32_t* rank_of_block) {
   return 0;
 }
 
+static int count_blocks(hlb_dom_t d, const int64_t* lo, const int64_t* hi, int32_t* counts, int32_t* boundary);
+
 int hlb_dom_count_block_sites(hlb_dom_t d, const int64_t* lo, const int64_t* hi, int32_t* counts) {
+  return count_blocks(d, lo, hi, counts, nullptr);
+}
+
+int hlb_dom_count_block_sites_typed(hlb_dom_t d, const int64_t* lo, const int64_t* hi, int32_t* counts,
+                                    int32_t* boundary_counts) {
+  if (!boundary_counts) return fail("null argument");
+  return count_blocks(d, lo, hi, counts, boundary_counts);
+}
+
+static int count_blocks(hlb_dom_t d, const int64_t* lo, const int64_t* hi, int32_t* counts, int32_t* boundary) {
   if (!d || !lo || !hi || !counts) return fail("null argument");
   if (d->source != 1) return fail("block counting needs the analytic shape source");
   CU(cudaSetDevice(d->cfg.device));
@@ -962,10 +996,19 @@ int hlb_dom_count_block_sites(hlb_dom_t d, const int64_t* lo, const int64_t* hi,
   int32_t* dcnt = nullptr;
   if (dmalloc(dcnt, nb)) return 1;
   Win W = {};
-  classify_blocks_kernel<true><<<(unsigned)nb, 512>>>(d->shape(), d->part(), W, box, nullptr, dcnt);
+  int32_t* dbnd = nullptr;
+  LatticeTab* dlat = nullptr;
+  if (boundary) {
+    if (dmalloc(dbnd, nb)) return 1;
+    if (upload(dlat, &d->L, 1)) return 1;
+  }
+  classify_blocks_kernel<true><<<(unsigned)nb, 512>>>(d->shape(), d->part(), W, box, nullptr, dcnt, dbnd, dlat);
   CU(cudaGetLastError());
   CU(cudaMemcpy(counts, dcnt, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost));
+  if (boundary) CU(cudaMemcpy(boundary, dbnd, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost));
   cudaFree(dcnt);
+  if (dbnd) cudaFree(dbnd);
+  if (dlat) cudaFree(dlat);
   return 0;
 }
 

@@ -112,6 +112,16 @@ class DeviceDomain:
         check(self.L.hlb_dom_count_block_sites(self.d, ptr(lo, C.c_int64), ptr(hi, C.c_int64), ptr(out, C.c_int32)))
         return out
 
+    def count_block_sites_typed(self, lo=None, hi=None):
+        """(fluid sites, boundary-typed sites) per block over the block box [lo, hi)."""
+        lo = np.zeros(3, np.int64) if lo is None else np.ascontiguousarray(lo, np.int64)
+        hi = self.block_dims.copy() if hi is None else np.ascontiguousarray(hi, np.int64)
+        shape = tuple(int(x) for x in (hi - lo))
+        out, bnd = np.zeros(shape, np.int32), np.zeros(shape, np.int32)
+        check(self.L.hlb_dom_count_block_sites_typed(self.d, ptr(lo, C.c_int64), ptr(hi, C.c_int64), ptr(out, C.c_int32),
+                                                     ptr(bnd, C.c_int32)))
+        return out, bnd
+
     def build(self):
         check(self.L.hlb_dom_build(self.d))
         n, S, nn = C.c_int64(), C.c_int64(), C.c_int()
@@ -251,6 +261,21 @@ def tree_shape(generations: int, root_radius: float, root_length: float, seed: i
             iolets.append(IoletPlane(3, k_out, Bp[k] - dk * 0.25, -dk, Rr[k] + 2))
             k_out += 1
     return capsule_array(A, Bp, Rr), iolets, shape
+
+
+def weighted_decomposition_of_counts(counts: np.ndarray, boundary: np.ndarray, nranks: int, wall="BFL",
+                                     architecture="B200", tolerance=0.03) -> np.ndarray:
+    """``partition.weighted_kway`` on dense (bx,by,bz) arrays of fluid / boundary-typed sites per block:
+    rank of every block in .gmy block order (-1 for empty blocks), for ``hlb_dom_set_partition_blocks``."""
+    from .partition import REFERENCE_WEIGHTS, weighted_kway
+    w = REFERENCE_WEIGHTS[architecture]
+    ijk = np.argwhere(counts > 0)
+    c, b = counts[counts > 0].astype(np.float64), boundary[counts > 0].astype(np.float64)
+    loads = w["bulk"] * (c - b) + w[wall] * b
+    part = weighted_kway(ijk, loads, nranks, tolerance)
+    out = np.full(counts.shape, -1, np.int32)
+    out[counts > 0] = part
+    return out.ravel()
 
 
 def basic_decomposition_of_counts(counts: np.ndarray, nranks: int) -> np.ndarray:

@@ -218,6 +218,11 @@ int hlb_dom_set_partition_blocks(hlb_dom_t d, const int32_t* rank_of_block);
 /* source B: fluid sites per block over a box of blocks [lo, hi) (the input of BasicDecomposition);
  * counts is x-major / z-fastest over the box */
 int hlb_dom_count_block_sites(hlb_dom_t d, const int64_t* lo, const int64_t* hi, int32_t* counts);
+/* same, plus how many of each block's sites are boundary-typed (some lattice link is cut by a wall
+ * or an iolet; Domain.cc:186-207) -- the vertex weights of a weighted decomposition
+ * (DecompositionWeights.h.in:25-62, OptimisedDecomposition::PopulateVertexWeightData) */
+int hlb_dom_count_block_sites_typed(hlb_dom_t d, const int64_t* lo, const int64_t* hi, int32_t* counts,
+                                    int32_t* boundary_counts);
 int hlb_dom_build(hlb_dom_t d);
 int hlb_dom_build_seconds(hlb_dom_t d, double* seconds);  /* device time of the last build */
 /* ---- the tables, reference form */

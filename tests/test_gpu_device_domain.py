@@ -205,3 +205,36 @@ def test_two_rank_engine_from_device_domain_host_staged_halo():
         sim.step(1)
     for r, (d, g) in enumerate(zip(doms, gpus)):
         assert np.array_equal(g.get_f()[:d.N * Q], sim.get_f(r)[:d.N * Q]), r
+
+
+@pytest.mark.parametrize("name", ["cylinder", "tree"])
+@pytest.mark.parametrize("Q", (15, 19, 27))
+def test_typed_block_counts_and_weighted_decomposition(name, Q):
+    """Per-block boundary-typed site counts (the vertex weights of the weighted decomposition) equal
+    the counts derived from the built tables; the weighted k-way block partition made from them is a
+    valid site -> rank rule: every rank's tables equal the host builder's."""
+    from hemelb_b200.devdomain import weighted_decomposition_of_counts
+    caps, iolets, shape = _shape(name)
+    dev = DeviceDomain.from_shape(caps, iolets, shape, Q)
+    g = dev.geometry()
+    counts, boundary = dev.count_block_sites_typed()
+    assert np.array_equal(counts, dev.count_block_sites())
+    # reference: boundary-typed sites of the single-rank tables, binned by block
+    t = dev.tables()
+    typed = (np.asarray(t["wallMask"]) != 0) | (np.asarray(t["ioletMask"]) != 0)
+    bc = (np.asarray(t["globalCoords"]).reshape(-1, 3) // g.block_size).astype(np.int64)
+    want = np.zeros(counts.shape, np.int64)
+    np.add.at(want, (bc[typed, 0], bc[typed, 1], bc[typed, 2]), 1)
+    assert np.array_equal(boundary, want)
+    R = 4
+    rob = weighted_decomposition_of_counts(counts, boundary, R, "BFL")
+    assert set(np.unique(rob[rob >= 0]).tolist()) == set(range(R))
+    bd = g.block_dims.astype(np.int64)
+    gc = (g.coords // g.block_size).astype(np.int64)
+    ros = rob[(gc[:, 0] * bd[1] + gc[:, 1]) * bd[2] + gc[:, 2]].astype(np.int32)
+    host = build_domains(g, Q, ros, R)
+    for r in range(R):
+        d = DeviceDomain.from_shape(caps, iolets, shape, Q, partition=("blocks", rob), rank=r, nranks=R)
+        _same(d, host[r], (name, Q, "weighted blocks", r))
+        d.close()
+    dev.close()
