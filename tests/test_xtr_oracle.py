@@ -98,7 +98,7 @@ def selector_cases(geom_name):
 
 @needs_ref
 @pytest.mark.parametrize("R", (1, 3))
-@pytest.mark.parametrize("geom_name,Q", [("four_cube", 15), ("cylinder", 19)])
+@pytest.mark.parametrize("geom_name,Q", [("four_cube", 15), ("cylinder", 19), ("cylinder", 27)])
 def test_files_identical_to_reference(tmp_path, geom_name, Q, R):
     if geom_name == "four_cube" and R > 1:
         pytest.skip("single-rank fixture")
