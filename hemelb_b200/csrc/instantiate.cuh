@@ -40,16 +40,13 @@ void launch_collide_stream(int wall, int iolet, const StepArgs& A, const void* m
 template <int Q, int KERNEL>
 bool launch_fused_mid(int wall, int inlet, int outlet, const StepArgs& A, const void* mrt, const IoletDev* inletIolets,
                       const double* inletDensity, const MidItem* items, int64_t nItems, void* stream) {
-  // only where it pays (see fused_mid_kernel): MRT and D3Q27
+  // only where it pays (see fused_mid_kernel): MRT and D3Q27; the bundles live in fused_q*_*.cu
   if constexpr (KERNEL == K_MRT || Q > 19) {
-    cudaStream_t s = (cudaStream_t)stream;
     const MrtArgs<Q>& M = *(const MrtArgs<Q>*)mrt;
-    constexpr int T = site_threads<Q>();
-#define HLB_FUSED(W, I, O)                                                                          \
-  if (wall == W && inlet == I && outlet == O) {                                                     \
-    if (nItems > 0)                                                                                 \
-      fused_mid_kernel<Q, KERNEL, W, I, O><<<(unsigned)nItems, T, 0, s>>>(A, M, inletIolets, inletDensity, items); \
-    return true;                                                                                    \
+#define HLB_FUSED(W, I, O)                                                                                   \
+  if (wall == W && inlet == I && outlet == O) {                                                              \
+    if (nItems > 0) launch_fused_bundle<Q, KERNEL, W, I, O>(A, M, inletIolets, inletDensity, items, nItems, stream); \
+    return true;                                                                                             \
   }
     // the policy bundles of BASELINE.json's configs (GZS keeps its two-kernel form)
     HLB_FUSED(W_SBB, I_NASH, I_NASH)

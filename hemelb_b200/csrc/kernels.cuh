@@ -864,6 +864,11 @@ typedef void (*LaunchFn)(int wall, int iolet, const StepArgs& A, const void* mrt
 template <int Q, int KERNEL>
 void launch_collide_stream(int wall, int iolet, const StepArgs& A, const void* mrt, int64_t first, int64_t count,
                            void* stream);
+// one fused bundle: declared here, defined in fused_impl.cuh and explicitly instantiated in its own
+// translation unit (fused_q*_*.cu) so that the long compilations run side by side
+template <int Q, int KERNEL, int WALL, int INLET, int OUTLET>
+void launch_fused_bundle(const StepArgs& A, const MrtArgs<Q>& M, const IoletDev* inletIolets, const double* inletDensity,
+                         const MidItem* items, int64_t nItems, void* stream);
 // returns false when the (wall, inlet, outlet) bundle has no fused instantiation
 template <int Q, int KERNEL>
 bool launch_fused_mid(int wall, int inlet, int outlet, const StepArgs& A, const void* mrt, const IoletDev* inletIolets,
