@@ -20,11 +20,25 @@ reference's own BasicDecomposition and the device Domain builder partition by):
    trade boundary blocks to tighten the balance.
 
 Plain numpy; a few million blocks (a 1e9-site tree has ~3e6 non-empty 8^3 blocks) take seconds.
+
+4. site-granular stage (``site_graph`` / ``refine_sites`` / ``partition_sites``): the graph the
+   reference hands to ParMETIS -- one vertex per fluid site, one edge per lattice direction that
+   leads to another fluid site (``OptimisedDecomposition::PopulateAdjacencyData``,
+   ``OptimisedDecomposition.cc:311-379``), vertex weights by collision type, no edge weights
+   (``wgtflag = 2``, ``:108``) -- refined k-way from the block partition: boundary sites move to the
+   adjacent part they have most links into when that lowers the number of cut links and the part
+   stays under ``ubvec`` x the mean load (the reference passes 1.001, ``:133``); over-full parts
+   first diffuse boundary sites to lighter neighbours.  Moves are made in bulk, one direction of
+   part index per sweep (the scheme ParMETIS' own parallel refinement uses against two neighbours
+   swapping), and a sweep that does not pay is undone, so the cut never grows once the balance is
+   met.  The result cuts through blocks, as a ParMETIS partition does; it enters the Domain
+   builder as ``rank_of_site`` (``hlb_dom_set_sites`` / ``DomainBuilder``).
 """
 from __future__ import annotations
 
 import numpy as np
 
+from .domain import _Lookup, lattice_vectors
 from .geometry import basic_decomposition_blocks, morton
 
 # DecompositionWeights.h.in:25-62 -- {bulk, wall[WALL], iolet[BC]} for HEMELB_COMPUTE_ARCHITECTURE
@@ -169,3 +183,192 @@ def partition_geometry(geom, site_type, wall="BFL", inlet="NASH", outlet="NASH",
     basic = basic_decomposition_blocks(ijk, counts, nranks)
     return part[inv].astype(np.int32), dict(weighted=quality(ijk, loads, part, nranks),
                                             basic=quality(ijk, loads, basic, nranks))
+
+
+# ---------------------------------------------------------------------------------------------
+# site-granular stage: the reference's ParMETIS graph, refined k-way without METIS
+# ---------------------------------------------------------------------------------------------
+def site_graph(geom, Q: int):
+    """CSR adjacency ``(xadj, adjncy)`` of the fluid-site graph, vertices in input-site (.gmy) order.
+
+    ``OptimisedDecomposition::PopulateAdjacencyData`` (``OptimisedDecomposition.cc:311-379``): for
+    every fluid site and every lattice direction l = 1..Q-1 (in that order) one adjacency when
+    ``site + c_l`` lies inside the block lattice and is itself fluid.  (The reference numbers its
+    vertices by octree block, then site id in the block -- ``PopulateSiteDistribution``, ``:225-
+    296``; ``reference_vertex_order`` gives that permutation.)"""
+    c = geom.coords.astype(np.int64)
+    n = geom.n_sites
+    look = _Lookup(geom)
+    vec = lattice_vectors(Q)
+    nb = np.empty((n, Q - 1), np.int64)
+    for l in range(1, Q):
+        nb[:, l - 1] = look(c + vec[l])  # -1 for solid / outside: _Lookup's window lies inside the range test
+    full = geom.block_dims.astype(np.int64) * geom.block_size
+    for l in range(1, Q):
+        p = c + vec[l]
+        nb[((p < 0) | (p >= full)).any(1), l - 1] = -1
+    ok = nb >= 0
+    xadj = np.concatenate([[0], np.cumsum(ok.sum(1))]).astype(np.int64)
+    return xadj, nb[ok]
+
+
+def reference_vertex_order(geom) -> np.ndarray:
+    """Input-site index of the reference's vertex 0, 1, ...: blocks in octree (Morton) order, sites
+    in .gmy order inside a block (``OptimisedDecomposition.cc:246-262, 280-295``)."""
+    B = geom.block_size
+    c = geom.coords.astype(np.int64)
+    s = c % B
+    key_site = (s[:, 0] * B + s[:, 1]) * B + s[:, 2]
+    return np.lexsort((key_site, morton(c // B)))
+
+
+def site_cut(xadj, adjncy, part) -> int:
+    """Number of graph edges whose ends lie in different parts (ParMETIS' ``edgecut``)."""
+    src = np.repeat(np.arange(xadj.size - 1), np.diff(xadj))
+    return int((part[src] != part[adjncy]).sum() // 2)
+
+
+class _CutState:
+    """Which directed graph edges are cut under ``part`` (modified in place by the caller), kept up
+    to date after moves by re-evaluating only the edges of the moved vertices and their neighbours."""
+
+    def __init__(self, xadj, adjncy, part):
+        self.xadj, self.adjncy, self.part = xadj, adjncy, part
+        self.deg = np.diff(xadj)
+        self.src = np.repeat(np.arange(part.size), self.deg)
+        self.ext = part[self.src] != part[adjncy]
+        self.cut2 = int(self.ext.sum())  # each cut edge is seen from both ends
+
+    def _edges_of(self, v):
+        cnt = self.deg[v]
+        return np.arange(int(cnt.sum())) - np.repeat(np.cumsum(cnt) - cnt, cnt) + np.repeat(self.xadj[v], cnt)
+
+    def moved(self, v):
+        v = np.unique(np.concatenate([v, self.adjncy[self._edges_of(v)]]))
+        e = self._edges_of(v)
+        new = self.part[self.src[e]] != self.part[self.adjncy[e]]
+        self.cut2 += int(new.sum()) - int(self.ext[e].sum())
+        self.ext[e] = new
+
+    def boundary(self, nranks):
+        """(vertex, other part, links into it, links inside the own part) for every boundary vertex
+        and every part it touches, sorted by vertex."""
+        e = np.nonzero(self.ext)[0]
+        key, cnt = np.unique(self.src[e] * nranks + self.part[self.adjncy[e]], return_counts=True)
+        u = key // nranks
+        if u.size == 0:
+            return u, u.astype(np.int32), cnt, cnt
+        first = np.r_[0, np.nonzero(np.diff(u))[0] + 1]
+        outside = np.repeat(np.add.reduceat(cnt, first), np.diff(np.r_[first, u.size]))
+        return u, (key % nranks).astype(np.int32), cnt, self.deg[u] - outside
+
+
+def _take_within(group, order_key, w, budget, half=None):
+    """Mask of the candidates accepted when each ``group`` g may take ``budget[g]`` weight, best
+    ``order_key`` first (``half``: accept the candidate that overshoots by less than half its weight)."""
+    o = np.lexsort((order_key, group))
+    g, ww = group[o], w[o]
+    cum = np.cumsum(ww)
+    first = np.r_[0, np.nonzero(np.diff(g))[0] + 1]
+    base = np.repeat(cum[first] - ww[first], np.diff(np.r_[first, g.size]))
+    keep = np.zeros(group.size, bool)
+    keep[o] = (cum - base) - (0 if half is None else half[o]) <= budget[g]
+    return keep
+
+
+def refine_sites(xadj, adjncy, vwgt, part, nranks, ubvec=1.001, passes=40):
+    """Step 4.  Returns the refined site -> part array (a copy).  Deterministic."""
+    part = np.asarray(part, np.int32).copy()
+    vwgt = np.asarray(vwgt, np.float64)
+    n = part.size
+    if n == 0 or nranks < 2:
+        return part
+    mean = vwgt.sum() / nranks
+    cap = max(ubvec * mean, mean + vwgt.max())  # a part can always take one more site than the mean
+    pl = np.bincount(part, weights=vwgt, minlength=nranks)
+    for e in np.nonzero(pl == 0)[0]:
+        # an empty part (fewer heavy blocks than ranks) is seeded with the first site of the heaviest
+        # one and grows by diffusion
+        part[np.nonzero(part == int(np.argmax(pl)))[0][0]] = e
+        pl = np.bincount(part, weights=vwgt, minlength=nranks)
+
+    state = _CutState(xadj, adjncy, part)
+
+    def best_per_vertex(u, q, gain):
+        o = np.lexsort((q, -gain, u))
+        u, q, gain = u[o], q[o], gain[o]
+        f = np.r_[True, u[1:] != u[:-1]]
+        return u[f], q[f], gain[f]
+
+    for it in range(passes):
+        # (i) balance: while a part is above the cap, loads diffuse over the part graph -- flows on
+        # its edges from the potential x that solves L x = load - mean (L its Laplacian), carried one
+        # layer of boundary sites per pass, the sites with most links into the receiving part first
+        if pl.max() > cap:
+            u, q, cnt, internal = state.boundary(nranks)
+            p = part[u]
+            A = np.zeros((nranks, nranks))
+            A[p, q] = 1.0
+            A = np.maximum(A, A.T)
+            x = np.linalg.lstsq(np.diag(A.sum(1)) - A, pl - mean, rcond=None)[0]
+            flow = A * (x[:, None] - x[None, :])
+            ok = flow[p, q] > 0.5 * vwgt[u]
+            if not ok.any():
+                break
+            u, q, gain = best_per_vertex(u[ok], q[ok], (cnt[ok] - internal[ok]).astype(np.int64))
+            p = part[u]
+            w = vwgt[u]
+            keep = _take_within(p.astype(np.int64) * nranks + q, -gain, w, flow.ravel(), half=w / 2)
+            if not keep.any():
+                break
+            part[u[keep]] = q[keep]
+            state.moved(u[keep])
+            pl = np.bincount(part, weights=vwgt, minlength=nranks)
+            continue
+        # (ii) cut: one sweep upwards (to a higher part index), one downwards
+        moved = 0
+        for up in (True, False):
+            u, q, cnt, internal = state.boundary(nranks)
+            p = part[u]
+            gain = (cnt - internal).astype(np.int64)
+            w = vwgt[u]
+            ok = ((q > p) if up else (q < p)) & ((gain > 0) | ((gain == 0) & (pl[p] - pl[q] > 2 * w)))
+            if not ok.any():
+                continue
+            u, q, gain = best_per_vertex(u[ok], q[ok], gain[ok])
+            keep = _take_within(q.astype(np.int64), -gain, vwgt[u], cap - pl)
+            if not keep.any():
+                continue
+            u, q = u[keep], q[keep]
+            before = state.cut2
+            old = part[u].copy()
+            part[u] = q
+            state.moved(u)
+            if state.cut2 > before:  # stale gains of neighbours moving together
+                part[u] = old
+                state.moved(u)
+                continue
+            pl = np.bincount(part, weights=vwgt, minlength=nranks)
+            moved += u.size
+        if not moved:
+            break
+    return part
+
+
+def site_quality(xadj, adjncy, vwgt, part, nranks):
+    pl = np.bincount(part, weights=vwgt, minlength=nranks)
+    return dict(imbalance=float(pl.max() / pl.mean()), edge_cut=site_cut(xadj, adjncy, part),
+                parts=int(np.unique(part).size))
+
+
+def partition_sites(geom, site_type, Q=19, wall="BFL", inlet="NASH", outlet="NASH", nranks=2, architecture="B200",
+                    ubvec=1.001, block_tolerance=0.03, passes=40):
+    """Site -> rank through all four steps: weighted block k-way, then site-granular refinement over
+    the reference's ParMETIS graph.  Returns the rank array and the quality of both stages on the
+    site graph (imbalance of the weighted load, number of cut lattice links)."""
+    blocks, _ = partition_geometry(geom, site_type, wall, inlet, outlet, nranks, architecture, block_tolerance)
+    xadj, adjncy = site_graph(geom, Q)
+    vwgt = site_weights(wall, inlet, outlet, architecture)[np.asarray(site_type)]
+    sites = refine_sites(xadj, adjncy, vwgt, blocks, nranks, ubvec, passes)
+    return sites, dict(blocks=site_quality(xadj, adjncy, vwgt, blocks, nranks),
+                       sites=site_quality(xadj, adjncy, vwgt, sites, nranks))

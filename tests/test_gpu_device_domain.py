@@ -36,6 +36,11 @@ def test_explicit_source_tables_bit_exact(name, Q):
     cases = [(None, 1), (G.slab_decomposition(geom, 2, axis=2), 2), (G.slab_decomposition(geom, 3, axis=0), 3)]
     if name != "four_cube":
         cases.append((G.basic_decomposition(geom, 5), 5))
+    if name in ("tree", "sac") and Q == 19:
+        # a ParMETIS-like site partition (cuts through blocks): hemelb_b200/partition.py step 4
+        from hemelb_b200.partition import partition_sites
+        from tests.test_partition import collision_types
+        cases.append((partition_sites(geom, collision_types(geom, Q), Q, nranks=4)[0], 4))
     for ros, R in cases:
         host = build_domains(geom, Q, ros, R)
         for r in range(R):

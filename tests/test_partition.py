@@ -79,11 +79,85 @@ def test_refinement_does_not_increase_the_cut():
         assert q1["parts"] == nranks
 
 
-def test_partition_is_a_valid_domain_input():
+def test_site_graph_is_the_parmetis_graph_of_the_reference():
+    """OptimisedDecomposition.cc:311-379 on four_cube (a 4^3 box of fluid): one adjacency per lattice
+    direction with a fluid site at the other end, in direction order; symmetric."""
+    geom = G.four_cube()
+    for Q, vec in ((15, P.lattice_vectors(15)), (19, P.lattice_vectors(19)), (27, P.lattice_vectors(27))):
+        xadj, adjncy = P.site_graph(geom, Q)
+        want = sum(int(np.prod(4 - np.abs(vec[l]))) for l in range(1, Q))  # pairs at offset c_l inside the box
+        assert xadj[0] == 0 and xadj[-1] == adjncy.size == want
+        c = geom.coords.astype(np.int64)
+        site_at = {tuple(x): i for i, x in enumerate(c.tolist())}
+        for i in (0, 21, 42, 63):
+            expect = [site_at[tuple(c[i] + vec[l])] for l in range(1, Q) if tuple(c[i] + vec[l]) in site_at]
+            assert adjncy[xadj[i]:xadj[i + 1]].tolist() == expect
+        src = np.repeat(np.arange(geom.n_sites), np.diff(xadj))
+        assert {(a, b) for a, b in zip(src.tolist(), adjncy.tolist())} == {(b, a) for a, b in zip(src.tolist(), adjncy.tolist())}
+    # the reference numbers vertices by octree block, then by site id in the block
+    geom = geometry("tree")
+    order = P.reference_vertex_order(geom)
+    assert np.array_equal(np.sort(order), np.arange(geom.n_sites))
+    B = geom.block_size
+    m = G.morton(geom.coords[order].astype(np.int64) // B).astype(np.int64)
+    assert (np.diff(m) >= 0).all()
+    s = geom.coords[order].astype(np.int64) % B
+    sid = (s[:, 0] * B + s[:, 1]) * B + s[:, 2]
+    assert (np.diff(sid)[np.diff(m) == 0] > 0).all()
+    # solid neighbours and the lattice's edge are no vertices
+    xadj, adjncy = P.site_graph(geom, 19)
+    assert adjncy.min() >= 0 and adjncy.max() < geom.n_sites and (np.diff(xadj) <= 18).all()
+
+
+@pytest.mark.parametrize("geom_name,nranks", [("tree", 2), ("tree", 4), ("tree", 8), ("sac", 3), ("sac", 8),
+                                              ("cylinder_long", 5)])
+def test_site_granular_refinement(geom_name, nranks):
+    """Step 4 (the ParMETIS stage, OptimisedDecomposition.cc:100-154): balance within ubvec (or one
+    site of the mean on these small cases), no rank left empty, deterministic, and from a balanced
+    start the number of cut links never grows."""
+    geom = geometry(geom_name)
+    types = collision_types(geom)
+    for wall, arch in (("BFL", "B200"), ("GZS", "AMDBULLDOZER")):
+        rank, q = P.partition_sites(geom, types, 19, wall, "NASH", "NASH", nranks, arch, ubvec=1.001)
+        assert rank.dtype == np.int32 and rank.shape == (geom.n_sites,)
+        assert q["sites"]["parts"] == nranks
+        vw = P.site_weights(wall, "NASH", "NASH", arch)[types]
+        mean = vw.sum() / nranks
+        assert q["sites"]["imbalance"] <= max(1.001, 1 + vw.max() / mean) + 1e-12
+        assert q["sites"]["imbalance"] <= q["blocks"]["imbalance"] + 1e-12
+        rank2, _ = P.partition_sites(geom, types, 19, wall, "NASH", "NASH", nranks, arch, ubvec=1.001)
+        assert np.array_equal(rank, rank2)
+        xadj, adjncy = P.site_graph(geom, 19)
+        again = P.refine_sites(xadj, adjncy, vw, rank, nranks, 1.001)
+        assert P.site_cut(xadj, adjncy, again) <= q["sites"]["edge_cut"]
+        assert P.site_quality(xadj, adjncy, vw, again, nranks)["imbalance"] <= max(1.001, 1 + vw.max() / mean) + 1e-12
+
+
+def test_site_refinement_shrinks_the_halo():
+    """The cut links are the halo: totalSharedFs of the built tables (FieldData.cc:27-39 sizes) equals
+    the directed cut of the site graph, and the site stage does not leave it above the block stage on
+    the tree when both are balanced."""
+    geom, Q, R = geometry("tree"), 19, 4
+    types = collision_types(geom)
+    rank, q = P.partition_sites(geom, types, Q, nranks=R)
+    xadj, adjncy = P.site_graph(geom, Q)
+    doms = build_domains(geom, Q, rank, R)
+    assert sum(int(d.tables()["totalSharedFs"]) for d in doms) == 2 * P.site_cut(xadj, adjncy, rank)
+    assert q["sites"]["edge_cut"] <= q["blocks"]["edge_cut"]
+
+
+@pytest.mark.parametrize("stage", ["blocks", "sites"])
+def test_partition_is_a_valid_domain_input(stage):
     """Tables built for the partition drive a 4-rank emulated run that equals the single-rank run."""
     geom = geometry("tree")
     Q = 19
-    rank, _ = P.partition_geometry(geom, collision_types(geom), "BFL", "NASH", "NASH", 4)
+    if stage == "blocks":
+        rank, _ = P.partition_geometry(geom, collision_types(geom), "BFL", "NASH", "NASH", 4)
+    else:
+        rank, _ = P.partition_sites(geom, collision_types(geom), Q, "BFL", "NASH", "NASH", 4)
+        B = geom.block_size
+        key = (geom.coords // B).astype(np.int64) @ np.array([1 << 40, 1 << 20, 1])
+        assert any(np.unique(rank[key == k]).size > 1 for k in np.unique(key))  # cuts through blocks
     inlets, outlets = iolets_for(geom, "NASH", "NASH")
     one = O.OracleSim(O.OracleDomains(geom, Q), "LBGK", "BFL", tau=0.8, inlets=inlets, outlets=outlets)
     doms = O.OracleDomains(geom, Q, rank, 4)
