@@ -15,6 +15,7 @@
 #ifndef HEMELB_GEOMETRY_FIELDDATA_H
 #define HEMELB_GEOMETRY_FIELDDATA_H
 
+#include <map>
 #include <memory>
 #include <vector>
 
@@ -38,7 +39,28 @@ namespace hemelb::geometry {
     double tau = 0.0;
     lb::BoundaryValues* inletValues = nullptr;
     lb::BoundaryValues* outletValues = nullptr;
+    // what hlb_gpu_set_step_scalars was last given: the twelve StreamAndCollide calls of one time
+    // step (lb.hpp:176-255) push the scalars once, not twelve times -- every push would flush the
+    // engine's deferred mid-domain launches and cost a host-to-device copy
+    bool scalarsPushed = false;
+    unsigned long long pushedStep = 0;
+    unsigned pushedMask = 0;
+    std::vector<double> pushedIn, pushedOut;
+    // LBM calls every streamer twice per phase, domain-edge range first (PreSend / PostReceive's
+    // first half), mid-domain range second; the ranges themselves cannot tell the two apart when
+    // they are empty, so the outlet-wall streamer (the last of the six) counts its calls
+    unsigned lastSlotStreams = 0, lastSlotPostSteps = 0;
   };
+
+  // The six streamers are constructed from InitParams (LBM::InitCollisions, lb.hpp:75-114), which
+  // names the Domain but not the FieldData; each constructor files its policy here under the
+  // Domain, so that the engine -- built when the first range is asked for -- knows the wall and
+  // iolet policies of all six.
+  inline std::map<const Domain*, GpuPolicy>& GpuPolicies() {
+    static std::map<const Domain*, GpuPolicy> all;
+    return all;
+  }
+  inline GpuPolicy& GpuPolicyFor(const Domain* d) { return GpuPolicies()[d]; }
 
   class FieldData {
   public:
@@ -49,7 +71,7 @@ namespace hemelb::geometry {
         m_force(d->GetLocalFluidSiteCount()),
         m_neighbouringFields{std::make_unique<neighbouring::NeighbouringFieldData>(d->neighbouringData)} {}
 
-    ~FieldData() { if (m_gpu) hlb_gpu_destroy(m_gpu); }
+    ~FieldData() { if (m_gpu) hlb_gpu_destroy(m_gpu); GpuPolicies().erase(m_domain.get()); }
     FieldData(FieldData const&) = delete;
 
     domain_type& GetDomain() { return *m_domain; }
@@ -76,10 +98,13 @@ namespace hemelb::geometry {
       m_mirrorOld.swap(m_mirrorNew);
     }
     void SendAndReceive(net::Net*) {  // FieldData.cc:27-39 -> NCCL send/recv posted after PreSend
-      if (m_gpu) Check(hlb_gpu_request_comms(m_gpu));
+      // LBM::RequestComms is the first call of every time step, the first step included: the
+      // engine is built here if it does not exist yet (the streamers were constructed, and filed
+      // their policies, in LBM::InitCollisions)
+      Check(hlb_gpu_request_comms(Engine()));
     }
     void CopyReceived() {  // FieldData.cc:41-48
-      if (m_gpu) Check(hlb_gpu_copy_received(m_gpu));
+      Check(hlb_gpu_copy_received(Engine()));
     }
 
     void ResetForces(LatticeForceVector const& f = LatticeForceVector(0, 0, 0)) { std::fill(m_force.begin(), m_force.end(), f); }
@@ -88,7 +113,7 @@ namespace hemelb::geometry {
     void AddToForceAtSite(site_t i, LatticeForceVector const& f) { m_force[i] += f; }
 
     // ---- used by the Gpu*Streamer policy classes ------------------------------------------------
-    GpuPolicy& Policy() { return m_policy; }
+    GpuPolicy& Policy() { return GpuPolicyFor(m_domain.get()); }
     hlb_gpu_t Engine() { EnsureEngine(); PushIfDirty(); m_deviceNewer = true; return m_gpu; }
     static void Check(int rc) { if (rc) throw Exception() << "hemelb_b200: " << hlb_gpu_last_error(); }
 
@@ -116,7 +141,6 @@ namespace hemelb::geometry {
     std::vector<distribn_t> m_mirrorOld, m_mirrorNew;
     std::vector<LatticeForceVector> m_force;
     std::unique_ptr<neighbouring::NeighbouringFieldData> m_neighbouringFields;
-    GpuPolicy m_policy;
     hlb_gpu_t m_gpu = nullptr;
     bool m_hostDirty = true, m_deviceNewer = false;
     friend struct GpuEngineBuilder;

@@ -9,6 +9,8 @@
 #ifndef HEMELB_LB_STREAMERS_GPUSTREAMERS_H
 #define HEMELB_LB_STREAMERS_GPUSTREAMERS_H
 
+#include <algorithm>
+#include <limits>
 #include <type_traits>
 #include <vector>
 
@@ -62,37 +64,37 @@ namespace hemelb::lb::gpu {
     using LatticeType = typename C::LatticeType;
     using VarsType = typename C::VarsType;
 
-    explicit GpuStreamer(InitParams& ip) : boundary(ip.boundaryObject), tau(ip.lbmParams->GetTau()) {}
+    explicit GpuStreamer(InitParams& ip) {
+      auto& pol = geometry::GpuPolicyFor(ip.latDat);
+      pol.kernel = kernel_id<KernelType>::value;
+      pol.tau = ip.lbmParams->GetTau();
+      if constexpr (WALL::value >= 0) pol.wall = WALL::value;
+      if constexpr (IOLET::value >= 0) {
+        if (SLOT == 2 || SLOT == 4) { pol.inlet = IOLET::value; pol.inletValues = ip.boundaryObject; }
+        else { pol.outlet = IOLET::value; pol.outletValues = ip.boundaryObject; }
+      }
+    }
 
     void StreamAndCollide(const site_t first, const site_t count, const LbmParameters* lbmParams,
                           geometry::FieldData& latDat, MacroscopicPropertyCache& cache) {
-      Register(latDat, lbmParams);
       hlb_gpu_t h = latDat.Engine();
       PushStepScalars(h, latDat, cache);
       geometry::FieldData::Check(hlb_gpu_stream_and_collide(h, SLOT, first, count));
-      // the last domain-edge range of LBM::PreSend (lb.hpp:176-212) releases the halo send
-      if (SLOT == 5 && first >= latDat.GetDomain().GetMidDomainSiteCount())
+      // the last domain-edge range of LBM::PreSend (lb.hpp:176-212) releases the halo send: the
+      // outlet-wall streamer's first call of a step (its second is LBM::PreReceive's, lb.hpp:214-255)
+      if (SLOT == 5 && (latDat.Policy().lastSlotStreams++ & 1u) == 0)
         geometry::FieldData::Check(hlb_gpu_edge_done(h));
     }
 
     void PostStep(const site_t first, const site_t count, const LbmParameters*, geometry::FieldData& latDat,
                   MacroscopicPropertyCache& cache) {
       geometry::FieldData::Check(hlb_gpu_post_step(latDat.Engine(), SLOT, first, count));
-      // after the last PostStep of LBM::PostReceive the refreshed caches are brought to the host
-      if (SLOT == 5 && first < latDat.GetDomain().GetMidDomainSiteCount()) PullCaches(latDat, cache);
+      // after the last PostStep of LBM::PostReceive (lb.hpp:257-309: domain-edge ranges, then the
+      // mid-domain ones) the refreshed caches are brought to the host
+      if (SLOT == 5 && (latDat.Policy().lastSlotPostSteps++ & 1u) == 1) PullCaches(latDat, cache);
     }
 
   private:
-    void Register(geometry::FieldData& latDat, const LbmParameters* p) {
-      auto& pol = latDat.Policy();
-      pol.kernel = kernel_id<KernelType>::value;
-      pol.tau = p->GetTau();
-      if constexpr (WALL::value >= 0) pol.wall = WALL::value;
-      if constexpr (IOLET::value >= 0) {
-        if (SLOT == 2 || SLOT == 4) { pol.inlet = IOLET::value; pol.inletValues = boundary; }
-        else { pol.outlet = IOLET::value; pol.outletValues = boundary; }
-      }
-    }
     static void PushStepScalars(hlb_gpu_t h, geometry::FieldData& latDat, MacroscopicPropertyCache& cache) {
       auto& pol = latDat.Policy();
       std::vector<double> in, out;
@@ -101,7 +103,15 @@ namespace hemelb::lb::gpu {
       if (pol.outletValues)
         for (unsigned i = 0; i < pol.outletValues->GetLocalIoletCount(); ++i) out.push_back(pol.outletValues->GetBoundaryDensity(i));
       const auto t = pol.inletValues ? pol.inletValues->GetTimeStep() : (pol.outletValues ? pol.outletValues->GetTimeStep() : 1);
-      geometry::FieldData::Check(hlb_gpu_set_step_scalars(h, t, in.data(), out.data(), CacheMask(cache)));
+      const uint32_t mask = CacheMask(cache);
+      if (pol.scalarsPushed && pol.pushedStep == t && pol.pushedMask == mask && pol.pushedIn == in && pol.pushedOut == out)
+        return;  // same step, same values: the engine already has them
+      geometry::FieldData::Check(hlb_gpu_set_step_scalars(h, t, in.data(), out.data(), mask));
+      pol.scalarsPushed = true;
+      pol.pushedStep = t;
+      pol.pushedMask = mask;
+      pol.pushedIn.swap(in);
+      pol.pushedOut.swap(out);
     }
     static void PullCaches(geometry::FieldData& latDat, MacroscopicPropertyCache& cache) {
       hlb_gpu_t h = latDat.Engine();
@@ -136,8 +146,6 @@ namespace hemelb::lb::gpu {
         }
       }
     }
-    BoundaryValues* boundary;
-    distribn_t tau;
   };
 
   // Traits-ready aliases: STREAMER, WALL_BOUNDARY, INLET_BOUNDARY, OUTLET_BOUNDARY template
@@ -167,15 +175,17 @@ namespace hemelb::geometry {
   inline void FieldData::EnsureEngine() {
     if (m_gpu) return;
     Domain& d = *m_domain;
+    GpuPolicy& pol = Policy();
+    if (pol.kernel < 0) throw Exception() << "hemelb_b200: no Gpu streamer was constructed for this Domain";
     const int Q = d.latticeInfo.GetNumVectors();
     const site_t N = d.GetLocalFluidSiteCount();
     hlb_gpu_config cfg{};
     cfg.lattice = Q;
-    cfg.kernel = m_policy.kernel;
-    cfg.wall = m_policy.wall < 0 ? HLB_WALL_SIMPLEBOUNCEBACK : m_policy.wall;
-    cfg.inlet = m_policy.inlet < 0 ? HLB_IOLET_NASHZEROTHORDERPRESSURE : m_policy.inlet;
-    cfg.outlet = m_policy.outlet < 0 ? HLB_IOLET_NASHZEROTHORDERPRESSURE : m_policy.outlet;
-    cfg.tau = m_policy.tau;
+    cfg.kernel = pol.kernel;
+    cfg.wall = pol.wall < 0 ? HLB_WALL_SIMPLEBOUNCEBACK : pol.wall;
+    cfg.inlet = pol.inlet < 0 ? HLB_IOLET_NASHZEROTHORDERPRESSURE : pol.inlet;
+    cfg.outlet = pol.outlet < 0 ? HLB_IOLET_NASHZEROTHORDERPRESSURE : pol.outlet;
+    cfg.tau = pol.tau;
     cfg.rank = d.GetLocalRank();
     cfg.nranks = d.GetCommunicator().Size();
     int ndev = 1;
@@ -189,7 +199,13 @@ namespace hemelb::geometry {
     cfg.total_shared_fs = d.totalSharedFs;
     cfg.reorder = 1;
     cfg.n_neighbours = (int)d.neighbouringProcs.size();
-    auto records = [](lb::BoundaryValues* bv) {
+    // LBM::PrepareBoundaryObjects (lb.hpp:128-152): the minimum density over every iolet
+    double minDensity = std::numeric_limits<double>::max();
+    for (lb::BoundaryValues* bv : {pol.inletValues, pol.outletValues})
+      if (bv)
+        for (unsigned i = 0; i < bv->GetLocalIoletCount(); ++i)
+          minDensity = std::min(minDensity, (double)bv->GetLocalIolet(i)->GetDensityMin());
+    auto records = [minDensity](lb::BoundaryValues* bv) {
       std::vector<double> r;
       if (!bv) return r;
       for (unsigned i = 0; i < bv->GetLocalIoletCount(); ++i) {
@@ -205,12 +221,12 @@ namespace hemelb::geometry {
         } else {
           rec[9] = io->GetDensityMin(); rec[12] = 1.0;  // densities still arrive per step from BoundaryValues
         }
-        rec[14] = io->GetDensityMin();
+        rec[14] = minDensity;
         r.insert(r.end(), rec, rec + HLB_IOLET_RECORD_DOUBLES);
       }
       return r;
     };
-    auto rin = records(m_policy.inletValues), rout = records(m_policy.outletValues);
+    auto rin = records(pol.inletValues), rout = records(pol.outletValues);
     cfg.n_inlets = (int)(rin.size() / HLB_IOLET_RECORD_DOUBLES);
     cfg.n_outlets = (int)(rout.size() / HLB_IOLET_RECORD_DOUBLES);
     Check(hlb_gpu_create(&cfg, &m_gpu));

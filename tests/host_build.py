@@ -1,0 +1,68 @@
+"""Builds the runnable C++ host-side check (tests/host_lbm_run.cc) into tests/_build/:
+
+  host_lbm_run_mock   linked against the recording C-ABI stand-in (tests/host_mock_abi.cc), CPU
+  host_lbm_run        linked against hemelb_b200/libhemelb_b200.so, GPU
+
+Both compile the reference's own LbmParameters / SimulationState / InOutLet / SiteData /
+MacroscopicPropertyCache sources where they lie under /root/reference (never copied), so they can
+only be built where the reference exists; the binaries travel to the GPU box with the snapshot
+(tests/_build/ is git-ignored, not gpurun-ignored).  Test infrastructure only."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tests", "_build")
+REF = "/root/reference/Code"
+REF_SRCS = ["lb/MacroscopicPropertyCache.cc", "lb/SimulationState.cc", "geometry/SiteDataBare.cc", "util/Matrix3D.cc",
+            "util/Vector3D.cc", "lb/kernels/DHumieresD3Q19MRTBasis.cc", "lb/iolets/InOutLet.cc",
+            "lb/iolets/InOutLetCosine.cc", "lb/iolets/InOutLetVelocity.cc", "lb/iolets/InOutLetParabolicVelocity.cc"]
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources if os.path.exists(s))
+
+
+def build_host_binaries(verbose=False):
+    """No-op when the reference is absent (prebuilt binaries are used) or everything is up to date."""
+    if not os.path.isdir(REF):
+        return False
+    os.makedirs(BUILD, exist_ok=True)
+    host = os.path.join(ROOT, "hemelb_b200", "host")
+    deps = [os.path.join(ROOT, "tests", "host_lbm_run.cc"), os.path.join(ROOT, "include", "hemelb_b200.h"),
+            os.path.join(host, "geometry", "FieldData.h"), os.path.join(host, "lb", "streamers", "GpuStreamers.h"),
+            os.path.join(ROOT, "tests", "host_shim", "geometry", "Domain.h"), os.path.abspath(__file__)]
+    common = ["g++", "-std=c++20", "-O1", "-w", "-I" + host, "-I" + os.path.join(ROOT, "include"),
+              "-I" + os.path.join(ROOT, "tests", "host_shim"), "-I" + os.path.join(ROOT, "oracle", "ref_shim"), "-I" + REF]
+    obj = os.path.join(BUILD, "host_lbm_run.o")
+    refobj = os.path.join(BUILD, "host_ref_objs.o")
+    if _stale(obj, deps):
+        subprocess.run(common + ["-c", deps[0], "-o", obj], check=True)
+    if _stale(refobj, [os.path.abspath(__file__)]):
+        objs = []
+        for i, s in enumerate(REF_SRCS):
+            o = os.path.join(BUILD, "ref_%d.o" % i)
+            subprocess.run(common + ["-c", os.path.join(REF, s), "-o", o], check=True)
+            objs.append(o)
+        subprocess.run(["ld", "-r", "-o", refobj] + objs, check=True)
+        for o in objs:
+            os.remove(o)
+    mock = os.path.join(BUILD, "host_lbm_run_mock")
+    mock_src = os.path.join(ROOT, "tests", "host_mock_abi.cc")
+    if _stale(mock, [obj, refobj, mock_src]):
+        subprocess.run(common + [obj, refobj, mock_src, "-o", mock], check=True)
+    lib = os.path.join(ROOT, "hemelb_b200", "libhemelb_b200.so")
+    real = os.path.join(BUILD, "host_lbm_run")
+    if os.path.exists(lib) and _stale(real, [obj, refobj, lib]):
+        # rpath relative to the binary: the snapshot is unpacked at another path on the GPU box
+        subprocess.run(["g++", obj, refobj, "-L" + os.path.dirname(lib), "-lhemelb_b200",
+                        "-Wl,-rpath,$ORIGIN/../../hemelb_b200", "-Wl,--allow-shlib-undefined", "-o", real], check=True)
+    if verbose:
+        print("host binaries in", BUILD)
+    return True
+
+
+if __name__ == "__main__":
+    build_host_binaries(True)

@@ -1,0 +1,77 @@
+// Recording stand-in for the C ABI (include/hemelb_b200.h), for the CPU test of the C++ host-side
+// drop-in's call sequence (tests/test_host_lbm.py).  Every entry point the host headers use writes
+// one line to $HLB_MOCK_LOG and succeeds; nothing is computed.  Test infrastructure only -- the
+// product library has no CPU path.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "hemelb_b200.h"
+
+struct hlb_gpu_handle { hlb_gpu_config cfg; };
+
+namespace {
+  FILE* out() {
+    static FILE* fh = nullptr;
+    if (!fh) {
+      const char* p = getenv("HLB_MOCK_LOG");
+      fh = p ? fopen(p, "w") : stderr;
+    }
+    return fh;
+  }
+  long long ll(int64_t v) { return (long long)v; }
+}
+
+extern "C" {
+const char* hlb_gpu_last_error(void) { return "mock"; }
+int hlb_gpu_device_count(int* n) { *n = 1; return 0; }
+int hlb_gpu_create(const hlb_gpu_config* c, hlb_gpu_t* h) {
+  *h = new hlb_gpu_handle{*c};
+  fprintf(out(), "create lattice=%d kernel=%d wall=%d inlet=%d outlet=%d tau=%.17g rank=%d nranks=%d n_sites=%lld "
+          "mid=%lld,%lld,%lld,%lld,%lld,%lld edge=%lld,%lld,%lld,%lld,%lld,%lld shared=%lld neighbours=%d inlets=%d outlets=%d reorder=%d\n",
+          c->lattice, c->kernel, c->wall, c->inlet, c->outlet, c->tau, c->rank, c->nranks, ll(c->n_sites),
+          ll(c->mid_count[0]), ll(c->mid_count[1]), ll(c->mid_count[2]), ll(c->mid_count[3]), ll(c->mid_count[4]), ll(c->mid_count[5]),
+          ll(c->edge_count[0]), ll(c->edge_count[1]), ll(c->edge_count[2]), ll(c->edge_count[3]), ll(c->edge_count[4]), ll(c->edge_count[5]),
+          ll(c->total_shared_fs), c->n_neighbours, c->n_inlets, c->n_outlets, c->reorder);
+  return 0;
+}
+int hlb_gpu_destroy(hlb_gpu_t h) { fprintf(out(), "destroy\n"); fflush(out()); delete h; return 0; }
+int hlb_gpu_set_neighbour_indices(hlb_gpu_t, int64_t a, int64_t n, const int64_t* idx) {
+  fprintf(out(), "set_neighbour_indices %lld %lld first=%lld\n", ll(a), ll(n), ll(idx[0])); return 0; }
+int hlb_gpu_set_site_data(hlb_gpu_t, int64_t a, int64_t n, const uint32_t* w, const uint32_t* i, const int32_t*) {
+  fprintf(out(), "set_site_data %lld %lld wall0=%u iolet0=%u\n", ll(a), ll(n), w[0], i[0]); return 0; }
+int hlb_gpu_set_wall_distances(hlb_gpu_t, int64_t a, int64_t n, const double*) { fprintf(out(), "set_wall_distances %lld %lld\n", ll(a), ll(n)); return 0; }
+int hlb_gpu_set_wall_normals(hlb_gpu_t, int64_t a, int64_t n, const double*) { fprintf(out(), "set_wall_normals %lld %lld\n", ll(a), ll(n)); return 0; }
+int hlb_gpu_set_site_coords(hlb_gpu_t, int64_t a, int64_t n, const int64_t*) { fprintf(out(), "set_site_coords %lld %lld\n", ll(a), ll(n)); return 0; }
+int hlb_gpu_set_neighbours(hlb_gpu_t, const int*, const int64_t*, const int64_t*) { fprintf(out(), "set_neighbours\n"); return 0; }
+int hlb_gpu_set_streaming_indices(hlb_gpu_t, const int64_t*) { fprintf(out(), "set_streaming_indices\n"); return 0; }
+int hlb_gpu_set_iolets(hlb_gpu_t, int which, int n, const double* r) {
+  fprintf(out(), "set_iolets %d %d kind0=%d min_density=%.17g\n", which, n, (int)r[0], r[14]); return 0; }
+int hlb_gpu_finalise(hlb_gpu_t) { fprintf(out(), "finalise\n"); return 0; }
+int hlb_gpu_comm_unique_id(void* id) { memset(id, 0, 128); return 0; }
+int hlb_gpu_comm_init(hlb_gpu_t, const void*) { fprintf(out(), "comm_init\n"); return 0; }
+int hlb_gpu_set_f(hlb_gpu_t, int which, const double* f) { fprintf(out(), "set_f %d f0=%.17g\n", which, f[0]); return 0; }
+int hlb_gpu_get_f(hlb_gpu_t h, int which, double* f) {
+  fprintf(out(), "get_f %d\n", which);
+  memset(f, 0, sizeof(double) * (h->cfg.n_sites * h->cfg.lattice + 1 + h->cfg.total_shared_fs));
+  return 0;
+}
+int hlb_gpu_request_comms(hlb_gpu_t) { fprintf(out(), "request_comms\n"); return 0; }
+int hlb_gpu_copy_received(hlb_gpu_t) { fprintf(out(), "copy_received\n"); return 0; }
+int hlb_gpu_swap(hlb_gpu_t) { fprintf(out(), "swap\n"); return 0; }
+int hlb_gpu_set_step_scalars(hlb_gpu_t h, uint64_t t, const double* in, const double* o, uint32_t mask) {
+  fprintf(out(), "set_step_scalars t=%llu mask=%u", (unsigned long long)t, mask);
+  for (int i = 0; i < h->cfg.n_inlets; ++i) fprintf(out(), " in%d=%.17g", i, in[i]);
+  for (int i = 0; i < h->cfg.n_outlets; ++i) fprintf(out(), " out%d=%.17g", i, o[i]);
+  fprintf(out(), "\n");
+  return 0;
+}
+int hlb_gpu_stream_and_collide(hlb_gpu_t, int slot, int64_t a, int64_t n) { fprintf(out(), "stream_and_collide %d %lld %lld\n", slot, ll(a), ll(n)); return 0; }
+int hlb_gpu_post_step(hlb_gpu_t, int slot, int64_t a, int64_t n) { fprintf(out(), "post_step %d %lld %lld\n", slot, ll(a), ll(n)); return 0; }
+int hlb_gpu_edge_done(hlb_gpu_t) { fprintf(out(), "edge_done\n"); return 0; }
+int hlb_gpu_get_cache(hlb_gpu_t h, uint32_t which, double* o) {
+  fprintf(out(), "get_cache %u\n", which);
+  const int w = which == HLB_CACHE_STRESS_TENSOR ? 9 : (which & (HLB_CACHE_VELOCITY | HLB_CACHE_TRACTION | HLB_CACHE_TANGENTIAL_TRACTION) ? 3 : 1);
+  for (int64_t i = 0; i < h->cfg.n_sites * w; ++i) o[i] = (double)which;
+  return 0;
+}
+}

@@ -12,6 +12,7 @@
 #include "geometry/Site.h"
 #include "geometry/neighbouring/NeighbouringDomain.h"
 #include "lb/lattices/LatticeInfo.h"
+struct HostDomainFiller;
 namespace hemelb::geometry {
   struct NeighbouringProcessor { proc_t Rank; site_t SharedDistributionCount; site_t FirstSharedDistribution; };
   struct FakeComm {
@@ -21,12 +22,13 @@ namespace hemelb::geometry {
   class FieldData;
   class Domain {
     friend class FieldData;
+    friend struct ::HostDomainFiller;  // tests/host_lbm_run.cc fills the tables
     template <class> friend class Site;
   public:
     explicit Domain(const lb::LatticeInfo& li) : latticeInfo(li) {}
     FakeComm const& GetCommunicator() const { return comms; }
     site_t const& GetLocalFluidSiteCount() const { return nSites; }
-    site_t GetMidDomainSiteCount() const { return 0; }
+    site_t GetMidDomainSiteCount() const { site_t n = 0; for (auto c : mid) n += c; return n; }
     site_t const& GetMidDomainCollisionCount(unsigned t) const { return mid[t]; }
     site_t const& GetDomainEdgeCollisionCount(unsigned t) const { return edge[t]; }
     int GetLocalRank() const { return 0; }
