@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <span>
 #include <string>
+#include <type_traits>
 #include <variant>
 #include <vector>
 
@@ -26,6 +27,23 @@
 
 namespace hemelb::extraction::gpu
 {
+  // The C ABI's enums are the reference's orders (OutputField.h:33-44, io/formats/extraction.h:50-57);
+  // pinned here so that a reordering upstream breaks the build, not the files.
+  namespace detail {
+    template <int I, class T> constexpr bool source_is = std::is_same_v<std::variant_alternative_t<I, source::Type>, T>;
+    static_assert(source_is<HLB_XTR_PRESSURE, source::Pressure> && source_is<HLB_XTR_VELOCITY, source::Velocity> &&
+                  source_is<HLB_XTR_SHEARSTRESS, source::ShearStress> && source_is<HLB_XTR_VONMISESSTRESS, source::VonMisesStress> &&
+                  source_is<HLB_XTR_SHEARRATE, source::ShearRate> && source_is<HLB_XTR_STRESSTENSOR, source::StressTensor> &&
+                  source_is<HLB_XTR_TRACTION, source::Traction> &&
+                  source_is<HLB_XTR_TANGENTIALPROJECTIONTRACTION, source::TangentialProjectionTraction> &&
+                  source_is<HLB_XTR_DISTRIBUTIONS, source::Distributions> && source_is<HLB_XTR_MPIRANK, source::MpiRank>);
+    static_assert(std::variant_size_v<source::Type> == 10);
+    using io::formats::extraction::TypeCode;
+    static_assert(int(TypeCode::FLOAT) == HLB_XTR_FLOAT && int(TypeCode::DOUBLE) == HLB_XTR_DOUBLE &&
+                  int(TypeCode::INT32) == HLB_XTR_INT32 && int(TypeCode::UINT32) == HLB_XTR_UINT32 &&
+                  int(TypeCode::INT64) == HLB_XTR_INT64 && int(TypeCode::UINT64) == HLB_XTR_UINT64);
+  }
+
   // the util::UnitConverter constructor arguments (Code/util/UnitConverter.cc:14-24) as SimBuilder has them
   struct Units
   {
