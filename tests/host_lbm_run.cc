@@ -38,9 +38,9 @@ namespace g = hemelb::lb::gpu;
 
 namespace {
   struct Case {
-    int64_t head[24];
+    int64_t head[32];
     double phys[4];  // dt, dx, rho, eta -> LbmParameters
-    std::vector<int64_t> neighbourIndices, globalCoords;
+    std::vector<int64_t> neighbourIndices, globalCoords, procs3, streamingIndices;
     std::vector<uint32_t> wallMask, ioletMask;
     std::vector<int32_t> ioletId, siteType;
     std::vector<double> distanceToWall, wallNormal, inletRec, outletRec, f0;
@@ -57,7 +57,7 @@ namespace {
     Case c;
     FILE* fh = fopen(path, "rb");
     if (!fh) throw std::runtime_error(std::string("cannot open ") + path);
-    if (fread(c.head, sizeof(int64_t), 24, fh) != 24 || c.head[0] != 0x484C4231) throw std::runtime_error("bad case header");
+    if (fread(c.head, sizeof(int64_t), 32, fh) != 32 || c.head[0] != 0x484C4231) throw std::runtime_error("bad case header");
     if (fread(c.phys, sizeof(double), 4, fh) != 4) throw std::runtime_error("case file truncated");
     const size_t N = c.N(), Q = c.Q(), S = c.head[19];
     get(fh, c.neighbourIndices, N * Q);
@@ -71,6 +71,8 @@ namespace {
     get(fh, c.inletRec, HLB_IOLET_RECORD_DOUBLES * c.head[20]);
     get(fh, c.outletRec, HLB_IOLET_RECORD_DOUBLES * c.head[21]);
     get(fh, c.f0, N * Q + 1 + S);
+    get(fh, c.procs3, 3 * c.head[26]);  // {rank, SharedDistributionCount, FirstSharedDistribution} per neighbour
+    get(fh, c.streamingIndices, S);
     fclose(fh);
     return c;
   }
@@ -110,6 +112,12 @@ struct HostDomainFiller {
       d.siteData[i] = geometry::SiteData(gs);
     }
     d.neighbouringData = std::make_shared<geometry::neighbouring::NeighbouringDomain>();
+    d.comms.rank = (int)c.head[24];
+    d.comms.size = (int)c.head[25];
+    if (const char* f = getenv("HLB_HOST_ID_FILE")) d.comms.idFile = f;
+    for (size_t p = 0; p * 3 < c.procs3.size(); ++p)
+      d.neighbouringProcs.push_back({(proc_t)c.procs3[3 * p], c.procs3[3 * p + 1], c.procs3[3 * p + 2]});
+    d.streamingIndicesForReceivedDistributions.assign(c.streamingIndices.begin(), c.streamingIndices.end());
   }
 };
 

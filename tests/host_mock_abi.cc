@@ -42,8 +42,18 @@ int hlb_gpu_set_site_data(hlb_gpu_t, int64_t a, int64_t n, const uint32_t* w, co
 int hlb_gpu_set_wall_distances(hlb_gpu_t, int64_t a, int64_t n, const double*) { fprintf(out(), "set_wall_distances %lld %lld\n", ll(a), ll(n)); return 0; }
 int hlb_gpu_set_wall_normals(hlb_gpu_t, int64_t a, int64_t n, const double*) { fprintf(out(), "set_wall_normals %lld %lld\n", ll(a), ll(n)); return 0; }
 int hlb_gpu_set_site_coords(hlb_gpu_t, int64_t a, int64_t n, const int64_t*) { fprintf(out(), "set_site_coords %lld %lld\n", ll(a), ll(n)); return 0; }
-int hlb_gpu_set_neighbours(hlb_gpu_t, const int*, const int64_t*, const int64_t*) { fprintf(out(), "set_neighbours\n"); return 0; }
-int hlb_gpu_set_streaming_indices(hlb_gpu_t, const int64_t*) { fprintf(out(), "set_streaming_indices\n"); return 0; }
+int hlb_gpu_set_neighbours(hlb_gpu_t h, const int* r, const int64_t* c, const int64_t* f) {
+  fprintf(out(), "set_neighbours");
+  for (int i = 0; i < h->cfg.n_neighbours; ++i) fprintf(out(), " %d:%lld:%lld", r[i], ll(c[i]), ll(f[i]));
+  fprintf(out(), "\n");
+  return 0;
+}
+int hlb_gpu_set_streaming_indices(hlb_gpu_t h, const int64_t* idx) {
+  long long sum = 0;
+  for (int64_t i = 0; i < h->cfg.total_shared_fs; ++i) sum += (i + 1) * idx[i];
+  fprintf(out(), "set_streaming_indices weighted_sum=%lld\n", sum);
+  return 0;
+}
 int hlb_gpu_set_iolets(hlb_gpu_t, int which, int n, const double* r) {
   fprintf(out(), "set_iolets %d %d kind0=%d min_density=%.17g\n", which, n, (int)r[0], r[14]); return 0; }
 int hlb_gpu_finalise(hlb_gpu_t) { fprintf(out(), "finalise\n"); return 0; }

@@ -2,8 +2,13 @@
 // through `friend class FieldData` (Code/geometry/Domain.h:55,71-82,257-282,340,495-530), so the
 // host headers can be compile-checked here without MPI / Boost.
 #pragma once
+#include <chrono>
+#include <cstdio>
 #include <memory>
 #include <span>
+#include <stdexcept>
+#include <string>
+#include <thread>
 #include <vector>
 #include "units.h"
 #include "constants.h"
@@ -15,9 +20,33 @@
 struct HostDomainFiller;
 namespace hemelb::geometry {
   struct NeighbouringProcessor { proc_t Rank; site_t SharedDistributionCount; site_t FirstSharedDistribution; };
+  // stand-in for net::MpiCommunicator: size / rank as the harness sets them; Broadcast goes
+  // through a file when one is named (two harness processes, one per GPU, sharing the NCCL id)
   struct FakeComm {
-    int Size() const { return 1; }
-    template <class T, std::size_t N> void Broadcast(std::span<T, N>, int) const {}
+    int size = 1, rank = 0;
+    std::string idFile;
+    int Size() const { return size; }
+    int Rank() const { return rank; }
+    template <class T, std::size_t N> void Broadcast(std::span<T, N> data, int root) const {
+      if (idFile.empty()) return;
+      if (rank == root) {
+        const std::string tmp = idFile + ".tmp";
+        FILE* fh = fopen(tmp.c_str(), "wb");
+        if (!fh || fwrite(data.data(), sizeof(T), data.size(), fh) != data.size()) throw std::runtime_error("FakeComm: cannot write " + tmp);
+        fclose(fh);
+        if (rename(tmp.c_str(), idFile.c_str())) throw std::runtime_error("FakeComm: cannot publish " + idFile);
+      } else {
+        for (int tries = 0; tries < 6000; ++tries) {
+          if (FILE* fh = fopen(idFile.c_str(), "rb")) {
+            const size_t n = fread(data.data(), sizeof(T), data.size(), fh);
+            fclose(fh);
+            if (n == data.size()) return;
+          }
+          std::this_thread::sleep_for(std::chrono::milliseconds(10));
+        }
+        throw std::runtime_error("FakeComm: nothing arrived in " + idFile);
+      }
+    }
   };
   class FieldData;
   class Domain {
@@ -31,7 +60,7 @@ namespace hemelb::geometry {
     site_t GetMidDomainSiteCount() const { site_t n = 0; for (auto c : mid) n += c; return n; }
     site_t const& GetMidDomainCollisionCount(unsigned t) const { return mid[t]; }
     site_t const& GetDomainEdgeCollisionCount(unsigned t) const { return edge[t]; }
-    int GetLocalRank() const { return 0; }
+    int GetLocalRank() const { return comms.rank; }
     Site<Domain> GetSite(site_t i) { return Site<Domain>(i, *this); }
     template <class L> distribn_t GetCutDistance(site_t i, int d) const { return distanceToWall[i * (L::NUMVECTORS - 1) + d - 1]; }
     distribn_t* GetCutDistances(site_t i) { return &distanceToWall[i]; }

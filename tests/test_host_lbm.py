@@ -38,16 +38,18 @@ def reference_tau(dt):
     return 0.5 + (dt * ETA / RHO) / (cs2 * DX * DX)
 
 
-def write_case(path, dom, kernel, wall, inlet, outlet, inlets, outlets, f0, steps, want, dt):
+def write_case(path, dom, kernel, wall, inlet, outlet, inlets, outlets, f0, steps, want, dt, rank=0, nranks=1):
     t = dom.tables()
     Q, N = int(t["Q"]), int(t["N"])
-    head = np.zeros(24, np.int64)
+    head = np.zeros(32, np.int64)
     head[0] = 0x484C4231
     head[1:7] = [Q, KERNELS[kernel], WALLS[wall], IOLETS[inlet], IOLETS[outlet], N]
     head[7:13] = t["mid"]
     head[13:19] = t["edge"]
     head[19] = t["totalSharedFs"]
     head[20], head[21], head[22], head[23] = len(inlets), len(outlets), steps, want
+    procs = np.asarray(t["procs"], np.int64).reshape(-1, 3)
+    head[24], head[25], head[26] = rank, nranks, procs.shape[0]
     with open(path, "wb") as fh:
         fh.write(head.tobytes())
         fh.write(np.array([dt, DX, RHO, ETA], np.float64).tobytes())
@@ -59,6 +61,8 @@ def write_case(path, dom, kernel, wall, inlet, outlet, inlets, outlets, f0, step
             for r in recs:
                 fh.write(np.asarray(r, np.float64).tobytes())
         fh.write(np.asarray(f0, np.float64).tobytes())
+        fh.write(procs.tobytes())
+        fh.write(np.ascontiguousarray(t["streamingIndices"], np.int64).tobytes())
     return Q, N
 
 
@@ -215,3 +219,99 @@ def test_cxx_host_runs_on_the_gpu_and_matches_the_oracle(tmp_path, name, Q, kern
     rho, vel = sim.get_cache("density"), sim.get_cache("velocity")
     assert np.abs(out[N * Q:N * Q + N] - rho).max() <= 1e-10 * np.abs(rho).max()
     assert np.abs(out[N * Q + N:] - vel.reshape(-1)).max() <= 1e-10 * max(np.abs(vel).max(), 1e-300) + 1e-15
+
+
+@needs_reference_or_prebuilt
+def test_cxx_host_multi_rank_construction_and_sequence(tmp_path):
+    """Two ranks of a slab-cut cylinder: what FieldData::EnsureEngine tells the engine about the halo
+    (neighbouringProcs, streamingIndicesForReceivedDistributions, the NCCL id broadcast over the
+    communicator) and the per-step calls with non-empty domain-edge ranges."""
+    build_host_binaries()
+    geom, Q, R = geometry("cylinder"), 19, 2
+    doms = build_domains(geom, Q, G.slab_decomposition(geom, R, axis=2), R)
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    steps, dt = 2, physical_dt(0.8)
+    for r, dom in enumerate(doms):
+        assert dom.totalSharedFs > 0 and sum(dom.edge) > 0
+        f0 = np.zeros(dom.N * Q + 1 + dom.totalSharedFs)
+        f0[:dom.N * Q] = anisotropic_f(dom.N, Q, 0)[:dom.N * Q]
+        case = tmp_path / ("case%d.bin" % r)
+        write_case(case, dom, "LBGK", "BFL", "NASH", "NASH", inlets, outlets, f0, steps, 0, dt, rank=r, nranks=R)
+        env = dict(os.environ, HLB_MOCK_LOG=str(tmp_path / ("calls%d.log" % r)), HLB_HOST_ID_FILE=str(tmp_path / "nccl_id"))
+        p = subprocess.run([os.path.join(BUILD, "host_lbm_run_mock"), str(case), str(tmp_path / "out.bin")], env=env,
+                           capture_output=True, text=True, timeout=120)
+        assert p.returncode == 0, p.stderr
+        log = open(tmp_path / ("calls%d.log" % r)).read().splitlines()
+        kv = dict(x.split("=") for x in log[0].split()[1:])
+        assert (int(kv["rank"]), int(kv["nranks"]), int(kv["shared"]), int(kv["neighbours"])) == \
+            (r, R, int(dom.totalSharedFs), dom.procs.shape[0])
+        assert [int(x) for x in kv["edge"].split(",")] == [int(x) for x in dom.edge]
+        build = log[:log.index("finalise") + 1]
+        assert "set_neighbours " + " ".join("%d:%d:%d" % tuple(int(v) for v in row) for row in dom.procs) in build
+        ws = int(((np.arange(dom.totalSharedFs, dtype=np.int64) + 1) * np.asarray(dom.streamingIndices, np.int64)).sum())
+        assert "set_streaming_indices weighted_sum=%d" % ws in build
+        # boundary-typed tables for both halves of the site order
+        mid_total, n_bulk, e_bulk = int(sum(dom.mid)), int(dom.mid[0]), int(dom.edge[0])
+        assert "set_wall_distances %d %d" % (n_bulk, mid_total - n_bulk) in build
+        assert "set_wall_distances %d %d" % (mid_total + e_bulk, dom.N - mid_total - e_bulk) in build
+        # the NCCL communicator comes up right after the tables, before the distributions go up
+        after = log[log.index("finalise") + 1:]
+        assert after[0] == "comm_init" and after[1].startswith("set_f 0 ")
+        got = [ln for ln in after[3:] if not ln.startswith("set_f ")]
+        want_calls = expected_calls(dom, steps, 1, 1, 0)
+        assert got[-3:] == ["get_f 0", "get_f 1", "destroy"]
+        got = got[:-3]
+        assert len(got) == len(want_calls)
+        for g_, w_ in zip(got, want_calls):
+            assert g_ == w_ if not isinstance(w_, tuple) else g_.startswith("set_step_scalars t=%d mask=0" % w_[1])
+    assert os.path.getsize(tmp_path / "nccl_id") == 128
+
+
+@pytest.mark.gpu
+def test_cxx_host_two_ranks_over_nccl(tmp_path):
+    """Two harness processes, one per GPU (rank r -> device r), the NCCL id broadcast through the
+    stand-in communicator; each rank's distributions against the oracle's emulated 2-rank run.
+    Needs 2 GPUs (gpurun --gpus 2); skipped otherwise."""
+    from tests.test_gpu_multi import _gpu_count
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = os.path.join(BUILD, "host_lbm_run")
+    if not os.path.exists(exe):
+        if not os.path.isdir("/root/reference/Code"):
+            pytest.skip("tests/_build/host_lbm_run was not prebuilt (needs the reference headers)")
+        build_host_binaries()
+    import sysconfig
+    import oracle as O
+    geom, Q, R = geometry("cylinder"), 19, 2
+    ros = G.slab_decomposition(geom, R, axis=2)
+    doms = build_domains(geom, Q, ros, R)
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    steps, dt = 6, physical_dt(0.8)
+    tau = reference_tau(dt)
+    extra = ["/usr/local/cuda/lib64", os.path.join(sysconfig.get_paths()["purelib"], "nvidia", "cuda_runtime", "lib"),
+             os.path.join(sysconfig.get_paths()["purelib"], "nvidia", "nccl", "lib")]
+    env = dict(os.environ, LD_LIBRARY_PATH=":".join([os.environ.get("LD_LIBRARY_PATH", "")] + extra).strip(":"),
+               HLB_HOST_ID_FILE=str(tmp_path / "nccl_id"))
+    f0s, procs = [], []
+    for r, dom in enumerate(doms):
+        f0s.append(anisotropic_f(dom.N, Q, dom.totalSharedFs, site_offset=7 * r))
+        write_case(tmp_path / ("case%d.bin" % r), dom, "LBGK", "BFL", "NASH", "NASH", inlets, outlets, f0s[r], steps, 0, dt,
+                   rank=r, nranks=R)
+        procs.append(subprocess.Popen([exe, str(tmp_path / ("case%d.bin" % r)), str(tmp_path / ("out%d.bin" % r))], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for r, p in enumerate(procs):
+        try:
+            out, _ = p.communicate(timeout=300)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out, _ = p.communicate()
+        assert p.returncode == 0, "rank %d failed:\n%s" % (r, out[-3000:])
+    sim = O.OracleSim(O.OracleDomains(geom, Q, ros, R), "LBGK", "BFL", "NASH", "NASH", tau=tau, inlets=inlets,
+                      outlets=outlets)
+    for r in range(R):
+        sim.set_f(f0s[r], r)
+    sim.step(steps)
+    for r, dom in enumerate(doms):
+        got = np.fromfile(tmp_path / ("out%d.bin" % r), np.float64)
+        assert got.size == dom.N * Q
+        assert np.abs(got - sim.get_f(r)[:dom.N * Q]).max() <= 1e-13
