@@ -66,6 +66,7 @@ struct Nccl {
   int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool Load() {
     if (lib) return true;
@@ -83,12 +84,14 @@ struct Nccl {
     SYM(Recv, "ncclRecv");
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
+    SYM(AllReduce, "ncclAllReduce");
     SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
     return GetUniqueId && CommInitRank && Send && Recv && GroupStart && GroupEnd;
   }
 } g_nccl;
 const int kNcclDouble = 8;  // ncclFloat64
+const int kNcclMin = 3;     // ncclRedOp_t: ncclSum 0, ncclProd 1, ncclMax 2, ncclMin 3
 
 // ---------------------------------------------------------------- host-side iolet providers
 // InOutLetCosine::GetDensity, Code/lb/iolets/InOutLetCosine.cc:26-43
@@ -1845,6 +1848,34 @@ int hlb_gpu_monitor(hlb_gpu_t h, double* out4) {
   CU(cudaMemcpyAsync(out4, h->monitorDev + 4, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->compute));
   if (join_aux(h)) return 1;
   CU(cudaStreamSynchronize(h->compute));
+  return 0;
+}
+
+int hlb_gpu_monitor_global(hlb_gpu_t h, double* out4) {
+  // StabilityTester / IncompressibilityChecker pass their values up and down a PhasedBroadcast tree
+  // (Code/net/PhasedBroadcastRegular.h); here the four extrema of every rank meet in one
+  // ncclAllReduce: min over {min f, min density, -max density, -max |u|}
+  if (!h || !out4) return fail("null argument");
+  double v[4];
+  if (hlb_gpu_monitor(h, v)) return 1;  // this rank's values; the compute stream is drained on return
+  if (h->cfg.nranks > 1) {
+    if (!h->comm_nccl)
+      return fail("hlb_gpu_monitor_global needs hlb_gpu_comm_init (host-staged runs reduce hlb_gpu_monitor's values "
+                  "over their own communicator)");
+    if (!g_nccl.AllReduce) return fail("ncclAllReduce not found in libnccl");
+    v[2] = -v[2];
+    v[3] = -v[3];
+    // on the halo stream, behind whatever exchange was posted there: every NCCL call of this
+    // communicator is issued on one stream, in the same order on every rank
+    CU(cudaMemcpyAsync(h->monitorDev, v, sizeof(v), cudaMemcpyHostToDevice, h->comm));
+    const int rc = g_nccl.AllReduce(h->monitorDev, h->monitorDev, 4, kNcclDouble, kNcclMin, h->comm_nccl, h->comm);
+    if (rc) return fail(std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc));
+    CU(cudaMemcpyAsync(v, h->monitorDev, sizeof(v), cudaMemcpyDeviceToHost, h->comm));
+    CU(cudaStreamSynchronize(h->comm));
+    v[2] = -v[2];
+    v[3] = -v[3];
+  }
+  for (int k = 0; k < 4; ++k) out4[k] = v[k];
   return 0;
 }
 

@@ -365,6 +365,12 @@ class GpuLBM:
         check(self.L.hlb_gpu_monitor(self.h, ptr(out, C.c_double)))
         return dict(min_f=out[0], min_density=out[1], max_density=out[2], max_speed=out[3])
 
+    def monitor_global(self):
+        """The same extrema over all ranks (one ncclAllReduce; collective)."""
+        out = np.zeros(4)
+        check(self.L.hlb_gpu_monitor_global(self.h, ptr(out, C.c_double)))
+        return dict(min_f=out[0], min_density=out[1], max_density=out[2], max_speed=out[3])
+
     def launch_count(self) -> int:
         n = C.c_int64()
         check(self.L.hlb_gpu_launch_count(self.h, C.byref(n)))

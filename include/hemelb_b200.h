@@ -169,6 +169,12 @@ int hlb_gpu_time_steps_detail(hlb_gpu_t h, int nsteps, float* total_ms, float* b
  * values were gathered by the collide kernels from the distributions ENTERING the last step(s)
  * since the previous call (no extra pass); otherwise one pass over the current f_old. */
 int hlb_gpu_monitor(hlb_gpu_t h, double* out4);
+/* the same four values over ALL ranks: one ncclAllReduce on the handle's communicator
+ * (hlb_gpu_comm_init) in place of the PhasedBroadcast trees of lb::StabilityTester
+ * (Code/lb/StabilityTester.h:51-150) and lb::IncompressibilityChecker
+ * (Code/lb/IncompressibilityChecker.hpp); collective -- every rank calls it at the same point of the
+ * step sequence.  One rank: same as hlb_gpu_monitor. */
+int hlb_gpu_monitor_global(hlb_gpu_t h, double* out4);
 /* number of kernels launched by this handle so far */
 int hlb_gpu_launch_count(hlb_gpu_t h, int64_t* n);
 /* the device-resident tables, converted back to reference form (for parity tests) */

@@ -50,6 +50,15 @@ for (kernel, wall, inlet, outlet) in (("LBGK", "BFL", "NASH", "NASH"), ("MRT", "
     err = float(np.abs(mine - want).max())
     assert err <= 1e-13, (kernel, wall, err)
     assert np.array_equal(mine, want), (kernel, wall, "not bit-identical", err)
+    # the monitors over all ranks (ncclAllReduce) against the per-rank ones combined on the host
+    local = gpu.monitor()
+    every = [None] * world
+    dist.all_gather_object(every, local)
+    glob = gpu.monitor_global()
+    assert glob["min_f"] == min(m["min_f"] for m in every)
+    assert glob["min_density"] == min(m["min_density"] for m in every)
+    assert glob["max_density"] == max(m["max_density"] for m in every)
+    assert glob["max_speed"] == max(m["max_speed"] for m in every)
     gpu.close()
     dist.barrier()
 print("rank", rank, "ok")

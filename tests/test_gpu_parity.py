@@ -282,6 +282,7 @@ def test_monitor_matches_numpy():
     f0 = anisotropic_f(dom.N, Q, 0)
     gpu.set_f(f0)
     m = gpu.monitor()
+    assert gpu.monitor_global() == m  # one rank: nothing to reduce
     f = f0[:dom.N * Q].reshape(dom.N, Q)
     rho = f.sum(1)
     assert m["min_f"] == f.min()
