@@ -258,7 +258,7 @@ int hlb_gpu_create_from_domain(hlb_dom_t d, const hlb_gpu_config* policy, hlb_gp
  * Replaces, for one rank, the per-site loops of extraction::LocalPropertyOutput::Write
  * (Code/extraction/LocalPropertyOutput.cc:262-367) over extraction::LbDataSourceIterator
  * (Code/extraction/LbDataSourceIterator.cc:36-87: property cache -> physical units through
- * util::UnitConverter) and the geometry selectors (Code/extraction/*GeometrySelector.cc), and the
+ * util::UnitConverter) and the geometry selectors (Code/extraction/{Whole,Plane,StraightLine,...}GeometrySelector.cc), and the
  * record decoding of extraction::LocalDistributionInput::LoadDistribution
  * (Code/extraction/LocalDistributionInput.cc:107-165).  The bytes are the reference's file format
  * (doc/dev/file-formats/extraction.md, version 5, XDR big-endian) exactly.  File offsets across

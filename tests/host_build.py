@@ -16,6 +16,9 @@ REF = "/root/reference/Code"
 REF_SRCS = ["lb/MacroscopicPropertyCache.cc", "lb/SimulationState.cc", "geometry/SiteDataBare.cc", "util/Matrix3D.cc",
             "util/Vector3D.cc", "lb/kernels/DHumieresD3Q19MRTBasis.cc", "lb/iolets/InOutLet.cc",
             "lb/iolets/InOutLetCosine.cc", "lb/iolets/InOutLetVelocity.cc", "lb/iolets/InOutLetParabolicVelocity.cc"]
+XTR_REF_SRCS = ["util/Vector3D.cc", "extraction/GeometrySelector.cc", "extraction/WholeGeometrySelector.cc",
+                "extraction/GeometrySurfaceSelector.cc", "extraction/PlaneGeometrySelector.cc",
+                "extraction/StraightLineGeometrySelector.cc", "extraction/SurfacePointSelector.cc"]
 
 
 def _stale(target, sources):
@@ -59,6 +62,11 @@ def build_host_binaries(verbose=False):
         # rpath relative to the binary: the snapshot is unpacked at another path on the GPU box
         subprocess.run(["g++", obj, refobj, "-L" + os.path.dirname(lib), "-lhemelb_b200",
                         "-Wl,-rpath,$ORIGIN/../../hemelb_b200", "-Wl,--allow-shlib-undefined", "-o", real], check=True)
+    # the extraction face (extraction/GpuPropertyEncoder.h) against the recording ABI
+    xtr = os.path.join(BUILD, "host_xtr_run_mock")
+    xtr_src = os.path.join(ROOT, "tests", "host_xtr_run.cc")
+    if _stale(xtr, [xtr_src, mock_src, os.path.join(host, "extraction", "GpuPropertyEncoder.h"), deps[1], os.path.abspath(__file__)]):
+        subprocess.run(common + [xtr_src, mock_src] + [os.path.join(REF, s) for s in XTR_REF_SRCS] + ["-o", xtr], check=True)
     if verbose:
         print("host binaries in", BUILD)
     return True

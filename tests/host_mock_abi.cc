@@ -85,3 +85,35 @@ int hlb_gpu_get_cache(hlb_gpu_t h, uint32_t which, double* o) {
   return 0;
 }
 }
+
+// ---- extraction entry points used by extraction/GpuPropertyEncoder.h
+struct hlb_xtr_handle { int n_fields; };
+extern "C" {
+int hlb_xtr_create(hlb_gpu_t, const hlb_xtr_spec* s, const int64_t* c, hlb_xtr_t* x) {
+  fprintf(out(), "xtr_create selector=%d params=%.9g,%.9g,%.9g,%.9g,%.9g,%.9g,%.9g units=%.17g,%.17g,%.17g,%.17g,%.17g,%.17g,%.17g coords0=%lld,%lld,%lld",
+          s->selector, s->selector_params[0], s->selector_params[1], s->selector_params[2], s->selector_params[3],
+          s->selector_params[4], s->selector_params[5], s->selector_params[6], s->time_step, s->voxel_size, s->origin[0],
+          s->origin[1], s->origin[2], s->fluid_density, s->reference_pressure, ll(c[0]), ll(c[1]), ll(c[2]));
+  for (int i = 0; i < s->n_fields; ++i) {
+    const hlb_xtr_field& f = s->fields[i];
+    fprintf(out(), " field=%s:%d:%d:%u", f.name, f.source, f.typecode, f.n_offsets);
+    for (uint32_t k = 0; k < f.n_offsets; ++k) fprintf(out(), ":%.17g", f.offsets[k]);
+  }
+  fprintf(out(), "\n");
+  *x = new hlb_xtr_handle{s->n_fields};
+  return 0;
+}
+int hlb_xtr_destroy(hlb_xtr_t x) { fprintf(out(), "xtr_destroy\n"); fflush(out()); delete x; return 0; }
+int hlb_xtr_sizes(hlb_xtr_t x, uint64_t* n, uint64_t* len, uint64_t* head) { *n = 3; *len = 8 * x->n_fields; *head = 60 + 4 * x->n_fields; return 0; }
+int hlb_xtr_required_caches(hlb_xtr_t x, uint32_t* m) { *m = 100 + x->n_fields; return 0; }
+int hlb_xtr_header(hlb_xtr_t x, uint64_t global, void* buf, uint64_t cap) {
+  fprintf(out(), "xtr_header global=%llu capacity=%llu\n", (unsigned long long)global, (unsigned long long)cap);
+  memset(buf, 'H', cap);
+  return 0;
+}
+int hlb_xtr_encode(hlb_xtr_t, uint64_t first, uint64_t n, void* buf, uint64_t cap) {
+  fprintf(out(), "xtr_encode first=%llu n=%llu capacity=%llu\n", (unsigned long long)first, (unsigned long long)n, (unsigned long long)cap);
+  memset(buf, 'R', cap);
+  return 0;
+}
+}

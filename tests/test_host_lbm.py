@@ -315,3 +315,49 @@ def test_cxx_host_two_ranks_over_nccl(tmp_path):
         got = np.fromfile(tmp_path / ("out%d.bin" % r), np.float64)
         assert got.size == dom.N * Q
         assert np.abs(got - sim.get_f(r)[:dom.N * Q]).max() <= 1e-13
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Code") and not os.path.exists(os.path.join(BUILD, "host_xtr_run_mock")),
+                    reason="reference checkout absent and no prebuilt tests/_build")
+def test_cxx_property_encoder_translates_the_reference_spec(tmp_path):
+    """extraction/GpuPropertyEncoder.h: the reference's PropertyOutputFile objects (one per selector
+    class, every source type among the fields) as they reach hlb_xtr_create, and the sizes / header /
+    record calls LocalPropertyOutput's members map to."""
+    build_host_binaries()
+    env = dict(os.environ, HLB_MOCK_LOG=str(tmp_path / "xtr.log"))
+    r = subprocess.run([os.path.join(BUILD, "host_xtr_run_mock")], env=env, capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    log = open(tmp_path / "xtr.log").read().splitlines()
+    creates = [ln for ln in log if ln.startswith("xtr_create")]
+    assert len(creates) == 6
+
+    def parse(ln):
+        parts = ln.split()
+        kv = dict(p.split("=", 1) for p in parts[1:] if not p.startswith("field="))
+        return int(kv["selector"]), [float(x) for x in kv["params"].split(",")], kv["units"], kv["coords0"], \
+            [p[6:] for p in parts if p.startswith("field=")]
+
+    f32 = lambda x: float(np.float32(x))
+    # HLB_XTR_* selectors: whole 0, surface 1, line 3, surface point 4, plane with the constructor-normalised normal 5
+    sel, par, units, c0, fields = parse(creates[0])
+    assert (sel, c0) == (0, "3,4,5")
+    assert units == "0.0001,0.00020000000000000001,0.10000000000000001,0.20000000000000001,0.29999999999999999,1000,80"
+    # name : source (OutputField.h:33-44 order) : type code : offsets
+    assert fields == ["pressure:0:0:1:80", "velocity:1:0:0", "distributions:8:1:0"]
+    sel, par, _, _, fields = parse(creates[1])
+    assert sel == 1 and fields == ["shearstress:2:0:0", "traction:6:1:0"]
+    sel, par, _, _, fields = parse(creates[2])
+    assert sel == 5 and fields == ["velocity:1:1:0", "stresstensor:5:0:0", "rank:9:2:0"]
+    assert np.allclose(par, [f32(0.001), f32(0.002), f32(0.003), 0, 0, 1, f32(0.004)], rtol=1e-8, atol=0)
+    sel, par, _, _, fields = parse(creates[3])  # infinite plane: radius 0, normal (3,0,4)/5 in float
+    assert sel == 5 and np.allclose(par, [0.5, 0, 0, f32(0.6), 0, f32(0.8), 0], rtol=1e-7, atol=0)
+    sel, par, _, _, fields = parse(creates[4])
+    assert sel == 3 and np.allclose(par, [0, 0, 0, 0, 0, f32(0.01), 0], rtol=1e-8, atol=0)
+    assert fields == ["vonmisesstress:3:0:0", "shearrate:4:0:0"]
+    sel, par, _, _, fields = parse(creates[5])
+    assert sel == 4 and np.allclose(par[:3], [f32(0.01), f32(0.02), f32(0.03)], rtol=1e-8, atol=0)
+    assert fields == ["tangentialprojectiontraction:7:0:0"]
+    # per encoder: header of HeaderLength bytes for the global count, records of count x site length
+    assert log[1:4] == ["xtr_header global=1234 capacity=72", "xtr_encode first=0 n=3 capacity=72", "xtr_destroy"]
+    out = r.stdout.splitlines()
+    assert out[0] == "sites=3 site_len=24 header_len=72 header0=H records0=R caches=103"
