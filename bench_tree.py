@@ -48,6 +48,9 @@ def main():
     ap.add_argument("--decomposition", default="basic", choices=["basic", "weighted"],
                     help="basic: the reference's BasicDecomposition over Morton blocks; weighted: the METIS-free "
                          "weighted k-way block partition (hemelb_b200/partition.py)")
+    ap.add_argument("--partition-start", default="morton", choices=["morton", "rcb", "best"],
+                    help="weighted only: start from the bisection of the Morton-ordered blocks (as measured in "
+                         "profiles/), from recursive coordinate bisection, or from the better of the two")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -93,7 +96,8 @@ def main():
     if world > 1:
         if weighted:
             from hemelb_b200.devdomain import weighted_decomposition_of_counts
-            rob = weighted_decomposition_of_counts(counts, boundary_counts, world, args.wall)
+            rob = weighted_decomposition_of_counts(counts, boundary_counts, world, args.wall,
+                                                   initial=args.partition_start)
         else:
             rob = basic_decomposition_of_counts(counts, world)
         dom.set_partition(("blocks", rob))
@@ -162,7 +166,8 @@ def main():
                       % (args.generations, r0, l0, Q, args.kernel, args.wall, args.inlet, args.outlet),
             "n_gpus": world, "sites": sum(per_rank), "sites_counted": n_global, "sites_per_rank": per_rank,
             "halo_doubles_per_rank": halo, "neighbours_per_rank": nbrs,
-            "decomposition": ("weighted k-way over blocks (hemelb_b200/partition.py)" if args.decomposition == "weighted"
+            "decomposition": ("weighted k-way over blocks, %s start (hemelb_b200/partition.py)" % args.partition_start
+                              if args.decomposition == "weighted"
                               else "BasicDecomposition over Morton-ordered blocks") if world > 1 else "single rank",
             "MLUPS": mlups, "ms_per_step": ms / args.steps, "bytes_per_site": B,
             "whole_step_frac_of_hbm_roofline": mlups * 1e6 * B / 1e9 / peak / world,

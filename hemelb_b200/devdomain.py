@@ -264,15 +264,16 @@ def tree_shape(generations: int, root_radius: float, root_length: float, seed: i
 
 
 def weighted_decomposition_of_counts(counts: np.ndarray, boundary: np.ndarray, nranks: int, wall="BFL",
-                                     architecture="B200", tolerance=0.03) -> np.ndarray:
+                                     architecture="B200", tolerance=0.03, initial="morton") -> np.ndarray:
     """``partition.weighted_kway`` on dense (bx,by,bz) arrays of fluid / boundary-typed sites per block:
-    rank of every block in .gmy block order (-1 for empty blocks), for ``hlb_dom_set_partition_blocks``."""
+    rank of every block in .gmy block order (-1 for empty blocks), for ``hlb_dom_set_partition_blocks``.
+    ``initial``: "morton" | "rcb" | "best" (``partition.weighted_kway``)."""
     from .partition import REFERENCE_WEIGHTS, weighted_kway
     w = REFERENCE_WEIGHTS[architecture]
     ijk = np.argwhere(counts > 0)
     c, b = counts[counts > 0].astype(np.float64), boundary[counts > 0].astype(np.float64)
     loads = w["bulk"] * (c - b) + w[wall] * b
-    part = weighted_kway(ijk, loads, nranks, tolerance)
+    part = weighted_kway(ijk, loads, nranks, tolerance, initial=initial)
     out = np.full(counts.shape, -1, np.int32)
     out[counts > 0] = part
     return out.ravel()

@@ -21,6 +21,12 @@ reference's own BasicDecomposition and the device Domain builder partition by):
 
 Plain numpy; a few million blocks (a 1e9-site tree has ~3e6 non-empty 8^3 blocks) take seconds.
 
+   Alternative start for 2 (``initial="rcb"``, or ``"best"`` = try both and keep the smaller cut):
+   recursive *coordinate* bisection -- split the longest extent at the weighted median -- which
+   cuts vessels across instead of along the Morton curve: on a 4.5e5-site tree, 4 / 8 ranks, 35 % /
+   30 % fewer cut links after the site stage than from the Morton start, and 3 / 11 neighbour pairs
+   instead of 5 / 15.
+
 4. site-granular stage (``site_graph`` / ``refine_sites`` / ``partition_sites``): the graph the
    reference hands to ParMETIS -- one vertex per fluid site, one edge per lattice direction that
    leads to another fluid site (``OptimisedDecomposition::PopulateAdjacencyData``,
@@ -91,6 +97,32 @@ def weighted_bisection(ijk: np.ndarray, loads: np.ndarray, nranks: int) -> np.nd
     return basic_decomposition_blocks(np.asarray(ijk, np.int64), np.maximum(1, np.round(loads * scale)).astype(np.int64), nranks)
 
 
+def coordinate_bisection(points: np.ndarray, weights: np.ndarray, nranks: int) -> np.ndarray:
+    """Recursive coordinate bisection: the point set is split across its longest extent at the
+    weighted median (ties broken by the other two coordinates, so the split is exact), parts
+    floor(n/2) : n - floor(n/2) as BasicDecomposition divides its ranks.  Deterministic."""
+    points = np.asarray(points, np.int64)
+    weights = np.asarray(weights, np.float64)
+    part = np.zeros(points.shape[0], np.int32)
+    todo = [(np.arange(points.shape[0]), nranks, 0)]
+    while todo:
+        idx, n, first = todo.pop()
+        if n == 1 or idx.size == 0:
+            part[idx] = first
+            continue
+        c = points[idx]
+        ext = c.max(0) - c.min(0)
+        ax = int(np.argmax(ext))
+        o = np.lexsort((c[:, (ax + 2) % 3], c[:, (ax + 1) % 3], c[:, ax]))
+        cum = np.cumsum(weights[idx][o])
+        lo = n // 2
+        k = int(np.searchsorted(cum, cum[-1] * lo / n))
+        k = min(max(k + 1, lo), idx.size - (n - lo))  # every part keeps at least one point per rank
+        todo.append((idx[o[:k]], lo, first))
+        todo.append((idx[o[k:]], n - lo, first + lo))
+    return part
+
+
 def edge_cut(pairs: np.ndarray, edge_w: np.ndarray, part: np.ndarray) -> float:
     return float(edge_w[part[pairs[:, 0]] != part[pairs[:, 1]]].sum())
 
@@ -148,16 +180,29 @@ def refine(ijk, loads, part, nranks, tolerance=0.03, passes=8):
     return part
 
 
-def weighted_kway(ijk, loads, nranks, tolerance=0.03, refine_passes=8):
-    """Block -> rank.  ``ijk``: (n, 3) coordinates of the non-empty blocks; ``loads``: their vertex weights."""
+def weighted_kway(ijk, loads, nranks, tolerance=0.03, refine_passes=8, initial="morton"):
+    """Block -> rank.  ``ijk``: (n, 3) coordinates of the non-empty blocks; ``loads``: their vertex weights.
+    ``initial``: "morton" (the reference's bisection of the Morton-ordered blocks), "rcb" (coordinate
+    bisection) or "best" (both, refined; the one with the smaller cut among those within tolerance)."""
     ijk = np.asarray(ijk, np.int64)
     loads = np.asarray(loads, np.float64)
     if ijk.shape[0] < nranks:
         raise ValueError("More ranks than blocks")
-    part = weighted_bisection(ijk, loads, nranks)
-    if refine_passes > 0 and nranks > 1:
-        part = refine(ijk, loads, part, nranks, tolerance, refine_passes)
-    return part.astype(np.int32)
+    if initial not in ("morton", "rcb", "best"):
+        raise ValueError("initial must be morton, rcb or best")
+    found = []
+    for start in (("morton", "rcb") if initial == "best" else (initial,)):
+        part = weighted_bisection(ijk, loads, nranks) if start == "morton" else coordinate_bisection(ijk, loads, nranks)
+        if refine_passes > 0 and nranks > 1:
+            part = refine(ijk, loads, part, nranks, tolerance, refine_passes)
+        found.append(part.astype(np.int32))
+    if len(found) == 1:
+        return found[0]
+    q = [quality(ijk, loads, p, nranks) for p in found]
+    slack = loads.max() / (loads.sum() / nranks)
+    ok = [x["parts"] == nranks and x["imbalance"] <= 1.0 + tolerance + slack for x in q]
+    order = sorted(range(len(found)), key=lambda i: (not ok[i], q[i]["edge_cut"] if ok[i] else q[i]["imbalance"], i))
+    return found[order[0]]
 
 
 def quality(ijk, loads, part, nranks):
@@ -168,7 +213,7 @@ def quality(ijk, loads, part, nranks):
 
 
 def partition_geometry(geom, site_type, wall="BFL", inlet="NASH", outlet="NASH", nranks=2, architecture="B200",
-                       tolerance=0.03):
+                       tolerance=0.03, initial="morton"):
     """Site -> rank for a host ``Geometry`` (whole blocks), with the quality figures of the weighted
     k-way partition and of the reference's BasicDecomposition on the same weights."""
     B = geom.block_size
@@ -179,7 +224,7 @@ def partition_geometry(geom, site_type, wall="BFL", inlet="NASH", outlet="NASH",
     ijk = np.stack([uniq // (bd[1] * bd[2]), (uniq // bd[2]) % bd[1], uniq % bd[2]], 1)
     loads = block_loads(inv, np.asarray(site_type), site_weights(wall, inlet, outlet, architecture), uniq.size)
     counts = np.bincount(inv, minlength=uniq.size)
-    part = weighted_kway(ijk, loads, nranks, tolerance)
+    part = weighted_kway(ijk, loads, nranks, tolerance, initial=initial)
     basic = basic_decomposition_blocks(ijk, counts, nranks)
     return part[inv].astype(np.int32), dict(weighted=quality(ijk, loads, part, nranks),
                                             basic=quality(ijk, loads, basic, nranks))
@@ -362,13 +407,25 @@ def site_quality(xadj, adjncy, vwgt, part, nranks):
 
 
 def partition_sites(geom, site_type, Q=19, wall="BFL", inlet="NASH", outlet="NASH", nranks=2, architecture="B200",
-                    ubvec=1.001, block_tolerance=0.03, passes=40):
+                    ubvec=1.001, block_tolerance=0.03, passes=40, initial="best"):
     """Site -> rank through all four steps: weighted block k-way, then site-granular refinement over
-    the reference's ParMETIS graph.  Returns the rank array and the quality of both stages on the
-    site graph (imbalance of the weighted load, number of cut lattice links)."""
+    the reference's ParMETIS graph.  ``initial``: "morton" (start from the block stage as the
+    reference starts ParMETIS from BasicDecomposition), "rcb" (coordinate bisection of the sites) or
+    "best" (both; the smaller cut among the results within the balance bound).  Returns the rank
+    array and the quality on the site graph (imbalance of the weighted load, number of cut lattice
+    links) of the block stage and of the result."""
+    if initial not in ("morton", "rcb", "best"):
+        raise ValueError("initial must be morton, rcb or best")
     blocks, _ = partition_geometry(geom, site_type, wall, inlet, outlet, nranks, architecture, block_tolerance)
     xadj, adjncy = site_graph(geom, Q)
     vwgt = site_weights(wall, inlet, outlet, architecture)[np.asarray(site_type)]
-    sites = refine_sites(xadj, adjncy, vwgt, blocks, nranks, ubvec, passes)
-    return sites, dict(blocks=site_quality(xadj, adjncy, vwgt, blocks, nranks),
-                       sites=site_quality(xadj, adjncy, vwgt, sites, nranks))
+    bound = max(ubvec, 1.0 + vwgt.max() / (vwgt.sum() / nranks)) + 1e-12
+    found = []
+    for start in (("morton", "rcb") if initial == "best" else (initial,)):
+        first = blocks if start == "morton" else coordinate_bisection(geom.coords, vwgt, nranks)
+        sites = refine_sites(xadj, adjncy, vwgt, first, nranks, ubvec, passes)
+        found.append((start, sites, site_quality(xadj, adjncy, vwgt, sites, nranks)))
+    found.sort(key=lambda f: (not (f[2]["parts"] == nranks and f[2]["imbalance"] <= bound),
+                              f[2]["edge_cut"], f[0]))
+    start, sites, q = found[0]
+    return sites, dict(blocks=site_quality(xadj, adjncy, vwgt, blocks, nranks), sites=q, initial=start)

@@ -181,3 +181,56 @@ def test_partition_is_a_valid_domain_input(stage):
     want = np.zeros_like(f_input)
     want[np.asarray(t1["inputIndex"])] = one.get_f(0)[:t1["N"] * Q].reshape(-1, Q)
     assert np.array_equal(got, want)
+
+
+def test_coordinate_bisection():
+    """Exact weighted-median splits across the longest extent; floor(n/2) : n - floor(n/2) ranks."""
+    rng = np.random.default_rng(20261017)
+    pts = rng.integers(0, 50, size=(4000, 3)) * np.array([4, 1, 1])  # longest along x
+    w = rng.integers(1, 5, size=4000).astype(np.float64)
+    for n in (1, 2, 3, 5, 8):
+        part = P.coordinate_bisection(pts, w, n)
+        assert part.min() == 0 and part.max() == n - 1
+        loads = np.bincount(part, weights=w, minlength=n)
+        assert loads.max() / loads.mean() <= 1 + n * w.max() / w.sum() * n + 1e-12
+        assert np.array_equal(part, P.coordinate_bisection(pts, w, n))
+    two = P.coordinate_bisection(pts, w, 2)
+    assert pts[two == 0, 0].max() <= pts[two == 1, 0].min()  # one cut across x
+    # more ranks than distinct coordinates still leaves no rank empty
+    line = np.stack([np.arange(6), np.zeros(6, int), np.zeros(6, int)], 1)
+    assert np.array_equal(np.sort(P.coordinate_bisection(line, np.array([100., 1, 1, 1, 1, 1]), 6)), np.arange(6))
+
+
+@pytest.mark.parametrize("geom_name,nranks", [("tree", 4), ("cylinder_long", 4), ("sac", 3)])
+def test_best_start_is_never_worse_and_valid(geom_name, nranks):
+    """"best" keeps the smaller cut of the two starts (block stage and site stage), and the tables
+    built for its partitions are the oracle's (any site -> rank map is a valid Domain input)."""
+    from tests.test_domain_tables import _same_tables
+    geom = geometry(geom_name)
+    types = collision_types(geom)
+    res = {ini: P.partition_sites(geom, types, 19, nranks=nranks, initial=ini) for ini in ("morton", "rcb", "best")}
+    vw = P.site_weights("BFL", "NASH", "NASH")[types]
+    bound = max(1.001, 1 + vw.max() / (vw.sum() / nranks)) + 1e-12
+    ok = [k for k in ("morton", "rcb") if res[k][1]["sites"]["imbalance"] <= bound]
+    assert res["best"][1]["sites"]["edge_cut"] == min(res[k][1]["sites"]["edge_cut"] for k in ok)
+    assert res["best"][1]["initial"] in ok
+    _same_tables(geom, 19, res["best"][0], nranks)
+    blocks_best, qb = P.partition_geometry(geom, types, nranks=nranks, initial="best", tolerance=0.05)
+    for ini in ("morton", "rcb"):
+        _, q = P.partition_geometry(geom, types, nranks=nranks, initial=ini, tolerance=0.05)
+        slack = 0.05 + (vw.max() * geom.block_size ** 3) / (vw.sum() / nranks)
+        if q["weighted"]["imbalance"] <= 1 + slack:
+            assert qb["weighted"]["edge_cut"] <= q["weighted"]["edge_cut"] + 1e-9
+    _same_tables(geom, 19, blocks_best, nranks)
+
+
+def test_coordinate_start_cuts_tubes_across():
+    """On the long cylinder the coordinate start gives z-slabs: two neighbours at most, and far fewer
+    cut links than the Morton start."""
+    geom = geometry("cylinder_long")
+    types = collision_types(geom)
+    rank, q = P.partition_sites(geom, types, 19, nranks=4, initial="rcb")
+    _, qm = P.partition_sites(geom, types, 19, nranks=4, initial="morton")
+    assert q["sites"]["edge_cut"] < 0.6 * qm["sites"]["edge_cut"]
+    doms = build_domains(geom, 19, rank, 4)
+    assert max(d.procs.shape[0] for d in doms) <= 2
