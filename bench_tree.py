@@ -48,9 +48,9 @@ def main():
     ap.add_argument("--decomposition", default="basic", choices=["basic", "weighted"],
                     help="basic: the reference's BasicDecomposition over Morton blocks; weighted: the METIS-free "
                          "weighted k-way block partition (hemelb_b200/partition.py)")
-    ap.add_argument("--partition-start", default="morton", choices=["morton", "rcb", "best"],
+    ap.add_argument("--partition-start", default="morton", choices=["morton", "rcb", "inertial", "best"],
                     help="weighted only: start from the bisection of the Morton-ordered blocks (as measured in "
-                         "profiles/), from recursive coordinate bisection, or from the better of the two")
+                         "profiles/), from recursive coordinate / inertial bisection, or from the best of the three")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

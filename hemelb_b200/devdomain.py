@@ -267,7 +267,7 @@ def weighted_decomposition_of_counts(counts: np.ndarray, boundary: np.ndarray, n
                                      architecture="B200", tolerance=0.03, initial="morton") -> np.ndarray:
     """``partition.weighted_kway`` on dense (bx,by,bz) arrays of fluid / boundary-typed sites per block:
     rank of every block in .gmy block order (-1 for empty blocks), for ``hlb_dom_set_partition_blocks``.
-    ``initial``: "morton" | "rcb" | "best" (``partition.weighted_kway``)."""
+    ``initial``: "morton" | "rcb" | "inertial" | "best" (``partition.weighted_kway``)."""
     from .partition import REFERENCE_WEIGHTS, weighted_kway
     w = REFERENCE_WEIGHTS[architecture]
     ijk = np.argwhere(counts > 0)

@@ -21,11 +21,12 @@ reference's own BasicDecomposition and the device Domain builder partition by):
 
 Plain numpy; a few million blocks (a 1e9-site tree has ~3e6 non-empty 8^3 blocks) take seconds.
 
-   Alternative start for 2 (``initial="rcb"``, or ``"best"`` = try both and keep the smaller cut):
-   recursive *coordinate* bisection -- split the longest extent at the weighted median -- which
-   cuts vessels across instead of along the Morton curve: on a 4.5e5-site tree, 4 / 8 ranks, 35 % /
-   30 % fewer cut links after the site stage than from the Morton start, and 3 / 11 neighbour pairs
-   instead of 5 / 15.
+   Alternative starts for 2 (``initial="rcb"`` / ``"inertial"``, or ``"best"`` = try all and keep
+   the smallest cut): recursive *geometric* bisection -- split at the weighted median across the
+   longest coordinate extent, or along the principal axis of the weighted covariance -- which cuts
+   vessels across instead of along the Morton curve: on a 4.5e5-site tree, 4 / 8 ranks, the site
+   stage ends with 35 / 30 % (rcb) and 61 / 49 % (inertial) fewer cut links than from the Morton
+   start.
 
 4. site-granular stage (``site_graph`` / ``refine_sites`` / ``partition_sites``): the graph the
    reference hands to ParMETIS -- one vertex per fluid site, one edge per lattice direction that
@@ -57,6 +58,9 @@ REFERENCE_WEIGHTS = {
     # update of the mid-fluid kernel = 1 unit of 4; wall sites incl. their PostStep / per-link kernel
     "B200": dict(bulk=4, SBB=8, BFL=14, GZS=60, NASH=20, LADD=24),
 }
+
+
+STARTS = ("morton", "rcb", "inertial")
 
 
 def site_weights(wall: str, inlet: str, outlet: str, architecture: str = "B200") -> np.ndarray:
@@ -97,10 +101,12 @@ def weighted_bisection(ijk: np.ndarray, loads: np.ndarray, nranks: int) -> np.nd
     return basic_decomposition_blocks(np.asarray(ijk, np.int64), np.maximum(1, np.round(loads * scale)).astype(np.int64), nranks)
 
 
-def coordinate_bisection(points: np.ndarray, weights: np.ndarray, nranks: int) -> np.ndarray:
-    """Recursive coordinate bisection: the point set is split across its longest extent at the
-    weighted median (ties broken by the other two coordinates, so the split is exact), parts
-    floor(n/2) : n - floor(n/2) as BasicDecomposition divides its ranks.  Deterministic."""
+def coordinate_bisection(points: np.ndarray, weights: np.ndarray, nranks: int, inertial: bool = False) -> np.ndarray:
+    """Recursive geometric bisection: the point set is split at the weighted median across its longest
+    coordinate extent (ties broken by the other two coordinates, so the split is exact) or, with
+    ``inertial``, along the principal axis of its weighted covariance (the direction a vessel
+    runs in; ties broken by point index).  Parts floor(n/2) : n - floor(n/2), as BasicDecomposition
+    divides its ranks.  Deterministic."""
     points = np.asarray(points, np.int64)
     weights = np.asarray(weights, np.float64)
     part = np.zeros(points.shape[0], np.int32)
@@ -111,10 +117,17 @@ def coordinate_bisection(points: np.ndarray, weights: np.ndarray, nranks: int) -
             part[idx] = first
             continue
         c = points[idx]
-        ext = c.max(0) - c.min(0)
-        ax = int(np.argmax(ext))
-        o = np.lexsort((c[:, (ax + 2) % 3], c[:, (ax + 1) % 3], c[:, ax]))
-        cum = np.cumsum(weights[idx][o])
+        w = weights[idx]
+        if inertial:
+            d = c - (c * w[:, None]).sum(0) / w.sum()
+            _, vec = np.linalg.eigh((d * w[:, None]).T @ d)
+            axis = vec[:, -1]
+            axis = axis if axis[np.argmax(np.abs(axis))] > 0 else -axis  # eigenvectors carry no sign
+            o = np.argsort(d @ axis, kind="stable")
+        else:
+            ax = int(np.argmax(c.max(0) - c.min(0)))
+            o = np.lexsort((c[:, (ax + 2) % 3], c[:, (ax + 1) % 3], c[:, ax]))
+        cum = np.cumsum(w[o])
         lo = n // 2
         k = int(np.searchsorted(cum, cum[-1] * lo / n))
         k = min(max(k + 1, lo), idx.size - (n - lo))  # every part keeps at least one point per rank
@@ -183,16 +196,18 @@ def refine(ijk, loads, part, nranks, tolerance=0.03, passes=8):
 def weighted_kway(ijk, loads, nranks, tolerance=0.03, refine_passes=8, initial="morton"):
     """Block -> rank.  ``ijk``: (n, 3) coordinates of the non-empty blocks; ``loads``: their vertex weights.
     ``initial``: "morton" (the reference's bisection of the Morton-ordered blocks), "rcb" (coordinate
-    bisection) or "best" (both, refined; the one with the smaller cut among those within tolerance)."""
+    bisection), "inertial" (bisection along principal axes) or "best" (all three, refined; the one
+    with the smallest cut among those within tolerance)."""
     ijk = np.asarray(ijk, np.int64)
     loads = np.asarray(loads, np.float64)
     if ijk.shape[0] < nranks:
         raise ValueError("More ranks than blocks")
-    if initial not in ("morton", "rcb", "best"):
-        raise ValueError("initial must be morton, rcb or best")
+    if initial not in STARTS + ("best",):
+        raise ValueError("initial must be one of %s or best" % ", ".join(STARTS))
     found = []
-    for start in (("morton", "rcb") if initial == "best" else (initial,)):
-        part = weighted_bisection(ijk, loads, nranks) if start == "morton" else coordinate_bisection(ijk, loads, nranks)
+    for start in (STARTS if initial == "best" else (initial,)):
+        part = (weighted_bisection(ijk, loads, nranks) if start == "morton"
+                else coordinate_bisection(ijk, loads, nranks, inertial=start == "inertial"))
         if refine_passes > 0 and nranks > 1:
             part = refine(ijk, loads, part, nranks, tolerance, refine_passes)
         found.append(part.astype(np.int32))
@@ -411,18 +426,19 @@ def partition_sites(geom, site_type, Q=19, wall="BFL", inlet="NASH", outlet="NAS
     """Site -> rank through all four steps: weighted block k-way, then site-granular refinement over
     the reference's ParMETIS graph.  ``initial``: "morton" (start from the block stage as the
     reference starts ParMETIS from BasicDecomposition), "rcb" (coordinate bisection of the sites) or
-    "best" (both; the smaller cut among the results within the balance bound).  Returns the rank
+    "inertial" (bisection along principal axes) or "best" (all; the smallest cut among the results
+    within the balance bound).  Returns the rank
     array and the quality on the site graph (imbalance of the weighted load, number of cut lattice
     links) of the block stage and of the result."""
-    if initial not in ("morton", "rcb", "best"):
-        raise ValueError("initial must be morton, rcb or best")
+    if initial not in STARTS + ("best",):
+        raise ValueError("initial must be one of %s or best" % ", ".join(STARTS))
     blocks, _ = partition_geometry(geom, site_type, wall, inlet, outlet, nranks, architecture, block_tolerance)
     xadj, adjncy = site_graph(geom, Q)
     vwgt = site_weights(wall, inlet, outlet, architecture)[np.asarray(site_type)]
     bound = max(ubvec, 1.0 + vwgt.max() / (vwgt.sum() / nranks)) + 1e-12
     found = []
-    for start in (("morton", "rcb") if initial == "best" else (initial,)):
-        first = blocks if start == "morton" else coordinate_bisection(geom.coords, vwgt, nranks)
+    for start in (STARTS if initial == "best" else (initial,)):
+        first = blocks if start == "morton" else coordinate_bisection(geom.coords, vwgt, nranks, inertial=start == "inertial")
         sites = refine_sites(xadj, adjncy, vwgt, first, nranks, ubvec, passes)
         found.append((start, sites, site_quality(xadj, adjncy, vwgt, sites, nranks)))
     found.sort(key=lambda f: (not (f[2]["parts"] == nranks and f[2]["imbalance"] <= bound),

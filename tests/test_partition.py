@@ -196,6 +196,15 @@ def test_coordinate_bisection():
         assert np.array_equal(part, P.coordinate_bisection(pts, w, n))
     two = P.coordinate_bisection(pts, w, 2)
     assert pts[two == 0, 0].max() <= pts[two == 1, 0].min()  # one cut across x
+    # inertial: a slanted rod is cut across its own axis, whatever the coordinate axes are
+    s_ = np.arange(3000)
+    rod = np.stack([s_, s_ // 2, s_ // 3], 1) + rng.integers(-3, 4, size=(3000, 3))
+    ib = P.coordinate_bisection(rod, np.ones(3000), 4, inertial=True)
+    along = rod @ np.array([1.0, 0.5, 1 / 3.0])
+    for k in range(3):
+        assert np.percentile(along[ib == k], 99) < np.percentile(along[ib == k + 1], 1) + 30
+    assert np.bincount(ib).tolist() == [750] * 4
+    assert np.array_equal(ib, P.coordinate_bisection(rod, np.ones(3000), 4, inertial=True))
     # more ranks than distinct coordinates still leaves no rank empty
     line = np.stack([np.arange(6), np.zeros(6, int), np.zeros(6, int)], 1)
     assert np.array_equal(np.sort(P.coordinate_bisection(line, np.array([100., 1, 1, 1, 1, 1]), 6)), np.arange(6))
@@ -208,15 +217,15 @@ def test_best_start_is_never_worse_and_valid(geom_name, nranks):
     from tests.test_domain_tables import _same_tables
     geom = geometry(geom_name)
     types = collision_types(geom)
-    res = {ini: P.partition_sites(geom, types, 19, nranks=nranks, initial=ini) for ini in ("morton", "rcb", "best")}
+    res = {ini: P.partition_sites(geom, types, 19, nranks=nranks, initial=ini) for ini in P.STARTS + ("best",)}
     vw = P.site_weights("BFL", "NASH", "NASH")[types]
     bound = max(1.001, 1 + vw.max() / (vw.sum() / nranks)) + 1e-12
-    ok = [k for k in ("morton", "rcb") if res[k][1]["sites"]["imbalance"] <= bound]
+    ok = [k for k in P.STARTS if res[k][1]["sites"]["imbalance"] <= bound]
     assert res["best"][1]["sites"]["edge_cut"] == min(res[k][1]["sites"]["edge_cut"] for k in ok)
     assert res["best"][1]["initial"] in ok
     _same_tables(geom, 19, res["best"][0], nranks)
     blocks_best, qb = P.partition_geometry(geom, types, nranks=nranks, initial="best", tolerance=0.05)
-    for ini in ("morton", "rcb"):
+    for ini in P.STARTS:
         _, q = P.partition_geometry(geom, types, nranks=nranks, initial=ini, tolerance=0.05)
         slack = 0.05 + (vw.max() * geom.block_size ** 3) / (vw.sum() / nranks)
         if q["weighted"]["imbalance"] <= 1 + slack:
