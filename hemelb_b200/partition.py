@@ -261,12 +261,11 @@ def site_graph(geom, Q: int):
     look = _Lookup(geom)
     vec = lattice_vectors(Q)
     nb = np.empty((n, Q - 1), np.int64)
-    for l in range(1, Q):
-        nb[:, l - 1] = look(c + vec[l])  # -1 for solid / outside: _Lookup's window lies inside the range test
     full = geom.block_dims.astype(np.int64) * geom.block_size
     for l in range(1, Q):
         p = c + vec[l]
-        nb[((p < 0) | (p >= full)).any(1), l - 1] = -1
+        nb[:, l - 1] = look(p)  # -1: solid, or outside the sites' bounding box
+        nb[((p < 0) | (p >= full)).any(1), l - 1] = -1  # the reference's range test (:333-335)
     ok = nb >= 0
     xadj = np.concatenate([[0], np.cumsum(ok.sum(1))]).astype(np.int64)
     return xadj, nb[ok]
@@ -360,7 +359,7 @@ def refine_sites(xadj, adjncy, vwgt, part, nranks, ubvec=1.001, passes=40):
         f = np.r_[True, u[1:] != u[:-1]]
         return u[f], q[f], gain[f]
 
-    for it in range(passes):
+    for _ in range(passes):
         # (i) balance: while a part is above the cap, loads diffuse over the part graph -- flows on
         # its edges from the potential x that solves L x = load - mean (L its Laplacian), carried one
         # layer of boundary sites per pass, the sites with most links into the receiving part first
@@ -424,12 +423,12 @@ def site_quality(xadj, adjncy, vwgt, part, nranks):
 def partition_sites(geom, site_type, Q=19, wall="BFL", inlet="NASH", outlet="NASH", nranks=2, architecture="B200",
                     ubvec=1.001, block_tolerance=0.03, passes=40, initial="best"):
     """Site -> rank through all four steps: weighted block k-way, then site-granular refinement over
-    the reference's ParMETIS graph.  ``initial``: "morton" (start from the block stage as the
-    reference starts ParMETIS from BasicDecomposition), "rcb" (coordinate bisection of the sites) or
-    "inertial" (bisection along principal axes) or "best" (all; the smallest cut among the results
-    within the balance bound).  Returns the rank
-    array and the quality on the site graph (imbalance of the weighted load, number of cut lattice
-    links) of the block stage and of the result."""
+    the reference's ParMETIS graph.  ``initial``: "morton" (start from the block stage, as the
+    reference starts ParMETIS from BasicDecomposition), "rcb" (coordinate bisection of the sites),
+    "inertial" (bisection along principal axes) or "best" (all three; the smallest cut among the
+    results within the balance bound).  Returns the rank array and the quality on the site graph
+    (imbalance of the weighted load, number of cut lattice links) of the block stage and of the
+    result, with the start that won."""
     if initial not in STARTS + ("best",):
         raise ValueError("initial must be one of %s or best" % ", ".join(STARTS))
     blocks, _ = partition_geometry(geom, site_type, wall, inlet, outlet, nranks, architecture, block_tolerance)
