@@ -197,6 +197,11 @@ def main():
     ap.add_argument("--host-tables", action="store_true", help="voxelise and build the Domain tables on the host (numpy)")
     ap.add_argument("--block-size", type=int, default=8, help="sites per block side of the synthetic .gmy (HemeLB default 8)")
     args = ap.parse_args()
+    # stdout carries the JSON line and nothing else: whatever a library prints to fd 1 (NCCL's version
+    # banner, for one) goes to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -215,7 +220,7 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config,
                 "cpu_baseline": base,
                 "e2e": {"value": base["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out, flush=True)
         return 0
 
     from hemelb_b200.lbm import GpuLBM
@@ -339,7 +344,7 @@ def main():
             line["cpu_baseline"] = base
         except Exception as e:  # the baseline must not take the GPU line down
             line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "unavailable", "sample": repr(e)}
-    print(json.dumps(line))
+    print(json.dumps(line), file=json_out, flush=True)
     return 0
 
 
