@@ -41,6 +41,8 @@ SYMBOLS = [
     "hlb_xtr_create", "hlb_xtr_create_from_domain", "hlb_xtr_destroy", "hlb_xtr_sizes", "hlb_xtr_required_caches",
     "hlb_xtr_header", "hlb_xtr_encode", "hlb_xtr_pinned_buffer", "hlb_xtr_last_encode_ms",
     "hlb_gpu_load_distributions", "hlb_gpu_load_distributions_from_domain",
+    # METIS-free partition of the site graph (host code)
+    "hlb_part_refine_kway", "hlb_part_bisect",
 ]
 
 

@@ -329,6 +329,25 @@ int hlb_xtr_last_encode_ms(hlb_xtr_t x, float* ms);
 int hlb_gpu_load_distributions(hlb_gpu_t h, const void* records, uint64_t n_bytes, const int64_t* site_coords);
 int hlb_gpu_load_distributions_from_domain(hlb_gpu_t h, hlb_dom_t d, const void* records, uint64_t n_bytes);
 
+/* ==== METIS-free k-way partition of the site graph (host code) ====================
+ * Stands where the reference calls ParMETIS_V3_PartKway (Code/geometry/decomposition/
+ * OptimisedDecomposition.cc:138-154), on one process: the CSR graph of PopulateAdjacencyData
+ * (:311-379; xadj[n + 1], adjncy[xadj[n]], symmetric), vertex weights by collision type
+ * (DecompositionWeights.h.in:25-62, integer-valued), nparts, ubvec (:133).  `part` holds the
+ * partition the vertices arrive with (BasicDecomposition's, or hlb_part_bisect's) and is refined in
+ * place: parts above max(ubvec x mean, mean + heaviest vertex) diffuse boundary vertices along flows
+ * solved on the part graph; then boundary vertices move, in bulk sweeps, to the part they have most
+ * links into while the number of cut links falls.  Deterministic.  edgecut (may be NULL): cut links
+ * of the result, as ParMETIS reports them. */
+int hlb_part_refine_kway(int64_t n, const int64_t* xadj, const int64_t* adjncy, const double* vwgt, int nparts,
+                         double ubvec, int passes, int32_t* part, int64_t* edgecut);
+/* recursive geometric bisection of weighted points (coords: n x 3 voxel or block coordinates) into
+ * nparts, floor(k/2) : k - floor(k/2) as BasicDecomposition.cc:21-96 divides its ranks: at the
+ * weighted median across the longest coordinate extent (inertial = 0) or along the principal axis
+ * of the weighted covariance (inertial = 1) -- cuts vessels across rather than along the Morton
+ * curve. */
+int hlb_part_bisect(int64_t n, const int64_t* coords, const double* weights, int nparts, int inertial, int32_t* part);
+
 #ifdef __cplusplus
 }
 #endif

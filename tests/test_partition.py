@@ -243,3 +243,47 @@ def test_coordinate_start_cuts_tubes_across():
     assert q["sites"]["edge_cut"] < 0.6 * qm["sites"]["edge_cut"]
     doms = build_domains(geom, 19, rank, 4)
     assert max(d.procs.shape[0] for d in doms) <= 2
+
+
+@pytest.mark.parametrize("geom_name", ["tree", "sac", "cylinder_long"])
+def test_library_partitioner_makes_the_same_moves(geom_name):
+    """hlb_part_bisect / hlb_part_refine_kway (csrc/partition.cu, what a HemeLB build calls in place of
+    ParMETIS_V3_PartKway) against the numpy statement of the algorithm: identical partitions from four
+    different starts, two weight tables, 2..8 parts; the reported edge cut is the graph's."""
+    geom = geometry(geom_name)
+    types = collision_types(geom)
+    xadj, adjncy = P.site_graph(geom, 19)
+    for wall, arch in (("BFL", "B200"), ("GZS", "AMDBULLDOZER")):
+        vw = P.site_weights(wall, "NASH", "NASH", arch)[types]
+        for R in (2, 3, 5, 8):
+            rcb = P.coordinate_bisection(geom.coords, vw, R)
+            assert np.array_equal(rcb, P.coordinate_bisection_native(geom.coords, vw, R))
+            rib = P.coordinate_bisection_native(geom.coords, vw, R, inertial=True)
+            assert np.bincount(rib, minlength=R).min() > 0
+            if geom_name != "cylinder_long":  # (a round tube's two short principal axes are degenerate)
+                assert np.array_equal(rib, P.coordinate_bisection(geom.coords, vw, R, inertial=True))
+            blocks, _ = P.partition_geometry(geom, types, wall, nranks=R, architecture=arch)
+            for first in (blocks, rcb, rib, G.basic_decomposition(geom, R)):
+                want = P.refine_sites(xadj, adjncy, vw, first, R)
+                got, cut = P.refine_sites_native(xadj, adjncy, vw, first, R)
+                assert np.array_equal(got, want)
+                assert cut == P.site_cut(xadj, adjncy, want)
+    start = "rcb" if geom_name == "cylinder_long" else "best"
+    a, qa = P.partition_sites(geom, types, 19, nranks=4, native=True, initial=start)
+    b, qb = P.partition_sites(geom, types, 19, nranks=4, native=False, initial=start)
+    assert np.array_equal(a, b) and qa == qb
+
+
+def test_library_partitioner_argument_checks():
+    from hemelb_b200.capi import lib
+    xadj = np.array([0, 1, 2], np.int64)
+    adj = np.array([1, 0], np.int64)
+    w = np.ones(2)
+    with pytest.raises(RuntimeError, match="initial part outside"):
+        P.refine_sites_native(xadj, adj, w, np.array([0, 5], np.int32), 2)
+    part, cut = P.refine_sites_native(xadj, adj, w, np.array([0, 1], np.int32), 2)
+    assert part.tolist() == [0, 1] and cut == 1
+    part, cut = P.refine_sites_native(xadj, adj, w, np.array([0, 0], np.int32), 1)
+    assert part.tolist() == [0, 0] and cut == 0
+    assert P.coordinate_bisection_native(np.zeros((0, 3), np.int64), np.zeros(0), 3).size == 0
+    assert lib().hlb_part_bisect(2, None, None, 2, 0, None) != 0
