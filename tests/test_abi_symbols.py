@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     src = open(os.path.join(ROOT, "include", "hemelb_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(hlb_(?:gpu|dom|xtr)_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(hlb_(?:gpu|dom|xtr|part)_\w+)\s*\(", src)))
 
 
 def test_header_and_binding_agree():
