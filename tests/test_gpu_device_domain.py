@@ -40,7 +40,7 @@ def test_explicit_source_tables_bit_exact(name, Q):
         # a ParMETIS-like site partition (cuts through blocks): hemelb_b200/partition.py step 4
         from hemelb_b200.partition import partition_sites
         from tests.test_partition import collision_types
-        cases.append((partition_sites(geom, collision_types(geom, Q), Q, nranks=4)[0], 4))
+        cases.append((partition_sites(geom, collision_types(geom, Q), Q, nranks=4, initial="morton")[0], 4))
     for ros, R in cases:
         host = build_domains(geom, Q, ros, R)
         for r in range(R):
