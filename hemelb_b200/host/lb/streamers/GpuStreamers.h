@@ -75,7 +75,7 @@ namespace hemelb::lb::gpu {
       }
     }
 
-    void StreamAndCollide(const site_t first, const site_t count, const LbmParameters* lbmParams,
+    void StreamAndCollide(const site_t first, const site_t count, const LbmParameters*,
                           geometry::FieldData& latDat, MacroscopicPropertyCache& cache) {
       hlb_gpu_t h = latDat.Engine();
       PushStepScalars(h, latDat, cache);
