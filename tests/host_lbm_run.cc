@@ -11,6 +11,7 @@
 // Linked against tests/host_mock_abi.cc it records the C-ABI calls (CPU test of the call sequence);
 // linked against libhemelb_b200.so it runs on the GPU and the result is compared with the oracle.
 // Test infrastructure: built by __graft_entry__.build() where /root/reference exists.
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -247,7 +248,15 @@ namespace {
     }
     const int64_t steps = c.head[22];
     const unsigned want = (unsigned)c.head[23];
+    // HLB_HOST_TIMING=1: wall-clock MLUPS of steps 2..K as this host drives them (stderr); step 1
+    // builds the engine and uploads the tables
+    const bool timing = getenv("HLB_HOST_TIMING") != nullptr && steps > 1;
+    auto t0 = std::chrono::steady_clock::now();
     for (int64_t s = 0; s < steps; ++s) {
+      if (timing && s == 1) {
+        geometry::FieldData::Check(hlb_gpu_sync(fd.Engine()));
+        t0 = std::chrono::steady_clock::now();
+      }
       cache.ResetRequirements();
       if (s == steps - 1) {  // a PropertyActor asking for output on the last step
         if (want & 1) cache.densityCache.SetRefreshFlag();
@@ -260,6 +269,12 @@ namespace {
       lbm.EndIteration();
       fd.SwapOldAndNew();
       state.Increment();
+    }
+    if (timing) {
+      geometry::FieldData::Check(hlb_gpu_sync(fd.Engine()));
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      fprintf(stderr, "host_lbm_run: %lld sites, %lld timed steps, %.6f s, %.1f MLUPS\n", (long long)N,
+              (long long)(steps - 1), dt, N * double(steps - 1) / dt / 1e6);
     }
     FILE* fh = fopen(outPath, "wb");
     if (!fh) throw std::runtime_error("cannot write the result");

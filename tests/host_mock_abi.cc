@@ -68,6 +68,7 @@ int hlb_gpu_get_f(hlb_gpu_t h, int which, double* f) {
 int hlb_gpu_request_comms(hlb_gpu_t) { fprintf(out(), "request_comms\n"); return 0; }
 int hlb_gpu_copy_received(hlb_gpu_t) { fprintf(out(), "copy_received\n"); return 0; }
 int hlb_gpu_swap(hlb_gpu_t) { fprintf(out(), "swap\n"); return 0; }
+int hlb_gpu_sync(hlb_gpu_t) { fprintf(out(), "sync\n"); return 0; }
 int hlb_gpu_set_step_scalars(hlb_gpu_t h, uint64_t t, const double* in, const double* o, uint32_t mask) {
   fprintf(out(), "set_step_scalars t=%llu mask=%u", (unsigned long long)t, mask);
   for (int i = 0; i < h->cfg.n_inlets; ++i) fprintf(out(), " in%d=%.17g", i, in[i]);
