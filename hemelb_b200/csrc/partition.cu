@@ -5,8 +5,11 @@
 // (:311-379), vertex weights by collision type (DecompositionWeights.h.in:25-62), the number of
 // parts, the balance tolerance ubvec (:133) -- and the same output, a part per vertex, refined from
 // the partition the vertices arrive with (the reference's BasicDecomposition, or hlb_part_bisect).
-// ParMETIS itself is not in this image and no reference test pins a partition: parity is unpinned
-// by design; the numpy statement of the same algorithm (hemelb_b200/partition.py) is what the
+// ParMETIS (4.0.2, dependencies/ParMETIS/build.cmake:7; a third-party dependency whose source is not
+// under the reference tree) is not in this image and no reference test pins a partition: parity is
+// unpinned by design.  What is kept of its published scheme (Karypis & Kumar's parallel multilevel
+// k-way) is the refinement half: balance first, by diffusion over the part graph, then greedy
+// boundary moves to the best-connected part in alternating directions of part index; the numpy statement of the same algorithm (hemelb_b200/partition.py) is what the
 // tests compare with, move for move.
 //
 // No device code: partitions are made once, before the tables are built.

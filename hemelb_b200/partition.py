@@ -2,7 +2,8 @@
 
 The reference refines its ``BasicDecomposition`` with ParMETIS (``OptimisedDecomposition.cc:138-154``:
 ``ParMETIS_V3_PartKway`` over the site graph, vertex weights by collision type from
-``DecompositionWeights.h.in:25-62``).  ParMETIS is not in this image and no reference test pins a
+``DecompositionWeights.h.in:25-62``).  ParMETIS (4.0.2, ``dependencies/ParMETIS/build.cmake:7``,
+source not under the reference tree) is not in this image and no reference test pins a
 partition, so parity is unpinned by design: any assignment is a valid input of the Domain builder
 (``hlb_dom_set_partition_blocks`` / ``rank_of_site``), the tables are bit-exact *given* it.
 
