@@ -26,12 +26,23 @@ from tests.cases import anisotropic_f, iolets_for
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
 Q, L, radius, steps = 19, 48, 5.3, 6
-# rank-local construction: own slab + one halo slice (what bench.py does per GPU)
-sub, sub_rank = G.cylinder_slab(radius, L, world, rank)
-dom = DomainBuilder(sub, Q, sub_rank, world).domains[rank]
-# the oracle needs a geometry it can run: the full one, but this process only drives its own rank
-full = G.cylinder_extruded(radius, L)
-full_rank = np.minimum((full.coords[:, 2].astype(np.int64) - 2) // (L // world), world - 1).astype(np.int32)
+if os.environ.get("HLB_CASE") == "tree_sites":
+    # a site-granular partition of the tree (hemelb_b200/partition.py, inertial start + site stage):
+    # ranks share blocks and have several neighbours each
+    from hemelb_b200 import partition as P
+    from tests.cases import geometry
+    from tests.test_partition import collision_types
+    full = geometry("tree")
+    full_rank, quality = P.partition_sites(full, collision_types(full, Q), Q, nranks=world, initial="inertial", native=True)
+    dom = DomainBuilder(full, Q, full_rank, world).domains[rank]
+    assert dom.procs.shape[0] >= 1
+else:
+    # rank-local construction: own slab + one halo slice (what bench.py does per GPU)
+    sub, sub_rank = G.cylinder_slab(radius, L, world, rank)
+    dom = DomainBuilder(sub, Q, sub_rank, world).domains[rank]
+    # the oracle needs a geometry it can run: the full one, but this process only drives its own rank
+    full = G.cylinder_extruded(radius, L)
+    full_rank = np.minimum((full.coords[:, 2].astype(np.int64) - 2) // (L // world), world - 1).astype(np.int32)
 inlets, outlets = iolets_for(full, "NASH", "NASH")
 odom = O.OracleDomains(full, Q, full_rank, world)
 t = odom.tables(rank)
@@ -98,14 +109,15 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world", [2])
-def test_two_process_halo_exchange(tmp_path, world):
+@pytest.mark.parametrize("world,case", [(2, "cylinder_slabs"), (3, "tree_sites")])
+def test_two_process_halo_exchange(tmp_path, world, case):
     script = tmp_path / "worker.py"
     script.write_text(WORKER % {"root": ROOT})
     port = _free_port()
     procs = []
     for r in range(world):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   HLB_CASE=case)
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.STDOUT, text=True))
     outs = []
