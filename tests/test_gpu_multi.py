@@ -25,10 +25,19 @@ rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
 Q, L, radius, steps = 19, 64, 6.3, 12
 for (kernel, wall, inlet, outlet) in (("LBGK", "BFL", "NASH", "NASH"), ("MRT", "SBB", "LADD", "NASH")):
-    sub, sub_rank = G.cylinder_slab(radius, L, world, rank)
-    dom = DomainBuilder(sub, Q, sub_rank, world).domains[rank]
-    full = G.cylinder_extruded(radius, L)
-    full_rank = np.minimum((full.coords[:, 2].astype(np.int64) - 2) // (L // world), world - 1).astype(np.int32)
+    if os.environ.get("HLB_CASE") == "tree_sites":
+        # site-granular partition of the tree (inertial start + site stage): shared blocks, several neighbours
+        from hemelb_b200 import partition as P
+        from tests.cases import geometry
+        from tests.test_partition import collision_types
+        full = geometry("tree")
+        full_rank, _ = P.partition_sites(full, collision_types(full, Q), Q, nranks=world, initial="inertial", native=True)
+        dom = DomainBuilder(full, Q, full_rank, world).domains[rank]
+    else:
+        sub, sub_rank = G.cylinder_slab(radius, L, world, rank)
+        dom = DomainBuilder(sub, Q, sub_rank, world).domains[rank]
+        full = G.cylinder_extruded(radius, L)
+        full_rank = np.minimum((full.coords[:, 2].astype(np.int64) - 2) // (L // world), world - 1).astype(np.int32)
     inlets, outlets = iolets_for(full, inlet, outlet)
     gpu = GpuLBM(dom, kernel, wall, inlet, outlet, tau=0.8, inlets=inlets, outlets=outlets, device=rank)
     uid = [GpuLBM.comm_unique_id() if rank == 0 else None]
@@ -74,8 +83,8 @@ def _gpu_count():
     return n.value
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_nccl_halo_matches_oracle(tmp_path, world):
+@pytest.mark.parametrize("world,case", [(2, "cylinder_slabs"), (4, "cylinder_slabs"), (2, "tree_sites"), (4, "tree_sites")])
+def test_nccl_halo_matches_oracle(tmp_path, world, case):
     if _gpu_count() < world:
         pytest.skip("needs %d GPUs" % world)
     script = tmp_path / "worker.py"
@@ -86,7 +95,8 @@ def test_nccl_halo_matches_oracle(tmp_path, world):
     s.close()
     procs = []
     for r in range(world):
-        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   HLB_CASE=case)
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.STDOUT, text=True))
     outs = []
