@@ -187,8 +187,8 @@ def cpu_reference_run(steps, warmup, target_seconds=12.0, radius=40.0, length=32
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)   # time >= 200 steps
+    ap.add_argument("--warmup", type=int, default=20)  # ... after >= 20 warm-up steps
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--radius", type=float, default=146.0)
     ap.add_argument("--length", type=int, default=1500)
