@@ -243,7 +243,7 @@ inline int64_t host_bidx(const hlb_gpu_handle* h, int64_t site) {
 }
 
 __global__ void convert_nbr_kernel(const int64_t* __restrict__ aos, uint32_t* __restrict__ nbr, int64_t first,
-                                   int64_t n, int Q, int64_t N, int64_t stride, int* bad) {
+                                   int64_t n, int Q, int64_t N, int64_t stride, int64_t S, int* bad) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= n * Q) return;
   const int d = (int)(tid / n);
@@ -255,7 +255,7 @@ __global__ void convert_nbr_kernel(const int64_t* __restrict__ aos, uint32_t* __
     return;
   }
   int64_t internal;
-  if (v < 0 || v > N * Q + ((int64_t)1 << 40)) {
+  if (v < 0 || v > N * Q + S) {  // local slots, the rubbish slot N*Q, the S halo slots behind it
     atomicExch(bad, 2);
     return;
   }
@@ -756,7 +756,8 @@ int launch_range(hlb_gpu_t h, int slot, int64_t first, int64_t count, bool post)
     if (first == h->rangeFirst[k] && first + count == h->rangeFirst[k + 1]) whole = k;
   // whole mid-domain ranges are deferred: when all of them have been asked for they leave as ONE
   // fused launch (flush_mid), at the next call that is not such a request
-  if (!post && ((h->fuse && h->midItems) || (h->fillHoles && h->allMidMask)) && whole >= 0 && whole < 6 && !h->inFlush) {
+  if (!post && ((h->fuse && h->midItems) || (h->fillHoles && h->allMidMask)) && whole >= 0 && whole < 6 && slot == whole &&
+      !h->inFlush) {
     if (h->pendingMid & (1u << whole)) {
       if (flush_mid(h)) return 1;
     }
@@ -914,8 +915,9 @@ int upload_densities(hlb_gpu_t h, int which, const double* d) {
   if (!d) return fail("iolet densities missing");
   // ring of pinned slots: a slot is reused only after the stream drained (every kPinnedSlots steps)
   const int slot = (int)(h->pinnedCursor[which]++ % kPinnedSlots);
-  if (slot == 0 && h->pinnedCursor[which] > 1) if (join_aux(h)) return 1;
-  CU(cudaStreamSynchronize(h->compute));
+  // (the H2D copies out of the ring are stream-ordered on `compute`; join_aux above put the
+  // boundary stream behind it, so a drained `compute` means every earlier slot has been read)
+  if (slot == 0 && h->pinnedCursor[which] > 1) CU(cudaStreamSynchronize(h->compute));
   double* src = h->ioletDensityPinned[which] + (size_t)slot * n;
   std::memcpy(src, d, sizeof(double) * n);
   CU(cudaMemcpyAsync(h->ioletDensityDev[which], src, sizeof(double) * n, cudaMemcpyHostToDevice, h->compute));
@@ -1236,7 +1238,7 @@ int hlb_gpu_set_neighbour_indices(hlb_gpu_t h, int64_t first, int64_t n, const i
     const int64_t m = std::min(kChunkSites, n - s0);
     CU(cudaMemcpy(h->staging, idx + s0 * Q, sizeof(int64_t) * m * Q, cudaMemcpyHostToDevice));
     convert_nbr_kernel<<<blocks_for(m * Q), 256>>>((const int64_t*)h->staging, h->nbr, first + s0, m, Q, h->N,
-                                                   h->stride, bad);
+                                                   h->stride, h->S, bad);
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
   }
@@ -1340,6 +1342,7 @@ int hlb_gpu_set_site_coords(hlb_gpu_t h, int64_t first, int64_t n, const int64_t
 
 int hlb_gpu_set_neighbours(hlb_gpu_t h, const int* rank, const int64_t* count, const int64_t* first) {
   if (!h) return fail("null argument");
+  if (h->cfg.n_neighbours > 0 && (!rank || !count || !first)) return fail("null neighbour arrays");
   h->neighbours.clear();
   int64_t expect = h->N * h->Q + 1, total = 0;
   for (int i = 0; i < h->cfg.n_neighbours; ++i) {
@@ -1444,8 +1447,24 @@ int hlb_gpu_finalise(hlb_gpu_t h) {
   if (!h->haveIolets[0] || !h->haveIolets[1]) return fail("iolets not set");
   CU(cudaSetDevice(h->cfg.device));
   const int Q = h->Q;
-  for (int64_t b = 0; b < h->NB; ++b)
-    if (h->hIolet[b] && (h->hIoletId[b] < 0)) return fail("iolet site without an iolet id");
+  {
+    // iolet ids index the BoundaryValues object of the site's own streamer: the inlet table for the
+    // inlet / inlet-wall ranges, the outlet table for the outlet / outlet-wall ranges
+    // (lb.hpp:87-113 hands inletValues / outletValues to the respective streamers)
+    const int64_t nbMid = h->midTotal - h->midBulk;
+    for (int64_t b = 0; b < h->NB; ++b) {
+      if (!h->hIolet[b]) continue;
+      const int64_t site = b < nbMid ? b + h->midBulk : b - nbMid + h->midTotal + h->edgeBulk;
+      int k = 0;
+      while (k < 11 && site >= h->rangeFirst[k + 1]) ++k;
+      const int type = k % 6;
+      const int limit = (type == 2 || type == 4) ? h->cfg.n_inlets : (type == 3 || type == 5) ? h->cfg.n_outlets : 0;
+      if (h->hIoletId[b] < 0) return fail("iolet site without an iolet id");
+      if (h->hIoletId[b] >= limit)
+        return fail("iolet id of a site is outside the iolet table of its range (ids index the inlet table in "
+                    "inlet-typed ranges and the outlet table in outlet-typed ranges)");
+    }
+  }
   h->allMidMask = 0;
   for (int t = 0; t < 6; ++t)
     if (h->mid[t] > 0) h->allMidMask |= 1u << t;

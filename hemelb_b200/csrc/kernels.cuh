@@ -1,7 +1,7 @@
-// Fused collide-and-stream kernels over HemeLB's type-ordered sparse site ranges (sm_100a).
+// Fused collide-and-stream kernels over HemeLB's sparse fluid-site arrays (sm_100a).
 //
-// One kernel instantiation per (lattice, collision kernel, wall link, iolet link) policy bundle --
-// the device-side counterpart of the reference's
+// One kernel instantiation per (lattice, collision kernel, wall link, inlet link, outlet link)
+// policy bundle -- the device-side counterpart of the reference's
 //   lb::BulkStreamer<C>                       Code/lb/streamers/BulkStreamer.h:57-99
 //   lb::StreamerTypeFactory<WallLink,IoletLink> Code/lb/streamers/StreamerTypeFactory.h:24-109
 // with C = lb::Normal<LBGK|MRT|TRT>.  One thread owns one site: it loads the Q pre-collision
@@ -9,6 +9,14 @@
 // fully coalesced 256 B request), collides in registers, and pushes each post-collision
 // population through the 32-bit neighbour table into f_new.  Macroscopic-moment extraction
 // (UpdateCachePostCollision, Common.h:21-130) is fused behind a run-time mask.
+//
+// Site order on the device: inside the mid-domain part and inside the domain-edge part the sites
+// of ALL six collision types are sorted together by lattice position (x, y, z) -- a wall site sits
+// between the mid-fluid sites of its lattice row, so the 32 pushes of a warp land on consecutive
+// addresses whatever the types of its sites, and the 32 B sectors of f_new leave L2 whole.  The
+// reference's type-ordered ranges are an API-level view (perm / iperm); which link policy a site
+// runs is decided per site from a bitmap of the boundary-typed sites (bInfo: one 8 B word per 32
+// sites) and that site's wall / iolet masks, in the order of StreamerTypeFactory.h:65-79.
 //
 // HBM traffic per site update: Q*8 B read + Q*8 B written + (Q-1)*4 B of indices.
 #pragma once

@@ -24,7 +24,8 @@ from tests.cases import anisotropic_f, iolets_for
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
 Q, L, radius, steps = 19, 64, 6.3, 12
-for (kernel, wall, inlet, outlet) in (("LBGK", "BFL", "NASH", "NASH"), ("MRT", "SBB", "LADD", "NASH")):
+for (kernel, wall, inlet, outlet) in (("LBGK", "BFL", "NASH", "NASH"), ("MRT", "SBB", "LADD", "NASH"),
+                                     ("LBGK", "GZS", "LADD", "NASH")):
     if os.environ.get("HLB_CASE") == "tree_sites":
         # site-granular partition of the tree (inertial start + site stage): shared blocks, several neighbours
         from hemelb_b200 import partition as P
@@ -35,11 +36,20 @@ for (kernel, wall, inlet, outlet) in (("LBGK", "BFL", "NASH", "NASH"), ("MRT", "
         dom = DomainBuilder(full, Q, full_rank, world).domains[rank]
     else:
         sub, sub_rank = G.cylinder_slab(radius, L, world, rank)
-        dom = DomainBuilder(sub, Q, sub_rank, world).domains[rank]
         full = G.cylinder_extruded(radius, L)
         full_rank = np.minimum((full.coords[:, 2].astype(np.int64) - 2) // (L // world), world - 1).astype(np.int32)
+        if wall == "GZS":
+            # the phase-0 site halo (NeighbouringDataManager.cc:101-142) names sites of other ranks:
+            # tables from the whole geometry
+            dom = DomainBuilder(full, Q, full_rank, world).domains[rank]
+        else:
+            dom = DomainBuilder(sub, Q, sub_rank, world).domains[rank]
     inlets, outlets = iolets_for(full, inlet, outlet)
     gpu = GpuLBM(dom, kernel, wall, inlet, outlet, tau=0.8, inlets=inlets, outlets=outlets, device=rank)
+    if wall == "GZS":
+        needs = [None] * world
+        dist.all_gather_object(needs, int(gpu.gzs_need.shape[0]))
+        assert sum(needs) > 0, "no GZS link extrapolates across a rank boundary: the case tests nothing"
     uid = [GpuLBM.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     gpu.comm_init(uid[0])

@@ -137,7 +137,8 @@ def test_tables_round_trip_on_device():
     geom = geometry("tree")
     for Q in (15, 19, 27):
         dom = build_domains(geom, Q)[0]
-        gpu = GpuLBM(dom)
+        inlets, outlets = iolets_for(geom, "NASH", "NASH")
+        gpu = GpuLBM(dom, inlets=inlets, outlets=outlets)
         assert np.array_equal(gpu.get_neighbour_indices(), dom.neighbour_indices())
 
 
@@ -268,7 +269,10 @@ def test_error_paths():
     with pytest.raises(HlbError, match="No MRT basis for D3Q27"):
         GpuLBM(dom, "MRT")
     dom = build_domains(geom, 15)[0]
-    gpu = GpuLBM(dom)
+    with pytest.raises(HlbError, match="outside the iolet table"):
+        GpuLBM(dom)  # iolet sites, but no iolet records: the kernels would index an empty table
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    gpu = GpuLBM(dom, inlets=inlets, outlets=outlets)
     with pytest.raises(HlbError, match="outside the local fluid sites"):
         gpu.stream_and_collide(0, 0, dom.N + 1)
     with pytest.raises(HlbError, match="bulk-typed"):
@@ -278,7 +282,8 @@ def test_error_paths():
 def test_monitor_matches_numpy():
     geom, Q = geometry("cylinder"), 19
     dom = build_domains(geom, Q)[0]
-    gpu = GpuLBM(dom)
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    gpu = GpuLBM(dom, inlets=inlets, outlets=outlets)
     f0 = anisotropic_f(dom.N, Q, 0)
     gpu.set_f(f0)
     m = gpu.monitor()
@@ -294,13 +299,24 @@ def test_monitor_matches_numpy():
     assert m2["min_f"] == f.min()
     assert abs(m2["min_density"] - rho.min()) < 1e-12 and abs(m2["max_density"] - rho.max()) < 1e-12
     assert abs(m2["max_speed"] - m["max_speed"]) < 1e-12
-    # and it re-arms: the next step reports the new state, equal to a stand-alone pass over it
+    # and it re-arms: the next step reports the state that entered it, equal to a stand-alone pass
+    f1 = gpu.get_f()[:dom.N * Q].reshape(dom.N, Q)
     gpu.step(1)
     m3 = gpu.monitor()
+    rho1 = f1.sum(1)
+    assert m3["min_f"] == f1.min()
+    assert abs(m3["min_density"] - rho1.min()) < 1e-12 and abs(m3["max_density"] - rho1.max()) < 1e-12
+    c = O.lattice(Q)[0].astype(np.float64)
+    u1 = (f1 @ c) / rho1[:, None]
+    assert abs(m3["max_speed"] - np.sqrt((u1 * u1).sum(1)).max()) < 1e-12
+    assert m3["min_f"] != m2["min_f"]
+    # the stand-alone pass (monitor not fused) over the current state
     gpu.set_cache_mask(0)
     gpu.step(0)
-    f1 = gpu.get_f()[:dom.N * Q].reshape(dom.N, Q)
-    assert m3["min_f"] != m2["min_f"]
+    f2 = gpu.get_f()[:dom.N * Q].reshape(dom.N, Q)
+    m4 = gpu.monitor()
+    assert m4["min_f"] == f2.min()
+    assert abs(m4["min_density"] - f2.sum(1).min()) < 1e-12
 
 
 @pytest.mark.parametrize("geom_name,Q,kernel,wall,inlet,outlet", [
