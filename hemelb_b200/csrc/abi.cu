@@ -28,10 +28,9 @@
 
 namespace hlb {
 // per-(lattice, kernel) launchers, defined in cs_q*_*.cu
-#define HLB_DECL(Q, K) \
-  extern template void launch_collide_stream<Q, K>(int, int, const StepArgs&, const void*, int64_t, int64_t, void*); \
-  extern template bool launch_fused_mid<Q, K>(int, int, int, const StepArgs&, const void*, const IoletDev*,          \
-                                              const double*, const MidItem*, int64_t, void*);
+#define HLB_DECL(Q, K)                                                                                       \
+  extern template void launch_collide_stream<Q, K>(int, int, int, const StepArgs&, const void*, int64_t, int64_t, \
+                                                   const uint32_t*, int64_t, int64_t, void*);
 HLB_DECL(15, K_LBGK) HLB_DECL(15, K_MRT) HLB_DECL(15, K_TRT)
 HLB_DECL(19, K_LBGK) HLB_DECL(19, K_MRT) HLB_DECL(19, K_TRT)
 HLB_DECL(27, K_LBGK) HLB_DECL(27, K_TRT)
@@ -121,12 +120,8 @@ struct hlb_gpu_handle {
   int Q = 0;
   int64_t N = 0, stride = 0, S = 0, fLen = 0;
   int64_t mid[6], edge[6], midTotal = 0, midBulk = 0, edgeBulk = 0, NB = 0, bStride = 0;
-  cudaStream_t compute = nullptr, comm = nullptr, aux = nullptr;
-  cudaEvent_t evEdge = nullptr, evComm = nullptr, evT0 = nullptr, evT1 = nullptr, evFork = nullptr, evJoin = nullptr;
-  // mid-domain boundary ranges run on `aux` beside the mid-fluid (bulk) kernel: they read f_old and
-  // write disjoint (site, direction) slots of f_new, so the only ordering needed is "after what
-  // preceded the bulk launch" (evFork) and "before anything that follows the streaming" (join_aux)
-  bool overlap = true, forkValid = false, auxPending = false;
+  cudaStream_t compute = nullptr, comm = nullptr;
+  cudaEvent_t evEdge = nullptr, evComm = nullptr, evT0 = nullptr, evT1 = nullptr;
   double* f[2] = {nullptr, nullptr};
   int cur = 0;
   uint32_t* nbr = nullptr;
@@ -148,14 +143,34 @@ struct hlb_gpu_handle {
   uint64_t timeStep = 1;  // SimulationState.cc:16
   std::vector<char> mrt;
   LaunchFn launch = nullptr;
-  FusedLaunchFn launchFused = nullptr;
-  // fused mid-domain launch (kernels.cuh, fused_mid_kernel): the work items of the six mid ranges
-  // merged by lattice position; whole-range mid launches are deferred and flushed as one kernel
-  MidItem* midItems = nullptr;
-  int64_t nMidItems = 0;
-  uint32_t allMidMask = 0, pendingMid = 0;
-  bool fuse = true, inFlush = false, fuseDefault = true, overlapDefault = true;
-  bool fillHoles = true, fillHolesDefault = true, holesNow = false;
+  // ---- the product schedule.  Device order: all sites of the mid-domain part sorted by lattice
+  // position whatever their collision type, then all sites of the domain-edge part likewise; one
+  // site-kernel launch per part, every site running the streamer of its own type.  Whole-range
+  // requests of the phase API (hlb_gpu_stream_and_collide with the range's own streamer) are held
+  // until every non-empty range of the part has been asked for and then leave as that one launch;
+  // when the caller has announced a whole step (hlb_gpu_request_comms, LBM::RequestComms) the
+  // part is launched at its first request and the later requests of the step find it done.
+  // Everything else (sub-ranges, a streamer on another type's range, hlb_gpu_set_overlap(0)) runs at
+  // once, one launch per request, in the caller's order.
+  struct Deferred { uint32_t all = 0, pending = 0, done = 0; };
+  Deferred sc[2];   // stream-and-collide: [0] mid-domain ranges, [1] domain-edge ranges (bit = type)
+  Deferred post;    // PostStep: bit k of the 12 ranges (BFL only)
+  bool schedule = true, scheduleDefault = true, announced = false, inFlush = false;
+  // boundary-typed sites in device order
+  uint2* bInfo = nullptr;      // per 32 internal sites {bitmap, ordinal of the first}
+  uint32_t* bSite = nullptr;   // internal site of boundary ordinal b
+  uint4* bRec = nullptr;       // per boundary-typed site: masks, iolet id, cut distances (StepArgs::bRec)
+  int64_t nbMid = 0;           // boundary-typed sites of the mid-domain part (ordinals [0, nbMid))
+  std::vector<int64_t> refOrdToB;  // boundary ordinal in reference order -> device ordinal
+  // BFL PostStep links {slot of f_new[site, inv d], slot of f_new[site, d], q}, device site order
+  uint32_t *postI = nullptr, *postD = nullptr;
+  float* postQ = nullptr;
+  int64_t nPost = 0;
+  // what hlb_gpu_set_step_scalars was last given
+  bool scalarsSet = false;
+  uint64_t lastStep = 0;
+  uint32_t lastMask = 0;
+  std::vector<double> lastDens[2];
   double omegaMinus = 0;
   // host staging of the boundary tables until finalise
   std::vector<uint32_t> hWall, hIolet;
@@ -180,11 +195,6 @@ struct hlb_gpu_handle {
   uint32_t* iperm = nullptr;   // internal site -> reference site
   int32_t* coordsAll = nullptr;  // 3 planes of stride, reference order, until finalise
   int64_t coordsCovered = 0;
-  // run-compressed neighbour table, per whole range
-  uint32_t* nbrFlags = nullptr;
-  uint32_t* nbrBase = nullptr;
-  int64_t groupStride = 0;
-  int64_t groupOffset[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   int64_t rangeFirst[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   // GZS site halo (NeighbouringDataManager): whole f_old rows of remote sites, once per step
   struct GzsPeer { int rank; int64_t first, count; };
@@ -200,7 +210,7 @@ struct hlb_gpu_handle {
   cudaEvent_t evGzsPack = nullptr, evGzsDone = nullptr;
   bool gzsGhostProvided = false;
   bool profileBulk = false;
-  std::vector<cudaEvent_t> profEv;  // pairs around the mid-fluid (bulk) range launches
+  std::vector<cudaEvent_t> profEv;  // pairs around the mid-domain site-kernel launches
   size_t profUsed = 0;
   int64_t profSites = 0;
 };
@@ -220,21 +230,18 @@ int ensure_staging(hlb_gpu_t h, size_t bytes) {
   return 0;
 }
 
-int flush_mid(hlb_gpu_t h);
+int flush_deferred(hlb_gpu_t h);
 
-// make `compute` wait for the boundary kernels that were put on `aux`
-int join_aux(hlb_gpu_t h) {
-  if (h->pendingMid && flush_mid(h)) return 1;
-  if (h->auxPending) {
-    CU(cudaEventRecord(h->evJoin, h->aux));
-    CU(cudaStreamWaitEvent(h->compute, h->evJoin, 0));
-    h->auxPending = false;
-  }
-  h->forkValid = false;
-  return 0;
+// f_old changed (swap, upload, initial condition): nothing of the current step has run yet
+void new_step_state(hlb_gpu_t h) {
+  h->sc[0].done = h->sc[1].done = h->post.done = 0;
+  h->announced = false;
 }
 
-// boundary ordinal of a site, or -1 for bulk-typed sites
+// every ordering point (copy, swap, read-back, scalar change): whatever was held back leaves now
+int join_aux(hlb_gpu_t h) { return flush_deferred(h); }
+
+// boundary ordinal, in REFERENCE site order, of a reference site id; -1 for bulk-typed sites
 inline int64_t host_bidx(const hlb_gpu_handle* h, int64_t site) {
   if (site < h->midBulk) return -1;
   if (site < h->midTotal) return site - h->midBulk;
@@ -294,19 +301,127 @@ __global__ void coords_to_planes_kernel(const int64_t* __restrict__ aos, int32_t
   const int64_t s = tid % n;
   planes[(int64_t)k * stride + first + s] = (int32_t)aos[s * 3 + k];
 }
-struct RangeTable { int64_t first[13]; };
-// sort key: (site range, x, y, z) -- sites stay inside their (mid/edge x collision type) range and
-// become long z-runs, so the pushes of a warp land on consecutive addresses
-__global__ void sort_keys_kernel(const int32_t* __restrict__ coords, int64_t stride, int64_t N, RangeTable R, int lox,
-                                 int loy, int loz, int64_t Ly, int64_t Lz, uint64_t* __restrict__ keys,
+// sort key: (part, x, y, z) -- sites stay inside their part (mid-domain / domain-edge) and become
+// long z-runs whatever their collision type, so the pushes of a warp land on consecutive addresses
+__global__ void sort_keys_kernel(const int32_t* __restrict__ coords, int64_t stride, int64_t N, int64_t midTotal,
+                                 int lox, int loy, int loz, int64_t Ly, int64_t Lz, uint64_t* __restrict__ keys,
                                  uint32_t* __restrict__ vals) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= N) return;
-  int r = 0;
-  while (r < 11 && s >= R.first[r + 1]) ++r;
+  const uint64_t part = s >= midTotal ? 1u : 0u;
   const int64_t x = coords[s] - lox, y = coords[stride + s] - loy, z = coords[2 * stride + s] - loz;
-  keys[s] = ((uint64_t)r << 58) | (uint64_t)((x * Ly + y) * Lz + z);
+  keys[s] = (part << 58) | (uint64_t)((x * Ly + y) * Lz + z);
   vals[s] = (uint32_t)s;
+}
+// which device sites are boundary-typed: one bitmap word per 32 sites
+__global__ void boundary_bits_kernel(const uint32_t* __restrict__ iperm, int64_t N, int64_t nWords, int64_t midBulk,
+                                     int64_t midTotal, int64_t edgeBulk, uint32_t* __restrict__ bits,
+                                     uint32_t* __restrict__ counts) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((s >> 5) >= nWords) return;
+  bool isB = false;
+  if (s < N) {
+    const int64_t ref = iperm ? (int64_t)iperm[s] : s;
+    isB = (ref >= midBulk && ref < midTotal) || ref >= midTotal + edgeBulk;
+  }
+  const unsigned w = __ballot_sync(0xffffffffu, isB);
+  if ((threadIdx.x & 31) == 0) {
+    bits[s >> 5] = w;
+    counts[s >> 5] = __popc(w);
+  }
+}
+__global__ void boundary_info_kernel(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ base,
+                                     int64_t nWords, uint2* __restrict__ info, uint32_t* __restrict__ bSite) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t w = s >> 5;
+  if (w >= nWords) return;
+  const unsigned lane = threadIdx.x & 31;
+  const uint32_t bm = bits[w], b0 = base[w];
+  if (lane == 0) info[w] = make_uint2(bm, b0);
+  if ((bm >> lane) & 1u) bSite[b0 + __popc(bm & ((1u << lane) - 1u))] = (uint32_t)s;
+}
+// device ordinal of every boundary-typed site, listed in reference order
+__global__ void ref_ordinal_kernel(const uint32_t* __restrict__ perm, const uint2* __restrict__ info, int64_t NB,
+                                   int64_t nbMid, int64_t midBulk, int64_t midTotal, int64_t edgeBulk,
+                                   int32_t* __restrict__ out) {
+  const int64_t rb = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (rb >= NB) return;
+  const int64_t ref = rb < nbMid ? rb + midBulk : rb - nbMid + midTotal + edgeBulk;
+  const int64_t s = perm ? (int64_t)perm[ref] : ref;
+  const uint2 bi = info[s >> 5];
+  const unsigned lane = (unsigned)s & 31u;
+  out[rb] = ((bi.x >> lane) & 1u) ? (int32_t)(bi.y + __popc(bi.x & ((1u << lane) - 1u))) : -1;
+}
+// PostStep: only BFL does work (BouzidiFirdaousLallemand.h:72-91), after all streaming and the
+// halo unpack.  Which links it touches is fixed by the geometry: they are listed once
+// (hlb_gpu_finalise) as {slot of f_new[site, inv d], slot of f_new[site, d], q}, in site order, and
+// one thread corrects one link -- two loads and a store, no mask -> distance -> value chain.  The
+// links are independent of one another (the corrected slot belongs to a direction without a wall
+// link, the slot read to one with).
+__global__ void __launch_bounds__(256) bfl_post_links_kernel(double* __restrict__ fNew, const uint32_t* __restrict__ slotI,
+                                                             const uint32_t* __restrict__ slotD,
+                                                             const float* __restrict__ cut, int64_t n) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double q = (double)cut[k];
+  const uint32_t i = slotI[k];
+  const double fd = fNew[slotD[k]];
+  fNew[i] = 2.0 * q * fNew[i] + (1.0 - 2.0 * q) * fd;
+}
+
+// the site kernel's per-site record (kernels.cuh, StepArgs::bRec) from the plane-major tables
+__global__ void boundary_records_kernel(const uint32_t* __restrict__ wallMask, const uint32_t* __restrict__ ioletMask,
+                                        const int32_t* __restrict__ ioletId, const float* __restrict__ cut,
+                                        int64_t bStride, int64_t NB, int Q, int words, uint32_t* __restrict__ rec) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= NB * words) return;
+  const int64_t b = tid / words;
+  const int w = (int)(tid % words);
+  uint32_t v = 0;
+  if (w == 0) v = wallMask[b];
+  else if (w == 1) v = ioletMask[b];
+  else if (w == 2) v = (uint32_t)ioletId[b];
+  else if (w >= 4 && w < 4 + Q - 1) v = __float_as_uint(cut[(int64_t)(w - 4) * bStride + b]);
+  rec[tid] = v;
+}
+// BFL PostStep links (BouzidiFirdaousLallemand.h:72-91) of boundary site b: wall link d whose
+// opposite is not a wall link and whose cut distance is below one half
+__global__ void post_links_count_kernel(const uint32_t* __restrict__ wallMask, const float* __restrict__ cut,
+                                        int64_t bStride, int64_t NB, int Q, uint32_t* __restrict__ counts) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= NB) return;
+  const uint32_t wm = wallMask[b];
+  uint32_t n = 0;
+  for (int d = 1; d < Q; ++d) {
+    if (!((wm >> (d - 1)) & 1u)) continue;
+    const int id = inv_dir(d);
+    if ((wm >> (id - 1)) & 1u) continue;
+    if ((double)cut[(int64_t)(d - 1) * bStride + b] < 0.5) ++n;
+  }
+  counts[b] = n;
+}
+__global__ void post_links_fill_kernel(const uint32_t* __restrict__ wallMask, const float* __restrict__ cut,
+                                       int64_t bStride, int64_t NB, int Q, int64_t stride,
+                                       const uint32_t* __restrict__ bSite, const uint32_t* __restrict__ offset,
+                                       uint32_t* __restrict__ slotI, uint32_t* __restrict__ slotD,
+                                       float* __restrict__ q) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= NB) return;
+  const uint32_t wm = wallMask[b];
+  const int64_t site = bSite[b];
+  uint32_t k = offset[b];
+  for (int d = 1; d < Q; ++d) {
+    if (!((wm >> (d - 1)) & 1u)) continue;
+    const int id = inv_dir(d);
+    if ((wm >> (id - 1)) & 1u) continue;
+    const float c = cut[(int64_t)(d - 1) * bStride + b];
+    if ((double)c < 0.5) {
+      slotI[k] = (uint32_t)((int64_t)id * stride + site);
+      slotD[k] = (uint32_t)((int64_t)d * stride + site);
+      q[k] = c;
+      ++k;
+    }
+  }
 }
 __global__ void invert_perm_kernel(const uint32_t* __restrict__ iperm, uint32_t* __restrict__ perm, int64_t N) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -328,10 +443,6 @@ __global__ void remap_stream_kernel(uint32_t* __restrict__ idx, const uint32_t* 
   const int64_t v = idx[i];
   idx[i] = (uint32_t)((v / stride) * stride + perm[v % stride]);
 }
-__global__ void site_list_kernel(const uint32_t* __restrict__ perm, uint32_t* __restrict__ out, int64_t first, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = perm[first + i];
-}
 // pack whole f_old rows (site-major) of the sites other ranks' GZS links extrapolate from
 __global__ void gzs_pack_kernel(const double* __restrict__ f, const uint32_t* __restrict__ sites, int64_t n, int Q,
                                 int64_t stride, double* __restrict__ out) {
@@ -341,30 +452,6 @@ __global__ void gzs_pack_kernel(const double* __restrict__ f, const uint32_t* __
   const int j = (int)(tid % Q);
   out[tid] = f[(int64_t)j * stride + sites[k]];
 }
-// one warp per group of 32 consecutive sites of a range: which directions push to 32 consecutive
-// targets?  (flags, first target) per group
-__global__ void compress_nbr_kernel(const uint32_t* __restrict__ nbr, int Q, int64_t stride, int64_t rangeFirst,
-                                    int64_t rangeCount, int64_t groupOffset, int64_t groupStride,
-                                    uint32_t* __restrict__ flags, uint32_t* __restrict__ base) {
-  const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const int64_t nGroups = (rangeCount + 31) / 32;
-  if (g >= nGroups) return;
-  const int64_t site = rangeFirst + g * 32 + lane;
-  const bool valid = site < rangeFirst + rangeCount;
-  uint32_t bits = 0;
-  for (int d = 1; d < Q; ++d) {
-    const uint32_t v = valid ? nbr[(int64_t)(d - 1) * stride + site] : 0u;
-    const uint32_t v0 = __shfl_sync(0xffffffffu, v, 0);
-    const bool ok = !valid || v == v0 + (uint32_t)lane;
-    if (__all_sync(0xffffffffu, ok)) {
-      bits |= 1u << (d - 1);
-      if (lane == 0) base[(int64_t)(d - 1) * groupStride + groupOffset + g] = v0;
-    }
-  }
-  if (lane == 0) flags[groupOffset + g] = bits;
-}
-
 __global__ void aos_to_soa_kernel(const double* __restrict__ aos, double* __restrict__ f, int64_t first, int64_t n,
                                   int Q, int64_t stride, const uint32_t* __restrict__ perm) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -400,13 +487,12 @@ __global__ void copy_received_kernel(double* __restrict__ fNew, const double* __
   fNew[streamIdx[tid]] = fOldShared[tid];
 }
 __global__ void gzs_neighbour_kernel(const uint32_t* __restrict__ nbr, int32_t* __restrict__ out, int Q, int64_t stride,
-                                     int64_t bStride, int64_t NB, int64_t midBulk, int64_t midTotal, int64_t edgeBulk) {
+                                     int64_t bStride, int64_t NB, const uint32_t* __restrict__ bSite) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= NB * (Q - 1)) return;
   const int d = (int)(tid / NB) + 1;
   const int64_t b = tid % NB;
-  const int64_t nbMid = midTotal - midBulk;
-  const int64_t site = b < nbMid ? b + midBulk : b - nbMid + midTotal + edgeBulk;
+  const int64_t site = bSite[b];
   const int64_t in = nbr[(int64_t)(d - 1) * stride + site];
   int32_t v = INT32_MIN;  // not a local fluid neighbour (rubbish / remote)
   if (in < (int64_t)Q * stride) v = (int32_t)(in - (int64_t)d * stride);
@@ -484,7 +570,7 @@ __global__ void monitor_decode_kernel(unsigned long long* io) {
 
 inline unsigned blocks_for(int64_t n) { return (unsigned)((n + 255) / 256); }
 
-StepArgs make_args(hlb_gpu_t h, int which /*0 inlet BoundaryValues, 1 outlet*/) {
+StepArgs make_args(hlb_gpu_t h) {
   StepArgs A;
   std::memset(&A, 0, sizeof(A));
   A.fOld = h->f[h->cur];
@@ -498,14 +584,16 @@ StepArgs make_args(hlb_gpu_t h, int which /*0 inlet BoundaryValues, 1 outlet*/) 
   A.wallNormal = h->wallNormal;
   A.coords = h->coords;
   A.bStride = h->bStride;
-  A.midBulk = h->midBulk;
-  A.midTotal = h->midTotal;
-  A.edgeBulk = h->edgeBulk;
+  A.bInfo = h->bInfo;
+  A.bRec = h->bRec;
   A.gzsNeighbour = h->gzsNeighbour;
   A.gzsGhost = h->gzsGhost;
-  A.ghostStride = 0;
-  A.iolets = h->ioletsDev[which];
-  A.ioletDensity = h->ioletDensityDev[which];
+  for (int w = 0; w < 2; ++w) {
+    A.iolets[w] = h->ioletsDev[w];
+    A.ioletDensity[w] = h->ioletDensityDev[w];
+  }
+  A.wallOn = 1;
+  A.ioletSel = kIoletByType;
   A.timeStep = h->timeStep;
   A.tau = h->cfg.tau;
   A.omega = -1.0 / h->cfg.tau;  // LbmParameters.h:36
@@ -562,8 +650,6 @@ void fill_mrt(hlb_gpu_t h) {
 // Renumber the sites inside each of the 12 ranges by (x, y, z): long z-runs.  Everything indexed by
 // site moves with it: the neighbour table (positions and values), the streaming indices of the
 // received distributions and the staged boundary tables.  Halo slots and range bounds do not move.
-int build_mid_items(hlb_gpu_t h, const int lo[3], int64_t Ly, int64_t Lz);
-
 int build_permutation(hlb_gpu_t h) {
   const int Q = h->Q;
   const int64_t N = h->N;
@@ -595,9 +681,8 @@ int build_permutation(hlb_gpu_t h) {
   CU(cudaMalloc(&valsIn, sizeof(uint32_t) * N));
   CU(cudaMalloc(&h->iperm, sizeof(uint32_t) * N));
   CU(cudaMalloc(&h->perm, sizeof(uint32_t) * N));
-  RangeTable R;
-  for (int k = 0; k < 13; ++k) R.first[k] = h->rangeFirst[k];
-  sort_keys_kernel<<<blocks_for(N), 256>>>(h->coordsAll, h->stride, N, R, lo[0], lo[1], lo[2], Ly, Lz, keysIn, valsIn);
+  sort_keys_kernel<<<blocks_for(N), 256>>>(h->coordsAll, h->stride, N, h->midTotal, lo[0], lo[1], lo[2], Ly, Lz, keysIn,
+                                           valsIn);
   CU(cudaGetLastError());
   {
     void* tmp = nullptr;
@@ -627,19 +712,60 @@ int build_permutation(hlb_gpu_t h) {
     remap_stream_kernel<<<blocks_for(h->S), 256>>>(h->streamIdx, h->perm, h->S, h->stride);
     CU(cudaGetLastError());
   }
-  // staged boundary tables: reference boundary ordinal -> internal boundary ordinal
+  return 0;
+}
+
+// The boundary-typed sites in device order: bitmap + running ordinal per 32 sites (bInfo), the site of
+// every ordinal (bSite), and where each boundary ordinal of the reference order went (refOrdToB);
+// then the staged boundary tables, which arrive in reference order, move to device order.
+int build_boundary_order(hlb_gpu_t h) {
+  const int Q = h->Q;
+  const int64_t nWords = h->stride / 32;
+  uint32_t *bits = nullptr, *counts = nullptr, *base = nullptr;
+  CU(cudaMalloc(&bits, sizeof(uint32_t) * nWords));
+  CU(cudaMalloc(&counts, sizeof(uint32_t) * nWords));
+  CU(cudaMalloc(&base, sizeof(uint32_t) * nWords));
+  CU(cudaMalloc(&h->bInfo, sizeof(uint2) * nWords));
+  CU(cudaMalloc(&h->bSite, sizeof(uint32_t) * std::max<int64_t>(h->NB, 1)));
+  boundary_bits_kernel<<<blocks_for(nWords * 32), 256>>>(h->iperm, h->N, nWords, h->midBulk, h->midTotal, h->edgeBulk,
+                                                         bits, counts);
+  CU(cudaGetLastError());
+  {
+    void* tmp = nullptr;
+    size_t tmpBytes = 0;
+    cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, counts, base, (int)nWords);
+    CU(cudaMalloc(&tmp, tmpBytes + 16));
+    cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, counts, base, (int)nWords);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    cudaFree(tmp);
+  }
+  boundary_info_kernel<<<blocks_for(nWords * 32), 256>>>(bits, base, nWords, h->bInfo, h->bSite);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  cudaFree(bits);
+  cudaFree(counts);
+  cudaFree(base);
+  h->nbMid = h->midTotal - h->midBulk;
+  h->refOrdToB.assign(h->NB, 0);
   if (h->NB) {
-    std::vector<uint32_t> hp(h->NB);
-    const int64_t nbMid = h->midTotal - h->midBulk;
-    if (nbMid) CU(cudaMemcpy(hp.data(), h->perm + h->midBulk, sizeof(uint32_t) * nbMid, cudaMemcpyDeviceToHost));
-    if (h->NB - nbMid)
-      CU(cudaMemcpy(hp.data() + nbMid, h->perm + h->midTotal + h->edgeBulk, sizeof(uint32_t) * (h->NB - nbMid),
-                    cudaMemcpyDeviceToHost));
-    std::vector<int64_t> to(h->NB);
-    for (int64_t b = 0; b < h->NB; ++b) {
-      to[b] = host_bidx(h, (int64_t)hp[b]);
-      if (to[b] < 0 || to[b] >= h->NB) return fail("internal error: renumbering moved a site out of its range");
+    int32_t* dOrd = nullptr;
+    CU(cudaMalloc(&dOrd, sizeof(int32_t) * h->NB));
+    ref_ordinal_kernel<<<blocks_for(h->NB), 256>>>(h->perm, h->bInfo, h->NB, h->nbMid, h->midBulk, h->midTotal,
+                                                   h->edgeBulk, dOrd);
+    CU(cudaGetLastError());
+    std::vector<int32_t> ord(h->NB);
+    CU(cudaMemcpy(ord.data(), dOrd, sizeof(int32_t) * h->NB, cudaMemcpyDeviceToHost));
+    cudaFree(dOrd);
+    std::vector<char> seen(h->NB, 0);
+    for (int64_t rb = 0; rb < h->NB; ++rb) {
+      if (ord[rb] < 0 || ord[rb] >= h->NB || seen[ord[rb]])
+        return fail("internal error: the boundary-typed sites did not keep their count under renumbering");
+      if ((rb < h->nbMid) != (ord[rb] < h->nbMid)) return fail("internal error: renumbering moved a site out of its part");
+      seen[ord[rb]] = 1;
+      h->refOrdToB[rb] = ord[rb];
     }
+    auto& to = h->refOrdToB;
     auto move = [&](auto& v, int planes) {
       auto old = v;
       for (int k = 0; k < planes; ++k)
@@ -652,158 +778,104 @@ int build_permutation(hlb_gpu_t h) {
     move(h->hNormal, 3);
     move(h->hCoords, 3);
   }
-  return build_mid_items(h, lo, Ly, Lz);
+  return 0;
 }
 
-// (x, y, z) key of the first site of each work item (internal id -> reference id -> coordinates)
-__global__ void mid_item_keys_kernel(const MidItem* __restrict__ items, int64_t n, const uint32_t* __restrict__ iperm,
-                                     const int32_t* __restrict__ coords, int64_t stride, int lox, int loy, int loz,
-                                     int64_t Ly, int64_t Lz, uint64_t* __restrict__ keys) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const int64_t s = iperm[items[j].first];
-  const int64_t x = coords[s] - lox, y = coords[stride + s] - loy, z = coords[2 * stride + s] - loz;
-  keys[j] = (uint64_t)((x * Ly + y) * Lz + z);
-}
-
-// work items of the fused mid-domain kernel: every mid range cut into pieces of <= T sites, all
-// pieces ordered by the lattice position of their first site (needs the renumbered order, in which
-// every range is sorted by that same key)
-int build_mid_items(hlb_gpu_t h, const int lo[3], int64_t Ly, int64_t Lz) {
-  h->allMidMask = 0;
-  for (int t = 0; t < 6; ++t)
-    if (h->mid[t] > 0) h->allMidMask |= 1u << t;
-  if (!(h->cfg.kernel == HLB_KERNEL_MRT || h->Q > 19)) return 0;  // no fused kernel for the rest
-  const int T = h->Q > 19 ? HLB_Q27_THREADS : 256;
-  std::vector<MidItem> items;
-  h->allMidMask = 0;
-  for (int t = 0; t < 6; ++t) {
-    if (h->mid[t] > 0) h->allMidMask |= 1u << t;
-    for (int64_t o = 0; o < h->mid[t]; o += T) {
-      MidItem it;
-      it.first = (uint32_t)(h->rangeFirst[t] + o);
-      it.countSlot = (uint32_t)std::min<int64_t>(T, h->mid[t] - o) | ((uint32_t)t << 16);
-      items.push_back(it);
-    }
-  }
-  const int64_t n = (int64_t)items.size();
-  h->nMidItems = n;
-  if (n == 0) return 0;
-  MidItem* dItems = nullptr;
-  uint64_t* dKeys = nullptr;
-  CU(cudaMalloc(&dItems, sizeof(MidItem) * n));
-  CU(cudaMalloc(&dKeys, sizeof(uint64_t) * n));
-  CU(cudaMemcpy(dItems, items.data(), sizeof(MidItem) * n, cudaMemcpyHostToDevice));
-  mid_item_keys_kernel<<<blocks_for(n), 256>>>(dItems, n, h->iperm, h->coordsAll, h->stride, lo[0], lo[1], lo[2], Ly, Lz,
-                                               dKeys);
+// the BFL PostStep link list, once the boundary tables are on the device
+int build_post_links(hlb_gpu_t h) {
+  h->nPost = 0;
+  if (h->cfg.wall != HLB_WALL_BFL || h->NB == 0) return 0;
+  uint32_t *counts = nullptr, *offset = nullptr;
+  CU(cudaMalloc(&counts, sizeof(uint32_t) * (h->NB + 1)));
+  CU(cudaMalloc(&offset, sizeof(uint32_t) * (h->NB + 1)));
+  CU(cudaMemset(counts, 0, sizeof(uint32_t) * (h->NB + 1)));
+  post_links_count_kernel<<<blocks_for(h->NB), 256>>>(h->wallMask, h->cutDist, h->bStride, h->NB, h->Q, counts);
   CU(cudaGetLastError());
-  std::vector<uint64_t> keys(n);
-  CU(cudaMemcpy(keys.data(), dKeys, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
-  cudaFree(dKeys);
-  std::vector<int64_t> order(n);
-  for (int64_t j = 0; j < n; ++j) order[j] = j;
-  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return keys[a] < keys[b]; });
-  std::vector<MidItem> sorted(n);
-  for (int64_t j = 0; j < n; ++j) sorted[j] = items[order[j]];
-  CU(cudaMemcpy(dItems, sorted.data(), sizeof(MidItem) * n, cudaMemcpyHostToDevice));
-  h->midItems = dItems;
-  return 0;
-}
-
-int build_compressed(hlb_gpu_t h) {
-  const int Q = h->Q;
-  int64_t total = 0;
-  for (int k = 0; k < 12; ++k) {
-    h->groupOffset[k] = total;
-    total += (h->rangeFirst[k + 1] - h->rangeFirst[k] + 31) / 32;
-  }
-  h->groupStride = ((total + 63) / 64) * 64;
-  if (h->groupStride == 0) h->groupStride = 64;
-  CU(cudaMalloc(&h->nbrFlags, sizeof(uint32_t) * h->groupStride));
-  CU(cudaMalloc(&h->nbrBase, sizeof(uint32_t) * (Q - 1) * h->groupStride));
-  CU(cudaMemset(h->nbrFlags, 0, sizeof(uint32_t) * h->groupStride));
-  for (int k = 0; k < 12; ++k) {
-    const int64_t cnt = h->rangeFirst[k + 1] - h->rangeFirst[k];
-    if (cnt <= 0) continue;
-    const int64_t groups = (cnt + 31) / 32;
-    compress_nbr_kernel<<<blocks_for(groups * 32), 256>>>(h->nbr, Q, h->stride, h->rangeFirst[k], cnt,
-                                                          h->groupOffset[k], h->groupStride, h->nbrFlags, h->nbrBase);
+  {
+    void* tmp = nullptr;
+    size_t tmpBytes = 0;
+    cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, counts, offset, (int)(h->NB + 1));
+    CU(cudaMalloc(&tmp, tmpBytes + 16));
+    cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, counts, offset, (int)(h->NB + 1));
     CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    cudaFree(tmp);
   }
-  CU(cudaDeviceSynchronize());
+  uint32_t total = 0;
+  CU(cudaMemcpy(&total, offset + h->NB, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  h->nPost = total;
+  if (total) {
+    CU(cudaMalloc(&h->postI, sizeof(uint32_t) * total));
+    CU(cudaMalloc(&h->postD, sizeof(uint32_t) * total));
+    CU(cudaMalloc(&h->postQ, sizeof(float) * total));
+    post_links_fill_kernel<<<blocks_for(h->NB), 256>>>(h->wallMask, h->cutDist, h->bStride, h->NB, h->Q, h->stride,
+                                                       h->bSite, offset, h->postI, h->postD, h->postQ);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+  }
+  cudaFree(counts);
+  cudaFree(offset);
   return 0;
 }
 
-// site range of a streamer slot -> is it a whole range (fast path) or an arbitrary sub-range
-int launch_range(hlb_gpu_t h, int slot, int64_t first, int64_t count, bool post) {
-  if (!h->finalised) return fail("handle not finalised");
-  if (slot < 0 || slot > 5) return fail("streamer slot out of range");
+int prof_begin(hlb_gpu_t h) {
+  while (h->profEv.size() < h->profUsed + 2) {
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    h->profEv.push_back(e);
+  }
+  CU(cudaEventRecord(h->profEv[h->profUsed], h->compute));
+  return 0;
+}
+int prof_end(hlb_gpu_t h, int64_t sites) {
+  CU(cudaEventRecord(h->profEv[h->profUsed + 1], h->compute));
+  h->profUsed += 2;
+  h->profSites += sites;
+  return 0;
+}
+
+// One launch of the site kernel over a whole part (0 mid-domain, 1 domain-edge): every site runs
+// the streamer of its own collision type -- what LBM::PreReceive / PreSend ask for with their six
+// StreamAndCollide calls (lb.hpp:176-251), which read f_old and write disjoint slots of f_new.
+int launch_part(hlb_gpu_t h, int part) {
+  const int64_t first = part ? h->midTotal : 0;
+  const int64_t count = part ? h->N - h->midTotal : h->midTotal;
   if (count <= 0) return 0;
-  if (first < 0 || first + count > h->N) return fail("site range outside the local fluid sites");
-  const bool isBoundarySlot = slot != 0;
-  if (isBoundarySlot) {
-    // boundary streamers read per-site tables that only exist for boundary-typed sites
-    if (host_bidx(h, first) < 0 || host_bidx(h, first + count - 1) < 0 ||
-        (first < h->midTotal && first + count > h->midTotal))
-      return fail("boundary streamer called on bulk-typed sites");
-  }
-  const bool isInletSlot = (slot == 2 || slot == 4);
-  StepArgs A = make_args(h, isInletSlot ? 0 : 1);
-  // whole ranges run on the internal order with the run-compressed table; an arbitrary sub-range
-  // (reference ids) goes through an explicit site list when the sites were renumbered
-  int whole = -1;
-  for (int k = 0; k < 12; ++k)
-    if (first == h->rangeFirst[k] && first + count == h->rangeFirst[k + 1]) whole = k;
-  // whole mid-domain ranges are deferred: when all of them have been asked for they leave as ONE
-  // fused launch (flush_mid), at the next call that is not such a request
-  if (!post && ((h->fuse && h->midItems) || (h->fillHoles && h->allMidMask)) && whole >= 0 && whole < 6 && slot == whole &&
-      !h->inFlush) {
-    if (h->pendingMid & (1u << whole)) {
-      if (flush_mid(h)) return 1;
-    }
-    h->pendingMid |= 1u << whole;
-    // the last of the non-empty mid ranges: nothing more to wait for
-    if (h->pendingMid == h->allMidMask) return flush_mid(h);
-    return 0;
-  }
-  if (h->pendingMid && !h->inFlush && flush_mid(h)) return 1;
-  // which stream: whole mid-domain boundary ranges go beside the bulk kernel (see `aux`)
-  cudaStream_t st = h->compute;
-  const bool midWhole = !post && h->overlap && !h->holesNow && whole >= 0 && whole < 6;
-  if (h->holesNow && slot == 0) {
-    A.holeFirst = (uint32_t)h->midBulk;
-    A.holeCount = (uint32_t)(h->midTotal - h->midBulk);
-  }
-  if (midWhole && slot == 0) {
-    if (!h->auxPending) {
-      CU(cudaEventRecord(h->evFork, h->compute));
-      h->forkValid = true;
-    }
-  } else if (midWhole && h->forkValid) {
-    st = h->aux;
-    if (!h->auxPending) CU(cudaStreamWaitEvent(h->aux, h->evFork, 0));
-    h->auxPending = true;
-  } else if (join_aux(h)) {
-    return 1;
-  }
-  if (whole >= 0 && h->nbrFlags && !post) {
-    A.nbrFlags = h->nbrFlags;
-    A.nbrBase = h->nbrBase;
-    A.groupStride = h->groupStride;
-    A.groupOffset = h->groupOffset[whole];
-  } else if (whole < 0 && h->perm) {
-    if (h->siteListCap < count) {
-      if (h->siteListDev) cudaFree(h->siteListDev);
-      h->siteListDev = nullptr;
-      CU(cudaMalloc(&h->siteListDev, sizeof(uint32_t) * count));
-      h->siteListCap = count;
-    }
-    // (stream-ordered: a previous launch may still read the list)
-    site_list_kernel<<<blocks_for(count), 256, 0, h->compute>>>(h->perm, h->siteListDev, first, count);
-    A.siteList = h->siteListDev;
-  }
+  StepArgs A = make_args(h);
+  const bool prof = h->profileBulk && part == 0;
+  if (prof && prof_begin(h)) return 1;
+  const int64_t gFirst = part ? h->nbMid : 0, gCount = part ? h->NB - h->nbMid : h->nbMid;
+  h->launch(h->cfg.wall, h->cfg.inlet, h->cfg.outlet, A, h->mrt.data(), first, count, h->bSite + gFirst, 0, gCount,
+            h->compute);
+  h->launches++;
+  if (h->cfg.wall == HLB_WALL_GZS && gCount > 0) h->launches++;  // the per-link kernel behind the per-site one
+  if (h->cacheMask & C_MONITOR) h->monitorLaunches++;
+  if (prof && prof_end(h, count)) return 1;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// every BFL PostStep of the step in one launch over the link list
+int launch_post_links(hlb_gpu_t h) {
+  if (h->nPost == 0) return 0;
+  bfl_post_links_kernel<<<blocks_for(h->nPost), 256, 0, h->compute>>>(h->f[h->cur ^ 1], h->postI, h->postD, h->postQ,
+                                                                      h->nPost);
+  h->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// One streamer on one range of reference site ids, at once: `slot` decides the link policies,
+// whatever the types of the sites (as the reference's streamer objects behave when
+// StreamerTests.cc calls them on a range of its choosing).
+int launch_now(hlb_gpu_t h, int slot, int64_t first, int64_t count, bool post) {
   const bool canWall = (slot == 1 || slot == 4 || slot == 5);
   const bool canIolet = slot >= 2;
+  const bool isInletSlot = (slot == 2 || slot == 4);
+  StepArgs A = make_args(h);
+  A.wallOn = canWall ? 1 : 0;
+  A.ioletSel = canIolet ? (isInletSlot ? 0 : 1) : kIoletNone;
+  if (h->perm) A.siteList = h->perm + first;  // reference id -> device site, contiguous in reference order
   if (post) {
     // StreamerTypeFactory::PostStep: only the BFL wall link does anything
     if (!canWall || h->cfg.wall != HLB_WALL_BFL) return 0;
@@ -816,77 +888,102 @@ int launch_range(hlb_gpu_t h, int slot, int64_t first, int64_t count, bool post)
     CU(cudaGetLastError());
     return 0;
   }
-  const int wall = canWall ? h->cfg.wall : W_NONE;
-  const int iolet = canIolet ? (isInletSlot ? h->cfg.inlet : h->cfg.outlet) : I_NONE;
   const bool prof = h->profileBulk && slot == 0;
-  if (prof) {
-    while (h->profEv.size() < h->profUsed + 2) {
-      cudaEvent_t e;
-      CU(cudaEventCreate(&e));
-      h->profEv.push_back(e);
-    }
-    CU(cudaEventRecord(h->profEv[h->profUsed], h->compute));
-  }
-  h->launch(wall, iolet, A, h->mrt.data(), first, count, st);
-  if (wall == W_GZS) h->launches++;  // the per-link kernel behind the per-site one
-  if (h->cacheMask & C_MONITOR) h->monitorLaunches++;
-  if (prof) {
-    CU(cudaEventRecord(h->profEv[h->profUsed + 1], h->compute));
-    h->profUsed += 2;
-    h->profSites += count;
-  }
+  if (prof && prof_begin(h)) return 1;
+  h->launch(h->cfg.wall, h->cfg.inlet, h->cfg.outlet, A, h->mrt.data(), first, count, nullptr, first, count, h->compute);
   h->launches++;
+  if (canWall && h->cfg.wall == HLB_WALL_GZS) h->launches++;
+  if (h->cacheMask & C_MONITOR) h->monitorLaunches++;
+  if (prof && prof_end(h, count)) return 1;
   CU(cudaGetLastError());
   return 0;
 }
 
-int flush_mid(hlb_gpu_t h) {
-  const uint32_t pending = h->pendingMid;
-  h->pendingMid = 0;
+int flush_sc(hlb_gpu_t h, int part) {
+  const uint32_t pending = h->sc[part].pending;
+  h->sc[part].pending = 0;
   if (!pending) return 0;
-  h->holesNow = false;
-  if (pending == h->allMidMask && !(h->midItems && h->fuse) && h->fillHoles) {
-    // every mid range was asked for and runs below in slot order on one stream: the mid-fluid
-    // kernel may pre-write the slots that the boundary ranges fill after it
-    h->holesNow = true;
-  }
-  if (pending == h->allMidMask && h->midItems && h->fuse) {
-    StepArgs A = make_args(h, 1);
-    const bool prof = h->profileBulk;
-    if (prof) {
-      while (h->profEv.size() < h->profUsed + 2) {
-        cudaEvent_t e;
-        CU(cudaEventCreate(&e));
-        h->profEv.push_back(e);
-      }
-      CU(cudaEventRecord(h->profEv[h->profUsed], h->compute));
-    }
-    if (h->launchFused(h->cfg.wall, h->cfg.inlet, h->cfg.outlet, A, h->mrt.data(), h->ioletsDev[0],
-                       h->ioletDensityDev[0], h->midItems, h->nMidItems, h->compute)) {
-      h->launches++;
-      if (h->cacheMask & C_MONITOR) h->monitorLaunches++;
-      if (prof) {
-        CU(cudaEventRecord(h->profEv[h->profUsed + 1], h->compute));
-        h->profUsed += 2;
-        h->profSites += h->midTotal;
-      }
-      CU(cudaGetLastError());
-      return 0;
-    }
-  }
-  // not every mid range was requested, or this policy bundle has no fused kernel: one by one
-  h->inFlush = true;
+  if (pending == h->sc[part].all) return launch_part(h, part);
+  // not every range of the part was asked for: one by one
   int rc = 0;
   for (int t = 0; t < 6 && !rc; ++t)
-    if (pending & (1u << t)) rc = launch_range(h, t, h->rangeFirst[t], h->mid[t], false);
-  h->inFlush = false;
-  h->holesNow = false;
+    if (pending & (1u << t)) {
+      const int k = part ? 6 + t : t;
+      rc = launch_now(h, t, h->rangeFirst[k], h->rangeFirst[k + 1] - h->rangeFirst[k], false);
+    }
   return rc;
+}
+
+int flush_post(hlb_gpu_t h) {
+  const uint32_t pending = h->post.pending;
+  h->post.pending = 0;
+  if (!pending) return 0;
+  if (pending == h->post.all) return launch_post_links(h);
+  int rc = 0;
+  // (the reference's order: domain-edge ranges, then mid-domain ranges, lb.hpp:257-309)
+  for (int k : {6, 7, 8, 9, 10, 11, 0, 1, 2, 3, 4, 5})
+    if (!rc && (pending & (1u << k)))
+      rc = launch_now(h, k % 6, h->rangeFirst[k], h->rangeFirst[k + 1] - h->rangeFirst[k], true);
+  return rc;
+}
+
+int flush_deferred(hlb_gpu_t h) {
+  if (flush_sc(h, 1) || flush_sc(h, 0)) return 1;
+  return flush_post(h);
+}
+
+// a request of the phase API: streamer `slot` over reference sites [first, first + count)
+int launch_range(hlb_gpu_t h, int slot, int64_t first, int64_t count, bool post) {
+  if (!h->finalised) return fail("handle not finalised");
+  if (slot < 0 || slot > 5) return fail("streamer slot out of range");
+  if (count <= 0) return 0;
+  if (first < 0 || first + count > h->N) return fail("site range outside the local fluid sites");
+  if (slot != 0) {
+    // boundary streamers read per-site tables that only exist for boundary-typed sites
+    if (host_bidx(h, first) < 0 || host_bidx(h, first + count - 1) < 0 ||
+        (first < h->midTotal && first + count > h->midTotal))
+      return fail("boundary streamer called on bulk-typed sites");
+  }
+  int whole = -1;
+  for (int k = 0; k < 12; ++k)
+    if (first == h->rangeFirst[k] && first + count == h->rangeFirst[k + 1]) whole = k;
+  if (h->schedule && whole >= 0 && slot == whole % 6) {
+    const uint32_t bit = 1u << (whole % 6);
+    if (post) {
+      const uint32_t pbit = 1u << whole;
+      if (flush_sc(h, 1) || flush_sc(h, 0)) return 1;  // PostStep follows all streaming
+      if (!(h->post.all & pbit)) return 0;             // nothing to do on this range
+      if (h->post.done & pbit) return 0;
+      if (h->announced) {
+        h->post.done = h->post.all;
+        return launch_post_links(h);
+      }
+      if ((h->post.pending & pbit) && flush_post(h)) return 1;
+      h->post.pending |= pbit;
+      if (h->post.pending == h->post.all) return flush_post(h);
+      return 0;
+    }
+    const int part = whole / 6;
+    hlb_gpu_handle::Deferred& D = h->sc[part];
+    if (D.done & bit) return 0;  // ran with the rest of its part earlier in this announced step
+    if (h->announced) {
+      if (flush_sc(h, part)) return 1;
+      D.done = D.all;
+      return launch_part(h, part);
+    }
+    if ((D.pending & bit) && flush_sc(h, part)) return 1;
+    D.pending |= bit;
+    if (D.pending == D.all) return flush_sc(h, part);
+    return 0;
+  }
+  if (flush_deferred(h)) return 1;
+  return launch_now(h, slot, first, count, post);
 }
 
 int post_comms(hlb_gpu_t h) {
   // FieldData::SendAndReceive (FieldData.cc:27-39): per neighbour, receive into the slice of
   // f_old and send the same slice of f_new, on the comm stream after the edge ranges finished.
+  if (flush_sc(h, 1)) return 1;  // the domain-edge sites write what is sent
   if (h->neighbours.empty()) return 0;
   if (!h->comm_nccl) return 0;  // host-staged exchange: the caller moves the halo (get_halo / set_halo)
   CU(cudaEventRecord(h->evEdge, h->compute));
@@ -911,12 +1008,11 @@ int post_comms(hlb_gpu_t h) {
 int upload_densities(hlb_gpu_t h, int which, const double* d) {
   const int n = which ? h->cfg.n_outlets : h->cfg.n_inlets;
   if (n == 0) return 0;
-  if (join_aux(h)) return 1;
+  if (join_aux(h)) return 1;  // held-back launches belong to the step whose densities are still set
   if (!d) return fail("iolet densities missing");
-  // ring of pinned slots: a slot is reused only after the stream drained (every kPinnedSlots steps)
+  // ring of pinned slots: a slot is reused only after the stream drained (every kPinnedSlots uploads;
+  // the H2D copies out of the ring are stream-ordered on `compute`)
   const int slot = (int)(h->pinnedCursor[which]++ % kPinnedSlots);
-  // (the H2D copies out of the ring are stream-ordered on `compute`; join_aux above put the
-  // boundary stream behind it, so a drained `compute` means every earlier slot has been read)
   if (slot == 0 && h->pinnedCursor[which] > 1) CU(cudaStreamSynchronize(h->compute));
   double* src = h->ioletDensityPinned[which] + (size_t)slot * n;
   std::memcpy(src, d, sizeof(double) * n);
@@ -954,6 +1050,8 @@ int exchange_site_halo(hlb_gpu_t h) {
 
 int one_step(hlb_gpu_t h) {
   if (exchange_site_halo(h)) return 1;
+  h->scalarsSet = false;  // the densities below replace whatever hlb_gpu_set_step_scalars uploaded
+  h->sc[0].done = h->sc[1].done = h->post.done = 0;
   // BoundaryValues::GetBoundaryDensity -> iolet->GetDensity(Get0IndexedTimeStep())
   for (int w = 0; w < 2; ++w) {
     const int n = w ? h->cfg.n_outlets : h->cfg.n_inlets;
@@ -984,8 +1082,10 @@ int one_step(hlb_gpu_t h) {
     if (launch_range(h, t, off, h->mid[t], true)) return 1;
     off += h->mid[t];
   }
+  if (flush_deferred(h)) return 1;
   h->cur ^= 1;    // FieldData::SwapOldAndNew
   h->timeStep++;  // SimulationState::Increment
+  new_step_state(h);
   return 0;
 }
 
@@ -1030,9 +1130,7 @@ int hlb_gpu_internal_view(hlb_gpu_t h, hlb_gpu_view* out) {
   out->nranks = h->cfg.nranks;
   out->N = h->N;
   out->stride = h->stride;
-  out->midBulk = h->midBulk;
-  out->midTotal = h->midTotal;
-  out->edgeBulk = h->edgeBulk;
+  out->bInfo = h->bInfo;
   out->bStride = h->bStride;
   out->f[0] = h->f[h->cur];
   out->f[1] = h->f[h->cur ^ 1];
@@ -1107,24 +1205,11 @@ int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
   CU(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&h->comm, cudaStreamNonBlocking));
   {
-    int lo = 0, hi = 0;  // (numerically lowest = highest priority)
-    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    CU(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, hi));
-    // measured (profiles/README.md): +0.6 % on a 1e8-site single-GPU step and +4..16 % on small
-    // ones, but -0.9 % on the 2-GPU tree where NCCL traffic shares the machine -> default on for
-    // a single rank only; HLB_OVERLAP=0/1 or hlb_gpu_set_overlap override
-    const char* eh = getenv("HLB_FILL_HOLES");
-    h->fillHoles = !(eh && eh[0] == '0');
-    const char* ef = getenv("HLB_FUSE");
-    h->fuse = !(ef && ef[0] == '0');
-    const char* e = getenv("HLB_OVERLAP");
-    h->overlap = e ? (e[0] != '0') : (cfg->nranks <= 1);
-    h->overlapDefault = h->overlap;
-    h->fuseDefault = h->fuse;
-    h->fillHolesDefault = h->fillHoles;
+    // HLB_SCHEDULE=0: every request its own launch, in the caller's order (as hlb_gpu_set_overlap(0))
+    const char* e = getenv("HLB_SCHEDULE");
+    h->schedule = !(e && e[0] == '0');
+    h->scheduleDefault = h->schedule;
   }
-  CU(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
-  CU(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&h->evEdge, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&h->evComm, cudaEventDisableTiming));
   CU(cudaEventCreate(&h->evT0));
@@ -1162,7 +1247,6 @@ int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
 #define HLB_PICK(QQ, KK, KE)                                      \
   if (Q == QQ && cfg->kernel == KK) {                             \
     h->launch = &launch_collide_stream<QQ, KE>;                   \
-    h->launchFused = &launch_fused_mid<QQ, KE>;                   \
     fill_mrt<QQ>(h);                                              \
   }
   HLB_PICK(15, 0, K_LBGK) HLB_PICK(15, 1, K_MRT) HLB_PICK(15, 2, K_TRT)
@@ -1210,17 +1294,17 @@ int hlb_gpu_destroy(hlb_gpu_t h) {
   if (h->evGzsDone) cudaEventDestroy(h->evGzsDone);
   cudaFree(h->iperm);
   cudaFree(h->coordsAll);
-  cudaFree(h->nbrFlags);
-  cudaFree(h->nbrBase);
+  cudaFree(h->bInfo);
+  cudaFree(h->bSite);
+  cudaFree(h->bRec);
+  cudaFree(h->postI);
+  cudaFree(h->postD);
+  cudaFree(h->postQ);
   cudaEventDestroy(h->evEdge);
   cudaEventDestroy(h->evComm);
   cudaEventDestroy(h->evT0);
   cudaEventDestroy(h->evT1);
   cudaStreamDestroy(h->compute);
-  if (h->aux) cudaStreamDestroy(h->aux);
-  if (h->midItems) cudaFree(h->midItems);
-  if (h->evFork) cudaEventDestroy(h->evFork);
-  if (h->evJoin) cudaEventDestroy(h->evJoin);
   cudaStreamDestroy(h->comm);
   delete h;
   return 0;
@@ -1463,16 +1547,25 @@ int hlb_gpu_finalise(hlb_gpu_t h) {
       if (h->hIoletId[b] >= limit)
         return fail("iolet id of a site is outside the iolet table of its range (ids index the inlet table in "
                     "inlet-typed ranges and the outlet table in outlet-typed ranges)");
+      // which of the two BoundaryValues objects the id indexes travels with the id
+      if (type == 3 || type == 5) h->hIoletId[b] |= kOutletTypedBit;
     }
   }
-  h->allMidMask = 0;
-  for (int t = 0; t < 6; ++t)
-    if (h->mid[t] > 0) h->allMidMask |= 1u << t;
+  for (int part = 0; part < 2; ++part) {
+    h->sc[part] = hlb_gpu_handle::Deferred();
+    for (int t = 0; t < 6; ++t)
+      if ((part ? h->edge[t] : h->mid[t]) > 0) h->sc[part].all |= 1u << t;
+  }
+  h->post = hlb_gpu_handle::Deferred();
+  if (h->cfg.wall == HLB_WALL_BFL)
+    for (int k = 0; k < 12; ++k)
+      if ((k % 6 == 1 || k % 6 >= 4) && h->rangeFirst[k + 1] > h->rangeFirst[k]) h->post.all |= 1u << k;
   if (h->cfg.reorder && h->N > 0) {
     if (h->coordsCovered != h->N)
       return fail("reorder requested but hlb_gpu_set_site_coords did not cover every site exactly once");
     if (build_permutation(h)) return 1;
   }
+  if (build_boundary_order(h)) return 1;
   CU(cudaMemcpy(h->wallMask, h->hWall.data(), sizeof(uint32_t) * h->bStride, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->ioletMask, h->hIolet.data(), sizeof(uint32_t) * h->bStride, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(h->ioletId, h->hIoletId.data(), sizeof(int32_t) * h->bStride, cudaMemcpyHostToDevice));
@@ -1482,7 +1575,7 @@ int hlb_gpu_finalise(hlb_gpu_t h) {
   if (h->cfg.wall == HLB_WALL_GZS && h->NB) {
     CU(cudaMalloc(&h->gzsNeighbour, sizeof(int32_t) * (Q - 1) * h->bStride));
     gzs_neighbour_kernel<<<blocks_for(h->NB * (Q - 1)), 256>>>(h->nbr, h->gzsNeighbour, Q, h->stride, h->bStride,
-                                                               h->NB, h->midBulk, h->midTotal, h->edgeBulk);
+                                                               h->NB, h->bSite);
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
     // a GZS link that would extrapolate from a site on another rank needs the phase-0 site halo
@@ -1507,7 +1600,7 @@ int hlb_gpu_finalise(hlb_gpu_t h) {
     }
     auto internal = [&](int64_t s) { return hp.empty() ? s : (int64_t)hp[s]; };
     for (int64_t k = 0; k < h->nGzsNeed; ++k) {
-      const int64_t b = host_bidx(h, internal(h->gzsNeedSite[k]));
+      const int64_t b = h->refOrdToB[host_bidx(h, h->gzsNeedSite[k])];
       g[(size_t)(h->gzsNeedDir[k] - 1) * h->bStride + b] = (int32_t)(-(k + 1));
       if (h->gzsRecvPeers.empty() || h->gzsRecvPeers.back().rank != h->gzsNeedOwner[k])
         h->gzsRecvPeers.push_back({h->gzsNeedOwner[k], k, 0});
@@ -1538,11 +1631,16 @@ int hlb_gpu_finalise(hlb_gpu_t h) {
     CU(cudaEventCreateWithFlags(&h->evGzsDone, cudaEventDisableTiming));
   }
   {
-    // run-compressed neighbour table: measured slower than the plain table on B200 in round 1
-    // (89% vs 94% of HBM peak for the bulk kernel), so it is opt-in: HLB_COMPRESS=1
-    const char* e = getenv("HLB_COMPRESS");
-    if (h->N > 0 && e && e[0] == '1' && build_compressed(h)) return 1;
+    const int words = Q == 15 ? brec_words<15>() : (Q == 19 ? brec_words<19>() : brec_words<27>());
+    CU(cudaMalloc(&h->bRec, sizeof(uint32_t) * words * std::max<int64_t>(h->NB, 1)));
+    if (h->NB) {
+      boundary_records_kernel<<<blocks_for(h->NB * words), 256>>>(h->wallMask, h->ioletMask, h->ioletId, h->cutDist,
+                                                                  h->bStride, h->NB, Q, words, (uint32_t*)h->bRec);
+      CU(cudaGetLastError());
+      CU(cudaDeviceSynchronize());
+    }
   }
+  if (build_post_links(h)) return 1;
   if (h->coordsAll) {
     cudaFree(h->coordsAll);
     h->coordsAll = nullptr;
@@ -1660,13 +1758,34 @@ int hlb_gpu_set_step_scalars(hlb_gpu_t h, uint64_t timeStep, const double* inDen
                              uint32_t cacheMask) {
   if (!h) return fail("null argument");
   CU(cudaSetDevice(h->cfg.device));
+  {
+    // the same values again (every streamer of a step pushes them): nothing to do, and nothing held
+    // back has to leave early
+    bool same = h->scalarsSet && h->lastStep == timeStep && h->lastMask == cacheMask;
+    for (int w = 0; w < 2 && same; ++w) {
+      const int n = w ? h->cfg.n_outlets : h->cfg.n_inlets;
+      const double* d = w ? outDens : inDens;
+      if (n && !d) return fail("iolet densities missing");
+      same = (int)h->lastDens[w].size() == n && (n == 0 || std::memcmp(h->lastDens[w].data(), d, sizeof(double) * n) == 0);
+    }
+    if (same) return 0;
+  }
   if (join_aux(h)) return 1;  // deferred launches belong to the step whose scalars are still set
+  h->sc[0].done = h->sc[1].done = h->post.done = 0;  // what follows runs with the new scalars
   h->timeStep = timeStep;
   if (ensure_caches(h, cacheMask)) return 1;
   h->cacheMask = cacheMask;
   h->monitorFused = (cacheMask & C_MONITOR) != 0;
   if (upload_densities(h, 0, inDens)) return 1;
   if (upload_densities(h, 1, outDens)) return 1;
+  h->scalarsSet = true;
+  h->lastStep = timeStep;
+  h->lastMask = cacheMask;
+  for (int w = 0; w < 2; ++w) {
+    const int n = w ? h->cfg.n_outlets : h->cfg.n_inlets;
+    const double* d = w ? outDens : inDens;
+    h->lastDens[w].assign(d, d + n);
+  }
   return 0;
 }
 
@@ -1710,8 +1829,11 @@ int hlb_gpu_set_gzs_ghost(hlb_gpu_t h, const double* in) {
 int hlb_gpu_request_comms(hlb_gpu_t h) {
   // LBM::RequestComms only *registers* the sends/receives with the Net (lb.hpp:162-173); they are
   // issued after PreSend.  Mirror that: remember, and post when the edge ranges have been issued.
+  // It is also the first call of every time step of lb::LBM: a whole step follows, so each part may
+  // leave as one launch at its first request (see hlb_gpu_handle::Deferred).
   if (!h) return fail("null argument");
   h->edgePending = true;
+  h->announced = true;
   return 0;
 }
 
@@ -1754,6 +1876,7 @@ int hlb_gpu_swap(hlb_gpu_t h) {
   if (!h) return fail("null argument");
   if (join_aux(h)) return 1;
   h->cur ^= 1;
+  new_step_state(h);
   return 0;
 }
 
@@ -1784,9 +1907,7 @@ int hlb_gpu_step(hlb_gpu_t h, int nsteps) {
 int hlb_gpu_set_overlap(hlb_gpu_t h, int enabled) {
   if (!h) return fail("null argument");
   if (join_aux(h)) return 1;
-  h->overlap = enabled ? h->overlapDefault : false;
-  h->fuse = enabled ? h->fuseDefault : false;
-  h->fillHoles = enabled ? h->fillHolesDefault : false;
+  h->schedule = enabled ? h->scheduleDefault : false;
   return 0;
 }
 

@@ -1,7 +1,6 @@
 // D3Q15 TRT: collide-and-stream kernels for all wall / iolet link policies.
 #include "instantiate.cuh"
 namespace hlb {
-template void launch_collide_stream<15, K_TRT>(int, int, const StepArgs&, const void*, int64_t, int64_t, void*);
-template bool launch_fused_mid<15, K_TRT>(int, int, int, const StepArgs&, const void*, const IoletDev*, const double*,
-                                               const MidItem*, int64_t, void*);
+template void launch_collide_stream<15, K_TRT>(int, int, int, const StepArgs&, const void*, int64_t, int64_t, const uint32_t*,
+                                             int64_t, int64_t, void*);
 }

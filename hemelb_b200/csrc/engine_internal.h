@@ -4,6 +4,7 @@
 // C ABI (include/hemelb_b200.h); both translation units live in the same shared library.
 #pragma once
 #include <cstdint>
+#include <vector_types.h>
 
 #include "../../include/hemelb_b200.h"
 
@@ -33,7 +34,8 @@ int hlb_internal_fail(const char* msg);
 // (extraction.cu): where the distributions, caches and boundary tables live on the device.
 struct hlb_gpu_view {
   int Q, device, rank, nranks;
-  int64_t N, stride, midBulk, midTotal, edgeBulk, bStride;
+  int64_t N, stride, bStride;
+  const uint2* bInfo;         // per 32 internal sites {bitmap of boundary-typed sites, ordinal of the first}
   double* f[2];               // f[0] = current f_old, f[1] = current f_new (SoA, `stride`)
   const uint32_t* perm;       // reference site -> internal site, or null (identity)
   const uint32_t* wallMask;   // by boundary ordinal of the INTERNAL site

@@ -59,7 +59,8 @@ struct EncodeArgs {
   const uint32_t* sites;     // included sites (reference ids), ascending
   const uint32_t* coordsBE;  // 3 big-endian words per included site
   const double* f;           // current f_old (SoA)
-  int64_t stride, midBulk, midTotal, edgeBulk, bStride;
+  int64_t stride, bStride;
+  const uint2* bInfo;
   const uint32_t* perm;
   const double* wallNormal;
   const double* cache[8];
@@ -68,11 +69,11 @@ struct EncodeArgs {
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 
-__device__ __forceinline__ int64_t bidx_of(int64_t site, int64_t midBulk, int64_t midTotal, int64_t edgeBulk) {
-  if (site < midBulk) return -1;
-  if (site < midTotal) return site - midBulk;
-  if (site < midTotal + edgeBulk) return -1;
-  return site - midTotal - edgeBulk + (midTotal - midBulk);
+// boundary ordinal of a device site (-1: bulk-typed), as the engine's kernels find it
+__device__ __forceinline__ int64_t bidx_of(int64_t site, const uint2* __restrict__ bInfo) {
+  const uint2 bi = bInfo[site >> 5];
+  const unsigned lane = (unsigned)site & 31u;
+  return ((bi.x >> lane) & 1u) ? (int64_t)bi.y + __popc(bi.x & ((1u << lane) - 1u)) : -1;
 }
 
 // x86-64 conversions of a double to the integer file types (cvttsd2si semantics)
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(kTileSites) xtr_encode_kernel(EncodeArgs A, ui
         case 6: {  // Traction: t * latticePressure + (normal * ref) * mmHg; the normal of a site the
                    // geometry file gave none is Vector3D<float>(NO_VALUE) = +inf (Domain.cc:209-211)
           const int64_t i = A.perm ? (int64_t)A.perm[s] : s;
-          const int64_t b = bidx_of(i, A.midBulk, A.midTotal, A.edgeBulk);
+          const int64_t b = bidx_of(i, A.bInfo);
           for (int c = 0; c < 3; ++c) {
             const double nrm = b >= 0 ? A.wallNormal[(int64_t)c * A.bStride + b] : (double)INFINITY;
             double v = A.cache[6][3 * s + c] * C.latticePressure;
@@ -251,7 +252,7 @@ __device__ __forceinline__ float dot3(const float* a, const float* b) {
 
 __global__ void xtr_select_kernel(SelectorDev S, const int32_t* __restrict__ coords, int64_t coordStride, int64_t first,
                                   int64_t n, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ wallMask,
-                                  int64_t midBulk, int64_t midTotal, int64_t edgeBulk, int32_t* __restrict__ flags) {
+                                  const uint2* __restrict__ bInfo, int32_t* __restrict__ flags) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int64_t s = first + k;
@@ -260,7 +261,7 @@ __global__ void xtr_select_kernel(SelectorDev S, const int32_t* __restrict__ coo
     bool isWall = false;
     if (S.kind == 1 || S.kind == 4) {
       const int64_t i = perm ? (int64_t)perm[s] : s;
-      const int64_t b = bidx_of(i, midBulk, midTotal, edgeBulk);
+      const int64_t b = bidx_of(i, bInfo);
       isWall = b >= 0 && wallMask[b] != 0;  // SiteData::IsWall, SiteDataBare.cc:92-95
     }
     float x[3];
@@ -519,8 +520,7 @@ int build_site_list(hlb_xtr_handle* x, const hlb_xtr_spec* spec, const int32_t* 
         cp = planes;
         cstride = m;
       }
-      xtr_select_kernel<<<blocks_for(m), 256>>>(S, cp, cstride, s0, m, V.perm, V.wallMask, V.midBulk, V.midTotal,
-                                                V.edgeBulk, flags);
+      xtr_select_kernel<<<blocks_for(m), 256>>>(S, cp, cstride, s0, m, V.perm, V.wallMask, V.bInfo, flags);
       cub::DeviceScan::ExclusiveSum(scanTmp, scanBytes, flags, pos, (int)m);
       if (pass == 0) {
         int32_t lastPos = 0, lastFlag = 0;
@@ -721,9 +721,7 @@ int hlb_xtr_encode(hlb_xtr_t x, uint64_t first_site, uint64_t n_sites, void* hos
   A.coordsBE = x->coordsBE;
   A.f = x->V.f[0];
   A.stride = x->V.stride;
-  A.midBulk = x->V.midBulk;
-  A.midTotal = x->V.midTotal;
-  A.edgeBulk = x->V.edgeBulk;
+  A.bInfo = x->V.bInfo;
   A.bStride = x->V.bStride;
   A.perm = x->V.perm;
   A.wallNormal = x->V.wallNormal;

@@ -30,6 +30,9 @@
 #ifndef HLB_Q27_MIN_CTAS
 #define HLB_Q27_MIN_CTAS 3
 #endif
+#ifndef HLB_MIN_CTAS
+#define HLB_MIN_CTAS 2
+#endif
 
 namespace hlb {
 
@@ -57,29 +60,37 @@ struct StepArgs {
   double* __restrict__ fNew;
   const uint32_t* __restrict__ nbr;  // (Q-1) planes: target of direction d at nbr[(d-1)*stride + s]
   int64_t stride;
-  // boundary-site tables, indexed by boundary ordinal b (see bidx())
+  // which internal sites are boundary-typed (collision types 1..5), 32 sites per word:
+  // bInfo[s >> 5] = {bitmap, boundary ordinal of the word's first boundary-typed site}
+  const uint2* __restrict__ bInfo;
+  // boundary-site tables, indexed by boundary ordinal b (see bidx()); ordinals ascend with the
+  // internal site id
   const uint32_t* __restrict__ wallMask;
   const uint32_t* __restrict__ ioletMask;
-  const int32_t* __restrict__ ioletId;
+  const int32_t* __restrict__ ioletId;   // SiteData::GetIoletId() | kOutletTypedBit for outlet / outlet-wall typed sites
   const float* __restrict__ cutDist;     // (Q-1) planes of bStride
   const double* __restrict__ wallNormal; // 3 planes of bStride
   const int32_t* __restrict__ coords;    // 3 planes of bStride
   int64_t bStride;
-  int64_t midBulk, midTotal, edgeBulk;   // bulk counts / mid-domain total, for bidx()
-  // GZS: whole-site f_old rows of remote neighbours (NeighbouringDataManager) live after the
-  // local planes: ghost row g of direction d at fOld[...]; not used unless WALL == W_GZS
+  // the same masks, iolet id and cut distances once more, one record per boundary-typed site
+  // (brec_words<Q>() 32-bit words: wallMask, ioletMask, ioletId, 0, then the Q-1 float cut distances,
+  // padded to 16 B): what the site kernel stages through shared memory with cp.async
+  const uint4* __restrict__ bRec;
+  // GZS: whole-site f_old rows of remote neighbours (NeighbouringDataManager); not used unless
+  // WALL == W_GZS
   const int32_t* __restrict__ gzsNeighbour;  // (Q-1) planes of bStride: local site id, or -(g+1)
   const double* __restrict__ gzsGhost;       // ghost row g = Q consecutive doubles at gzsGhost[g*Q]
-  int64_t ghostStride;                       // (unused; rows are site-major as they travel)
-  // iolets of this range's BoundaryValues object + per-step scalars
-  const IoletDev* __restrict__ iolets;
-  const double* __restrict__ ioletDensity;   // GetBoundaryDensity(id) for this step
-  uint64_t timeStep;                         // SimulationState::GetTimeStep() (1-indexed)
-  // mid-fluid launches that are known to be followed by the mid-domain boundary ranges (whole-step
-  // schedule): sites [holeFirst, holeFirst + holeCount) are those boundary sites.  A slot of a
-  // mid-fluid site fed by one of them is pre-written here so that the sector it shares with three
-  // mid-fluid-fed slots leaves L2 whole; the boundary streamer overwrites it afterwards.
-  uint32_t holeFirst, holeCount;
+  // the two BoundaryValues objects (lb.hpp:87-113: inletValues for the inlet / inlet-wall
+  // streamers, outletValues for the outlet / outlet-wall ones) + their per-step densities
+  const IoletDev* __restrict__ iolets[2];
+  const double* __restrict__ ioletDensity[2];  // GetBoundaryDensity(id) for this step
+  uint64_t timeStep;                           // SimulationState::GetTimeStep() (1-indexed)
+  // which link policies this launch applies (warp-uniform).  A whole-part launch runs every site
+  // with the streamer of its own collision type (ioletSel = kIoletByType, wallOn = 1); a launch for
+  // one streamer slot (StreamerTests-style sub-range calls, plain order) runs that streamer on
+  // whatever sites it is given: wallOn = the slot has a wall link; ioletSel = kIoletNone, or 0 / 1 =
+  // every iolet link goes to the inlet / outlet object with the inlet / outlet link policy
+  int wallOn, ioletSel;
   // LbmParameters
   double tau, omega, stressParameter, omegaMinus;
   // caches (MacroscopicPropertyCache), site-major like the reference
@@ -93,28 +104,27 @@ struct StepArgs {
   double* __restrict__ cTraction;
   double* __restrict__ cTangTraction;
   const uint32_t* __restrict__ refSiteOf;  // internal site -> reference site id (cache rows), or null
-  // optional explicit site list (sub-range calls that are not whole ranges)
+  // optional explicit site list (launches that are not a contiguous run of internal sites)
   const uint32_t* __restrict__ siteList;
-  // run-compressed neighbour table (whole-range launches only): for the g-th group of 32 sites of
-  // this launch, bit d-1 of nbrFlags says "the 32 targets of direction d are consecutive", and
-  // nbrBase then holds the first one -- one 4 B load per warp instead of 128 B
-  const uint32_t* __restrict__ nbrFlags;
-  const uint32_t* __restrict__ nbrBase;  // (Q-1) planes of groupStride
-  int64_t groupStride, groupOffset;
   // fused monitors (C_MONITOR): {min f, min rho, max rho, max u^2} as order-preserving u64 keys
   unsigned long long* __restrict__ monitorSlots;
 };
+constexpr int kIoletNone = -1, kIoletByType = 2;
+constexpr int32_t kOutletTypedBit = 1 << 30;
 
-template <int Q> constexpr int site_threads() { return Q > 19 ? HLB_Q27_THREADS : 256; }
-template <int Q> constexpr int site_min_ctas() { return Q > 19 ? HLB_Q27_MIN_CTAS : 2; }
+template <int Q> __host__ __device__ constexpr int brec_words() { return ((4 + Q - 1) + 3) / 4 * 4; }
+template <int Q> __host__ __device__ constexpr int site_threads() { return Q > 19 ? HLB_Q27_THREADS : 256; }
+template <int Q> __host__ __device__ constexpr int site_min_ctas() { return Q > 19 ? HLB_Q27_MIN_CTAS : HLB_MIN_CTAS; }
 
 template <int Q> struct MrtArgs {
   double SMn[mrt_k<Q>() > 0 ? mrt_k<Q>() : 1][Q];  // collisionMatrixDiagonals[k] * normalisedReducedMomentBasis[k][d]
 };
 
+// boundary ordinal of an internal site, or -1 for a bulk-typed one
 __device__ __forceinline__ int64_t bidx(const StepArgs& A, int64_t site) {
-  // boundary-typed sites are [midBulk, midTotal) and [midTotal+edgeBulk, N)
-  return site < A.midTotal ? site - A.midBulk : site - A.midTotal - A.edgeBulk + (A.midTotal - A.midBulk);
+  const uint2 bi = __ldg(A.bInfo + (site >> 5));
+  const unsigned lane = (unsigned)site & 31u;
+  return ((bi.x >> lane) & 1u) ? (int64_t)bi.y + __popc(bi.x & ((1u << lane) - 1u)) : -1;
 }
 
 // order-preserving map double -> u64 (so atomicMin/atomicMax on integers order doubles)
@@ -131,11 +141,14 @@ __device__ __forceinline__ double mon_dec(unsigned long long u) {
 // registers (Code/lb/StabilityTester.h:97-113: any f <= 0; IncompressibilityChecker: density
 // extrema, max speed): warp-reduce, then one relaxed atomic per value per warp, spread over slots.
 template <int Q>
-__device__ __forceinline__ void fused_monitor(const StepArgs& A, int64_t tid, const double (&f)[Q], double rho,
-                                              const double (&m)[3]) {
+__device__ __forceinline__ double min_population(const double (&f)[Q]) {
   double fmin = f[0];
 #pragma unroll
   for (int d = 1; d < Q; ++d) fmin = fmin < f[d] ? fmin : f[d];
+  return fmin;
+}
+__device__ __forceinline__ void fused_monitor(const StepArgs& A, int64_t tid, double fmin, double rho,
+                                              const double (&m)[3]) {
   double rmin = rho, rmax = rho;
   double u2 = (m[0] * m[0] + m[1] * m[1] + m[2] * m[2]) / (rho * rho);
   const unsigned mask = __activemask();
@@ -244,15 +257,14 @@ __device__ __forceinline__ void stress_tensor(double rho, double tau, const doub
 }
 
 template <int Q, int KERNEL>
-__device__ __forceinline__ void update_caches(const StepArgs& A, int64_t site, bool boundaryTyped, double rho,
+__device__ __forceinline__ void update_caches(const StepArgs& A, int64_t site, int64_t b, double rho,
                                            const double (&u)[3], const double (&fneq)[Q]) {
   // UpdateCachePostCollision, Common.h:21-130
   const int64_t row = A.refSiteOf ? A.refSiteOf[site] : site;
   const uint32_t mask = A.cacheMask;
   bool isWall = false;
   double nor[3] = {0, 0, 0};
-  if (boundaryTyped) {
-    const int64_t b = bidx(A, site);
+  if (b >= 0) {
     isWall = A.wallMask[b] != 0;
     nor[0] = A.wallNormal[b];
     nor[1] = A.wallNormal[A.bStride + b];
@@ -451,7 +463,9 @@ __device__ __forceinline__ void gzs_fill(const GzsNode<Q>& N, double (&fneqW)[Q]
 constexpr int kGzsTile = 128;  // (GzsNode::sf is typed on it)
 constexpr int kGzsThreads = 256;
 
-template <int Q, int KERNEL, int IOLET>
+// The launch covers `count` boundary-typed sites: siteList[0 .. count) (a whole part: the part's
+// slice of the boundary-site list), or the consecutive internal sites from `first`.
+template <int Q, int KERNEL>
 __global__ void __launch_bounds__(kGzsThreads, 2) gzs_links_kernel(const StepArgs A, const MrtArgs<Q> M, int64_t first,
                                                                int64_t count) {
   constexpr int T = kGzsTile;
@@ -472,8 +486,10 @@ __global__ void __launch_bounds__(kGzsThreads, 2) gzs_links_kernel(const StepArg
       const int64_t b = bidx(A, site);
       ssite[tx] = site;
       sb[tx] = (int32_t)b;
-      wall = A.wallMask[b];
-      if constexpr (IOLET != I_NONE) iol = A.ioletMask[b];
+      if (b >= 0) {
+        wall = A.wallMask[b];
+        if (A.ioletSel != kIoletNone) iol = A.ioletMask[b];
+      }
     }
     swall[tx] = wall;
     siolet[tx] = iol;
@@ -564,8 +580,10 @@ __global__ void __launch_bounds__(kGzsThreads, 2) gzs_links_kernel(const StepArg
     if (q < 0.75) {
       const bool hasIoletI = (ioletMask >> (i - 1)) & 1u;
       const bool hasWallI = (wallMask >> (i - 1)) & 1u;
-      if (IOLET != I_NONE && hasIoletI) {
-        const IoletDev& io = A.iolets[A.ioletId[b]];
+      if (hasIoletI) {
+        const int32_t enc = A.ioletId[b];
+        const int sel = A.ioletSel == kIoletByType ? ((enc & kOutletTypedBit) ? 1 : 0) : A.ioletSel;
+        const IoletDev& io = A.iolets[sel][enc & (kOutletTypedBit - 1)];
         if (io.kind != 1) {
           sbb = true;
         } else {
@@ -634,55 +652,168 @@ __global__ void __launch_bounds__(kGzsThreads, 2) gzs_links_kernel(const StepArg
 // ---------------------------------------------------------------------------------- the site kernel
 // Q <= 19: 256-thread CTAs, two resident per SM (<= 128 registers).  D3Q27 needs ~190 registers:
 // 128-thread CTAs, three resident (<= 168 registers; 12 warps per SM instead of 8).
-// One site: load, collide, stream, (rarely) extract moments.  `tid` only spreads the monitor atomics.
-template <int Q, int KERNEL, int WALL, int IOLET, bool COMPRESSED_TABLE>
-__device__ __forceinline__ void site_body(const StepArgs& A, const MrtArgs<Q>& M, const int64_t site, const int64_t tid,
-                                          const IoletDev* __restrict__ ioletTable,
-                                          const double* __restrict__ ioletDensityTable) {
-  constexpr bool HAS_WALL = WALL != W_NONE;
-  constexpr bool HAS_IOLET = IOLET != I_NONE;
 
+// per-site quantities of an iolet link policy (NashZerothOrderPressure.h:27-60 / LaddIolet.h:29-66)
+struct IoletSite {
+  const IoletDev* io;
+  double ghostRho, ghostD1, ghostMM, ghostM[3];  // Nash: the ghost site's density and momentum
+  double sx, sy, sz;                             // Ladd: the site's lattice position
+};
+
+template <int Q, int IOLET>
+__device__ __forceinline__ void iolet_site(const StepArgs& A, int sel, int id, int64_t b, double rho,
+                                           const double (&m)[3], IoletSite& S) {
+  S.io = A.iolets[sel] + id;
+  if constexpr (IOLET == I_NASH) {
+    S.ghostRho = A.ioletDensity[sel][id];
+    const float nf0 = (float)S.io->normal[0], nf1 = (float)S.io->normal[1], nf2 = (float)S.io->normal[2];
+    double dot = 0.0;
+    dot += m[0] * (double)nf0;
+    dot += m[1] * (double)nf1;
+    dot += m[2] * (double)nf2;
+    const double component = dot / rho;
+    S.ghostM[0] = ((double)nf0 * component) * S.ghostRho;
+    S.ghostM[1] = ((double)nf1 * component) * S.ghostRho;
+    S.ghostM[2] = ((double)nf2 * component) * S.ghostRho;
+    S.ghostD1 = 1. / S.ghostRho;
+    S.ghostMM = S.ghostM[0] * S.ghostM[0] + S.ghostM[1] * S.ghostM[1] + S.ghostM[2] * S.ghostM[2];
+  } else {
+    S.sx = (double)A.coords[b];
+    S.sy = (double)A.coords[A.bStride + b];
+    S.sz = (double)A.coords[2 * A.bStride + b];
+  }
+}
+
+// what an iolet link in direction D leaves in f_new[site, inv(D)]
+template <int Q, int IOLET, int D>
+__device__ __forceinline__ double iolet_link(const StepArgs& A, const IoletSite& S, double rho, double fpostD) {
+  constexpr int id = inv_dir(D);
+  if constexpr (IOLET == I_NASH) {
+    return feq_i<Q>(id, S.ghostRho, S.ghostD1, S.ghostMM, S.ghostM);
+  } else {
+    double x[3] = {S.sx + 0.5 * Lat<Q>::cx(D), S.sy + 0.5 * Lat<Q>::cy(D), S.sz + 0.5 * Lat<Q>::cz(D)};
+    double wallMom[3];
+    parabolic_velocity(*S.io, x, A.timeStep, wallMom);
+    wallMom[0] *= rho;
+    wallMom[1] *= rho;
+    wallMom[2] *= rho;
+    double dot = 0.0;
+    dot += wallMom[0] * (double)Lat<Q>::cx(D);
+    dot += wallMom[1] * (double)Lat<Q>::cy(D);
+    dot += wallMom[2] * (double)Lat<Q>::cz(D);
+    const double correction = 2. * Lat<Q>::W(D) * dot / kCs2;
+    return fpostD - correction;
+  }
+}
+
+// the cut links of one boundary-typed site, after its uncut links were pushed: iolet link first,
+// then wall link (StreamerTypeFactory.h:65-79)
+template <int Q, int WALL, int INLET, int OUTLET, int D>
+__device__ __forceinline__ void cut_links(const StepArgs& A, int64_t site, const uint32_t* __restrict__ rec,
+                                          uint32_t wallMask, uint32_t ioletMask, int sel, const IoletSite& S,
+                                          double rho, const double (&fpost)[Q]) {
+  if constexpr (D < Q) {
+    constexpr int id = inv_dir(D);
+    if ((ioletMask >> (D - 1)) & 1u) {
+      double v;
+      if constexpr (INLET == OUTLET) v = iolet_link<Q, INLET, D>(A, S, rho, fpost[D]);
+      else v = sel ? iolet_link<Q, OUTLET, D>(A, S, rho, fpost[D]) : iolet_link<Q, INLET, D>(A, S, rho, fpost[D]);
+      A.fNew[(int64_t)id * A.stride + site] = v;
+    } else if ((wallMask >> (D - 1)) & 1u) {
+      if constexpr (WALL == W_SBB) {  // SimpleBounceBack.h:23-42
+        A.fNew[(int64_t)id * A.stride + site] = fpost[D];
+      } else if constexpr (WALL == W_BFL) {  // BouzidiFirdaousLallemand.h:41-70
+        // word 4 + (D - 1) of the staged record: chunk (3 + D) / 4 of the thread's column
+        const double q = (double)__uint_as_float(rec[((3 + D) / 4) * (4 * site_threads<Q>()) + ((3 + D) & 3)]);
+        const bool invWall = (wallMask >> (id - 1)) & 1u;
+        double v;
+        if (invWall || q < 0.5) v = fpost[D];
+        else v = (fpost[D] + (2.0 * q - 1) * fpost[id]) / (2.0 * q);
+        A.fNew[(int64_t)id * A.stride + site] = v;
+      }
+      // W_GZS: gzs_links_kernel owns this population
+    }
+    cut_links<Q, WALL, INLET, OUTLET, D + 1>(A, site, rec, wallMask, ioletMask, sel, S, rho, fpost);
+  }
+}
+
+// The thread's index in the launch, read again from the special registers.  The rare blocks at
+// the end of the site kernel (moment extraction, monitors) use it instead of keeping the values
+// derived from the first read alive across the whole kernel (two registers that otherwise spill).
+__device__ __forceinline__ int64_t launch_tid_again() {
+  unsigned t, c, n;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+  asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(c));
+  asm volatile("mov.u32 %0, %%ntid.x;" : "=r"(n));
+  return (int64_t)c * n + t;
+}
+
+// The rare tail of the site kernel (moment extraction on output steps, monitors) as a real call,
+// so that the hot path reserves no registers for it.  The moments are extracted from f_old read
+// again (it is not written during a step): the same loads through the same arithmetic as the
+// site's collision, hence the same bits, but neither f nor f_neq has to outlive the collision.
+template <int Q, int KERNEL>
+__device__ __noinline__ void site_tail(const StepArgs& A, int64_t first, int b, double fmin, double rho0, double m0,
+                                       double m1, double m2) {
+  const int64_t tid = launch_tid_again();
+  if (A.cacheMask & 255u) {
+    const int64_t site = A.siteList ? (int64_t)A.siteList[tid] : first + tid;
+    double f[Q];
+#pragma unroll
+    for (int d = 0; d < Q; ++d) f[d] = A.fOld[(int64_t)d * A.stride + site];
+    double rho, m[3], u[3], fneq[Q];
+    density_momentum<Q>(f, rho, m);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) u[k] = m[k] / rho;
+    const double density_1 = 1. / rho;
+    const double mm = m[0] * m[0] + m[1] * m[1] + m[2] * m[2];
+#pragma unroll
+    for (int d = 0; d < Q; ++d) fneq[d] = f[d] - feq_i<Q>(d, rho, density_1, mm, m);
+    update_caches<Q, KERNEL>(A, site, b, rho, u, fneq);
+  }
+  if (A.cacheMask & C_MONITOR) {
+    const double m[3] = {m0, m1, m2};
+    fused_monitor(A, tid, fmin, rho0, m);
+  }
+}
+
+// One site: load, collide, stream, (rarely) extract moments.
+//
+// What a boundary-typed site needs beyond its populations -- masks, iolet id, cut distances: its
+// bRec record -- is fetched asynchronously (cp.async, 16 B chunks) into the thread's column of
+// `srec` as soon as the bitmap word says the site is boundary-typed, and is waited for after the
+// collision: no load of the kernel depends on another one except through that word (which is small
+// enough to stay in L2), whatever the site's type.
+template <int Q, int KERNEL, int WALL, int INLET, int OUTLET>
+__device__ __forceinline__ void site_body(const StepArgs& A, const MrtArgs<Q>& M, const int64_t site, const int64_t first,
+                                          uint4* __restrict__ srec) {
+  constexpr int T = site_threads<Q>(), RC = brec_words<Q>() / 4;
+  // is this a boundary-typed site?  One 8 B word per 32 sites, asked for first.
+  const uint2 bi = __ldg(A.bInfo + (site >> 5));
   double f[Q];
 #pragma unroll
   for (int d = 0; d < Q; ++d) f[d] = __ldcs(A.fOld + (int64_t)d * A.stride + site);
-  // boundary tables: issued with the distribution loads, not after the collision.  The BFL cut
-  // distances are fetched for every direction (plane-major, coalesced; the sectors are shared with
-  // the neighbouring wall sites and would be read anyway) so that no load waits for the wall mask.
-  uint32_t wallMask = 0, ioletMask = 0;
-  int64_t b = 0;
-  float cut[WALL == W_BFL ? Q : 1];
-  if constexpr (HAS_WALL || HAS_IOLET) {
-    b = bidx(A, site);
-    if constexpr (HAS_WALL) wallMask = __ldg(A.wallMask + b);
-    if constexpr (HAS_IOLET) ioletMask = __ldg(A.ioletMask + b);
-    if constexpr (WALL == W_BFL) {
-#pragma unroll
-      for (int d = 1; d < Q; ++d) cut[d] = __ldg(A.cutDist + (int64_t)(d - 1) * A.bStride + b);
-    }
-  }
   uint32_t target[Q];
   target[0] = (uint32_t)site;
-  if (COMPRESSED_TABLE && A.nbrFlags) {
-    const int64_t g = A.groupOffset + (tid >> 5);
-    const uint32_t flags = __ldg(A.nbrFlags + g);
-    const uint32_t lane = (uint32_t)(tid & 31);
-    // the per-group bases are fetched unconditionally (warp-uniform, independent of the flags, so
-    // they overlap the f loads); only the rare non-consecutive group pays a dependent table load
 #pragma unroll
-    for (int d = 1; d < Q; ++d) target[d] = __ldg(A.nbrBase + (int64_t)(d - 1) * A.groupStride + g) + lane;
+  for (int d = 1; d < Q; ++d) target[d] = __ldcs(A.nbr + (int64_t)(d - 1) * A.stride + site);
+  int b = -1;
+  {
+    const unsigned lane = (unsigned)site & 31u;
+    if ((bi.x >> lane) & 1u) {
+      b = (int)(bi.y + __popc(bi.x & ((1u << lane) - 1u)));
+      const uint4* src = A.bRec + (int64_t)b * RC;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(srec + threadIdx.x);
 #pragma unroll
-    for (int d = 1; d < Q; ++d)
-      if (!((flags >> (d - 1)) & 1u)) target[d] = __ldcs(A.nbr + (int64_t)(d - 1) * A.stride + site);
-  } else {
-#pragma unroll
-    for (int d = 1; d < Q; ++d) target[d] = __ldcs(A.nbr + (int64_t)(d - 1) * A.stride + site);
+      for (int c = 0; c < RC; ++c)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)(c * T * sizeof(uint4))), "l"(src + c)
+                     : "memory");
+    }
   }
 
   // CalculatePreCollision (Normal.h:29-33 -> kernel.CalculateDensityMomentumFeq)
-  double rho, m[3], u[3];
+  double rho, m[3];
   density_momentum<Q>(f, rho, m);
-#pragma unroll
-  for (int k = 0; k < 3; ++k) u[k] = m[k] / rho;
   double fneq[Q], fpost[Q];
   {
     const double density_1 = 1. / rho;
@@ -690,163 +821,62 @@ __device__ __forceinline__ void site_body(const StepArgs& A, const MrtArgs<Q>& M
 #pragma unroll
     for (int d = 0; d < Q; ++d) fneq[d] = f[d] - feq_i<Q>(d, rho, density_1, mm, m);
   }
-  // Where the (rare) moment extraction / monitor block sits decides which Q-arrays are live across
-  // the pushes.  Before the collision: f and f_neq die as f_post is formed (MRT, whose collision
-  // needs many temporaries, and D3Q27: 30-60 fewer registers).  After the pushes: the index and cut
-  // distance registers are free by then (LBGK / TRT on Q <= 19 fit 128 registers that way).
-  constexpr bool CACHES_FIRST = KERNEL == K_MRT || Q > 19;
-  if constexpr (CACHES_FIRST) {
-    if (A.cacheMask) {
-      if (A.cacheMask & 255u) update_caches<Q, KERNEL>(A, site, HAS_WALL || HAS_IOLET, rho, u, fneq);
-      if (A.cacheMask & C_MONITOR) fused_monitor<Q>(A, tid, f, rho, m);
-    }
-  }
+  // (the monitor's smallest population is taken now: f and f_neq die with the collision)
+  double fmin = 0.0;
+  if (A.cacheMask & C_MONITOR) fmin = min_population<Q>(f);
   collide<Q, KERNEL>(A, M, f, fneq, fpost);
 
-  // per-site iolet quantities (NashZerothOrderPressure.h:27-60 / LaddIolet.h:29-66)
-  double ghostRho = 0, ghostM[3] = {0, 0, 0}, ghostD1 = 0, ghostMM = 0;
-  double wallMom[3] = {0, 0, 0};
-  double sx = 0, sy = 0, sz = 0;
-  const IoletDev* io = nullptr;
-  if constexpr (HAS_IOLET) {
-    if (ioletMask) {
-      const int id = A.ioletId[b];
-      io = ioletTable + id;
-      if constexpr (IOLET == I_NASH) {
-        ghostRho = ioletDensityTable[id];
-        const float nf0 = (float)io->normal[0], nf1 = (float)io->normal[1], nf2 = (float)io->normal[2];
-        double dot = 0.0;
-        dot += m[0] * (double)nf0;
-        dot += m[1] * (double)nf1;
-        dot += m[2] * (double)nf2;
-        const double component = dot / rho;
-        ghostM[0] = ((double)nf0 * component) * ghostRho;
-        ghostM[1] = ((double)nf1 * component) * ghostRho;
-        ghostM[2] = ((double)nf2 * component) * ghostRho;
-        ghostD1 = 1. / ghostRho;
-        ghostMM = ghostM[0] * ghostM[0] + ghostM[1] * ghostM[1] + ghostM[2] * ghostM[2];
-      } else {
-        sx = (double)A.coords[b];
-        sy = (double)A.coords[A.bStride + b];
-        sz = (double)A.coords[2 * A.bStride + b];
-      }
-    }
+  // the record has had the whole collision to arrive
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  const uint32_t* rec = reinterpret_cast<const uint32_t*>(srec + threadIdx.x);
+  uint32_t cut = 0;
+  if (b >= 0) {
+    if (A.wallOn) cut = rec[0];
+    if (A.ioletSel != kIoletNone) cut |= rec[1];
   }
-
-  if constexpr (!HAS_WALL && !HAS_IOLET) {
-    if (A.holeCount) {
-#pragma unroll
-      for (int d = 1; d < Q; ++d) {
-        // the site that streams into slot d of this site is this site's neighbour in direction inv(d)
-        const uint32_t up = target[inv_dir(d)] - (uint32_t)(inv_dir(d) * A.stride);
-        if (up - A.holeFirst < A.holeCount) A.fNew[(int64_t)d * A.stride + site] = 0.0;
-      }
-    }
-  }
-  // stream: iolet link, else wall link, else bulk push (StreamerTypeFactory.h:65-79)
+  // stream the uncut links (BulkStreamer.h:31-39); a mid-fluid site has no others
   A.fNew[target[0]] = fpost[0];
 #pragma unroll
-  for (int d = 1; d < Q; ++d) {
-    constexpr int dummy = 0;
-    (void)dummy;
-    const int id = inv_dir(d);
-    const bool hasIolet = HAS_IOLET && ((ioletMask >> (d - 1)) & 1u);
-    const bool hasWall = HAS_WALL && ((wallMask >> (d - 1)) & 1u);
-    if (hasIolet) {
-      if constexpr (IOLET == I_NASH) {
-        A.fNew[(int64_t)id * A.stride + site] = feq_i<Q>(id, ghostRho, ghostD1, ghostMM, ghostM);
-      } else if constexpr (IOLET == I_LADD) {
-        double x[3] = {sx + 0.5 * Lat<Q>::cx(d), sy + 0.5 * Lat<Q>::cy(d), sz + 0.5 * Lat<Q>::cz(d)};
-        parabolic_velocity(*io, x, A.timeStep, wallMom);
-        wallMom[0] *= rho;
-        wallMom[1] *= rho;
-        wallMom[2] *= rho;
-        double dot = 0.0;
-        dot += wallMom[0] * (double)Lat<Q>::cx(d);
-        dot += wallMom[1] * (double)Lat<Q>::cy(d);
-        dot += wallMom[2] * (double)Lat<Q>::cz(d);
-        const double correction = 2. * Lat<Q>::W(d) * dot / kCs2;
-        A.fNew[(int64_t)id * A.stride + site] = fpost[d] - correction;
-      }
-    } else if (hasWall) {
-      if constexpr (WALL == W_SBB) {  // SimpleBounceBack.h:23-42
-        A.fNew[(int64_t)id * A.stride + site] = fpost[d];
-      } else if constexpr (WALL == W_BFL) {  // BouzidiFirdaousLallemand.h:41-70
-        const double q = (double)cut[d];
-        const bool invWall = (wallMask >> (id - 1)) & 1u;
-        double v;
-        if (invWall || q < 0.5) v = fpost[d];
-        else v = (fpost[d] + (2.0 * q - 1) * fpost[id]) / (2.0 * q);
-        A.fNew[(int64_t)id * A.stride + site] = v;
-      }
-      // W_GZS: gzs_links_kernel owns this population
-    } else {
-      A.fNew[target[d]] = fpost[d];  // BulkStreamer.h:31-39
+  for (int d = 1; d < Q; ++d)
+    if (!((cut >> (d - 1)) & 1u)) A.fNew[target[d]] = fpost[d];
+  if (cut) {
+    const uint32_t wallMask = A.wallOn ? rec[0] : 0u;
+    const uint32_t ioletMask = A.ioletSel != kIoletNone ? rec[1] : 0u;
+    IoletSite S;
+    int sel = 0;
+    if (ioletMask) {
+      const int32_t enc = (int32_t)rec[2];
+      sel = A.ioletSel == kIoletByType ? ((enc & kOutletTypedBit) ? 1 : 0) : A.ioletSel;
+      const int id = enc & (kOutletTypedBit - 1);
+      if constexpr (INLET == OUTLET) iolet_site<Q, INLET>(A, sel, id, b, rho, m, S);
+      else if (sel) iolet_site<Q, OUTLET>(A, sel, id, b, rho, m, S);
+      else iolet_site<Q, INLET>(A, sel, id, b, rho, m, S);
     }
+    cut_links<Q, WALL, INLET, OUTLET, 1>(A, site, rec, wallMask, ioletMask, sel, S, rho, fpost);
   }
 
-  if constexpr (!CACHES_FIRST) {
-    if (A.cacheMask) {
-      if (A.cacheMask & 255u) update_caches<Q, KERNEL>(A, site, HAS_WALL || HAS_IOLET, rho, u, fneq);
-      if (A.cacheMask & C_MONITOR) fused_monitor<Q>(A, tid, f, rho, m);
-    }
-  }
+  if (A.cacheMask) site_tail<Q, KERNEL>(A, first, b, fmin, rho, m[0], m[1], m[2]);
 }
 
-template <int Q, int KERNEL, int WALL, int IOLET>
-__global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) collide_stream_kernel(const StepArgs A, const MrtArgs<Q> M, int64_t first, int64_t count) {
+// `count` sites: siteList[0 .. count), or the consecutive internal sites from `first`
+template <int Q, int KERNEL, int WALL, int INLET, int OUTLET>
+__global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) collide_stream_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ MrtArgs<Q> M, int64_t first, int64_t count) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= count) return;
   const int64_t site = A.siteList ? (int64_t)A.siteList[tid] : first + tid;
-  site_body<Q, KERNEL, WALL, IOLET, true>(A, M, site, tid, A.iolets, A.ioletDensity);
+  __shared__ uint4 srec[(brec_words<Q>() / 4) * site_threads<Q>()];
+  site_body<Q, KERNEL, WALL, INLET, OUTLET>(A, M, site, first, srec);
 }
 
-// ---------------------------------------------------------------------------------- the fused mid-domain kernel
-// All six mid-domain ranges of LBM::PreReceive in ONE launch.  The ranges are cut into work items
-// of <= site_threads sites; the items of all ranges are merged by the (x, y, z) key of their first
-// site, so the CTA that updates the wall / inlet / outlet sites of a lattice row runs next to (in
-// time) the CTAs that update the row's mid-fluid sites, and the per-range kernel tails disappear.
-// Measured (profiles/README.md): +11..12 % on MRT and D3Q27 steps, whose mid-fluid kernel is not at
-// the HBM limit; -8 % on D3Q19 LBGK, where the stand-alone mid-fluid kernel runs at 98.5 % of the
-// peak and the item-descriptor load in front of every CTA's distribution loads costs more than
-// the fusion gains.  Hence instantiated, and used, for MRT and D3Q27 only (launch_fused_mid).
-struct MidItem {
-  uint32_t first;      // internal site id
-  uint32_t countSlot;  // sites in the item | streamer slot << 16
-};
-
-template <int Q, int KERNEL, int WALL, int INLET, int OUTLET>
-__global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) fused_mid_kernel(
-    const StepArgs A, const MrtArgs<Q> M, const IoletDev* __restrict__ inletIolets,
-    const double* __restrict__ inletDensity, const MidItem* __restrict__ items) {
-  const MidItem it = items[blockIdx.x];
-  const int count = (int)(it.countSlot & 0xffffu), slot = (int)(it.countSlot >> 16);
-  if ((int)threadIdx.x >= count) return;
-  const int64_t site = (int64_t)it.first + threadIdx.x;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot == 0) {
-    site_body<Q, KERNEL, W_NONE, I_NONE, false>(A, M, site, tid, nullptr, nullptr);
-  } else if (slot == 1) {
-    site_body<Q, KERNEL, WALL, I_NONE, false>(A, M, site, tid, A.iolets, A.ioletDensity);
-  } else if (slot == 2) {
-    site_body<Q, KERNEL, W_NONE, INLET, false>(A, M, site, tid, inletIolets, inletDensity);
-  } else if (slot == 3) {
-    site_body<Q, KERNEL, W_NONE, OUTLET, false>(A, M, site, tid, A.iolets, A.ioletDensity);
-  } else if (slot == 4) {
-    site_body<Q, KERNEL, WALL, INLET, false>(A, M, site, tid, inletIolets, inletDensity);
-  } else {
-    site_body<Q, KERNEL, WALL, OUTLET, false>(A, M, site, tid, A.iolets, A.ioletDensity);
-  }
-}
-
-// PostStep: only BFL does work (BouzidiFirdaousLallemand.h:72-91); runs after all streaming and
-// the halo unpack, one thread per boundary-typed site of the range.
+// PostStep of an arbitrary set of boundary-typed sites (sub-range calls), one thread per site; whole
+// steps go through the link list (bfl_post_links_kernel, abi.cu)
 template <int Q>
 __global__ void __launch_bounds__(256) bfl_post_step_kernel(const StepArgs A, int64_t first, int64_t count) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= count) return;
   const int64_t site = A.siteList ? (int64_t)A.siteList[tid] : first + tid;
   const int64_t b = bidx(A, site);
+  if (b < 0) return;
   const uint32_t wallMask = A.wallMask[b];
   if (!wallMask) return;
 #pragma unroll
@@ -863,23 +893,13 @@ __global__ void __launch_bounds__(256) bfl_post_step_kernel(const StepArgs A, in
   }
 }
 
-// Host-side launch entry, one per (Q, KERNEL) translation unit
-typedef bool (*FusedLaunchFn)(int wall, int inlet, int outlet, const StepArgs& A, const void* mrt,
-                              const IoletDev* inletIolets, const double* inletDensity, const MidItem* items,
-                              int64_t nItems, void* stream);
-typedef void (*LaunchFn)(int wall, int iolet, const StepArgs& A, const void* mrt, int64_t first, int64_t count,
-                         void* stream);
+// Host-side launch entry, one per (Q, KERNEL) translation unit: the site kernel of the
+// (wall, inlet, outlet) bundle over `count` sites, followed, for GuoZhengShi walls, by the per-link
+// kernel over the boundary-typed sites among them (gzsList / gzsCount, or the same sites when null)
+typedef void (*LaunchFn)(int wall, int inlet, int outlet, const StepArgs& A, const void* mrt, int64_t first,
+                         int64_t count, const uint32_t* gzsList, int64_t gzsFirst, int64_t gzsCount, void* stream);
 template <int Q, int KERNEL>
-void launch_collide_stream(int wall, int iolet, const StepArgs& A, const void* mrt, int64_t first, int64_t count,
-                           void* stream);
-// one fused bundle: declared here, defined in fused_impl.cuh and explicitly instantiated in its own
-// translation unit (fused_q*_*.cu) so that the long compilations run side by side
-template <int Q, int KERNEL, int WALL, int INLET, int OUTLET>
-void launch_fused_bundle(const StepArgs& A, const MrtArgs<Q>& M, const IoletDev* inletIolets, const double* inletDensity,
-                         const MidItem* items, int64_t nItems, void* stream);
-// returns false when the (wall, inlet, outlet) bundle has no fused instantiation
-template <int Q, int KERNEL>
-bool launch_fused_mid(int wall, int inlet, int outlet, const StepArgs& A, const void* mrt, const IoletDev* inletIolets,
-                      const double* inletDensity, const MidItem* items, int64_t nItems, void* stream);
+void launch_collide_stream(int wall, int inlet, int outlet, const StepArgs& A, const void* mrt, int64_t first,
+                           int64_t count, const uint32_t* gzsList, int64_t gzsFirst, int64_t gzsCount, void* stream);
 
 }  // namespace hlb
