@@ -17,7 +17,7 @@ OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libhemelb_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-fmad=false",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"] + os.environ.get("HLB_NVCC_EXTRA", "").split()
 
 
 def sources():

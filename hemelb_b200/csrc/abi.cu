@@ -30,7 +30,9 @@ namespace hlb {
 // per-(lattice, kernel) launchers, defined in cs_q*_*.cu
 #define HLB_DECL(Q, K)                                                                                       \
   extern template void launch_collide_stream<Q, K>(int, int, int, const StepArgs&, const void*, int64_t, int64_t, \
-                                                   const uint32_t*, int64_t, int64_t, void*);
+                                                   const uint32_t*, int64_t, int64_t, void*);            \
+  extern template void launch_site_tma<Q, K>(int, int, int, const StepArgs&, const void*, const CUtensorMap*,    \
+                                             const CUtensorMap*, int64_t, int, const uint32_t*, int64_t, void*);
 HLB_DECL(15, K_LBGK) HLB_DECL(15, K_MRT) HLB_DECL(15, K_TRT)
 HLB_DECL(19, K_LBGK) HLB_DECL(19, K_MRT) HLB_DECL(19, K_TRT)
 HLB_DECL(27, K_LBGK) HLB_DECL(27, K_TRT)
@@ -143,6 +145,11 @@ struct hlb_gpu_handle {
   uint64_t timeStep = 1;  // SimulationState.cc:16
   std::vector<char> mrt;
   LaunchFn launch = nullptr;
+  TmaLaunchFn launchTma = nullptr;
+  bool useTma = false;  // the mid-domain part through the TMA-staged persistent kernel (HLB_TMA=1; measured slower)
+  int prefetchCtas = 0;  // direct site kernel over a whole part: L2 prefetch distance in CTAs (HLB_PREFETCH)
+  int nSm = 148;
+  CUtensorMap mapF[2], mapN;  // f[0], f[1] and the push targets as 2-D tensors (rows = planes), boxes of one tile
   // ---- the product schedule.  Device order: all sites of the mid-domain part sorted by lattice
   // position whatever their collision type, then all sites of the domain-edge part likewise; one
   // site-kernel launch per part, every site running the streamer of its own type.  Whole-range
@@ -369,6 +376,18 @@ __global__ void __launch_bounds__(256) bfl_post_links_kernel(double* __restrict_
   fNew[i] = 2.0 * q * fNew[i] + (1.0 - 2.0 * q) * fd;
 }
 
+__global__ void iota_kernel(uint32_t* __restrict__ v, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (uint32_t)i;
+}
+__global__ void gather_links_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ dIn,
+                                    const float* __restrict__ qIn, uint32_t* __restrict__ dOut, float* __restrict__ qOut,
+                                    int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dOut[i] = dIn[order[i]];
+  qOut[i] = qIn[order[i]];
+}
 // the site kernel's per-site record (kernels.cuh, StepArgs::bRec) from the plane-major tables
 __global__ void boundary_records_kernel(const uint32_t* __restrict__ wallMask, const uint32_t* __restrict__ ioletMask,
                                         const int32_t* __restrict__ ioletId, const float* __restrict__ cut,
@@ -537,6 +556,56 @@ __global__ void __launch_bounds__(256) monitor_kernel(const double* __restrict__
     atomicMin(out + 1, enc(rmin));
     atomicMax(out + 2, enc(rmax));
     atomicMax(out + 3, enc(umax));
+  }
+}
+// StabilityTester's site loop (Code/lb/StabilityTester.h:97-141) as one reduction: out[0] = how many
+// populations of f_new fail "value > 0.0" (negative, zero or NaN), out[1] = the largest |u_new - u_old|
+// of any site as an order-preserving key (ComputeRelativeDifference, :156-180, before the division by
+// the reference value; momentum and density by the scalar Lattice::CalculateDensityAndMomentum)
+template <int Q>
+__global__ void __launch_bounds__(256) stability_kernel(const double* __restrict__ fNew, const double* __restrict__ fOld,
+                                                        int64_t N, int64_t stride, int withConvergence,
+                                                        unsigned long long* __restrict__ out) {
+  unsigned long long bad = 0;
+  double worst = 0.0;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < N; s += (int64_t)gridDim.x * blockDim.x) {
+    double v[Q];
+#pragma unroll
+    for (int d = 0; d < Q; ++d) v[d] = __ldcs(fNew + (int64_t)d * stride + s);
+#pragma unroll
+    for (int d = 0; d < Q; ++d)
+      if (!(v[d] > 0.0)) ++bad;
+    if (withConvergence) {
+      double rn, mn[3], ro, mo[3];
+      density_momentum<Q>(v, rn, mn);
+#pragma unroll
+      for (int d = 0; d < Q; ++d) v[d] = __ldcs(fOld + (int64_t)d * stride + s);
+      density_momentum<Q>(v, ro, mo);
+      const double dx = mn[0] / rn - mo[0] / ro, dy = mn[1] / rn - mo[1] / ro, dz = mn[2] / rn - mo[2] / ro;
+      double m2 = 0.0;  // std::inner_product from 0 (util/Vector3D.h:584-588)
+      m2 += dx * dx;
+      m2 += dy * dy;
+      m2 += dz * dz;
+      const double e = sqrt(m2);
+      // a NaN difference never compares greater than the tolerance in the reference either
+      worst = e > worst ? e : worst;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long b = __shfl_xor_sync(0xffffffffu, bad, o);
+    const double w = __shfl_xor_sync(0xffffffffu, worst, o);
+    bad += b;
+    worst = worst > w ? worst : w;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (bad) atomicAdd(out + 0, bad);
+    atomicMax(out + 1, mon_enc(worst));
+  }
+}
+__global__ void stability_decode_kernel(unsigned long long* io) {
+  if (threadIdx.x == 0) {
+    ((double*)io)[2] = (double)io[0];
+    ((double*)io)[3] = mon_dec(io[1]);
   }
 }
 // fold the spread slots of the fused monitor into slot 0..3 of `io` and re-arm them
@@ -720,7 +789,9 @@ int build_permutation(hlb_gpu_t h) {
 // then the staged boundary tables, which arrive in reference order, move to device order.
 int build_boundary_order(hlb_gpu_t h) {
   const int Q = h->Q;
-  const int64_t nWords = h->stride / 32;
+  // (one word more than the sites need: the sentinel {0, NB} behind the last word tells the TMA-staged
+  // kernel where the last tile's run of boundary records ends)
+  const int64_t nWords = h->stride / 32 + 1;
   uint32_t *bits = nullptr, *counts = nullptr, *base = nullptr;
   CU(cudaMalloc(&bits, sizeof(uint32_t) * nWords));
   CU(cudaMalloc(&counts, sizeof(uint32_t) * nWords));
@@ -781,6 +852,34 @@ int build_boundary_order(hlb_gpu_t h) {
   return 0;
 }
 
+// f[0], f[1] and the neighbour table as TMA tensor maps: 2-D, one row per plane (row pitch `stride`),
+// boxes of kTile sites x all planes -- what one bulk tensor copy of the TMA-staged site kernel moves
+int build_tensor_maps(hlb_gpu_t h) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled not available from the driver");
+    encode = (EncodeFn)fn;
+  }
+  const cuuint32_t ones[2] = {1, 1};
+  for (int i = 0; i < 3; ++i) {
+    const bool isF = i < 2;
+    const cuuint64_t dims[2] = {(cuuint64_t)h->stride, (cuuint64_t)(isF ? h->Q : h->Q - 1)};
+    const cuuint64_t pitch[1] = {(cuuint64_t)h->stride * (isF ? 8u : 4u)};
+    const cuuint32_t box[2] = {(cuuint32_t)kTile, (cuuint32_t)(isF ? h->Q : h->Q - 1)};
+    const CUresult rc = encode(isF ? &h->mapF[i] : &h->mapN, isF ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32,
+                               2, isF ? (void*)h->f[i] : (void*)h->nbr, dims, pitch, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (" + std::to_string((int)rc) + ")");
+  }
+  return 0;
+}
+
 // the BFL PostStep link list, once the boundary tables are on the device
 int build_post_links(hlb_gpu_t h) {
   h->nPost = 0;
@@ -811,7 +910,35 @@ int build_post_links(hlb_gpu_t h) {
     post_links_fill_kernel<<<blocks_for(h->NB), 256>>>(h->wallMask, h->cutDist, h->bStride, h->NB, h->Q, h->stride,
                                                        h->bSite, offset, h->postI, h->postD, h->postQ);
     CU(cudaGetLastError());
+    // in the order of the slot corrected: plane by plane, sites ascending -- neighbouring wall sites of a
+    // lattice row are cut in the same directions, so consecutive links touch consecutive addresses (the
+    // links are independent of one another: any order gives the same result)
+    uint32_t *keys = nullptr, *order = nullptr, *order2 = nullptr, *d2 = nullptr;
+    float* q2 = nullptr;
+    CU(cudaMalloc(&keys, sizeof(uint32_t) * total));
+    CU(cudaMalloc(&order, sizeof(uint32_t) * total));
+    CU(cudaMalloc(&order2, sizeof(uint32_t) * total));
+    CU(cudaMalloc(&d2, sizeof(uint32_t) * total));
+    CU(cudaMalloc(&q2, sizeof(float) * total));
+    iota_kernel<<<blocks_for(total), 256>>>(order, total);
+    void* tmp = nullptr;
+    size_t tmpBytes = 0;
+    cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, h->postI, keys, order, order2, (int)total);
+    CU(cudaMalloc(&tmp, tmpBytes + 16));
+    cub::DeviceRadixSort::SortPairs(tmp, tmpBytes, h->postI, keys, order, order2, (int)total);
+    CU(cudaGetLastError());
+    gather_links_kernel<<<blocks_for(total), 256>>>(order2, h->postD, h->postQ, d2, q2, total);
+    CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
+    cudaFree(tmp);
+    cudaFree(order);
+    cudaFree(order2);
+    cudaFree(h->postI);
+    cudaFree(h->postD);
+    cudaFree(h->postQ);
+    h->postI = keys;
+    h->postD = d2;
+    h->postQ = q2;
   }
   cudaFree(counts);
   cudaFree(offset);
@@ -845,8 +972,13 @@ int launch_part(hlb_gpu_t h, int part) {
   const bool prof = h->profileBulk && part == 0;
   if (prof && prof_begin(h)) return 1;
   const int64_t gFirst = part ? h->nbMid : 0, gCount = part ? h->NB - h->nbMid : h->nbMid;
-  h->launch(h->cfg.wall, h->cfg.inlet, h->cfg.outlet, A, h->mrt.data(), first, count, h->bSite + gFirst, 0, gCount,
-            h->compute);
+  if (part == 0) A.prefetchCtas = h->prefetchCtas;  // (tile-aligned planes: the part starts at site 0)
+  if (part == 0 && h->useTma)
+    h->launchTma(h->cfg.wall, h->cfg.inlet, h->cfg.outlet, A, h->mrt.data(), &h->mapF[h->cur], &h->mapN, count, h->nSm,
+                 h->bSite, gCount, h->compute);
+  else
+    h->launch(h->cfg.wall, h->cfg.inlet, h->cfg.outlet, A, h->mrt.data(), first, count, h->bSite + gFirst, 0, gCount,
+              h->compute);
   h->launches++;
   if (h->cfg.wall == HLB_WALL_GZS && gCount > 0) h->launches++;  // the per-link kernel behind the per-site one
   if (h->cacheMask & C_MONITOR) h->monitorLaunches++;
@@ -1124,6 +1256,7 @@ int hlb_gpu_internal_view(hlb_gpu_t h, hlb_gpu_view* out) {
   if (!h || !out) return fail("null argument");
   if (!h->finalised) return fail("handle not finalised");
   if (join_aux(h)) return 1;
+  new_step_state(h);  // (the checkpoint loader writes f through this view)
   out->Q = h->Q;
   out->device = h->cfg.device;
   out->rank = h->cfg.rank;
@@ -1198,8 +1331,8 @@ int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
   h->NB = h->N - h->midBulk - h->edgeBulk;
   h->bStride = ((h->NB + 63) / 64) * 64;
   if (h->bStride == 0) h->bStride = 64;
-  h->stride = ((h->N + 63) / 64) * 64;
-  if (h->stride == 0) h->stride = 64;
+  h->stride = ((h->N + 255) / 256) * 256;  // whole tiles of the TMA-staged kernel can be copied from every plane
+  if (h->stride == 0) h->stride = 256;
   h->fLen = (int64_t)Q * h->stride + 1 + h->S;
   if (h->fLen >= ((int64_t)1 << 32)) { delete h; return fail("too many sites for 32-bit streaming indices on one GPU"); }
   CU(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
@@ -1209,6 +1342,13 @@ int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
     const char* e = getenv("HLB_SCHEDULE");
     h->schedule = !(e && e[0] == '0');
     h->scheduleDefault = h->schedule;
+    const char* t = getenv("HLB_TMA");
+    h->useTma = t && t[0] == '1';
+    const char* pf = getenv("HLB_PREFETCH");
+    // measured on the 1e8-site tree: 13 070 MLUPS without, 13 830 / 14 080 / 14 118 / 14 095 at 20 / 80 / 150-200 /
+    // 250 CTAs ahead, 13 250 at 600 and 11 000 at 1200 (the lines leave L2 again before they are used)
+    h->prefetchCtas = pf ? atoi(pf) : 160;
+    CU(cudaDeviceGetAttribute(&h->nSm, cudaDevAttrMultiProcessorCount, cfg->device));
   }
   CU(cudaEventCreateWithFlags(&h->evEdge, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&h->evComm, cudaEventDisableTiming));
@@ -1247,6 +1387,7 @@ int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
 #define HLB_PICK(QQ, KK, KE)                                      \
   if (Q == QQ && cfg->kernel == KK) {                             \
     h->launch = &launch_collide_stream<QQ, KE>;                   \
+    h->launchTma = &launch_site_tma<QQ, KE>;                      \
     fill_mrt<QQ>(h);                                              \
   }
   HLB_PICK(15, 0, K_LBGK) HLB_PICK(15, 1, K_MRT) HLB_PICK(15, 2, K_TRT)
@@ -1641,6 +1782,7 @@ int hlb_gpu_finalise(hlb_gpu_t h) {
     }
   }
   if (build_post_links(h)) return 1;
+  if (h->useTma && build_tensor_maps(h)) return 1;
   if (h->coordsAll) {
     cudaFree(h->coordsAll);
     h->coordsAll = nullptr;
@@ -1674,6 +1816,7 @@ int hlb_gpu_set_f(hlb_gpu_t h, int which, const double* f) {
   if (!h->finalised) return fail("hlb_gpu_set_f before hlb_gpu_finalise");
   CU(cudaSetDevice(h->cfg.device));
   if (join_aux(h)) return 1;
+  new_step_state(h);
   CU(cudaStreamSynchronize(h->compute));
   double* dst = h->f[which ? h->cur ^ 1 : h->cur];
   const int Q = h->Q;
@@ -1733,6 +1876,8 @@ int hlb_gpu_set_halo(hlb_gpu_t h, int which, const double* in) {
 int hlb_gpu_set_equilibrium(hlb_gpu_t h, double rho, const double* m) {
   if (!h || !m) return fail("null argument");
   CU(cudaSetDevice(h->cfg.device));
+  if (join_aux(h)) return 1;
+  new_step_state(h);
   // Lattice::CalculateFeq (scalar path) on the host, then broadcast to every site of both arrays
   double feq[27];
   const double density_1 = 1. / rho;
@@ -2016,6 +2161,32 @@ int hlb_gpu_monitor_global(hlb_gpu_t h, double* out4) {
     v[3] = -v[3];
   }
   for (int k = 0; k < 4; ++k) out4[k] = v[k];
+  return 0;
+}
+
+int hlb_gpu_stability(hlb_gpu_t h, int with_convergence, double* out2) {
+  if (!h || !out2) return fail("null argument");
+  if (!h->finalised) return fail("handle not finalised");
+  CU(cudaSetDevice(h->cfg.device));
+  if (join_aux(h)) return 1;
+  unsigned long long init[2] = {0ull, 0x8000000000000000ull};  // {no failing population, mon_enc(+0.0)}
+  CU(cudaMemcpyAsync(h->monitorDev, init, sizeof(init), cudaMemcpyHostToDevice, h->compute));
+  if (h->N) {
+    const unsigned grid = (unsigned)std::min<int64_t>((h->N + 255) / 256, 148 * 16);
+    unsigned long long* mo = (unsigned long long*)h->monitorDev;
+    const double *fNew = h->f[h->cur ^ 1], *fOld = h->f[h->cur];
+    switch (h->Q) {
+      case 15: stability_kernel<15><<<grid, 256, 0, h->compute>>>(fNew, fOld, h->N, h->stride, with_convergence, mo); break;
+      case 19: stability_kernel<19><<<grid, 256, 0, h->compute>>>(fNew, fOld, h->N, h->stride, with_convergence, mo); break;
+      case 27: stability_kernel<27><<<grid, 256, 0, h->compute>>>(fNew, fOld, h->N, h->stride, with_convergence, mo); break;
+    }
+    h->launches++;
+  }
+  stability_decode_kernel<<<1, 32, 0, h->compute>>>((unsigned long long*)h->monitorDev);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out2, h->monitorDev + 2, sizeof(double) * 2, cudaMemcpyDeviceToHost, h->compute));
+  CU(cudaStreamSynchronize(h->compute));
   return 0;
 }
 

@@ -3,4 +3,6 @@
 namespace hlb {
 template void launch_collide_stream<15, K_TRT>(int, int, int, const StepArgs&, const void*, int64_t, int64_t, const uint32_t*,
                                              int64_t, int64_t, void*);
+template void launch_site_tma<15, K_TRT>(int, int, int, const StepArgs&, const void*, const CUtensorMap*, const CUtensorMap*, int64_t, int,
+                                       const uint32_t*, int64_t, void*);
 }

@@ -20,6 +20,7 @@
 //
 // HBM traffic per site update: Q*8 B read + Q*8 B written + (Q-1)*4 B of indices.
 #pragma once
+#include <cuda.h>  // CUtensorMap
 #include <cstdint>
 #include <cfloat>
 #include "lattice.cuh"
@@ -32,6 +33,9 @@
 #endif
 #ifndef HLB_MIN_CTAS
 #define HLB_MIN_CTAS 2
+#endif
+#ifndef HLB_SITE_THREADS
+#define HLB_SITE_THREADS 256
 #endif
 
 namespace hlb {
@@ -106,6 +110,9 @@ struct StepArgs {
   const uint32_t* __restrict__ refSiteOf;  // internal site -> reference site id (cache rows), or null
   // optional explicit site list (launches that are not a contiguous run of internal sites)
   const uint32_t* __restrict__ siteList;
+  // contiguous launches of the direct site kernel: every CTA asks L2 for what the CTA `prefetchCtas`
+  // later in the grid will load (0: off)
+  int prefetchCtas;
   // fused monitors (C_MONITOR): {min f, min rho, max rho, max u^2} as order-preserving u64 keys
   unsigned long long* __restrict__ monitorSlots;
 };
@@ -113,7 +120,7 @@ constexpr int kIoletNone = -1, kIoletByType = 2;
 constexpr int32_t kOutletTypedBit = 1 << 30;
 
 template <int Q> __host__ __device__ constexpr int brec_words() { return ((4 + Q - 1) + 3) / 4 * 4; }
-template <int Q> __host__ __device__ constexpr int site_threads() { return Q > 19 ? HLB_Q27_THREADS : 256; }
+template <int Q> __host__ __device__ constexpr int site_threads() { return Q > 19 ? HLB_Q27_THREADS : HLB_SITE_THREADS; }
 template <int Q> __host__ __device__ constexpr int site_min_ctas() { return Q > 19 ? HLB_Q27_MIN_CTAS : HLB_MIN_CTAS; }
 
 template <int Q> struct MrtArgs {
@@ -708,7 +715,7 @@ __device__ __forceinline__ double iolet_link(const StepArgs& A, const IoletSite&
 
 // the cut links of one boundary-typed site, after its uncut links were pushed: iolet link first,
 // then wall link (StreamerTypeFactory.h:65-79)
-template <int Q, int WALL, int INLET, int OUTLET, int D>
+template <int Q, int WALL, int INLET, int OUTLET, int RSTRIDE, int D>
 __device__ __forceinline__ void cut_links(const StepArgs& A, int64_t site, const uint32_t* __restrict__ rec,
                                           uint32_t wallMask, uint32_t ioletMask, int sel, const IoletSite& S,
                                           double rho, const double (&fpost)[Q]) {
@@ -724,7 +731,7 @@ __device__ __forceinline__ void cut_links(const StepArgs& A, int64_t site, const
         A.fNew[(int64_t)id * A.stride + site] = fpost[D];
       } else if constexpr (WALL == W_BFL) {  // BouzidiFirdaousLallemand.h:41-70
         // word 4 + (D - 1) of the staged record: chunk (3 + D) / 4 of the thread's column
-        const double q = (double)__uint_as_float(rec[((3 + D) / 4) * (4 * site_threads<Q>()) + ((3 + D) & 3)]);
+        const double q = (double)__uint_as_float(rec[((3 + D) / 4) * (4 * RSTRIDE) + ((3 + D) & 3)]);
         const bool invWall = (wallMask >> (id - 1)) & 1u;
         double v;
         if (invWall || q < 0.5) v = fpost[D];
@@ -733,7 +740,7 @@ __device__ __forceinline__ void cut_links(const StepArgs& A, int64_t site, const
       }
       // W_GZS: gzs_links_kernel owns this population
     }
-    cut_links<Q, WALL, INLET, OUTLET, D + 1>(A, site, rec, wallMask, ioletMask, sel, S, rho, fpost);
+    cut_links<Q, WALL, INLET, OUTLET, RSTRIDE, D + 1>(A, site, rec, wallMask, ioletMask, sel, S, rho, fpost);
   }
 }
 
@@ -752,12 +759,11 @@ __device__ __forceinline__ int64_t launch_tid_again() {
 // so that the hot path reserves no registers for it.  The moments are extracted from f_old read
 // again (it is not written during a step): the same loads through the same arithmetic as the
 // site's collision, hence the same bits, but neither f nor f_neq has to outlive the collision.
+// `key` only spreads the monitor atomics.
 template <int Q, int KERNEL>
-__device__ __noinline__ void site_tail(const StepArgs& A, int64_t first, int b, double fmin, double rho0, double m0,
-                                       double m1, double m2) {
-  const int64_t tid = launch_tid_again();
+__device__ __noinline__ void site_tail(const StepArgs& A, int64_t site, int64_t key, int b, double fmin, double rho0,
+                                       double m0, double m1, double m2) {
   if (A.cacheMask & 255u) {
-    const int64_t site = A.siteList ? (int64_t)A.siteList[tid] : first + tid;
     double f[Q];
 #pragma unroll
     for (int d = 0; d < Q; ++d) f[d] = A.fOld[(int64_t)d * A.stride + site];
@@ -773,21 +779,104 @@ __device__ __noinline__ void site_tail(const StepArgs& A, int64_t first, int b, 
   }
   if (A.cacheMask & C_MONITOR) {
     const double m[3] = {m0, m1, m2};
-    fused_monitor(A, tid, fmin, rho0, m);
+    fused_monitor(A, key, fmin, rho0, m);
   }
 }
 
-// One site: load, collide, stream, (rarely) extract moments.
+// One site, once its populations and push targets are in registers: collide, stream, (rarely)
+// extract moments.  `rec` is the thread's column of the shared-memory staging area for boundary
+// records (chunk c of the record at rec[4 * RSTRIDE * c ...]); with DIRECT the record is still on its
+// way (cp.async) and is waited for after the collision, and the tail works out the site again from
+// the launch index instead of keeping it alive.
 //
-// What a boundary-typed site needs beyond its populations -- masks, iolet id, cut distances: its
-// bRec record -- is fetched asynchronously (cp.async, 16 B chunks) into the thread's column of
-// `srec` as soon as the bitmap word says the site is boundary-typed, and is waited for after the
-// collision: no load of the kernel depends on another one except through that word (which is small
-// enough to stay in L2), whatever the site's type.
+// The push targets: in registers (DIRECT: `target`), or in the thread's column of the staged tile
+// (`tcol`: direction d at tcol[(d - 1) * TSTRIDE]), read as each push is made.
+template <int Q, int KERNEL, int WALL, int INLET, int OUTLET, int RSTRIDE, int TSTRIDE, bool DIRECT>
+__device__ __forceinline__ void site_finish(const StepArgs& A, const MrtArgs<Q>& M, const int64_t site, const int64_t first,
+                                            const int b, const double (&f)[Q], const uint32_t (&target)[Q],
+                                            const uint32_t* __restrict__ tcol, const uint32_t* __restrict__ rec) {
+  // CalculatePreCollision (Normal.h:29-33 -> kernel.CalculateDensityMomentumFeq)
+  double rho, m[3];
+  density_momentum<Q>(f, rho, m);
+  double fneq[Q], fpost[Q];
+  {
+    const double density_1 = 1. / rho;
+    const double mm = m[0] * m[0] + m[1] * m[1] + m[2] * m[2];
+#pragma unroll
+    for (int d = 0; d < Q; ++d) fneq[d] = f[d] - feq_i<Q>(d, rho, density_1, mm, m);
+  }
+  // (the monitor's smallest population is taken now: f and f_neq die with the collision)
+  double fmin = 0.0;
+  if (A.cacheMask & C_MONITOR) fmin = min_population<Q>(f);
+  collide<Q, KERNEL>(A, M, f, fneq, fpost);
+
+  // the record has had the whole collision to arrive
+  if constexpr (DIRECT) asm volatile("cp.async.wait_all;" ::: "memory");
+  uint32_t cut = 0;
+  if (b >= 0) {
+    if (A.wallOn) cut = rec[0];
+    if (A.ioletSel != kIoletNone) cut |= rec[1];
+  }
+  // stream the uncut links (BulkStreamer.h:31-39); a mid-fluid site has no others
+  A.fNew[site] = fpost[0];  // direction 0 streams to the site itself (Domain.cc:449)
+#pragma unroll
+  for (int d = 1; d < Q; ++d)
+    if (!((cut >> (d - 1)) & 1u)) A.fNew[DIRECT ? target[d] : tcol[(d - 1) * TSTRIDE]] = fpost[d];
+  if (cut) {
+    const uint32_t wallMask = A.wallOn ? rec[0] : 0u;
+    const uint32_t ioletMask = A.ioletSel != kIoletNone ? rec[1] : 0u;
+    IoletSite S;
+    int sel = 0;
+    if (ioletMask) {
+      const int32_t enc = (int32_t)rec[2];
+      sel = A.ioletSel == kIoletByType ? ((enc & kOutletTypedBit) ? 1 : 0) : A.ioletSel;
+      const int id = enc & (kOutletTypedBit - 1);
+      if constexpr (INLET == OUTLET) iolet_site<Q, INLET>(A, sel, id, b, rho, m, S);
+      else if (sel) iolet_site<Q, OUTLET>(A, sel, id, b, rho, m, S);
+      else iolet_site<Q, INLET>(A, sel, id, b, rho, m, S);
+    }
+    cut_links<Q, WALL, INLET, OUTLET, RSTRIDE, 1>(A, site, rec, wallMask, ioletMask, sel, S, rho, fpost);
+  }
+
+  if (A.cacheMask) {
+    if constexpr (DIRECT) {
+      const int64_t tid = launch_tid_again();
+      site_tail<Q, KERNEL>(A, A.siteList ? (int64_t)A.siteList[tid] : first + tid, tid, b, fmin, rho, m[0], m[1], m[2]);
+    } else {
+      site_tail<Q, KERNEL>(A, site, site, b, fmin, rho, m[0], m[1], m[2]);
+    }
+  }
+}
+
+// The direct form of the site kernel: `count` sites, siteList[0 .. count) or the consecutive device
+// sites from `first`, one thread each, every load issued by the thread itself.  What a boundary-typed
+// site needs beyond its populations -- masks, iolet id, cut distances: its bRec record -- is fetched
+// asynchronously (cp.async, 16 B chunks) into the thread's column of `srec` as soon as the bitmap
+// word says the site is boundary-typed: no load depends on another one except through that word
+// (small enough to stay in L2).  Used for the domain-edge part, for sub-ranges and site lists.
 template <int Q, int KERNEL, int WALL, int INLET, int OUTLET>
-__device__ __forceinline__ void site_body(const StepArgs& A, const MrtArgs<Q>& M, const int64_t site, const int64_t first,
-                                          uint4* __restrict__ srec) {
+__global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) collide_stream_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ MrtArgs<Q> M, int64_t first, int64_t count) {
   constexpr int T = site_threads<Q>(), RC = brec_words<Q>() / 4;
+  __shared__ uint4 srec[RC * T];
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (A.prefetchCtas) {
+    // The planes of f_old and of the push targets that a CTA further down the grid will read: one
+    // 128 B line per thread and round, into L2.  The loads of this kernel are then mostly L2 hits, and
+    // DRAM is kept busy by requests that do not wait for a warp to come round to its load phase.
+    const int64_t site0 = first + ((int64_t)blockIdx.x + A.prefetchCtas) * T;
+    if (site0 + T <= first + count) {
+      constexpr int fLines = Q * (T * 8 / 128), nLines = (Q - 1) * (T * 4 / 128);
+#pragma unroll
+      for (int l = threadIdx.x; l < fLines + nLines; l += T) {
+        const char* p = l < fLines
+            ? (const char*)(A.fOld + (int64_t)(l / (T * 8 / 128)) * A.stride + site0) + (l % (T * 8 / 128)) * 128
+            : (const char*)(A.nbr + (int64_t)((l - fLines) / (T * 4 / 128)) * A.stride + site0) + ((l - fLines) % (T * 4 / 128)) * 128;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+      }
+    }
+  }
+  if (tid >= count) return;
+  const int64_t site = A.siteList ? (int64_t)A.siteList[tid] : first + tid;
   // is this a boundary-typed site?  One 8 B word per 32 sites, asked for first.
   const uint2 bi = __ldg(A.bInfo + (site >> 5));
   double f[Q];
@@ -810,62 +899,166 @@ __device__ __forceinline__ void site_body(const StepArgs& A, const MrtArgs<Q>& M
                      : "memory");
     }
   }
-
-  // CalculatePreCollision (Normal.h:29-33 -> kernel.CalculateDensityMomentumFeq)
-  double rho, m[3];
-  density_momentum<Q>(f, rho, m);
-  double fneq[Q], fpost[Q];
-  {
-    const double density_1 = 1. / rho;
-    const double mm = m[0] * m[0] + m[1] * m[1] + m[2] * m[2];
-#pragma unroll
-    for (int d = 0; d < Q; ++d) fneq[d] = f[d] - feq_i<Q>(d, rho, density_1, mm, m);
-  }
-  // (the monitor's smallest population is taken now: f and f_neq die with the collision)
-  double fmin = 0.0;
-  if (A.cacheMask & C_MONITOR) fmin = min_population<Q>(f);
-  collide<Q, KERNEL>(A, M, f, fneq, fpost);
-
-  // the record has had the whole collision to arrive
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  const uint32_t* rec = reinterpret_cast<const uint32_t*>(srec + threadIdx.x);
-  uint32_t cut = 0;
-  if (b >= 0) {
-    if (A.wallOn) cut = rec[0];
-    if (A.ioletSel != kIoletNone) cut |= rec[1];
-  }
-  // stream the uncut links (BulkStreamer.h:31-39); a mid-fluid site has no others
-  A.fNew[target[0]] = fpost[0];
-#pragma unroll
-  for (int d = 1; d < Q; ++d)
-    if (!((cut >> (d - 1)) & 1u)) A.fNew[target[d]] = fpost[d];
-  if (cut) {
-    const uint32_t wallMask = A.wallOn ? rec[0] : 0u;
-    const uint32_t ioletMask = A.ioletSel != kIoletNone ? rec[1] : 0u;
-    IoletSite S;
-    int sel = 0;
-    if (ioletMask) {
-      const int32_t enc = (int32_t)rec[2];
-      sel = A.ioletSel == kIoletByType ? ((enc & kOutletTypedBit) ? 1 : 0) : A.ioletSel;
-      const int id = enc & (kOutletTypedBit - 1);
-      if constexpr (INLET == OUTLET) iolet_site<Q, INLET>(A, sel, id, b, rho, m, S);
-      else if (sel) iolet_site<Q, OUTLET>(A, sel, id, b, rho, m, S);
-      else iolet_site<Q, INLET>(A, sel, id, b, rho, m, S);
-    }
-    cut_links<Q, WALL, INLET, OUTLET, 1>(A, site, rec, wallMask, ioletMask, sel, S, rho, fpost);
-  }
-
-  if (A.cacheMask) site_tail<Q, KERNEL>(A, first, b, fmin, rho, m[0], m[1], m[2]);
+  site_finish<Q, KERNEL, WALL, INLET, OUTLET, T, 0, true>(A, M, site, first, b, f, target, nullptr,
+                                                        reinterpret_cast<const uint32_t*>(srec + threadIdx.x));
 }
 
-// `count` sites: siteList[0 .. count), or the consecutive internal sites from `first`
+// ---------------------------------------------------------------------------------- TMA-staged form
+// The site kernel for a whole part whose first site is tile-aligned (the mid-domain part): a
+// persistent kernel, one CTA per SM, whose warps work independently of one another.  A warp walks
+// its share of the part's tiles of 32 consecutive sites with two shared-memory stages of its own.
+// Everything a tile needs is brought into a stage by the TMA unit -- the Q x 32 box of f_old and the
+// (Q-1) x 32 box of push targets (one bulk tensor copy each: the planes are the rows of a 2-D tensor
+// map), and the contiguous run of boundary records of the tile's boundary-typed sites (a 1-D bulk
+// copy) -- with completion counted on the stage's mbarrier.  While the warp works on the tile in one
+// stage (populations to registers; targets, masks and cut distances read from the stage where they
+// are needed) its next tile is landing in the other; when it is through, lane 0 refills the stage
+// with the tile after next.  No load is waited for by an instruction stream that could be issuing
+// other loads: how many bytes are on their way from HBM does not depend on how many warps fit the
+// register file or on where in its stream a warp is (the direct form holds 2 x 8 warps x 7.2 KB only
+// while those warps are in their load phase; here one 7 KB tile per warp is in flight nearly all
+// the time, 12 warps per SM, against the ~43 KB per SM that 6.4 TB/s x 1 us needs), a warp delayed by
+// the cut links of its boundary-typed sites delays nobody else, and the register file is left to
+// 12 warps of up to 168 registers.
+constexpr int kTile = 32;
+
+template <int Q> struct TmaCfg {
+  static constexpr int warps = Q > 19 ? 8 : 12;
+  static constexpr int threads = warps * 32;
+  // registers are per SM sub-partition (16384 each): its share of the CTA's warps has to fit
+  static constexpr int perPartition = (warps + 3) / 4;
+  static constexpr int maxRegs = (16384 / perPartition / 32) / 8 * 8 > 255 ? 255 : (16384 / perPartition / 32) / 8 * 8;
+  static constexpr int fBytes = Q * kTile * 8, nBytes = (Q - 1) * kTile * 4;
+  static constexpr int recBytes = brec_words<Q>() * 4;
+  // boundary records staged per tile; a tile with more boundary-typed sites (a lattice row running
+  // along a wall) reads the rest of its records from global memory
+  static constexpr int recCap = Q > 19 ? 16 : 24;
+  static constexpr int stageBytes = fBytes + nBytes + (recCap * recBytes + 127) / 128 * 128;
+  static constexpr int smemBytes = warps * 2 * stageBytes + warps * 2 * 8 + 128;
+};
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst)),
+               "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+// one box of a 2-D tensor map (inner coordinate c0, outer c1) into shared memory
+__device__ __forceinline__ void tma_box_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          (unsigned)__cvta_generic_to_shared(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"((unsigned)__cvta_generic_to_shared(bar))
+      : "memory");
+}
+
+// tile `tile` into stage `st`; b0 / b1: the boundary ordinals at which the tile's run of boundary
+// records starts and ends (bInfo[tile].y, bInfo[tile + 1].y)
+template <int Q>
+__device__ __forceinline__ void tma_fill_stage(const StepArgs& A, const CUtensorMap* mapF, const CUtensorMap* mapN,
+                                               unsigned char* st, uint64_t* bar, int64_t tile, unsigned b0, unsigned b1) {
+  using C = TmaCfg<Q>;
+  const unsigned nrec = b1 - b0 < (unsigned)C::recCap ? b1 - b0 : (unsigned)C::recCap;
+  const unsigned recBytes = nrec * C::recBytes;
+  mbar_expect_tx(bar, C::fBytes + C::nBytes + recBytes);
+  tma_box_2d(st, mapF, (int)(tile * kTile), 0, bar);
+  tma_box_2d(st + C::fBytes, mapN, (int)(tile * kTile), 0, bar);
+  if (recBytes) bulk_g2s(st + C::fBytes + C::nBytes, A.bRec + (int64_t)b0 * (C::recBytes / 16), recBytes, bar);
+}
+
+// sites [0, count) of the device order; nTiles = ceil(count / kTile).  The arrays are padded so that
+// whole tiles can be copied (stride is a multiple of 256); bInfo -- one word per tile -- has a
+// sentinel word behind the last.
 template <int Q, int KERNEL, int WALL, int INLET, int OUTLET>
-__global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) collide_stream_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ MrtArgs<Q> M, int64_t first, int64_t count) {
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= count) return;
-  const int64_t site = A.siteList ? (int64_t)A.siteList[tid] : first + tid;
-  __shared__ uint4 srec[(brec_words<Q>() / 4) * site_threads<Q>()];
-  site_body<Q, KERNEL, WALL, INLET, OUTLET>(A, M, site, first, srec);
+__global__ void __launch_bounds__(TmaCfg<Q>::threads) __maxnreg__(TmaCfg<Q>::maxRegs) site_tma_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ MrtArgs<Q> M, const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapN, int64_t count, int64_t nTiles) {
+  using C = TmaCfg<Q>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* stage0 = smem + (size_t)warp * 2 * C::stageBytes;
+  uint64_t* bar0 = reinterpret_cast<uint64_t*>(smem + (size_t)C::warps * 2 * C::stageBytes) + 2 * warp;
+  if (lane == 0) {
+    mbar_init(bar0, 1);  // the filler's arrive; the copies complete the byte count
+    mbar_init(bar0 + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  // the warp's tiles: first, first + step, ...: concurrent warps work on neighbouring tiles
+  const int64_t first = (int64_t)blockIdx.x * C::warps + warp, step = (int64_t)gridDim.x * C::warps;
+  // lane 0 carries {bitmap, first boundary ordinal, ordinal behind the last} of the tiles in stage 0 / 1
+  uint2 info[2] = {make_uint2(0u, 0u), make_uint2(0u, 0u)};
+  unsigned end[2] = {0u, 0u};
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int64_t tile = first + s * step;
+      if (tile < nTiles) {
+        info[s] = __ldg(A.bInfo + tile);
+        end[s] = __ldg(&A.bInfo[tile + 1].y);
+        tma_fill_stage<Q>(A, &mapF, &mapN, stage0 + s * C::stageBytes, bar0 + s, tile, info[s].y, end[s]);
+      }
+    }
+  }
+  unsigned parity[2] = {0u, 0u};
+#pragma unroll 1
+  for (int64_t tile = first, k = 0; tile < nTiles; tile += step, ++k) {
+    const int s = (int)(k & 1);
+    unsigned char* st = stage0 + s * C::stageBytes;
+    // what the tile after next needs to be filled with: asked for now, used when this tile is done
+    const int64_t refill = tile + 2 * step;
+    uint2 nInfo = make_uint2(0u, 0u);
+    unsigned nEnd = 0u;
+    if (lane == 0 && refill < nTiles) {
+      nInfo = __ldg(A.bInfo + refill);
+      nEnd = __ldg(&A.bInfo[refill + 1].y);
+    }
+    const unsigned bits = __shfl_sync(0xffffffffu, s ? info[1].x : info[0].x, 0);
+    const unsigned b0 = __shfl_sync(0xffffffffu, s ? info[1].y : info[0].y, 0);
+    mbar_wait(bar0 + s, s ? parity[1] : parity[0]);
+    if (s) parity[1] ^= 1u; else parity[0] ^= 1u;
+    const int64_t site = tile * kTile + lane;
+    if (site < count) {
+      const double* sf = reinterpret_cast<const double*>(st);
+      double f[Q];
+#pragma unroll
+      for (int d = 0; d < Q; ++d) f[d] = sf[d * kTile + lane];
+      uint32_t target[Q];  // (unused: the targets are read from the stage)
+      int b = -1;
+      const uint32_t* rec = nullptr;
+      if ((bits >> lane) & 1u) {
+        const unsigned r = __popc(bits & ((1u << lane) - 1u));
+        b = (int)(b0 + r);
+        rec = r < (unsigned)C::recCap ? reinterpret_cast<const uint32_t*>(st + C::fBytes + C::nBytes) + r * brec_words<Q>()
+                                      : reinterpret_cast<const uint32_t*>(A.bRec) + (int64_t)b * brec_words<Q>();
+      }
+      site_finish<Q, KERNEL, WALL, INLET, OUTLET, 1, kTile, false>(
+          A, M, site, 0, b, f, target, reinterpret_cast<const uint32_t*>(st + C::fBytes) + lane, rec);
+    }
+    // every lane is through with the stage: it takes the tile after next
+    __syncwarp();
+    if (lane == 0) {
+      if (s) { info[1] = nInfo; end[1] = nEnd; } else { info[0] = nInfo; end[0] = nEnd; }
+      if (refill < nTiles) tma_fill_stage<Q>(A, &mapF, &mapN, st, bar0 + s, refill, nInfo.y, nEnd);
+    }
+  }
 }
 
 // PostStep of an arbitrary set of boundary-typed sites (sub-range calls), one thread per site; whole
@@ -901,5 +1094,13 @@ typedef void (*LaunchFn)(int wall, int inlet, int outlet, const StepArgs& A, con
 template <int Q, int KERNEL>
 void launch_collide_stream(int wall, int inlet, int outlet, const StepArgs& A, const void* mrt, int64_t first,
                            int64_t count, const uint32_t* gzsList, int64_t gzsFirst, int64_t gzsCount, void* stream);
+// mapF: the current f_old as a 2-D tensor {stride, Q} of doubles with boxes {kTile, Q}; mapN: the push
+// targets {stride, Q-1} of uint32 with boxes {kTile, Q-1}
+typedef void (*TmaLaunchFn)(int wall, int inlet, int outlet, const StepArgs& A, const void* mrt, const CUtensorMap* mapF,
+                            const CUtensorMap* mapN, int64_t count, int nSm, const uint32_t* gzsList, int64_t gzsCount,
+                            void* stream);
+template <int Q, int KERNEL>
+void launch_site_tma(int wall, int inlet, int outlet, const StepArgs& A, const void* mrt, const CUtensorMap* mapF,
+                     const CUtensorMap* mapN, int64_t count, int nSm, const uint32_t* gzsList, int64_t gzsCount, void* stream);
 
 }  // namespace hlb

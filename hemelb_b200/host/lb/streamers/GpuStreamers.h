@@ -10,6 +10,7 @@
 #define HEMELB_LB_STREAMERS_GPUSTREAMERS_H
 
 #include <algorithm>
+#include <cmath>
 #include <limits>
 #include <type_traits>
 #include <vector>
@@ -21,6 +22,7 @@
 #include "lb/iolets/BoundaryValues.h"
 #include "lb/iolets/InOutLetCosine.h"
 #include "lb/iolets/InOutLetParabolicVelocity.h"
+#include "lb/iolets/InOutLetVelocity.h"
 #include "lb/kernels/LBGK.h"
 #include "lb/kernels/MRT.h"
 #include "lb/kernels/TRT.h"
@@ -98,10 +100,11 @@ namespace hemelb::lb::gpu {
     static void PushStepScalars(hlb_gpu_t h, geometry::FieldData& latDat, MacroscopicPropertyCache& cache) {
       auto& pol = latDat.Policy();
       std::vector<double> in, out;
+      // by the index the sites carry: BoundaryValues::GetBoundaryDensity(id) = iolets[id]
       if (pol.inletValues)
-        for (unsigned i = 0; i < pol.inletValues->GetLocalIoletCount(); ++i) in.push_back(pol.inletValues->GetBoundaryDensity(i));
+        for (unsigned i = 0; i < pol.inletValues->GetGlobalIoletCount(); ++i) in.push_back(pol.inletValues->GetBoundaryDensity(i));
       if (pol.outletValues)
-        for (unsigned i = 0; i < pol.outletValues->GetLocalIoletCount(); ++i) out.push_back(pol.outletValues->GetBoundaryDensity(i));
+        for (unsigned i = 0; i < pol.outletValues->GetGlobalIoletCount(); ++i) out.push_back(pol.outletValues->GetBoundaryDensity(i));
       const auto t = pol.inletValues ? pol.inletValues->GetTimeStep() : (pol.outletValues ? pol.outletValues->GetTimeStep() : 1);
       const uint32_t mask = CacheMask(cache);
       if (pol.scalarsPushed && pol.pushedStep == t && pol.pushedMask == mask && pol.pushedIn == in && pol.pushedOut == out)
@@ -205,17 +208,39 @@ namespace hemelb::geometry {
       if (bv)
         for (unsigned i = 0; i < bv->GetLocalIoletCount(); ++i)
           minDensity = std::min(minDensity, (double)bv->GetLocalIolet(i)->GetDensityMin());
-    auto records = [minDensity](lb::BoundaryValues* bv) {
+    // One record per iolet of the SIMULATION, in the order of the BoundaryValues' own list: the id a
+    // site carries (SiteData::GetIoletId) indexes that list -- BoundaryValues::GetBoundaryDensity(id)
+    // reads iolets[id] (BoundaryValues.cc:162-165).  (The reference's link streamers take the
+    // iolet's geometry from GetLocalIolet(id) = iolets[localIoletIDs[id]], NashZerothOrderPressure.h:39,
+    // LaddIolet.h:46: the same object whenever the rank holds iolets 0..id, out of range or another
+    // iolet otherwise; the device table holds iolets[id].)
+    const bool velocityLinks = pol.wall == HLB_WALL_GZS;
+    auto records = [minDensity, velocityLinks](lb::BoundaryValues* bv, int linkPolicy) {
       std::vector<double> r;
       if (!bv) return r;
-      for (unsigned i = 0; i < bv->GetLocalIoletCount(); ++i) {
-        lb::InOutLet* io = bv->GetLocalIolet(i);
+      for (unsigned i = 0; i < bv->GetGlobalIoletCount(); ++i) {
+        lb::InOutLet* io = bv->GetGlobalIolet(i);
         double rec[HLB_IOLET_RECORD_DOUBLES] = {0};
         auto const& n = io->GetNormal();
         auto const& p = io->GetPosition();
         for (int k = 0; k < 3; ++k) { rec[1 + k] = n[k]; rec[4 + k] = p[k]; }
         if (auto* v = dynamic_cast<lb::InOutLetParabolicVelocity*>(io)) {
           rec[0] = 1; rec[7] = v->GetRadius(); rec[8] = v->GetMaxSpeed();
+          // the warm-up length has a setter only (InOutLetParabolicVelocity.h:29-36): read it off the
+          // ramp it produces, max * t / warmUpLength at the centre line for t = 1 < warmUpLength
+          // (InOutLetParabolicVelocity.cc:33-39); without a ramp at t = 1 there is none at any step
+          if (v->GetMaxSpeed() != 0.0) {
+            const double at1 = v->GetVelocity(v->GetPosition(), 1).GetMagnitude();
+            const double ratio = std::abs(v->GetMaxSpeed()) / at1;
+            if (at1 > 0.0 && ratio > 1.5) rec[13] = std::floor(ratio + 0.5);
+          }
+        } else if (dynamic_cast<lb::InOutLetVelocity*>(io)) {
+          // a velocity iolet whose profile the device does not evaluate (Womersley, file): the Ladd
+          // and GuoZhengShi links would silently apply zero velocity
+          if (linkPolicy == HLB_IOLET_LADD || velocityLinks)
+            throw Exception() << "hemelb_b200: velocity iolet " << i << " is not an InOutLetParabolicVelocity; the "
+                                 "device evaluates only the parabolic profile (LaddIolet.h:45-63, GuoZhengShi.h:163-189)";
+          rec[0] = 1;
         } else if (auto* c = dynamic_cast<lb::InOutLetCosine*>(io)) {
           rec[9] = c->GetDensityMean(); rec[10] = c->GetDensityAmp(); rec[11] = c->GetPhase(); rec[12] = c->GetPeriod();
         } else {
@@ -226,7 +251,7 @@ namespace hemelb::geometry {
       }
       return r;
     };
-    auto rin = records(pol.inletValues), rout = records(pol.outletValues);
+    auto rin = records(pol.inletValues, pol.inlet), rout = records(pol.outletValues, pol.outlet);
     cfg.n_inlets = (int)(rin.size() / HLB_IOLET_RECORD_DOUBLES);
     cfg.n_outlets = (int)(rout.size() / HLB_IOLET_RECORD_DOUBLES);
     Check(hlb_gpu_create(&cfg, &m_gpu));

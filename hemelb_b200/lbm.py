@@ -371,6 +371,13 @@ class GpuLBM:
         check(self.L.hlb_gpu_monitor_global(self.h, ptr(out, C.c_double)))
         return dict(min_f=out[0], min_density=out[1], max_density=out[2], max_speed=out[3])
 
+    def stability(self, with_convergence=False):
+        """``StabilityTester``'s site loop on the device, before the swap: (populations of f_new that fail
+        ``value > 0``, largest |u_new - u_old| over the local sites)."""
+        out = np.zeros(2)
+        check(self.L.hlb_gpu_stability(self.h, 1 if with_convergence else 0, ptr(out, C.c_double)))
+        return int(out[0]), float(out[1])
+
     def launch_count(self) -> int:
         n = C.c_int64()
         check(self.L.hlb_gpu_launch_count(self.h, C.byref(n)))

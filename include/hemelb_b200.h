@@ -177,6 +177,15 @@ int hlb_gpu_monitor(hlb_gpu_t h, double* out4);
 int hlb_gpu_monitor_global(hlb_gpu_t h, double* out4);
 /* number of kernels launched by this handle so far */
 int hlb_gpu_launch_count(hlb_gpu_t h, int64_t* n);
+/* lb::StabilityTester<LATTICE>::PostSendToParent's loop over the local sites
+ * (Code/lb/StabilityTester.h:97-141) as one device reduction, to be called where that loop runs:
+ * after the step's streaming, before SwapOldAndNew.  out2[0] = the number of populations of f_new
+ * that fail "value > 0.0" (zero, negative or NaN: Unstable when non-zero); out2[1] = the largest
+ * |u_new - u_old| over the local sites when with_convergence is non-zero (the absolute error of
+ * ComputeRelativeDifference, :156-180: relative difference = out2[1] / convergenceReferenceValue), else 0.
+ * 16 bytes leave the device instead of the two whole distribution arrays. */
+int hlb_gpu_stability(hlb_gpu_t h, int with_convergence, double* out2);
+
 /* the device-resident tables, converted back to reference form (for parity tests) */
 int hlb_gpu_get_neighbour_indices(hlb_gpu_t h, int64_t* idx);
 

@@ -8,10 +8,13 @@ namespace hemelb::lb {
   class BoundaryValues {
   public:
     std::vector<InOutLet*> iolets;
+    std::vector<int> localIoletIDs;  // empty: every iolet is local (one rank)
     SimulationState* state = nullptr;
     LatticeDensity GetBoundaryDensity(int i) { return iolets[i]->GetDensity(state->Get0IndexedTimeStep()); }
-    InOutLet* GetLocalIolet(unsigned i) { return iolets[i]; }
-    unsigned GetLocalIoletCount() const { return iolets.size(); }
+    InOutLet* GetLocalIolet(unsigned i) { return localIoletIDs.empty() ? iolets[i] : iolets[localIoletIDs[i]]; }
+    unsigned GetLocalIoletCount() const { return localIoletIDs.empty() ? iolets.size() : localIoletIDs.size(); }
+    InOutLet* GetGlobalIolet(unsigned i) { return iolets[i]; }
+    unsigned GetGlobalIoletCount() const { return iolets.size(); }
     LatticeTimeStep GetTimeStep() const { return state->GetTimeStep(); }
   };
 }

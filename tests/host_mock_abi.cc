@@ -55,7 +55,7 @@ int hlb_gpu_set_streaming_indices(hlb_gpu_t h, const int64_t* idx) {
   return 0;
 }
 int hlb_gpu_set_iolets(hlb_gpu_t, int which, int n, const double* r) {
-  fprintf(out(), "set_iolets %d %d kind0=%d min_density=%.17g\n", which, n, (int)r[0], r[14]); return 0; }
+  fprintf(out(), "set_iolets %d %d kind0=%d min_density=%.17g warmup0=%g\n", which, n, (int)r[0], r[14], r[13]); return 0; }
 int hlb_gpu_finalise(hlb_gpu_t) { fprintf(out(), "finalise\n"); return 0; }
 int hlb_gpu_comm_unique_id(void* id) { memset(id, 0, 128); return 0; }
 int hlb_gpu_comm_init(hlb_gpu_t, const void*) { fprintf(out(), "comm_init\n"); return 0; }

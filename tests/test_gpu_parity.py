@@ -319,6 +319,38 @@ def test_monitor_matches_numpy():
     assert abs(m4["min_density"] - f2.sum(1).min()) < 1e-12
 
 
+def test_stability_reduction_matches_the_reference_loop():
+    """hlb_gpu_stability = the site loop of lb::StabilityTester::PostSendToParent
+    (Code/lb/StabilityTester.h:97-141) run where the reference runs it: after the step's streaming,
+    before the swap."""
+    geom, Q = geometry("cylinder"), 19
+    dom = build_domains(geom, Q)[0]
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    gpu = GpuLBM(dom, "LBGK", "BFL", tau=0.8, inlets=inlets, outlets=outlets)
+    f0 = perturbed_equilibrium(dom.N, Q, 0, O.lattice(Q)[1])
+    gpu.set_f(f0)
+    gpu.step(3)
+    gpu.request_comms()
+    gpu.pre_send()
+    gpu.pre_receive()
+    gpu.post_receive()
+    bad, du = gpu.stability(True)
+    f_old = gpu.get_f(0)[:dom.N * Q].reshape(dom.N, Q)
+    f_new = gpu.get_f(1)[:dom.N * Q].reshape(dom.N, Q)
+    c = O.lattice(Q)[0].astype(np.float64)
+    u_old = (f_old @ c) / f_old.sum(1)[:, None]
+    u_new = (f_new @ c) / f_new.sum(1)[:, None]
+    want = np.sqrt(((u_new - u_old) ** 2).sum(1)).max()
+    assert bad == 0 and want > 0
+    assert abs(du - want) <= 1e-15 + 1e-12 * want
+    assert gpu.stability(False) == (0, 0.0)
+    # a negative and a NaN population in f_new are both "not > 0"
+    f1 = gpu.get_f(1)
+    f1[5], f1[Q * 7 + 3] = -1e-3, np.nan
+    gpu.set_f(f1, which=1)
+    assert gpu.stability(False)[0] == 2
+
+
 @pytest.mark.parametrize("geom_name,Q,kernel,wall,inlet,outlet", [
     ("cylinder", 19, "MRT", "BFL", "NASH", "NASH"), ("tree", 19, "MRT", "BFL", "LADD", "NASH"),
     ("sac", 27, "TRT", "BFL", "NASH", "NASH"), ("cylinder", 27, "LBGK", "SBB", "NASH", "NASH"),

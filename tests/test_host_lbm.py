@@ -116,6 +116,8 @@ def test_cxx_host_call_sequence(tmp_path, name, Q, kernel, wall, inlet, outlet):
     geom = geometry(name)
     dom = build_domains(geom, Q)[0]
     inlets, outlets = iolets_for(geom, inlet, outlet)
+    if inlet == "LADD":
+        inlets[0][13] = 7  # InOutLetParabolicVelocity::SetWarmup
     steps, want, dt = 3, 3, physical_dt(0.8)
     f0 = anisotropic_f(dom.N, Q, 0)
     write_case(tmp_path / "case.bin", dom, kernel, wall, inlet, outlet, inlets, outlets, f0, steps, want, dt)
@@ -149,8 +151,10 @@ def test_cxx_host_call_sequence(tmp_path, name, Q, kernel, wall, inlet, outlet):
         assert "set_wall_distances %d %d" % (n_bulk, mid_total - n_bulk) in build
     assert "set_site_coords 0 %d" % dom.N in build
     min_density = min(float(r_[14]) for r_ in list(inlets) + list(outlets))
-    assert "set_iolets 0 %d kind0=%d min_density=%.17g" % (len(inlets), IOLETS[inlet], min_density) in build
-    assert "set_iolets 1 %d kind0=%d min_density=%.17g" % (len(outlets), IOLETS[outlet], min_density) in build
+    # (a velocity iolet's warm-up length has no getter: the host classes read it off the ramp)
+    assert "set_iolets 0 %d kind0=%d min_density=%.17g warmup0=%g" % (
+        len(inlets), IOLETS[inlet], min_density, inlets[0][13] if inlet == "LADD" else 0) in build
+    assert "set_iolets 1 %d kind0=%d min_density=%.17g warmup0=0" % (len(outlets), IOLETS[outlet], min_density) in build
     # the host mirror (initial condition) goes up once, right after the engine exists
     after = rest[rest.index("finalise") + 1:]
     assert after[0].startswith("set_f 0 f0=%.17g" % f0[0]) and after[1].startswith("set_f 1 ")
@@ -196,6 +200,8 @@ def test_cxx_host_runs_on_the_gpu_and_matches_the_oracle(tmp_path, name, Q, kern
     geom = geometry(name)
     dom = build_domains(geom, Q)[0]
     inlets, outlets = iolets_for(geom, inlet, outlet)
+    if inlet == "LADD":
+        inlets[0][13] = 4  # warm-up ramp over the first steps (InOutLetParabolicVelocity.cc:33-39)
     steps, want, dt = 5, 3, physical_dt(0.8)
     tau = reference_tau(dt)
     f0 = anisotropic_f(dom.N, Q, 0)
