@@ -1,7 +1,10 @@
 #!/usr/bin/env python
-"""configs[2] / configs[3]: the synthetic bifurcating vascular tree, built and partitioned on the GPUs.
+"""configs[2] / configs[3] / configs[4]: the synthetic bifurcating vascular tree (or, --geometry sac, the
+rough-walled aneurysm-like sac), built and partitioned on the GPUs.
 
   python bench_tree.py [--sites 1.2e8] [--generations 6] [--steps 50] [--kernel LBGK --wall BFL]
+  python bench_tree.py --kernel MRT --wall GZS --inlet LADD                       # configs[3]
+  python bench_tree.py --geometry sac --lattice 27 --kernel TRT --wall BFL        # configs[4]
   python -m torch.distributed.run --nproc-per-node N ... bench_tree.py --sites 1e9
 
 Strong target size: ``--sites`` is the WHOLE tree (default 1.2e8 per GPU x N).  Pipeline, all on the
@@ -45,6 +48,8 @@ def main():
     ap.add_argument("--inlet", default="NASH")
     ap.add_argument("--outlet", default="NASH")
     ap.add_argument("--lattice", type=int, default=19)
+    ap.add_argument("--geometry", default="tree", choices=["tree", "sac"])
+    ap.add_argument("--roughness", type=float, default=3.0, help="sac: wall roughness amplitude in voxels")
     ap.add_argument("--decomposition", default="basic", choices=["basic", "weighted"],
                     help="basic: the reference's BasicDecomposition over Morton blocks; weighted: the METIS-free "
                          "weighted k-way block partition (hemelb_b200/partition.py)")
@@ -59,7 +64,7 @@ def main():
     total = args.sites or 1.2e8 * world
 
     from hemelb_b200.capi import iolet_record
-    from hemelb_b200.devdomain import DeviceDomain, basic_decomposition_of_counts, tree_shape
+    from hemelb_b200.devdomain import DeviceDomain, basic_decomposition_of_counts, sac_shape, tree_shape
     from hemelb_b200.lbm import GpuLBM, prepare_boundary_objects
 
     dist = None
@@ -70,9 +75,16 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     t0 = time.time()
-    r0, l0 = tree_for_sites(total, args.generations)
-    caps, iolets, shape = tree_shape(args.generations, r0, l0)
-    dom = DeviceDomain.from_shape(caps, iolets, shape, Q, 8, None, rank, world, local_rank, build=False)
+    rough = None
+    if args.geometry == "sac":
+        # sphere of radius R (4/3 pi R^3 sites) crossed by a neck of radius R/4 reaching R/3 beyond it
+        r0 = float((total / (4.0 / 3.0 * np.pi)) ** (1.0 / 3.0))
+        l0 = r0 / 3.0
+        caps, iolets, shape, rough = sac_shape(r0, r0 / 4.0, l0, roughness=args.roughness)
+    else:
+        r0, l0 = tree_for_sites(total, args.generations)
+        caps, iolets, shape = tree_shape(args.generations, r0, l0)
+    dom = DeviceDomain.from_shape(caps, iolets, shape, Q, 8, None, rank, world, local_rank, build=False, roughness=rough)
     bd = dom.block_dims
     # per-block fluid counts: each rank counts an x-slab of blocks
     xs = [int(bd[0]) * r // world for r in range(world + 1)]
@@ -114,7 +126,14 @@ def main():
     outs = [rec(p, args.outlet, False) for p in dom.meta["outlets"]]
     prepare_boundary_objects(ins, outs)
     t2 = time.time()
-    gpu = GpuLBM.from_device_domain(dom, args.kernel, args.wall, args.inlet, args.outlet, tau=0.8, inlets=ins, outlets=outs)
+    def all_gather(obj):
+        if dist is None:
+            return [obj]
+        parts = [None] * world
+        dist.all_gather_object(parts, obj)
+        return parts
+    gpu = GpuLBM.from_device_domain(dom, args.kernel, args.wall, args.inlet, args.outlet, tau=0.8, inlets=ins, outlets=outs,
+                                    all_gather=all_gather)
     if world > 1:
         uid = [GpuLBM.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -162,8 +181,11 @@ def main():
     B = 20 * Q
     mlups = sum(per_rank) * args.steps / (ms * 1e-3) / 1e6
     nb = int(dom.N - dom.mid[0] - dom.edge[0])
-    line = {"config": "configs[2]-style tree: %d generations, root r=%.1f l=%.1f, D3Q%d %s + %s walls, %s inlet / %s outlets"
-                      % (args.generations, r0, l0, Q, args.kernel, args.wall, args.inlet, args.outlet),
+    what = ("tree: %d generations, root r=%.1f l=%.1f" % (args.generations, r0, l0) if args.geometry == "tree" else
+            "sac: rough sphere r=%.1f (value noise +-%.1f voxels) + neck r=%.1f" % (r0, args.roughness, r0 / 4.0))
+    wall_links = None
+    line = {"config": "%s, D3Q%d %s + %s walls, %s inlet / %s outlets" % (what, Q, args.kernel, args.wall, args.inlet, args.outlet),
+            "gzs_remote_links_rank0": int(gpu.gzs_need.shape[0]),
             "n_gpus": world, "sites": sum(per_rank), "sites_counted": n_global, "sites_per_rank": per_rank,
             "halo_doubles_per_rank": halo, "neighbours_per_rank": nbrs,
             "decomposition": ("weighted k-way over blocks, %s start (hemelb_b200/partition.py)" % args.partition_start

@@ -32,7 +32,7 @@ SYMBOLS = [
     "hlb_gpu_get_cache", "hlb_gpu_step", "hlb_gpu_get_time_step", "hlb_gpu_sync", "hlb_gpu_time_steps", "hlb_gpu_time_steps_detail",
     "hlb_gpu_monitor", "hlb_gpu_monitor_global", "hlb_gpu_stability", "hlb_gpu_launch_count", "hlb_gpu_get_neighbour_indices", "hlb_gpu_set_overlap",
     # device-side Domain construction
-    "hlb_dom_create", "hlb_dom_destroy", "hlb_dom_set_sites", "hlb_dom_set_shape", "hlb_dom_set_partition_slabs",
+    "hlb_dom_create", "hlb_dom_destroy", "hlb_dom_set_sites", "hlb_dom_set_shape", "hlb_dom_set_roughness", "hlb_dom_gzs_needs", "hlb_dom_lookup_sites", "hlb_dom_set_partition_slabs",
     "hlb_dom_set_partition_blocks", "hlb_dom_count_block_sites", "hlb_dom_count_block_sites_typed", "hlb_dom_build", "hlb_dom_build_seconds",
     "hlb_dom_get_counts", "hlb_dom_get_neighbours", "hlb_dom_get_streaming_indices", "hlb_dom_get_neighbour_indices",
     "hlb_dom_get_site_coords", "hlb_dom_get_input_index", "hlb_dom_get_boundary_tables", "hlb_dom_get_geometry_sizes",

@@ -193,6 +193,7 @@ struct hlb_gpu_handle {
   uint32_t* siteListDev = nullptr;
   int64_t siteListCap = 0;
   double* monitorDev = nullptr;
+  double* monitorPinned = nullptr;
   unsigned long long* monitorSlots = nullptr;
   bool monitorFused = false;  // the collide kernels of the current step(s) feed the slots
   int64_t monitorLaunches = 0; // collide launches that fed the slots since the last fold
@@ -608,8 +609,13 @@ __global__ void stability_decode_kernel(unsigned long long* io) {
     ((double*)io)[3] = mon_dec(io[1]);
   }
 }
-// fold the spread slots of the fused monitor into slot 0..3 of `io` and re-arm them
-__global__ void monitor_fold_kernel(unsigned long long* __restrict__ slots, unsigned long long* __restrict__ io) {
+// the fused monitor's read-out in one launch: fold the spread slots, re-arm them, decode to doubles
+// (out[0..3] = min f, min rho, max rho, max |u|)
+__global__ void __launch_bounds__(256) monitor_fold_decode_kernel(unsigned long long* __restrict__ slots,
+                                                                 double* __restrict__ out) {
+  __shared__ unsigned long long sh[4];
+  if (threadIdx.x == 0) { sh[0] = ~0ull; sh[1] = ~0ull; sh[2] = 0ull; sh[3] = 0ull; }
+  __syncthreads();
   unsigned long long a = ~0ull, b = ~0ull, c = 0ull, d = 0ull;
   for (int i = threadIdx.x; i < kMonitorSlots; i += blockDim.x) {
     unsigned long long* s = slots + 4 * i;
@@ -619,10 +625,16 @@ __global__ void monitor_fold_kernel(unsigned long long* __restrict__ slots, unsi
     d = d > s[3] ? d : s[3];
     s[0] = ~0ull; s[1] = ~0ull; s[2] = 0ull; s[3] = 0ull;
   }
-  atomicMin(io + 0, a);
-  atomicMin(io + 1, b);
-  atomicMax(io + 2, c);
-  atomicMax(io + 3, d);
+  atomicMin(sh + 0, a);
+  atomicMin(sh + 1, b);
+  atomicMax(sh + 2, c);
+  atomicMax(sh + 3, d);
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double v = dec(sh[threadIdx.x]);
+    if (threadIdx.x == 3) v = sqrt(v);
+    out[threadIdx.x] = v;
+  }
 }
 __global__ void monitor_arm_kernel(unsigned long long* __restrict__ slots) {
   for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < kMonitorSlots; i += blockDim.x * gridDim.x) {
@@ -1426,6 +1438,7 @@ int hlb_gpu_destroy(hlb_gpu_t h) {
   cudaFree(h->staging);
   cudaFree(h->siteListDev);
   cudaFree(h->monitorDev);
+  if (h->monitorPinned) cudaFreeHost(h->monitorPinned);
   cudaFree(h->monitorSlots);
   cudaFree(h->perm);
   cudaFree(h->gzsGhost);
@@ -2110,14 +2123,22 @@ int hlb_gpu_monitor(hlb_gpu_t h, double* out4) {
   if (!h || !out4) return fail("null argument");
   CU(cudaSetDevice(h->cfg.device));
   if (join_aux(h)) return 1;
-  unsigned long long init[4] = {~0ull, ~0ull, 0ull, 0ull};
-  CU(cudaMemcpyAsync(h->monitorDev, init, sizeof(init), cudaMemcpyHostToDevice, h->compute));
+  if (!h->monitorPinned) CU(cudaMallocHost(&h->monitorPinned, sizeof(double) * 4));
   if (h->monitorFused && h->monitorLaunches > 0) {
     h->monitorLaunches = 0;
-    // gathered by the collide-and-stream kernels themselves during the last step(s)
-    monitor_fold_kernel<<<1, 256, 0, h->compute>>>(h->monitorSlots, (unsigned long long*)h->monitorDev);
+    // gathered by the collide-and-stream kernels themselves during the last step(s): one small launch
+    // and 32 bytes to pinned memory
+    monitor_fold_decode_kernel<<<1, 256, 0, h->compute>>>(h->monitorSlots, h->monitorDev + 4);
     h->launches++;
-  } else if (h->N) {
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h->monitorPinned, h->monitorDev + 4, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->compute));
+    CU(cudaStreamSynchronize(h->compute));
+    for (int k = 0; k < 4; ++k) out4[k] = h->monitorPinned[k];
+    return 0;
+  }
+  unsigned long long init[4] = {~0ull, ~0ull, 0ull, 0ull};
+  CU(cudaMemcpyAsync(h->monitorDev, init, sizeof(init), cudaMemcpyHostToDevice, h->compute));
+  if (h->N) {
     const unsigned grid = (unsigned)std::min<int64_t>((h->N + 255) / 256, 148 * 16);
     unsigned long long* mo = (unsigned long long*)h->monitorDev;
     switch (h->Q) {

@@ -109,13 +109,19 @@ struct Part {
   }
 };
 
-struct Capsule { double a[3], ab[3], L2, r; };
+struct Capsule { double a[3], ab[3], L2, r, rough; };  // rough: amplitude of the wall roughness (voxels), 0 = smooth
 struct IoletPlane { int kind, index; double pos[3], n[3], radius; };
 struct Shape {
   const Capsule* caps;
   int nCaps;
   const IoletPlane* iolets;
   int nIolets;
+  // seeded value noise on an ng^3 grid stretched over the lattice (geometry.py:sac): the surface of a
+  // rough capsule is displaced by rough * noise(p); wall normals then come from central differences
+  const double* noise;
+  int ng;
+  double ext[3];
+  double maxRough;
 };
 
 struct Explicit {
@@ -131,6 +137,7 @@ struct Explicit {
 };
 
 // ------------------------------------------------------------------------------- analytic shape
+// signed distance to the smooth capsule
 __device__ __forceinline__ double capsule_phi(const Capsule& c, double x, double y, double z) {
   const double d0 = x - c.a[0], d1 = y - c.a[1], d2 = z - c.a[2];
   double t = 0.0;
@@ -141,13 +148,40 @@ __device__ __forceinline__ double capsule_phi(const Capsule& c, double x, double
   const double e0 = d0 - t * c.ab[0], e1 = d1 - t * c.ab[1], e2 = d2 - t * c.ab[2];
   return sqrt(e0 * e0 + e1 * e1 + e2 * e2) - c.r;
 }
+// geometry.py:sac.value_noise -- trilinear interpolation of the seeded grid, corners in its order
+__device__ __forceinline__ double value_noise(const Shape& S, double x, double y, double z) {
+  const double p[3] = {x, y, z};
+  int i0[3];
+  double f[3];
+  for (int k = 0; k < 3; ++k) {
+    const double q = (p[k] / S.ext[k]) * (S.ng - 1);
+    int i = (int)floor(q);
+    i = i < 0 ? 0 : (i > S.ng - 2 ? S.ng - 2 : i);
+    i0[k] = i;
+    f[k] = q - i;
+  }
+  double acc = 0.0;
+  for (int dx = 0; dx < 2; ++dx)
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dz = 0; dz < 2; ++dz) {
+        const double w = (dx ? f[0] : 1 - f[0]) * (dy ? f[1] : 1 - f[1]) * (dz ? f[2] : 1 - f[2]);
+        acc += w * S.noise[((i0[0] + dx) * S.ng + i0[1] + dy) * S.ng + i0[2] + dz];
+      }
+  return acc;
+}
+// the capsule's implicit function: signed distance, displaced by the roughness
+__device__ __forceinline__ double capsule_phi(const Shape& S, const Capsule& c, double x, double y, double z) {
+  double v = capsule_phi(c, x, y, z);
+  if (c.rough != 0.0) v = v - c.rough * value_noise(S, x, y, z);
+  return v;
+}
 // min over a candidate list (nCand < 0: every capsule)
 __device__ __forceinline__ double shape_phi(const Shape& S, const int* cand, int nCand, double x, double y, double z) {
   double out = INFINITY;
   if (nCand < 0) {
-    for (int k = 0; k < S.nCaps; ++k) out = fmin(out, capsule_phi(S.caps[k], x, y, z));
+    for (int k = 0; k < S.nCaps; ++k) out = fmin(out, capsule_phi(S, S.caps[k], x, y, z));
   } else {
-    for (int k = 0; k < nCand; ++k) out = fmin(out, capsule_phi(S.caps[cand[k]], x, y, z));
+    for (int k = 0; k < nCand; ++k) out = fmin(out, capsule_phi(S, S.caps[cand[k]], x, y, z));
   }
   return out;
 }
@@ -166,7 +200,7 @@ __device__ __forceinline__ int clipped(const Shape& S, double x, double y, doubl
 __device__ __forceinline__ int site_candidates(const Shape& S, double x, double y, double z, int* cand) {
   int n = 0;
   for (int k = 0; k < S.nCaps; ++k)
-    if (capsule_phi(S.caps[k], x, y, z) < 2.5) {
+    if (capsule_phi(S.caps[k], x, y, z) < 2.5 + fabs(S.caps[k].rough)) {
       if (n == kMaxSiteCand) return -1;
       cand[n++] = k;
     }
@@ -208,6 +242,17 @@ __device__ LinkRes analytic_link(const Shape& S, const int* cand, int nCand, dou
 // wall normal at a site: the exact gradient of the signed distance to the nearest capsule (radially
 // away from its axis), the analytic counterpart of geometry.py's finite-difference default
 __device__ void analytic_normal(const Shape& S, const int* cand, int nCand, double x, double y, double z, float* out) {
+  if (S.maxRough != 0.0) {
+    // geometry.py:voxelise's default normal_fn: central differences of phi over +-0.25 voxel
+    double g[3];
+    g[0] = shape_phi(S, cand, nCand, x + 0.25, y, z) - shape_phi(S, cand, nCand, x - 0.25, y, z);
+    g[1] = shape_phi(S, cand, nCand, x, y + 0.25, z) - shape_phi(S, cand, nCand, x, y - 0.25, z);
+    g[2] = shape_phi(S, cand, nCand, x, y, z + 0.25) - shape_phi(S, cand, nCand, x, y, z - 0.25);
+    double len = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+    if (len == 0.0) len = 1.0;
+    for (int k = 0; k < 3; ++k) out[k] = (float)(g[k] / len);
+    return;
+  }
   double best = INFINITY;
   int kb = 0;
   const int n = nCand < 0 ? S.nCaps : nCand;
@@ -266,7 +311,7 @@ __global__ void __launch_bounds__(512) classify_blocks_kernel(Shape S, Part P, W
   // (+ one voxel of rim when the lattice neighbours of the block's sites are classified too)
   const double reach = 1.7320508075688772 * (h + (COUNT_ONLY && boundaryCount ? 1.0 : 0.0)) + 0.5;
   for (int k = t; k < S.nCaps; k += blockDim.x)
-    if (capsule_phi(S.caps[k], cxx, cyy, czz) < reach) {
+    if (capsule_phi(S.caps[k], cxx, cyy, czz) < reach + fabs(S.caps[k].rough)) {
       const int i = atomicAdd(&nCandS, 1);
       if (i < kMaxBlockCand) cand[i] = k;
     }
@@ -637,6 +682,45 @@ __global__ void __launch_bounds__(128) boundary_tables_kernel(Shape S, Explicit 
   for (int k = 0; k < 3; ++k) bNormal[(int64_t)k * NB + b] = R.navail ? R.normal[k] : INFINITY;
 }
 
+// GuoZhengShi's remote needs (GuoZhengShi.h:36-104): wall link d of a domain-edge site whose opposite
+// direction is neither wall nor iolet and leads to a site of another rank -> {site, opposite
+// direction, that rank, the neighbour's coordinates}
+struct GzsNeed { int64_t site; int32_t dir, rank; int64_t x, y, z; };
+__global__ void gzs_needs_kernel(Win W, LatticeTab L, const int32_t* __restrict__ grid,
+                                 const int32_t* __restrict__ coordsLocal, int64_t N, int64_t NB, int64_t nbMid,
+                                 int64_t midTotal, int64_t edgeBulk, int me, const uint32_t* __restrict__ bWall,
+                                 const uint32_t* __restrict__ bIolet, unsigned long long* __restrict__ counter,
+                                 unsigned long long cap, GzsNeed* __restrict__ out) {
+  const int64_t b = nbMid + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // domain-edge boundary sites only
+  if (b >= NB) return;
+  const uint32_t wall = bWall[b], iol = bIolet[b];
+  if (!wall) return;
+  const int64_t s = b - nbMid + midTotal + edgeBulk;
+  const int64_t x = coordsLocal[s], y = coordsLocal[N + s], z = coordsLocal[2 * N + s];
+  const int64_t key = W.key(x, y, z);
+  for (int d = 1; d < L.Q; ++d) {
+    if (!((wall >> (d - 1)) & 1u)) continue;
+    const int o = L.inv[d];
+    if (((wall >> (o - 1)) & 1u) || ((iol >> (o - 1)) & 1u)) continue;
+    const int32_t g = grid[key + W.offset(L.c[o][0], L.c[o][1], L.c[o][2])];
+    if (g > -2 || g == -2 - me) continue;
+    const unsigned long long k = atomicAdd(counter, 1ull);
+    if (k < cap) out[k] = GzsNeed{s, o, -2 - g, x + L.c[o][0], y + L.c[o][1], z + L.c[o][2]};
+  }
+}
+__global__ void lookup_sites_kernel(Win W, const int32_t* __restrict__ grid, int64_t n, const int64_t* __restrict__ coords,
+                                    int64_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t x = coords[3 * i], y = coords[3 * i + 1], z = coords[3 * i + 2];
+  int64_t v = -1;
+  if (W.holds(x, y, z)) {
+    const int32_t g = grid[W.key(x, y, z)];
+    if (g >= 0) v = g;
+  }
+  out[i] = v;
+}
+
 // geometry download (analytic source): one record per own site with a non-fluid 26-neighbour
 __global__ void __launch_bounds__(128) emit_records_kernel(Shape S, Explicit E, Win W, const int32_t* __restrict__ grid,
                                                           const int32_t* __restrict__ coordsLocal,
@@ -740,7 +824,12 @@ struct hlb_dom_handle {
     P.rankOfBlock = rankOfBlock;
     return P;
   }
-  Shape shape() const { return Shape{caps, nCaps, iolets, nIolets}; }
+  double* noise = nullptr;
+  int noiseGrid = 0;
+  double noiseExtent[3] = {1, 1, 1}, maxRough = 0.0;
+  Shape shape() const {
+    return Shape{caps, nCaps, iolets, nIolets, noise, noiseGrid, {noiseExtent[0], noiseExtent[1], noiseExtent[2]}, maxRough};
+  }
 };
 
 namespace {
@@ -771,8 +860,8 @@ int own_block_box(hlb_dom_t d, int64_t lo[3], int64_t hi[3]) {
   for (const Capsule& c : d->hCaps)
     for (int k = 0; k < 3; ++k) {
       const double e = c.a[k] + c.ab[k];
-      clo[k] = std::min(clo[k], std::min(c.a[k], e) - c.r - 1.0);
-      chi[k] = std::max(chi[k], std::max(c.a[k], e) + c.r + 1.0);
+      clo[k] = std::min(clo[k], std::min(c.a[k], e) - c.r - std::fabs(c.rough) - 1.0);
+      chi[k] = std::max(chi[k], std::max(c.a[k], e) + c.r + std::fabs(c.rough) + 1.0);
     }
   for (int k = 0; k < 3; ++k) {
     const int64_t vlo = (int64_t)std::floor(std::max(clo[k], 0.0));
@@ -917,6 +1006,7 @@ int hlb_dom_set_shape(hlb_dom_t d, int n_capsules, const double* capsules, int n
       o.L2 += o.ab[j] * o.ab[j];
     }
     o.r = c[6];
+    o.rough = 0.0;
     if (!(o.r > 0)) return fail("capsule radius must be positive");
   }
   std::vector<IoletPlane> io(std::max(n_iolets, 1));
@@ -933,6 +1023,25 @@ int hlb_dom_set_shape(hlb_dom_t d, int n_capsules, const double* capsules, int n
   d->nCaps = n_capsules;
   d->nIolets = n_iolets;
   d->source = 1;
+  return 0;
+}
+
+int hlb_dom_set_roughness(hlb_dom_t d, const double* amplitude, int grid, const double* noise, const double* extent) {
+  if (!d || !amplitude || !noise || !extent || grid < 2) return fail("bad argument");
+  if (d->source != 1) return fail("hlb_dom_set_roughness needs hlb_dom_set_shape first");
+  CU(cudaSetDevice(d->cfg.device));
+  d->maxRough = 0.0;
+  for (int k = 0; k < d->nCaps; ++k) {
+    d->hCaps[k].rough = amplitude[k];
+    d->maxRough = std::max(d->maxRough, std::fabs(amplitude[k]));
+  }
+  if (upload(d->caps, d->hCaps.data(), d->nCaps)) return 1;
+  if (upload(d->noise, noise, grid * grid * grid)) return 1;
+  d->noiseGrid = grid;
+  for (int k = 0; k < 3; ++k) {
+    if (!(extent[k] > 0)) return fail("noise extent must be positive");
+    d->noiseExtent[k] = extent[k];
+  }
   return 0;
 }
 
@@ -1372,6 +1481,68 @@ int hlb_dom_get_boundary_tables(hlb_dom_t d, uint32_t* wall, uint32_t* iolet, in
   CU(cudaMemcpy(t.data(), d->bNormal, sizeof(float) * t.size(), cudaMemcpyDeviceToHost));
   for (int64_t b = 0; b < NB; ++b)
     for (int k = 0; k < 3; ++k) normal[b * 3 + k] = (double)t[(size_t)k * NB + b];
+  return 0;
+}
+
+int hlb_dom_gzs_needs(hlb_dom_t d, int64_t capacity, int64_t* n, int64_t* local_site, int32_t* direction,
+                      int32_t* owner_rank, int64_t* coords) {
+  if (!d || !n) return fail("null argument");
+  if (!d->built) return fail("domain not built");
+  CU(cudaSetDevice(d->cfg.device));
+  *n = 0;
+  const int64_t midTotal = d->mid[0] + d->mid[1] + d->mid[2] + d->mid[3] + d->mid[4] + d->mid[5];
+  const int64_t nbMid = midTotal - d->mid[0];
+  const int64_t nEdgeB = d->NB - nbMid;
+  if (nEdgeB <= 0 || d->cfg.nranks <= 1) return 0;
+  unsigned long long* counter = nullptr;
+  GzsNeed* out = nullptr;
+  CU(cudaMalloc(&counter, sizeof(unsigned long long)));
+  CU(cudaMemset(counter, 0, sizeof(unsigned long long)));
+  if (capacity > 0) CU(cudaMalloc(&out, sizeof(GzsNeed) * capacity));
+  gzs_needs_kernel<<<blocks_for(nEdgeB), 256>>>(d->W, d->L, d->grid, d->coordsLocal, d->N, d->NB, nbMid, midTotal, d->edge[0],
+                                                d->cfg.rank, d->bWall, d->bIolet, counter, (unsigned long long)capacity, out);
+  CU(cudaGetLastError());
+  unsigned long long total = 0;
+  CU(cudaMemcpy(&total, counter, sizeof(total), cudaMemcpyDeviceToHost));
+  cudaFree(counter);
+  *n = (int64_t)total;
+  if (capacity > 0 && (int64_t)total <= capacity && total) {
+    if (!local_site || !direction || !owner_rank || !coords) { cudaFree(out); return fail("null argument"); }
+    std::vector<GzsNeed> h(total);
+    CU(cudaMemcpy(h.data(), out, sizeof(GzsNeed) * total, cudaMemcpyDeviceToHost));
+    // an order both sides of a pair can rely on: owner rank, then requesting site, then direction
+    std::sort(h.begin(), h.end(), [](const GzsNeed& a, const GzsNeed& b) {
+      if (a.rank != b.rank) return a.rank < b.rank;
+      if (a.site != b.site) return a.site < b.site;
+      return a.dir < b.dir;
+    });
+    for (size_t k = 0; k < h.size(); ++k) {
+      local_site[k] = h[k].site;
+      direction[k] = h[k].dir;
+      owner_rank[k] = h[k].rank;
+      coords[3 * k] = h[k].x;
+      coords[3 * k + 1] = h[k].y;
+      coords[3 * k + 2] = h[k].z;
+    }
+  }
+  cudaFree(out);
+  return 0;
+}
+
+int hlb_dom_lookup_sites(hlb_dom_t d, int64_t n, const int64_t* coords, int64_t* local_site) {
+  if (!d || (n && (!coords || !local_site))) return fail("null argument");
+  if (!d->built) return fail("domain not built");
+  if (n <= 0) return 0;
+  CU(cudaSetDevice(d->cfg.device));
+  int64_t *dc = nullptr, *ds = nullptr;
+  CU(cudaMalloc(&dc, sizeof(int64_t) * 3 * n));
+  CU(cudaMalloc(&ds, sizeof(int64_t) * n));
+  CU(cudaMemcpy(dc, coords, sizeof(int64_t) * 3 * n, cudaMemcpyHostToDevice));
+  lookup_sites_kernel<<<blocks_for(n), 256>>>(d->W, d->grid, n, dc, ds);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(local_site, ds, sizeof(int64_t) * n, cudaMemcpyDeviceToHost));
+  cudaFree(dc);
+  cudaFree(ds);
   return 0;
 }
 

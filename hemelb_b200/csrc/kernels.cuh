@@ -154,28 +154,37 @@ __device__ __forceinline__ double min_population(const double (&f)[Q]) {
   for (int d = 1; d < Q; ++d) fmin = fmin < f[d] ? fmin : f[d];
   return fmin;
 }
+// smallest / largest order-preserving key of a full warp: two 32-bit warp reductions (redux.sync) per
+// value -- the high words first, then the low words of the lanes that hold the winning high word
+__device__ __forceinline__ unsigned long long warp_min_key(unsigned long long k) {
+  const unsigned hi = (unsigned)(k >> 32);
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? (unsigned)k : 0xffffffffu);
+  return ((unsigned long long)mhi << 32) | mlo;
+}
+__device__ __forceinline__ unsigned long long warp_max_key(unsigned long long k) {
+  const unsigned hi = (unsigned)(k >> 32);
+  const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? (unsigned)k : 0u);
+  return ((unsigned long long)mhi << 32) | mlo;
+}
 __device__ __forceinline__ void fused_monitor(const StepArgs& A, int64_t tid, double fmin, double rho,
                                               const double (&m)[3]) {
-  double rmin = rho, rmax = rho;
-  double u2 = (m[0] * m[0] + m[1] * m[1] + m[2] * m[2]) / (rho * rho);
+  const double u2 = (m[0] * m[0] + m[1] * m[1] + m[2] * m[2]) / (rho * rho);
+  unsigned long long kf = mon_enc(fmin), krmin = mon_enc(rho), krmax = krmin, ku = mon_enc(u2);
   const unsigned mask = __activemask();
   unsigned long long* slot = A.monitorSlots + 4 * ((tid >> 5) & (kMonitorSlots - 1));
   if (mask == 0xffffffffu) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double a = __shfl_xor_sync(0xffffffffu, fmin, o), b = __shfl_xor_sync(0xffffffffu, rmin, o);
-      const double c = __shfl_xor_sync(0xffffffffu, rmax, o), e = __shfl_xor_sync(0xffffffffu, u2, o);
-      fmin = fmin < a ? fmin : a;
-      rmin = rmin < b ? rmin : b;
-      rmax = rmax > c ? rmax : c;
-      u2 = u2 > e ? u2 : e;
-    }
-    if ((tid & 31) != 0) return;
+    kf = warp_min_key(kf);
+    krmin = warp_min_key(krmin);
+    krmax = warp_max_key(krmax);
+    ku = warp_max_key(ku);
+    if ((threadIdx.x & 31) != 0) return;
   }
-  atomicMin(slot + 0, mon_enc(fmin));
-  atomicMin(slot + 1, mon_enc(rmin));
-  atomicMax(slot + 2, mon_enc(rmax));
-  atomicMax(slot + 3, mon_enc(u2));
+  atomicMin(slot + 0, kf);
+  atomicMin(slot + 1, krmin);
+  atomicMax(slot + 2, krmax);
+  atomicMax(slot + 3, ku);
 }
 
 // ---------------------------------------------------------------------------------- collisions
@@ -755,15 +764,13 @@ __device__ __forceinline__ int64_t launch_tid_again() {
   return (int64_t)c * n + t;
 }
 
-// The rare tail of the site kernel (moment extraction on output steps, monitors) as a real call,
+// The rare tail of the site kernel (moment extraction on output steps) as a real call,
 // so that the hot path reserves no registers for it.  The moments are extracted from f_old read
 // again (it is not written during a step): the same loads through the same arithmetic as the
 // site's collision, hence the same bits, but neither f nor f_neq has to outlive the collision.
-// `key` only spreads the monitor atomics.
 template <int Q, int KERNEL>
-__device__ __noinline__ void site_tail(const StepArgs& A, int64_t site, int64_t key, int b, double fmin, double rho0,
-                                       double m0, double m1, double m2) {
-  if (A.cacheMask & 255u) {
+__device__ __noinline__ void site_tail(const StepArgs& A, int64_t site, int b) {
+  {
     double f[Q];
 #pragma unroll
     for (int d = 0; d < Q; ++d) f[d] = A.fOld[(int64_t)d * A.stride + site];
@@ -776,10 +783,6 @@ __device__ __noinline__ void site_tail(const StepArgs& A, int64_t site, int64_t 
 #pragma unroll
     for (int d = 0; d < Q; ++d) fneq[d] = f[d] - feq_i<Q>(d, rho, density_1, mm, m);
     update_caches<Q, KERNEL>(A, site, b, rho, u, fneq);
-  }
-  if (A.cacheMask & C_MONITOR) {
-    const double m[3] = {m0, m1, m2};
-    fused_monitor(A, key, fmin, rho0, m);
   }
 }
 
@@ -839,11 +842,15 @@ __device__ __forceinline__ void site_finish(const StepArgs& A, const MrtArgs<Q>&
   }
 
   if (A.cacheMask) {
-    if constexpr (DIRECT) {
-      const int64_t tid = launch_tid_again();
-      site_tail<Q, KERNEL>(A, A.siteList ? (int64_t)A.siteList[tid] : first + tid, tid, b, fmin, rho, m[0], m[1], m[2]);
-    } else {
-      site_tail<Q, KERNEL>(A, site, site, b, fmin, rho, m[0], m[1], m[2]);
+    // the monitors need eight values that are live anyway; the moment extraction goes through the call
+    if (A.cacheMask & C_MONITOR) fused_monitor(A, DIRECT ? launch_tid_again() : site, fmin, rho, m);
+    if (A.cacheMask & 255u) {
+      if constexpr (DIRECT) {
+        const int64_t tid = launch_tid_again();
+        site_tail<Q, KERNEL>(A, A.siteList ? (int64_t)A.siteList[tid] : first + tid, b);
+      } else {
+        site_tail<Q, KERNEL>(A, site, b);
+      }
     }
   }
 }

@@ -77,9 +77,10 @@ class DeviceDomain:
 
     @classmethod
     def from_shape(cls, capsules, iolets, shape, Q: int, block_size=8, partition=None, rank=0, nranks=1, device=0,
-                   build=True):
+                   build=True, roughness=None):
         """``capsules``: (n,7); ``iolets``: IoletPlanes; ``shape``: voxel extent of the lattice.
-        ``partition``: None | ("slabs", axis, first_coord[nranks+1]) | ("blocks", rank_of_block)."""
+        ``partition``: None | ("slabs", axis, first_coord[nranks+1]) | ("blocks", rank_of_block).
+        ``roughness``: None | (amplitude per capsule, (g,g,g) noise grid): wall roughness, see ``sac_shape``."""
         shape = np.asarray(shape, np.int64)
         bdims = (shape + block_size - 1) // block_size
         self = cls(Q, block_size, bdims, rank, nranks, device)
@@ -88,6 +89,13 @@ class DeviceDomain:
         check(self.L.hlb_dom_set_shape(self.d, caps.shape[0], ptr(caps, C.c_double), ios.shape[0],
                                        ptr(ios, C.c_double) if ios.size else None))
         self.meta = dict(inlets=[i for i in iolets if i.kind == 2], outlets=[i for i in iolets if i.kind == 3])
+        if roughness is not None:
+            amp = np.ascontiguousarray(roughness[0], np.float64)
+            noise = np.ascontiguousarray(roughness[1], np.float64)
+            ext = np.ascontiguousarray(shape, np.float64)
+            assert amp.size == caps.shape[0] and noise.ndim == 3
+            check(self.L.hlb_dom_set_roughness(self.d, ptr(amp, C.c_double), int(noise.shape[0]), ptr(noise, C.c_double),
+                                               ptr(ext, C.c_double)))
         if partition is not None:
             self.set_partition(partition)
         return self.build() if build else self
@@ -143,6 +151,28 @@ class DeviceDomain:
         check(self.L.hlb_dom_build_seconds(self.d, C.byref(sec)))
         self.build_seconds = float(sec.value)
         return self
+
+    # ---- GuoZhengShi across ranks ---------------------------------------------------------------
+    def gzs_needs(self):
+        """(local site, direction, owner rank, neighbour coordinates (n,3)) of every GZS wall link that
+        extrapolates from a site on another rank, ordered by owner rank, site, direction."""
+        n = C.c_int64()
+        check(self.L.hlb_dom_gzs_needs(self.d, C.c_int64(0), C.byref(n), None, None, None, None))
+        k = int(n.value)
+        site, direction = np.zeros(max(k, 1), np.int64), np.zeros(max(k, 1), np.int32)
+        owner, coords = np.zeros(max(k, 1), np.int32), np.zeros((max(k, 1), 3), np.int64)
+        if k:
+            check(self.L.hlb_dom_gzs_needs(self.d, C.c_int64(k), C.byref(n), ptr(site, C.c_int64), ptr(direction, C.c_int32),
+                                           ptr(owner, C.c_int32), ptr(coords, C.c_int64)))
+        return site[:k], direction[:k], owner[:k], coords[:k]
+
+    def lookup_sites(self, coords) -> np.ndarray:
+        """Local site id of each global coordinate triple (-1: not a local fluid site)."""
+        coords = np.ascontiguousarray(coords, np.int64).reshape(-1, 3)
+        out = np.full(max(coords.shape[0], 1), -1, np.int64)
+        if coords.shape[0]:
+            check(self.L.hlb_dom_lookup_sites(self.d, C.c_int64(coords.shape[0]), ptr(coords, C.c_int64), ptr(out, C.c_int64)))
+        return out[:coords.shape[0]]
 
     # ---- reference-form tables ------------------------------------------------------------------
     @property
@@ -243,6 +273,26 @@ def cylinder_shape(radius: float, length: int, margin: int = 2):
     iolets = [IoletPlane(2, 0, np.array([c, c, z0 - 0.5]), np.array([0.0, 0.0, 1.0]), R + 2),
               IoletPlane(3, 0, np.array([c, c, z1 + 0.5]), np.array([0.0, 0.0, -1.0]), R + 2)]
     return caps, iolets, shape
+
+
+def sac_shape(radius: float, neck_radius: float, neck_length: float, roughness: float = 0.0, seed: int = 20261017,
+              margin: int = 3):
+    """configs[4] as capsules: the aneurysm-like sac of ``geometry.sac`` -- a sphere whose wall is displaced
+    by seeded value noise, crossed by a neck cylinder along z that the iolet caps close.  Returns
+    (capsules, iolets, voxel shape, roughness argument of ``DeviceDomain.from_shape``)."""
+    rng = np.random.default_rng(seed)
+    R = float(radius)
+    n = int(np.ceil(2 * (R + roughness))) + 2 * margin + 1
+    zlen = int(np.ceil(2 * R + 2 * neck_length)) + 2 * margin
+    c = np.array([(n - 1) / 2.0, (n - 1) / 2.0, (zlen - 1) / 2.0])
+    shape = (n, n, zlen)
+    noise = rng.uniform(-1.0, 1.0, (8, 8, 8))
+    far = 4.0 * zlen + 64.0
+    caps = capsule_array([c, [c[0], c[1], c[2] - far]], [c, [c[0], c[1], c[2] + far]], [R, float(neck_radius)])
+    zin, zout = margin - 0.5, zlen - margin - 0.5
+    iolets = [IoletPlane(2, 0, np.array([c[0], c[1], zin]), np.array([0.0, 0.0, 1.0]), neck_radius + 2),
+              IoletPlane(3, 0, np.array([c[0], c[1], zout]), np.array([0.0, 0.0, -1.0]), neck_radius + 2)]
+    return caps, iolets, shape, ((float(roughness), 0.0), noise)
 
 
 def tree_shape(generations: int, root_radius: float, root_length: float, seed: int = 20261017,

@@ -170,9 +170,11 @@ class GpuLBM:
 
     @classmethod
     def from_device_domain(cls, dd, kernel="LBGK", wall="SBB", inlet="NASH", outlet="NASH", tau=0.8, inlets=(),
-                           outlets=(), reorder=True):
+                           outlets=(), reorder=True, all_gather=None):
         """The engine for a ``devdomain.DeviceDomain``: the tables move device-to-device
-        (``hlb_gpu_create_from_domain``); nothing of size N crosses the host."""
+        (``hlb_gpu_create_from_domain``); nothing of size N crosses the host.  GuoZhengShi walls on more
+        than one rank need ``all_gather(obj) -> [obj of rank 0, ...]`` (collective) once, to tell the
+        owners which sites the phase-0 site halo has to carry (NeighbouringDataManager::ShareNeeds)."""
         self = cls.__new__(cls)
         self.L = lib()
         self.domain = dd
@@ -197,6 +199,34 @@ class GpuLBM:
         self._set_iolets(inlets, outlets)
         self.gzs_need = np.zeros((0, 4), np.int64)
         self.gzs_serve = np.zeros((0, 2), np.int64)
+        if wall == "GZS" and dd.nranks > 1:
+            if all_gather is None:
+                raise ValueError("GuoZhengShi walls on several ranks: from_device_domain needs all_gather")
+            site, direction, owner, coords = dd.gzs_needs()
+            # every rank learns what every other rank wants of it, in the requester's own order
+            wanted = all_gather({int(o): coords[owner == o] for o in np.unique(owner)})
+            sv_rank, sv_site = [], []
+            for r, asks in enumerate(wanted):
+                c = asks.get(dd.rank)
+                if r == dd.rank or c is None or not len(c):
+                    continue
+                local = dd.lookup_sites(c)
+                if (local < 0).any():
+                    raise capi.HlbError("rank %d asks rank %d for a site it does not own" % (r, dd.rank))
+                sv_rank.append(np.full(local.size, r, np.int32))
+                sv_site.append(local)
+            self.gzs_need = np.stack([site, direction.astype(np.int64), owner.astype(np.int64),
+                                      np.zeros(site.size, np.int64)], 1) if site.size else self.gzs_need
+            if site.size:
+                check(self.L.hlb_gpu_set_gzs_remote(h, C.c_int64(site.size), ptr(np.ascontiguousarray(site), C.c_int64),
+                                                    ptr(np.ascontiguousarray(direction), C.c_int32),
+                                                    ptr(np.ascontiguousarray(owner), C.c_int32),
+                                                    ptr(np.zeros(site.size, np.int64), C.c_int64)))
+            if sv_rank:
+                sr, ss = np.concatenate(sv_rank), np.concatenate(sv_site)
+                self.gzs_serve = np.stack([sr.astype(np.int64), ss], 1)
+                check(self.L.hlb_gpu_set_gzs_serve(h, C.c_int64(sr.size), ptr(np.ascontiguousarray(sr), C.c_int32),
+                                                   ptr(np.ascontiguousarray(ss), C.c_int64)))
         check(self.L.hlb_gpu_finalise(h))
         return self
 

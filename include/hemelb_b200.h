@@ -224,6 +224,12 @@ int hlb_dom_set_sites(hlb_dom_t d, int64_t n_sites, const int32_t* coords, const
  * {kind (2 inlet / 3 outlet), index, position[3], normal[3] (into the fluid), radius} (9 doubles
  * each), in voxel units of the block lattice. */
 int hlb_dom_set_shape(hlb_dom_t d, int n_capsules, const double* capsules, int n_iolets, const double* iolets);
+/* source B, optional: wall roughness.  The surface of capsule k is displaced by amplitude[k] x noise(p),
+ * noise = trilinear interpolation of grid^3 seeded values in [-1, 1] (x-major) stretched over
+ * extent[3] voxels (the lattice); cut distances by bisection on the displaced implicit function, wall
+ * normals by central differences (hemelb_b200/geometry.py: sac, voxelise -- configs[4], the
+ * aneurysm-like sac = one rough sphere + a neck cylinder).  After hlb_dom_set_shape. */
+int hlb_dom_set_roughness(hlb_dom_t d, const double* amplitude, int grid, const double* noise, const double* extent);
 /* site -> rank rule for source B: slabs along an axis (rank r owns first_coord[r] <= x < first_coord
  * [r+1]; nranks + 1 ascending values; cuts through blocks like a ParMETIS site partition), or
  * whole blocks (rank_of_block[prod(block_dims)], .gmy block order; what BasicDecomposition,
@@ -253,6 +259,16 @@ int hlb_dom_get_input_index(hlb_dom_t d, int64_t first_site, int64_t n, int64_t*
  * (3 per site, +inf where the file has none) */
 int hlb_dom_get_boundary_tables(hlb_dom_t d, uint32_t* wall_mask, uint32_t* iolet_mask, int32_t* iolet_id,
                                 double* dist, double* normal);
+/* GuoZhengShi across ranks: what the constructor loop of GuoZhengShiLink registers with the
+ * NeighbouringDataManager (Code/lb/streamers/GuoZhengShi.h:36-104) -- for every wall link of a local site
+ * whose opposite direction is neither wall nor iolet and leads to a site on another rank: the local site,
+ * that opposite direction, the owning rank and the neighbour's global coordinates -- ordered by owner
+ * rank, site, direction (the rows of hlb_gpu_set_gzs_remote).  *n = how many there are; the arrays are
+ * filled when capacity >= *n.  hlb_dom_lookup_sites: local site ids of global coordinates (-1: not a
+ * local fluid site) -- how the owner turns the coordinates it is asked for into its serve list. */
+int hlb_dom_gzs_needs(hlb_dom_t d, int64_t capacity, int64_t* n, int64_t* local_site, int32_t* direction,
+                      int32_t* owner_rank, int64_t* coords);
+int hlb_dom_lookup_sites(hlb_dom_t d, int64_t n, const int64_t* coords, int64_t* local_site);
 /* source B: the voxelised geometry in .gmy terms (sites in traversal order; one record per site
  * with a non-fluid 26-neighbour), e.g. to write a .gmy the reference can read */
 int hlb_dom_get_geometry_sizes(hlb_dom_t d, int64_t* n_sites, int64_t* n_records);

@@ -103,6 +103,31 @@ def test_device_voxeliser_matches_host_voxeliser(name):
     assert dn.max() <= 1e-6 if name == "cylinder" else np.quantile(dn, 0.8) <= 2e-2
 
 
+def test_device_voxeliser_rough_sac_matches_host_voxeliser():
+    """configs[4]: the rough-walled sac (sphere displaced by seeded value noise + neck) voxelised on the
+    device against geometry.sac -- same fluid sites, same cut links, cut distances and the
+    finite-difference wall normals to float32 rounding."""
+    from hemelb_b200.devdomain import sac_shape
+    caps, iolets, shape, rough = sac_shape(8, 3, 4, roughness=1.5)
+    dev = DeviceDomain.from_shape(caps, iolets, shape, 27, roughness=rough)
+    g = dev.geometry()
+    h = geometry("sac")
+    assert np.array_equal(g.block_dims, h.block_dims)
+    assert np.array_equal(g.coords, h.coords)
+    assert np.array_equal(g.bsite, h.bsite)
+    assert np.array_equal(g.btype, h.btype) and np.array_equal(g.biolet, h.biolet)
+    assert np.array_equal(g.bnavail, h.bnavail)
+    assert np.abs(g.bdist.astype(np.float64) - h.bdist.astype(np.float64)).max() <= 2e-6
+    assert np.abs(g.bnormal.astype(np.float64) - h.bnormal.astype(np.float64)).max() <= 1e-5
+    # and the tables the engine consumes, against the host builder on the host-voxelised geometry
+    want = build_domains(h, 27)[0].tables()
+    got = dev.tables()
+    for key in ("N", "totalSharedFs"):
+        assert got[key] == want[key]
+    for key in ("counts", "neighbourIndices", "wallMask", "ioletMask", "ioletId", "globalCoords"):
+        assert np.array_equal(got[key], want[key]), key
+
+
 @pytest.mark.parametrize("name", ["cylinder", "tree"])
 @pytest.mark.parametrize("Q", (15, 19, 27))
 def test_analytic_source_tables_bit_exact(name, Q):
@@ -210,6 +235,71 @@ def test_two_rank_engine_from_device_domain_host_staged_halo():
         sim.step(1)
     for r, (d, g) in enumerate(zip(doms, gpus)):
         assert np.array_equal(g.get_f()[:d.N * Q], sim.get_f(r)[:d.N * Q]), r
+
+
+@pytest.mark.parametrize("kernel,inlet", [("LBGK", "LADD"), ("MRT", "NASH")])
+def test_gzs_site_halo_from_device_domains(kernel, inlet):
+    """GuoZhengShi walls over three ranks built on the device: the remote needs come from
+    hlb_dom_gzs_needs, the owners' serve lists from hlb_dom_lookup_sites of the coordinates asked for, the
+    site halo (whole f_old rows) and the distribution halo move through the host: identical to the
+    oracle's three emulated ranks."""
+    Q, R = 19, 3
+    caps, iolets, shape = cylinder_shape(4.2, 44)
+    geom = DeviceDomain.from_shape(caps, iolets, shape, Q).geometry()
+    cuts = [2 + 15, 2 + 30]
+    first = np.array([-2**60] + cuts + [2**60], np.int64)
+    ros = np.searchsorted(np.array(cuts), geom.coords[:, 2], side="right").astype(np.int32)
+    inlets, outlets = iolets_for(geom, inlet, "NASH")
+    doms = [DeviceDomain.from_shape(caps, iolets, shape, Q, partition=("slabs", 2, first), rank=r, nranks=R)
+            for r in range(R)]
+    asks = []
+    for d in doms:
+        site, direction, owner, coords = d.gzs_needs()
+        asks.append({int(o): coords[owner == o] for o in np.unique(owner)})
+    assert sum(len(a) for a in asks) > 0
+    gpus = [GpuLBM.from_device_domain(d, kernel, "GZS", inlet, "NASH", tau=0.8, inlets=inlets, outlets=outlets,
+                                      all_gather=lambda obj: asks) for d in doms]
+    sim = O.OracleSim(O.OracleDomains(geom, Q, ros, R), kernel, "GZS", inlet, "NASH", tau=0.8, inlets=inlets, outlets=outlets)
+    for r, (d, g) in enumerate(zip(doms, gpus)):
+        f0 = anisotropic_f(d.N, Q, d.totalSharedFs, site_offset=5 * r)
+        g.set_f(f0)
+        sim.set_f(f0, r)
+    for _ in range(5):
+        for g in gpus:
+            g.exchange_site_halo()
+        sends = [g.get_gzs_send() for g in gpus]
+        for r, g in enumerate(gpus):
+            rows = np.zeros((g.gzs_need.shape[0], Q))
+            for p in range(R):
+                mine = np.nonzero(g.gzs_need[:, 2] == p)[0]
+                theirs = np.nonzero(gpus[p].gzs_serve[:, 0] == r)[0]
+                assert mine.size == theirs.size
+                rows[mine] = sends[p][theirs]
+            g.set_gzs_ghost(rows)
+        for g in gpus:
+            g.request_comms()
+            g.pre_send()
+            g.pre_receive()
+        halos = [g.get_halo(1) for g in gpus]
+        for a, (d, g) in enumerate(zip(doms, gpus)):
+            recv = np.zeros(d.totalSharedFs)
+            for (p, cnt, fst) in d.procs:
+                o = int(fst) - (d.N * Q + 1)
+                back = doms[p].procs
+                j = int(np.nonzero(back[:, 0] == a)[0][0])
+                po = int(back[j, 2]) - (doms[p].N * Q + 1)
+                recv[o:o + cnt] = halos[p][po:po + cnt]
+            g.set_halo(recv, 0)
+        for g in gpus:
+            g.post_receive()
+            g.swap_old_and_new()
+            g.state.increment()
+        sim.step(1)
+    for r, (d, g) in enumerate(zip(doms, gpus)):
+        if kernel == "LBGK":
+            assert np.array_equal(g.get_f()[:d.N * Q], sim.get_f(r)[:d.N * Q]), r
+        else:
+            assert np.abs(g.get_f()[:d.N * Q] - sim.get_f(r)[:d.N * Q]).max() <= 1e-13, r
 
 
 @pytest.mark.parametrize("name", ["cylinder", "tree"])

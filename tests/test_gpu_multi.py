@@ -124,6 +124,6 @@ def run_workers(tmp_path, world, case, check_monitor=False):
         assert p.returncode == 0, "rank %d failed:\n%s" % (r, out[-3000:])
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_nccl_halo_matches_oracle(tmp_path, world):
     run_workers(tmp_path, world, "cylinder_slabs")
