@@ -8,9 +8,10 @@
 // and BoundaryValues stay byte-identical.
 //
 // The distributions live on the GPU (handle from include/hemelb_b200.h).  GetFOld / GetFNew hand
-// out pointers into a host mirror that is refreshed on demand (initial conditions, checkpoints,
-// StabilityTester, extraction of distributions); SendAndReceive / CopyReceived / SwapOldAndNew
-// forward to the engine.  geometry::Domain declares `friend class FieldData`, which is how the
+// out pointers into host mirrors that are allocated and refreshed on demand, one array at a time
+// (initial conditions, checkpoints, extraction of distributions; the per-step readers of the
+// reference have device-side stand-ins: lb/StabilityTester.h here, the fused monitors);
+// SendAndReceive / CopyReceived / SwapOldAndNew forward to the engine.  geometry::Domain declares `friend class FieldData`, which is how the
 // index tables are read for upload.
 #ifndef HEMELB_GEOMETRY_FIELDDATA_H
 #define HEMELB_GEOMETRY_FIELDDATA_H
@@ -67,8 +68,7 @@ namespace hemelb::geometry {
     using domain_type = Domain;
 
     explicit FieldData(std::shared_ptr<domain_type> d) :
-        m_domain{d}, m_mirrorOld(CalcDistSize(*d)), m_mirrorNew(CalcDistSize(*d)),
-        m_force(d->GetLocalFluidSiteCount()),
+        m_domain{d}, m_force(d->GetLocalFluidSiteCount()),
         m_neighbouringFields{std::make_unique<neighbouring::NeighbouringFieldData>(d->neighbouringData)} {}
 
     ~FieldData() { if (m_gpu) hlb_gpu_destroy(m_gpu); GpuPolicies().erase(m_domain.get()); }
@@ -82,20 +82,24 @@ namespace hemelb::geometry {
     Site<FieldData> GetSite(site_t i) { return Site<FieldData>(i, *this); }
     Site<const FieldData> GetSite(site_t i) const { return Site<const FieldData>(i, *this); }
 
-    // Host views.  Writing through GetFOld/GetFNew marks the mirror dirty; it is pushed to the
-    // device before the next kernel.  Reading pulls it back first if the device copy is newer.
-    distribn_t* GetFOld(site_t idx) { PullIfStale(); m_hostDirty = true; return &m_mirrorOld[idx]; }
-    distribn_t const* GetFOld(site_t idx) const { const_cast<FieldData*>(this)->PullIfStale(); return &m_mirrorOld[idx]; }
-    distribn_t* GetFNew(site_t idx) { PullIfStale(); m_hostDirty = true; return &m_mirrorNew[idx]; }
-    distribn_t const* GetFNew(site_t idx) const { const_cast<FieldData*>(this)->PullIfStale(); return &m_mirrorNew[idx]; }
+    // Host views.  The two host mirrors are allocated when first asked for (a run that never looks at
+    // the distributions on the host -- monitors on the device, extraction encoded on the device --
+    // never pays for them) and each is refreshed on its own: reading one pulls that array only, and
+    // only if the device copy is newer; writing through the non-const overloads marks that array
+    // dirty, and it alone is pushed to the device before the next kernel.
+    distribn_t* GetFOld(site_t idx) { Pull(0); m_dirty[0] = true; return &m_mirror[0][idx]; }
+    distribn_t const* GetFOld(site_t idx) const { const_cast<FieldData*>(this)->Pull(0); return &m_mirror[0][idx]; }
+    distribn_t* GetFNew(site_t idx) { Pull(1); m_dirty[1] = true; return &m_mirror[1][idx]; }
+    distribn_t const* GetFNew(site_t idx) const { const_cast<FieldData*>(this)->Pull(1); return &m_mirror[1][idx]; }
     template <typename LatticeType> auto GetFNew(site_t site) {
       constexpr auto Q = LatticeType::NUMVECTORS;
       return MutDistSpan<Q>{GetFNew(site * Q), Q};
     }
 
     void SwapOldAndNew() {  // FieldData.h:165-167
-      if (m_gpu) { PushIfDirty(); Check(hlb_gpu_swap(m_gpu)); m_deviceNewer = true; }
-      m_mirrorOld.swap(m_mirrorNew);
+      if (m_gpu) { PushIfDirty(); Check(hlb_gpu_swap(m_gpu)); }
+      m_mirror[0].swap(m_mirror[1]);
+      std::swap(m_stale[0], m_stale[1]);
     }
     void SendAndReceive(net::Net*) {  // FieldData.cc:27-39 -> NCCL send/recv posted after PreSend
       // LBM::RequestComms is the first call of every time step, the first step included: the
@@ -114,35 +118,38 @@ namespace hemelb::geometry {
 
     // ---- used by the Gpu*Streamer policy classes ------------------------------------------------
     GpuPolicy& Policy() { return GpuPolicyFor(m_domain.get()); }
-    hlb_gpu_t Engine() { EnsureEngine(); PushIfDirty(); m_deviceNewer = true; return m_gpu; }
+    // for callers that are about to change the distributions on the device
+    hlb_gpu_t Engine() { EnsureEngine(); PushIfDirty(); m_stale[0] = m_stale[1] = true; return m_gpu; }
+    // for callers that only read them there (lb/StabilityTester.h): null until a streamer has run
+    hlb_gpu_t EngineIfBuilt() { if (m_gpu) PushIfDirty(); return m_gpu; }
     static void Check(int rc) { if (rc) throw Exception() << "hemelb_b200: " << hlb_gpu_last_error(); }
 
   private:
     static std::size_t CalcDistSize(Domain const& d) {
       return d.GetLocalFluidSiteCount() * d.latticeInfo.GetNumVectors() + 1 + d.totalSharedFs;
     }
-    void PullIfStale() {
-      if (m_gpu && m_deviceNewer) {
-        Check(hlb_gpu_get_f(m_gpu, 0, m_mirrorOld.data()));
-        Check(hlb_gpu_get_f(m_gpu, 1, m_mirrorNew.data()));
-        m_deviceNewer = false;
+    void Pull(int which) {
+      if (m_mirror[which].empty()) m_mirror[which].resize(CalcDistSize(*m_domain));
+      if (m_gpu && m_stale[which]) {
+        Check(hlb_gpu_get_f(m_gpu, which, m_mirror[which].data()));
+        m_stale[which] = false;
       }
     }
     void PushIfDirty() {
-      if (m_gpu && m_hostDirty) {
-        Check(hlb_gpu_set_f(m_gpu, 0, m_mirrorOld.data()));
-        Check(hlb_gpu_set_f(m_gpu, 1, m_mirrorNew.data()));
-        m_hostDirty = false;
-      }
+      for (int which = 0; m_gpu && which < 2; ++which)
+        if (m_dirty[which]) {
+          Check(hlb_gpu_set_f(m_gpu, which, m_mirror[which].data()));
+          m_dirty[which] = false;
+        }
     }
     void EnsureEngine();  // defined in lb/streamers/GpuStreamers.h (needs BoundaryValues)
 
     std::shared_ptr<domain_type> m_domain;
-    std::vector<distribn_t> m_mirrorOld, m_mirrorNew;
+    std::vector<distribn_t> m_mirror[2];  // [0] f_old, [1] f_new; empty until first asked for
     std::vector<LatticeForceVector> m_force;
     std::unique_ptr<neighbouring::NeighbouringFieldData> m_neighbouringFields;
     hlb_gpu_t m_gpu = nullptr;
-    bool m_hostDirty = true, m_deviceNewer = false;
+    bool m_dirty[2] = {false, false}, m_stale[2] = {false, false};
     friend struct GpuEngineBuilder;
   };
 }

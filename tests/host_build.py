@@ -36,6 +36,8 @@ def build_host_binaries(verbose=False):
     host = os.path.join(ROOT, "hemelb_b200", "host")
     deps = [os.path.join(ROOT, "tests", "host_lbm_run.cc"), os.path.join(ROOT, "include", "hemelb_b200.h"),
             os.path.join(host, "geometry", "FieldData.h"), os.path.join(host, "lb", "streamers", "GpuStreamers.h"),
+            os.path.join(host, "lb", "StabilityTester.h"), os.path.join(ROOT, "tests", "host_shim", "net", "PhasedBroadcastRegular.h"),
+            os.path.join(ROOT, "tests", "host_shim", "reporting", "Timers.h"),
             os.path.join(ROOT, "tests", "host_shim", "geometry", "Domain.h"), os.path.abspath(__file__)]
     common = ["g++", "-std=c++20", "-O1", "-w", "-I" + host, "-I" + os.path.join(ROOT, "include"),
               "-I" + os.path.join(ROOT, "tests", "host_shim"), "-I" + os.path.join(ROOT, "oracle", "ref_shim"), "-I" + REF]

@@ -33,6 +33,7 @@
 #include "lb/MacroscopicPropertyCache.h"
 #include "lb/SimulationState.h"
 #include "lb/streamers/GpuStreamers.h"
+#include "lb/StabilityTester.h"  // hemelb_b200/host: the device-side stand-in
 
 using namespace hemelb;
 namespace g = hemelb::lb::gpu;
@@ -251,6 +252,20 @@ namespace {
     // HLB_HOST_TIMING=1: wall-clock MLUPS of steps 2..K as this host drives them (stderr); step 1
     // builds the engine and uploads the tables
     const bool timing = getenv("HLB_HOST_TIMING") != nullptr && steps > 1;
+    // HLB_HOST_STABILITY=1 (2: with the velocity convergence check): an lb::StabilityTester assesses
+    // every step, after the streaming and before the swap, as SimulationMaster's step manager runs it
+    const int stabilityMode = getenv("HLB_HOST_STABILITY") ? atoi(getenv("HLB_HOST_STABILITY")) : 0;
+    reporting::Timers timers;
+    configuration::MonitoringConfig monitoring;
+    monitoring.doConvergenceCheck = stabilityMode == 2;
+    monitoring.convergenceVariable = extraction::source::Velocity{};
+    monitoring.convergenceReferenceValue = 0.01;
+    monitoring.convergenceRelativeTolerance = 1e-9;
+    std::unique_ptr<lb::StabilityTester<Lattice>> tester;
+    if (stabilityMode)
+      tester = std::make_unique<lb::StabilityTester<Lattice>>(
+          std::shared_ptr<const geometry::FieldData>(&fd, [](const geometry::FieldData*) {}), nullptr, &state, timers,
+          monitoring);
     auto t0 = std::chrono::steady_clock::now();
     for (int64_t s = 0; s < steps; ++s) {
       if (timing && s == 1) {
@@ -267,6 +282,10 @@ namespace {
       lbm.PreReceive();
       lbm.PostReceive();
       lbm.EndIteration();
+      if (tester) {
+        tester->RunCycle();
+        fprintf(stderr, "host_lbm_run: step %lld stability %d\n", (long long)s, (int)state.GetStability());
+      }
       fd.SwapOldAndNew();
       state.Increment();
     }

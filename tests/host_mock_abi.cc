@@ -78,6 +78,12 @@ int hlb_gpu_set_step_scalars(hlb_gpu_t h, uint64_t t, const double* in, const do
 }
 int hlb_gpu_stream_and_collide(hlb_gpu_t, int slot, int64_t a, int64_t n) { fprintf(out(), "stream_and_collide %d %lld %lld\n", slot, ll(a), ll(n)); return 0; }
 int hlb_gpu_post_step(hlb_gpu_t, int slot, int64_t a, int64_t n) { fprintf(out(), "post_step %d %lld %lld\n", slot, ll(a), ll(n)); return 0; }
+int hlb_gpu_stability(hlb_gpu_t, int conv, double* out2) {
+  fprintf(out(), "stability convergence=%d\n", conv);
+  out2[0] = 0.0;
+  out2[1] = conv ? 1e-3 : 0.0;
+  return 0;
+}
 int hlb_gpu_edge_done(hlb_gpu_t) { fprintf(out(), "edge_done\n"); return 0; }
 int hlb_gpu_get_cache(hlb_gpu_t h, uint32_t which, double* o) {
   fprintf(out(), "get_cache %u\n", which);

@@ -319,6 +319,28 @@ def test_monitor_matches_numpy():
     assert abs(m4["min_density"] - f2.sum(1).min()) < 1e-12
 
 
+@pytest.mark.parametrize("Q", (15, 19, 27))
+def test_equilibrium_initial_condition_matches_the_oracle(Q):
+    """EquilibriumInitialCondition::SetFs (Code/lb/InitialCondition.hpp:40-52): f_old = f_new =
+    f_eq(rho0, m0) everywhere -- with a non-zero momentum, bit for bit against the oracle, and the
+    trajectories that start there stay identical."""
+    geom = geometry("cylinder")
+    dom = build_domains(geom, Q)[0]
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    gpu = GpuLBM(dom, "LBGK", "BFL", tau=0.8, inlets=inlets, outlets=outlets)
+    sim = O.OracleSim(O.OracleDomains(geom, Q), "LBGK", "BFL", tau=0.8, inlets=inlets, outlets=outlets)
+    rho0, m0 = 1.0125, (0.011, -0.007, 0.023)
+    gpu.set_equilibrium(rho0, m0)
+    sim.set_equilibrium(rho0, m0)
+    for which in (0, 1):
+        assert np.array_equal(gpu.get_f(which)[:dom.N * Q], sim.get_f(0, which)[:dom.N * Q]), which
+    f = gpu.get_f()[:dom.N * Q].reshape(dom.N, Q)
+    assert np.all(f == f[0]) and abs(f[0].sum() - rho0) < 1e-14
+    gpu.step(4)
+    sim.step(4)
+    assert np.array_equal(gpu.get_f()[:dom.N * Q], sim.get_f()[:dom.N * Q])
+
+
 def test_stability_reduction_matches_the_reference_loop():
     """hlb_gpu_stability = the site loop of lb::StabilityTester::PostSendToParent
     (Code/lb/StabilityTester.h:97-141) run where the reference runs it: after the step's streaming,

@@ -162,9 +162,10 @@ def test_cxx_host_call_sequence(tmp_path, name, Q, kernel, wall, inlet, outlet):
     # ---- the per-step sequence
     got = [ln for ln in rest if ln not in build and not ln.startswith("set_f ")]
     want_calls = expected_calls(dom, steps, len(inlets), len(outlets), want)
-    # the final read-back of the distributions and the destructor
-    assert got[-3:] == ["get_f 0", "get_f 1", "destroy"]
-    got = got[:-3]
+    # the final read-back of the distributions (f_old only: the mirrors refresh one array at a time)
+    # and the destructor
+    assert got[-2:] == ["get_f 0", "destroy"]
+    got = got[:-2]
     assert len(got) == len(want_calls), (len(got), len(want_calls))
     for g_, w_ in zip(got, want_calls):
         if isinstance(w_, tuple):
@@ -182,6 +183,40 @@ def test_cxx_host_call_sequence(tmp_path, name, Q, kernel, wall, inlet, outlet):
         for s, ln in enumerate(scal):
             v = float(dict(x.split("=") for x in ln.split()[1:])["out0"])
             assert v == O.ref_lib().href_cosine_density(*[O.C.c_double(float(x)) for x in r0[9:13]], O.C.c_uint64(s))
+
+
+@needs_reference_or_prebuilt
+@pytest.mark.parametrize("mode", [1, 2])
+def test_cxx_stability_tester_moves_sixteen_bytes_a_step(tmp_path, mode):
+    """hemelb_b200/host/lb/StabilityTester.h in place of the reference's: with a stability check every
+    time step (mode 2: plus the velocity convergence check) the host never asks for the distribution
+    arrays -- no hlb_gpu_get_f between the steps, one hlb_gpu_stability per step, after the step's
+    last PostStep and before the swap -- and the verdict reaches SimulationState."""
+    build_host_binaries()
+    geom, Q = geometry("cylinder"), 19
+    dom = build_domains(geom, Q)[0]
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    steps, dt = 4, physical_dt(0.8)
+    f0 = anisotropic_f(dom.N, Q, 0)
+    write_case(tmp_path / "case.bin", dom, "LBGK", "BFL", "NASH", "NASH", inlets, outlets, f0, steps, 0, dt)
+    env = dict(os.environ, HLB_MOCK_LOG=str(tmp_path / "calls.log"), HLB_HOST_STABILITY=str(mode))
+    r = subprocess.run([os.path.join(BUILD, "host_lbm_run_mock"), str(tmp_path / "case.bin"), str(tmp_path / "out.bin")],
+                       env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    log = open(tmp_path / "calls.log").read().splitlines()
+    per_step = log[log.index("finalise") + 1:]
+    assert per_step.count("stability convergence=%d" % (1 if mode == 2 else 0)) == steps
+    assert [ln for ln in per_step if ln.startswith("get_f")] == ["get_f 0"]  # the harness's own final read-back
+    assert per_step.index("get_f 0") > len(per_step) - 3
+    k = 0
+    for _ in range(steps):
+        k = per_step.index("stability convergence=%d" % (1 if mode == 2 else 0), k)
+        assert per_step[k - 1].startswith("post_step 5 ") and per_step[k + 1] == "swap"
+        k += 1
+    # lb::Stability: Stable = 1; StableAndConverged = 2 needs |du| / reference <= tolerance: the stand-in
+    # reports 1e-3 / 0.01 against 1e-9, so "stable, not converged"
+    verdicts = [ln for ln in r.stderr.splitlines() if "stability" in ln]
+    assert len(verdicts) == steps and all(v.endswith("stability 1") for v in verdicts)
 
 
 @pytest.mark.gpu
@@ -209,10 +244,13 @@ def test_cxx_host_runs_on_the_gpu_and_matches_the_oracle(tmp_path, name, Q, kern
     # libhemelb_b200.so needs libcudart.so.12: the CUDA toolkit's, or the one torch ships
     import sysconfig
     extra = ["/usr/local/cuda/lib64", os.path.join(sysconfig.get_paths()["purelib"], "nvidia", "cuda_runtime", "lib")]
-    env = dict(os.environ, LD_LIBRARY_PATH=":".join([os.environ.get("LD_LIBRARY_PATH", "")] + extra).strip(":"))
+    env = dict(os.environ, LD_LIBRARY_PATH=":".join([os.environ.get("LD_LIBRARY_PATH", "")] + extra).strip(":"),
+               HLB_HOST_STABILITY="2")  # lb::StabilityTester (device-side stand-in) assessing every step
     r = subprocess.run([exe, str(tmp_path / "case.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True,
                        timeout=300, env=env)
     assert r.returncode == 0, r.stderr
+    verdicts = [ln for ln in r.stderr.splitlines() if "stability" in ln]
+    assert len(verdicts) == 5 and all(v.endswith("stability 1") or v.endswith("stability 2") for v in verdicts), verdicts
     out = np.fromfile(tmp_path / "out.bin", np.float64)
     N = dom.N
     assert out.size == N * Q + N + 3 * N
@@ -265,8 +303,8 @@ def test_cxx_host_multi_rank_construction_and_sequence(tmp_path):
         assert after[0] == "comm_init" and after[1].startswith("set_f 0 ")
         got = [ln for ln in after[3:] if not ln.startswith("set_f ")]
         want_calls = expected_calls(dom, steps, 1, 1, 0)
-        assert got[-3:] == ["get_f 0", "get_f 1", "destroy"]
-        got = got[:-3]
+        assert got[-2:] == ["get_f 0", "destroy"]
+        got = got[:-2]
         assert len(got) == len(want_calls)
         for g_, w_ in zip(got, want_calls):
             assert g_ == w_ if not isinstance(w_, tuple) else g_.startswith("set_step_scalars t=%d mask=0" % w_[1])

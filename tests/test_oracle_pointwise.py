@@ -103,6 +103,44 @@ def test_trt_conserves_and_reduces_to_lbgk(Q):
     assert np.allclose(a, b, atol=1e-15)
 
 
+@pytest.mark.parametrize("Q", LATTICES)
+@pytest.mark.parametrize("tau", [0.51, 0.62, 0.8, 1.3])
+def test_trt_against_the_published_two_relaxation_time_scheme(Q, tau):
+    """An anchor outside the reference (whose TRT.h does not compile): Ginzburg's two-relaxation-time
+    collision written independently -- split every population into its symmetric and antisymmetric
+    parts over the pair (i, i-bar), relax them with omega+ = 1/tau and omega- fixed by the magic
+    parameter Lambda = (1/omega+ - 1/2)(1/omega- - 1/2) -- must give the oracle's post-collision
+    populations, and the oracle's antisymmetric rate must put Lambda at 3/16 for every tau
+    (TRT.h:100-107), the value for which a half-way bounce-back wall sits exactly mid-link in
+    Poiseuille flow whatever the viscosity."""
+    c, w, inv = O.lattice(Q)
+    rng = np.random.default_rng(11)
+    f = w * (1 + 0.08 * rng.uniform(-1, 1, Q))
+    r = O.collide(Q, "TRT", tau, f)
+    feq = r["feq"]
+    lam = 3.0 / 16.0
+    om_p = 1.0 / tau
+    om_m = 1.0 / (0.5 + lam / (tau - 0.5))
+    fs, fa = 0.5 * (f + f[inv]), 0.5 * (f - f[inv])
+    es, ea = 0.5 * (feq + feq[inv]), 0.5 * (feq - feq[inv])
+    want = f - om_p * (fs - es) - om_m * (fa - ea)
+    assert np.abs(r["fpost"] - want).max() <= 4e-16
+    # the antisymmetric rate, measured: perturb one pair antisymmetrically around equilibrium
+    i = int(np.nonzero(inv != np.arange(Q))[0][0])
+    base = O.collide(Q, "TRT", tau, feq)["fpost"]          # equilibrium is a fixed point
+    assert np.abs(base - feq).max() <= 4e-16
+    g = feq.copy()
+    eps = 1e-3 * feq[i]
+    g[i] += eps
+    g[inv[i]] -= eps
+    out = O.collide(Q, "TRT", tau, g)
+    # (mass is unchanged, momentum changes: measure the pair's antisymmetric part against its own f_eq)
+    na_in = 0.5 * ((g[i] - out["feq"][i]) - (g[inv[i]] - out["feq"][inv[i]]))
+    na_out = 0.5 * ((out["fpost"][i] - out["feq"][i]) - (out["fpost"][inv[i]] - out["feq"][inv[i]]))
+    measured = 1.0 - na_out / na_in
+    assert abs((tau - 0.5) * (1.0 / measured - 0.5) - lam) <= 1e-9
+
+
 def test_tau_of_four_cube_xml():
     """dt = 0.0857 s, dx = 0.01 m => tau ~ 0.510284 (LbmParameters.h:35)."""
     tau = O.oracle_lib().hlbo_tau(O.C.c_double(0.0857), O.C.c_double(0.01), O.C.c_double(0.004), O.C.c_double(1000.0))
