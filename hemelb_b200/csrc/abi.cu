@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -1745,20 +1746,32 @@ int hlb_gpu_finalise(hlb_gpu_t h) {
         if (g[(size_t)(i - 1) * h->bStride + b] < 0 && g[(size_t)(i - 1) * h->bStride + b] == INT32_MIN)
           missing.push_back({b, i});
       }
-    // remote rows: ghost g = position in the need list (grouped by owner rank)
-    h->nGzsNeed = (int64_t)h->gzsNeedSite.size();
+    // remote rows: links that extrapolate from the same remote site (same owner rank and owner_site key)
+    // share one ghost row -- NeighbouringDataManager::RegisterNeededSite keeps a site once
+    // (NeighbouringDataManager.cc:27-39); rows are numbered in order of first appearance, which keeps
+    // them grouped by owner rank like the links
+    const int64_t nLinks = (int64_t)h->gzsNeedSite.size();
     std::vector<uint32_t> hp;
-    if (h->perm && (h->nGzsNeed || !h->gzsServeSite.empty())) {
+    if (h->perm && (nLinks || !h->gzsServeSite.empty())) {
       hp.resize(h->N);
       CU(cudaMemcpy(hp.data(), h->perm, sizeof(uint32_t) * h->N, cudaMemcpyDeviceToHost));
     }
     auto internal = [&](int64_t s) { return hp.empty() ? s : (int64_t)hp[s]; };
-    for (int64_t k = 0; k < h->nGzsNeed; ++k) {
-      const int64_t b = h->refOrdToB[host_bidx(h, h->gzsNeedSite[k])];
-      g[(size_t)(h->gzsNeedDir[k] - 1) * h->bStride + b] = (int32_t)(-(k + 1));
-      if (h->gzsRecvPeers.empty() || h->gzsRecvPeers.back().rank != h->gzsNeedOwner[k])
-        h->gzsRecvPeers.push_back({h->gzsNeedOwner[k], k, 0});
-      h->gzsRecvPeers.back().count++;
+    {
+      std::map<std::pair<int32_t, int64_t>, int64_t> rowOf;
+      for (int64_t k = 0; k < nLinks; ++k) {
+        const std::pair<int32_t, int64_t> key(h->gzsNeedOwner[k], h->gzsNeedOwnerSite[k]);
+        auto it = rowOf.find(key);
+        if (it == rowOf.end()) {
+          it = rowOf.emplace(key, (int64_t)rowOf.size()).first;
+          if (h->gzsRecvPeers.empty() || h->gzsRecvPeers.back().rank != key.first)
+            h->gzsRecvPeers.push_back({key.first, it->second, 0});
+          h->gzsRecvPeers.back().count++;
+        }
+        const int64_t b = h->refOrdToB[host_bidx(h, h->gzsNeedSite[k])];
+        g[(size_t)(h->gzsNeedDir[k] - 1) * h->bStride + b] = (int32_t)(-(it->second + 1));
+      }
+      h->nGzsNeed = (int64_t)rowOf.size();
     }
     for (auto& ms : missing)
       if (g[(size_t)(ms.second - 1) * h->bStride + ms.first] == INT32_MIN)

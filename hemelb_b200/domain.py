@@ -367,10 +367,11 @@ class DomainBuilder:
 
 def _gzs_site_halo(self):
     """The GZS site halo of every rank (GuoZhengShi.h:38-99 + NeighbouringDataManager::ShareNeeds):
-    ``need[r]`` = (local site, direction towards the neighbour, owner rank, owner's local site) and
-    ``serve[r]`` = (requester rank, local site).  Both grouped by the other rank ascending and,
-    inside a group, ordered by the requesting site's global (x, y, z) then direction -- an order
-    both sides can compute from coordinates alone."""
+    ``need[r]`` = one row per wall link: (local site, direction towards the neighbour, owner rank,
+    owner's local site); ``serve[r]`` = (requester rank, local site), one row per (requester, site).
+    Both grouped by the other rank ascending and, inside a group, ordered by the requesting site's
+    global (x, y, z) then direction -- an order both sides can compute from coordinates alone; a
+    site several links ask for is served once, where the requester first names it."""
     if getattr(self, "_gzs", None) is not None:
         return self._gzs
     Q = self.Q
@@ -414,6 +415,10 @@ def _gzs_site_halo(self):
             theirs = rec[rec[:, 1] == D.rank]
             o = np.lexsort((theirs[:, 3], theirs[:, 2], theirs[:, 0]))
             theirs = theirs[o]
+            # one row per (requester, site), in the order the requester first names it: links that
+            # extrapolate from the same site share a ghost row (NeighbouringDataManager.cc:27-39)
+            _, firsts = np.unique(theirs[:, [0, 5]], axis=0, return_index=True)
+            theirs = theirs[np.sort(firsts)]
             serve[D.rank] = np.stack([theirs[:, 0], self.local_of_input[theirs[:, 5]]], 1)
     self._gzs = (need, serve)
     return self._gzs

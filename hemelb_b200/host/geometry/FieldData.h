@@ -31,6 +31,7 @@
 
 namespace hemelb::net { class Net; }
 namespace hemelb::lb { class BoundaryValues; }
+namespace hemelb::geometry::neighbouring { class NeighbouringDataManager; }
 
 namespace hemelb::geometry {
 
@@ -51,6 +52,12 @@ namespace hemelb::geometry {
     // first half), mid-domain range second; the ranges themselves cannot tell the two apart when
     // they are empty, so the outlet-wall streamer (the last of the six) counts its calls
     unsigned lastSlotStreams = 0, lastSlotPostSteps = 0;
+    // GuoZhengShi across ranks: one entry per wall link that extrapolates from a site on another rank,
+    // in the order GuoZhengShiLink's constructor registers them (GuoZhengShi.h:36-104), and the
+    // manager the needs were registered with (its GetNeedsForProc lists give the serve side)
+    struct GzsLink { site_t site; int direction; site_t globalId; };
+    std::vector<GzsLink> gzsLinks;
+    neighbouring::NeighbouringDataManager* gzsManager = nullptr;
   };
 
   // The six streamers are constructed from InitParams (LBM::InitCollisions, lb.hpp:75-114), which
@@ -119,7 +126,18 @@ namespace hemelb::geometry {
     // ---- used by the Gpu*Streamer policy classes ------------------------------------------------
     GpuPolicy& Policy() { return GpuPolicyFor(m_domain.get()); }
     // for callers that are about to change the distributions on the device
-    hlb_gpu_t Engine() { EnsureEngine(); PushIfDirty(); m_stale[0] = m_stale[1] = true; return m_gpu; }
+    hlb_gpu_t Engine() {
+      EnsureEngine();
+      PushIfDirty();
+      if (m_needFirstSiteHalo) {
+        // the first time step's phase 0 (NeighbouringDataManager::RequestComms) ran before the engine
+        // existed: its site halo goes now, with the initial condition already on the device
+        m_needFirstSiteHalo = false;
+        Check(hlb_gpu_exchange_site_halo(m_gpu));
+      }
+      m_stale[0] = m_stale[1] = true;
+      return m_gpu;
+    }
     // for callers that only read them there (lb/StabilityTester.h): null until a streamer has run
     hlb_gpu_t EngineIfBuilt() { if (m_gpu) PushIfDirty(); return m_gpu; }
     static void Check(int rc) { if (rc) throw Exception() << "hemelb_b200: " << hlb_gpu_last_error(); }
@@ -149,7 +167,7 @@ namespace hemelb::geometry {
     std::vector<LatticeForceVector> m_force;
     std::unique_ptr<neighbouring::NeighbouringFieldData> m_neighbouringFields;
     hlb_gpu_t m_gpu = nullptr;
-    bool m_dirty[2] = {false, false}, m_stale[2] = {false, false};
+    bool m_dirty[2] = {false, false}, m_stale[2] = {false, false}, m_needFirstSiteHalo = false;
     friend struct GpuEngineBuilder;
   };
 }

@@ -16,6 +16,8 @@
 #include <vector>
 
 #include "geometry/FieldData.h"
+#include "geometry/neighbouring/NeighbouringDataManager.h"
+#include "geometry/neighbouring/RequiredSiteInformation.h"
 #include "lb/concepts.h"
 #include "lb/LbmParameters.h"
 #include "lb/MacroscopicPropertyCache.h"
@@ -75,6 +77,7 @@ namespace hemelb::lb::gpu {
         if (SLOT == 2 || SLOT == 4) { pol.inlet = IOLET::value; pol.inletValues = ip.boundaryObject; }
         else { pol.outlet = IOLET::value; pol.outletValues = ip.boundaryObject; }
       }
+      if constexpr (WALL::value == HLB_WALL_GZS) RegisterRemoteNeeds(ip, pol);
     }
 
     void StreamAndCollide(const site_t first, const site_t count, const LbmParameters*,
@@ -97,6 +100,35 @@ namespace hemelb::lb::gpu {
     }
 
   private:
+    // What the constructor of the reference's GuoZhengShiLink does (GuoZhengShi.h:36-104): for every
+    // wall link of the sites this streamer owns whose opposite direction is neither wall nor iolet, and
+    // whose neighbour in that direction lives on another rank, register that site with the
+    // NeighbouringDataManager.  The links themselves are kept as well: they are the rows of
+    // hlb_gpu_set_gzs_remote.
+    static void RegisterRemoteNeeds(InitParams& ip, geometry::GpuPolicy& pol) {
+      if (!ip.neighbouringDataManager) return;  // one rank: nothing can be remote
+      pol.gzsManager = ip.neighbouringDataManager;
+      for (auto [first, last] : ip.siteRanges)
+        for (site_t i = first; i < last; ++i) {
+          auto site = ip.latDat->GetSite(i);
+          if (!site.IsWall()) continue;
+          auto const& here = site.GetGlobalSiteCoords();
+          for (Direction d = 1; d < LatticeType::NUMVECTORS; ++d) {
+            if (!site.HasWall(d)) continue;
+            const Direction opp = LatticeType::INVERSEDIRECTIONS[d];
+            if (site.HasWall(opp) || site.HasIolet(opp)) continue;
+            const LatticeVector there = here + LatticeVector(LatticeType::CX[opp], LatticeType::CY[opp], LatticeType::CZ[opp]);
+            const proc_t owner = ip.latDat->GetProcIdFromGlobalCoords(there);
+            if (owner == SITE_OR_BLOCK_SOLID || owner == ip.latDat->GetLocalRank()) continue;
+            const site_t globalId = ip.latDat->GetGlobalNoncontiguousSiteIdFromGlobalCoords(there);
+            geometry::neighbouring::RequiredSiteInformation wanted(false);
+            wanted.Require(geometry::neighbouring::terms::Density);
+            wanted.Require(geometry::neighbouring::terms::Velocity);
+            ip.neighbouringDataManager->RegisterNeededSite(globalId, wanted);
+            pol.gzsLinks.push_back({i, (int)opp, globalId});
+          }
+        }
+    }
     static void PushStepScalars(hlb_gpu_t h, geometry::FieldData& latDat, MacroscopicPropertyCache& cache) {
       auto& pol = latDat.Policy();
       std::vector<double> in, out;
@@ -288,6 +320,41 @@ namespace hemelb::geometry {
     }
     if (cfg.n_inlets) Check(hlb_gpu_set_iolets(m_gpu, 0, cfg.n_inlets, rin.data()));
     if (cfg.n_outlets) Check(hlb_gpu_set_iolets(m_gpu, 1, cfg.n_outlets, rout.data()));
+    if (pol.gzsManager && cfg.nranks > 1) {
+      // GuoZhengShi across ranks: the links registered by the streamers, grouped by the rank that owns
+      // the neighbour (registration order kept inside a group: it is the order of the manager's
+      // neededSites, hence of the owner's GetNeedsForProc list); what this rank serves, from the lists
+      // NeighbouringDataManager::ShareNeeds gathered (SimBuilder.h:235 runs it before the first step)
+      if (!pol.gzsManager->NeedsShared())
+        throw Exception() << "hemelb_b200: NeighbouringDataManager::ShareNeeds has not run before the first time step";
+      std::vector<GpuPolicy::GzsLink> links = pol.gzsLinks;
+      std::vector<int32_t> owner(links.size());
+      std::vector<size_t> order(links.size());
+      for (size_t k = 0; k < links.size(); ++k) {
+        owner[k] = d.ProcProvidingSiteByGlobalNoncontiguousId(links[k].globalId);
+        order[k] = k;
+      }
+      std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return owner[a] < owner[b]; });
+      std::vector<int64_t> lsite, lkey;
+      std::vector<int32_t> ldir, lowner;
+      for (size_t k : order) {
+        lsite.push_back(links[k].site);
+        ldir.push_back(links[k].direction);
+        lowner.push_back(owner[k]);
+        lkey.push_back(links[k].globalId);
+      }
+      if (!lsite.empty())
+        Check(hlb_gpu_set_gzs_remote(m_gpu, (int64_t)lsite.size(), lsite.data(), ldir.data(), lowner.data(), lkey.data()));
+      std::vector<int32_t> srank;
+      std::vector<int64_t> ssite;
+      for (proc_t other = 0; other < cfg.nranks; ++other)
+        if (other != cfg.rank)
+          for (site_t globalId : pol.gzsManager->GetNeedsForProc(other)) {
+            srank.push_back(other);
+            ssite.push_back(d.GetLocalContiguousIdFromGlobalNoncontiguousId(globalId));
+          }
+      if (!srank.empty()) Check(hlb_gpu_set_gzs_serve(m_gpu, (int64_t)srank.size(), srank.data(), ssite.data()));
+    }
     Check(hlb_gpu_finalise(m_gpu));
     if (cfg.nranks > 1) {
       // NCCL bootstrap over the reference's own MPI communicator: rank 0 creates the id
@@ -296,6 +363,7 @@ namespace hemelb::geometry {
       d.GetCommunicator().Broadcast(std::span<char>(id, 128), 0);
       Check(hlb_gpu_comm_init(m_gpu, id));
     }
+    m_needFirstSiteHalo = pol.gzsManager != nullptr && cfg.nranks > 1;
   }
 }
 #endif

@@ -71,6 +71,32 @@ def prepare_boundary_objects(inlets, outlets):
         r[14] = m
 
 
+def gzs_device_domain_needs(dd):
+    """The GZS remote needs of a ``devdomain.DeviceDomain``: (need rows (n, 4): local site, direction, owner
+    rank, key of the remote site; {owner rank: coordinates of the sites asked of it, each once, in ghost-row
+    order}) -- the second is what the ranks all-gather (``GpuLBM.from_device_domain``)."""
+    site, direction, owner, coords = dd.gzs_needs()
+    if not site.size:
+        return np.zeros((0, 4), np.int64), {}
+    ext = dd.block_dims * dd.block_size
+    key = (coords[:, 0] * ext[1] + coords[:, 1]) * ext[2] + coords[:, 2]  # its position in the lattice
+    need = np.stack([site, direction.astype(np.int64), owner.astype(np.int64), key], 1)
+    _, firsts = np.unique(need[:, 2:4], axis=0, return_index=True)
+    firsts = np.sort(firsts)
+    return need, {int(o): coords[firsts][owner[firsts] == o] for o in np.unique(owner)}
+
+
+def gzs_ghost_rows(need):
+    """Owner rank of every ghost row of a GZS need list ((n, 4): local site, direction, owner rank, owner
+    site key): links with equal (owner rank, owner site) share a row; rows in order of first appearance
+    (``hlb_gpu_set_gzs_remote``)."""
+    need = np.asarray(need, np.int64).reshape(-1, 4)
+    if not need.shape[0]:
+        return np.zeros(0, np.int64)
+    _, firsts = np.unique(need[:, 2:4], axis=0, return_index=True)
+    return need[np.sort(firsts), 2]
+
+
 class GpuLBM:
     """One rank's collide-and-stream engine on one B200."""
 
@@ -160,6 +186,7 @@ class GpuLBM:
                 check(L.hlb_gpu_set_gzs_serve(h, C.c_int64(sv.shape[0]),
                                               ptr(np.ascontiguousarray(sv[:, 0], np.int32), C.c_int32),
                                               ptr(np.ascontiguousarray(sv[:, 1], np.int64), C.c_int64)))
+        self.gzs_row_owner = gzs_ghost_rows(self.gzs_need)
         check(L.hlb_gpu_finalise(h))
 
     def _set_iolets(self, inlets, outlets):
@@ -202,9 +229,10 @@ class GpuLBM:
         if wall == "GZS" and dd.nranks > 1:
             if all_gather is None:
                 raise ValueError("GuoZhengShi walls on several ranks: from_device_domain needs all_gather")
-            site, direction, owner, coords = dd.gzs_needs()
-            # every rank learns what every other rank wants of it, in the requester's own order
-            wanted = all_gather({int(o): coords[owner == o] for o in np.unique(owner)})
+            need, asks = gzs_device_domain_needs(dd)
+            # every rank learns which sites every other rank wants of it -- each once, in the order of the
+            # requester's ghost rows
+            wanted = all_gather(asks)
             sv_rank, sv_site = [], []
             for r, asks in enumerate(wanted):
                 c = asks.get(dd.rank)
@@ -215,18 +243,19 @@ class GpuLBM:
                     raise capi.HlbError("rank %d asks rank %d for a site it does not own" % (r, dd.rank))
                 sv_rank.append(np.full(local.size, r, np.int32))
                 sv_site.append(local)
-            self.gzs_need = np.stack([site, direction.astype(np.int64), owner.astype(np.int64),
-                                      np.zeros(site.size, np.int64)], 1) if site.size else self.gzs_need
-            if site.size:
-                check(self.L.hlb_gpu_set_gzs_remote(h, C.c_int64(site.size), ptr(np.ascontiguousarray(site), C.c_int64),
-                                                    ptr(np.ascontiguousarray(direction), C.c_int32),
-                                                    ptr(np.ascontiguousarray(owner), C.c_int32),
-                                                    ptr(np.zeros(site.size, np.int64), C.c_int64)))
+            self.gzs_need = need
+            if need.shape[0]:
+                check(self.L.hlb_gpu_set_gzs_remote(h, C.c_int64(need.shape[0]),
+                                                    ptr(np.ascontiguousarray(need[:, 0]), C.c_int64),
+                                                    ptr(np.ascontiguousarray(need[:, 1], np.int32), C.c_int32),
+                                                    ptr(np.ascontiguousarray(need[:, 2], np.int32), C.c_int32),
+                                                    ptr(np.ascontiguousarray(need[:, 3]), C.c_int64)))
             if sv_rank:
                 sr, ss = np.concatenate(sv_rank), np.concatenate(sv_site)
                 self.gzs_serve = np.stack([sr.astype(np.int64), ss], 1)
                 check(self.L.hlb_gpu_set_gzs_serve(h, C.c_int64(sr.size), ptr(np.ascontiguousarray(sr), C.c_int32),
                                                    ptr(np.ascontiguousarray(ss), C.c_int64)))
+        self.gzs_row_owner = gzs_ghost_rows(self.gzs_need)
         check(self.L.hlb_gpu_finalise(h))
         return self
 
@@ -301,6 +330,7 @@ class GpuLBM:
         return out[:self.gzs_serve.shape[0] * self.Q].reshape(-1, self.Q)
 
     def set_gzs_ghost(self, rows):
+        """``rows``: (ghost rows, Q) -- one per entry of ``gzs_row_owner``."""
         rows = np.ascontiguousarray(rows, np.float64)
         check(self.L.hlb_gpu_set_gzs_ghost(self.h, ptr(rows, C.c_double) if rows.size else None))
 

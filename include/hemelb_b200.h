@@ -88,12 +88,16 @@ int hlb_gpu_set_streaming_indices(hlb_gpu_t h, const int64_t* idx);
 int hlb_gpu_set_iolets(hlb_gpu_t h, int which, int n, const double* records);
 /* GZS site halo (geometry::neighbouring::NeighbouringDataManager, registered by
  * Code/lb/streamers/GuoZhengShi.h:93-99 and shared by NeighbouringDataManager::ShareNeeds):
- *  _remote: the rows THIS rank needs -- for each wall link whose GZS extrapolation reads the
- *           neighbour in `direction` (the inverse of the wall direction) of `local_site` and that
- *           neighbour lives on `owner_rank` as its local site `owner_site`; grouped by ascending
- *           owner rank.  Ghost row k of the per-step exchange is entry k of this list.
+ *  _remote: one entry per wall LINK whose GZS extrapolation reads the neighbour in `direction` (the
+ *           inverse of the wall direction) of `local_site` when that neighbour lives on
+ *           `owner_rank`; `owner_site` identifies the neighbour among that rank's sites (any id both
+ *           sides can form: the reference's global non-contiguous site id, the owner's local id ...).
+ *           Grouped by ascending owner rank.  Links with equal (owner_rank, owner_site) share ONE ghost
+ *           row, as NeighbouringDataManager::RegisterNeededSite keeps a site once
+ *           (NeighbouringDataManager.cc:27-39); ghost rows are numbered in order of first appearance.
  *  _serve:  the rows this rank SHIPS each step: (requester rank, local site), grouped by ascending
- *           requester rank and, within a rank, in that requester's _remote order. */
+ *           requester rank and, within a rank, in the order of that requester's ghost rows (what
+ *           NeighbouringDataManager::GetNeedsForProc(requester) lists). */
 int hlb_gpu_set_gzs_remote(hlb_gpu_t h, int64_t n, const int64_t* local_site, const int32_t* direction,
                            const int32_t* owner_rank, const int64_t* owner_site);
 int hlb_gpu_set_gzs_serve(hlb_gpu_t h, int64_t n, const int32_t* requester_rank, const int64_t* local_site);

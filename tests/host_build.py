@@ -13,7 +13,8 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "tests", "_build")
 REF = "/root/reference/Code"
-REF_SRCS = ["lb/MacroscopicPropertyCache.cc", "lb/SimulationState.cc", "geometry/SiteDataBare.cc", "util/Matrix3D.cc",
+REF_SRCS = ["net/IteratedAction.cc", "geometry/neighbouring/RequiredSiteInformation.cc",
+            "lb/MacroscopicPropertyCache.cc", "lb/SimulationState.cc", "geometry/SiteDataBare.cc", "util/Matrix3D.cc",
             "util/Vector3D.cc", "lb/kernels/DHumieresD3Q19MRTBasis.cc", "lb/iolets/InOutLet.cc",
             "lb/iolets/InOutLetCosine.cc", "lb/iolets/InOutLetVelocity.cc", "lb/iolets/InOutLetParabolicVelocity.cc"]
 XTR_REF_SRCS = ["util/Vector3D.cc", "extraction/GeometrySelector.cc", "extraction/WholeGeometrySelector.cc",
@@ -36,7 +37,9 @@ def build_host_binaries(verbose=False):
     host = os.path.join(ROOT, "hemelb_b200", "host")
     deps = [os.path.join(ROOT, "tests", "host_lbm_run.cc"), os.path.join(ROOT, "include", "hemelb_b200.h"),
             os.path.join(host, "geometry", "FieldData.h"), os.path.join(host, "lb", "streamers", "GpuStreamers.h"),
-            os.path.join(host, "lb", "StabilityTester.h"), os.path.join(ROOT, "tests", "host_shim", "net", "PhasedBroadcastRegular.h"),
+            os.path.join(host, "lb", "StabilityTester.h"),
+            os.path.join(host, "geometry", "neighbouring", "NeighbouringDataManager.h"),
+            os.path.join(ROOT, "tests", "host_shim", "net", "mixins", "InterfaceDelegationNet.h"), os.path.join(ROOT, "tests", "host_shim", "net", "PhasedBroadcastRegular.h"),
             os.path.join(ROOT, "tests", "host_shim", "reporting", "Timers.h"),
             os.path.join(ROOT, "tests", "host_shim", "geometry", "Domain.h"), os.path.abspath(__file__)]
     common = ["g++", "-std=c++20", "-O1", "-w", "-I" + host, "-I" + os.path.join(ROOT, "include"),

@@ -46,6 +46,8 @@ namespace {
     std::vector<uint32_t> wallMask, ioletMask;
     std::vector<int32_t> ioletId, siteType;
     std::vector<double> distanceToWall, wallNormal, inletRec, outletRec, f0;
+    std::vector<int64_t> whereIs;  // several ranks: {x, y, z, rank, local id} of every fluid site of the geometry
+    int64_t extent[3] = {1, 1, 1};
     int Q() const { return (int)head[1]; }
     int64_t N() const { return head[6]; }
   };
@@ -75,6 +77,10 @@ namespace {
     get(fh, c.f0, N * Q + 1 + S);
     get(fh, c.procs3, 3 * c.head[26]);  // {rank, SharedDistributionCount, FirstSharedDistribution} per neighbour
     get(fh, c.streamingIndices, S);
+    if (c.head[27] > 0) {  // the site -> (rank, local id) table, for GuoZhengShi across ranks
+      if (fread(c.extent, sizeof(int64_t), 3, fh) != 3) throw std::runtime_error("case file truncated");
+      get(fh, c.whereIs, 5 * c.head[27]);
+    }
     fclose(fh);
     return c;
   }
@@ -120,6 +126,11 @@ struct HostDomainFiller {
     for (size_t p = 0; p * 3 < c.procs3.size(); ++p)
       d.neighbouringProcs.push_back({(proc_t)c.procs3[3 * p], c.procs3[3 * p + 1], c.procs3[3 * p + 2]});
     d.streamingIndicesForReceivedDistributions.assign(c.streamingIndices.begin(), c.streamingIndices.end());
+    d.sites = util::Vector3D<site_t>(c.extent[0], c.extent[1], c.extent[2]);
+    for (size_t k = 0; k * 5 < c.whereIs.size(); ++k) {
+      const int64_t* w = &c.whereIs[5 * k];
+      d.whereIs[(w[0] * c.extent[1] + w[1]) * c.extent[2] + w[2]] = {(proc_t)w[3], (site_t)w[4]};
+    }
   }
 };
 
@@ -176,21 +187,39 @@ namespace {
     std::unique_ptr<tOutletWall> outletWall;
 
     HostLBM(geometry::FieldData* fd, const lb::LbmParameters& p, lb::BoundaryValues* in, lb::BoundaryValues* out,
-            lb::MacroscopicPropertyCache& c) : latDat(fd), params(p), inletValues(in), outletValues(out), cache(c) {
+            lb::MacroscopicPropertyCache& c, geometry::neighbouring::NeighbouringDataManager* ndm = nullptr) :
+        latDat(fd), params(p), inletValues(in), outletValues(out), cache(c) {
       PrepareBoundaryObjects();
+      // LBM::InitCollisions (lb.hpp:75-114): every streamer is told its mid-domain and its
+      // domain-edge range
+      auto& dom = fd->GetDomain();
       lb::InitParams ip;
-      ip.latDat = &fd->GetDomain();
+      ip.latDat = &dom;
       ip.lbmParams = &params;
-      ip.neighbouringDataManager = nullptr;
+      ip.neighbouringDataManager = ndm;
+      ip.siteRanges.resize(2);
+      ip.siteRanges[0].first = 0;
+      ip.siteRanges[1].first = dom.GetMidDomainSiteCount();
+      auto advance = [&](unsigned t) {
+        ip.siteRanges[0].second = ip.siteRanges[0].first + dom.GetMidDomainCollisionCount(t);
+        ip.siteRanges[1].second = ip.siteRanges[1].first + dom.GetDomainEdgeCollisionCount(t);
+      };
+      auto next = [&]() { ip.siteRanges[0].first = ip.siteRanges[0].second; ip.siteRanges[1].first = ip.siteRanges[1].second; };
       ip.boundaryObject = nullptr;
+      advance(0);
       midFluid = std::make_unique<tMidFluid>(ip);
+      next(); advance(1);
       wall = std::make_unique<tWall>(ip);
+      next(); advance(2);
       ip.boundaryObject = inletValues;
       inlet = std::make_unique<tInlet>(ip);
+      next(); advance(3);
       ip.boundaryObject = outletValues;
       outlet = std::make_unique<tOutlet>(ip);
+      next(); advance(4);
       ip.boundaryObject = inletValues;
       inletWall = std::make_unique<tInletWall>(ip);
+      next(); advance(5);
       ip.boundaryObject = outletValues;
       outletWall = std::make_unique<tOutletWall>(ip);
     }
@@ -240,7 +269,21 @@ namespace {
     make_iolets(c.inletRec, inStore, inletValues, &state);
     make_iolets(c.outletRec, outStore, outletValues, &state);
     lb::MacroscopicPropertyCache cache(state, *dom);
-    HostLBM<COLLISION, WALL, INLET, OUTLET> lbm(&fd, params, &inletValues, &outletValues, cache);
+    // several ranks: the NeighbouringDataManager (hemelb_b200/host's stand-in) over a stand-in net
+    // between the harness processes -- SimBuilder.h:153-160 constructs it, :235 shares the needs
+    std::unique_ptr<net::InterfaceDelegationNet> ndmNet;
+    std::unique_ptr<geometry::neighbouring::NeighbouringDataManager> ndm;
+    // (only where a streamer registers needs: ShareNeeds is collective, and the call-sequence tests run
+    // their ranks one after the other)
+    if (c.head[25] > 1 && getenv("HLB_HOST_ID_FILE") && std::is_same_v<WALL, g::GuoZhengShi>) {
+      ndmNet = std::make_unique<net::InterfaceDelegationNet>((int)c.head[24], (int)c.head[25], getenv("HLB_HOST_ID_FILE"));
+      ndm = std::make_unique<geometry::neighbouring::NeighbouringDataManager>(fd, fd.GetNeighbouringData(), *ndmNet);
+    }
+    HostLBM<COLLISION, WALL, INLET, OUTLET> lbm(&fd, params, &inletValues, &outletValues, cache, ndm.get());
+    if (ndm) {
+      ndm->ShareNeeds();
+      ndm->TransferNonFieldDependentInformation();
+    }
 
     // the initial condition is written through the host view, as lb::InitialCondition does
     for (size_t i = 0; i < c.f0.size(); ++i) {
@@ -277,6 +320,7 @@ namespace {
         if (want & 1) cache.densityCache.SetRefreshFlag();
         if (want & 2) cache.velocityCache.SetRefreshFlag();
       }
+      if (ndm) ndm->RequestComms();  // phase 0 (SimBuilder.h:160)
       lbm.RequestComms();
       lbm.PreSend();
       lbm.PreReceive();
@@ -339,6 +383,8 @@ int main(int argc, char** argv) {
       return run<LBGK19, g::BouzidiFirdaousLallemand, g::NashZerothOrderPressure, g::NashZerothOrderPressure>(c, argv[2]);
     if (Q == 19 && kernel == 1 && wall == 1 && in == 1 && out == 0)
       return run<MRT19, g::BouzidiFirdaousLallemand, g::LaddIolet, g::NashZerothOrderPressure>(c, argv[2]);
+    if (Q == 19 && kernel == 0 && wall == 2 && in == 1 && out == 0)
+      return run<LBGK19, g::GuoZhengShi, g::LaddIolet, g::NashZerothOrderPressure>(c, argv[2]);
     if (Q == 27 && kernel == 0 && wall == 0 && in == 0 && out == 0)
       return run<LBGK27, g::SimpleBounceBack, g::NashZerothOrderPressure, g::NashZerothOrderPressure>(c, argv[2]);
     fprintf(stderr, "policy combination not instantiated in this harness\n");

@@ -56,6 +56,19 @@ int hlb_gpu_set_streaming_indices(hlb_gpu_t h, const int64_t* idx) {
 }
 int hlb_gpu_set_iolets(hlb_gpu_t, int which, int n, const double* r) {
   fprintf(out(), "set_iolets %d %d kind0=%d min_density=%.17g warmup0=%g\n", which, n, (int)r[0], r[14], r[13]); return 0; }
+int hlb_gpu_set_gzs_remote(hlb_gpu_t, int64_t n, const int64_t* site, const int32_t* dir, const int32_t* owner, const int64_t* key) {
+  fprintf(out(), "set_gzs_remote %lld", ll(n));
+  for (int64_t k = 0; k < n; ++k) fprintf(out(), " %lld:%d:%d:%lld", ll(site[k]), dir[k], owner[k], ll(key[k]));
+  fprintf(out(), "\n");
+  return 0;
+}
+int hlb_gpu_set_gzs_serve(hlb_gpu_t, int64_t n, const int32_t* rank, const int64_t* site) {
+  fprintf(out(), "set_gzs_serve %lld", ll(n));
+  for (int64_t k = 0; k < n; ++k) fprintf(out(), " %d:%lld", rank[k], ll(site[k]));
+  fprintf(out(), "\n");
+  return 0;
+}
+int hlb_gpu_exchange_site_halo(hlb_gpu_t) { fprintf(out(), "exchange_site_halo\n"); return 0; }
 int hlb_gpu_finalise(hlb_gpu_t) { fprintf(out(), "finalise\n"); return 0; }
 int hlb_gpu_comm_unique_id(void* id) { memset(id, 0, 128); return 0; }
 int hlb_gpu_comm_init(hlb_gpu_t, const void*) { fprintf(out(), "comm_init\n"); return 0; }

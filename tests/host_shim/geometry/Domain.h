@@ -9,6 +9,7 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 #include "units.h"
 #include "constants.h"
@@ -62,6 +63,7 @@ namespace hemelb::geometry {
     site_t const& GetDomainEdgeCollisionCount(unsigned t) const { return edge[t]; }
     int GetLocalRank() const { return comms.rank; }
     Site<Domain> GetSite(site_t i) { return Site<Domain>(i, *this); }
+    Site<const Domain> GetSite(site_t i) const { return Site<const Domain>(i, *this); }
     template <class L> distribn_t GetCutDistance(site_t i, int d) const { return distanceToWall[i * (L::NUMVECTORS - 1) + d - 1]; }
     distribn_t* GetCutDistances(site_t i) { return &distanceToWall[i]; }
     const distribn_t* GetCutDistances(site_t i) const { return &distanceToWall[i]; }
@@ -71,7 +73,23 @@ namespace hemelb::geometry {
     SiteData& GetSiteData(site_t i) { return siteData[i]; }
     const SiteData& GetSiteData(site_t i) const { return siteData[i]; }
     const util::Vector3D<site_t>& GetGlobalSiteCoords(site_t i) const { return globalSiteCoords[i]; }
+    // where any fluid site of the whole geometry lives (Domain.h:215-242; the reference asks its
+    // distributed store): filled by the harness from the case file when there are several ranks
+    site_t GetGlobalNoncontiguousSiteIdFromGlobalCoords(const util::Vector3D<site_t>& c) const {
+      return (c.x() * sites.y() + c.y()) * sites.z() + c.z();
+    }
+    proc_t GetProcIdFromGlobalCoords(const util::Vector3D<site_t>& c) const {
+      auto it = whereIs.find(GetGlobalNoncontiguousSiteIdFromGlobalCoords(c));
+      return it == whereIs.end() ? SITE_OR_BLOCK_SOLID : it->second.first;
+    }
+    proc_t ProcProvidingSiteByGlobalNoncontiguousId(site_t id) const {
+      auto it = whereIs.find(id);
+      return it == whereIs.end() ? SITE_OR_BLOCK_SOLID : it->second.first;
+    }
+    site_t GetLocalContiguousIdFromGlobalNoncontiguousId(site_t id) const { return whereIs.at(id).second; }
   private:
+    util::Vector3D<site_t> sites{1, 1, 1};
+    std::unordered_map<site_t, std::pair<proc_t, site_t>> whereIs;  // global id -> (rank, local contiguous id)
     const lb::LatticeInfo& latticeInfo;
     site_t nSites = 0, mid[COLLISION_TYPES] = {}, edge[COLLISION_TYPES] = {};
     site_t totalSharedFs = 0;

@@ -252,10 +252,8 @@ def test_gzs_site_halo_from_device_domains(kernel, inlet):
     inlets, outlets = iolets_for(geom, inlet, "NASH")
     doms = [DeviceDomain.from_shape(caps, iolets, shape, Q, partition=("slabs", 2, first), rank=r, nranks=R)
             for r in range(R)]
-    asks = []
-    for d in doms:
-        site, direction, owner, coords = d.gzs_needs()
-        asks.append({int(o): coords[owner == o] for o in np.unique(owner)})
+    from hemelb_b200.lbm import gzs_device_domain_needs
+    asks = [gzs_device_domain_needs(d)[1] for d in doms]
     assert sum(len(a) for a in asks) > 0
     gpus = [GpuLBM.from_device_domain(d, kernel, "GZS", inlet, "NASH", tau=0.8, inlets=inlets, outlets=outlets,
                                       all_gather=lambda obj: asks) for d in doms]
@@ -269,9 +267,9 @@ def test_gzs_site_halo_from_device_domains(kernel, inlet):
             g.exchange_site_halo()
         sends = [g.get_gzs_send() for g in gpus]
         for r, g in enumerate(gpus):
-            rows = np.zeros((g.gzs_need.shape[0], Q))
+            rows = np.zeros((g.gzs_row_owner.size, Q))
             for p in range(R):
-                mine = np.nonzero(g.gzs_need[:, 2] == p)[0]
+                mine = np.nonzero(g.gzs_row_owner == p)[0]
                 theirs = np.nonzero(gpus[p].gzs_serve[:, 0] == r)[0]
                 assert mine.size == theirs.size
                 rows[mine] = sends[p][theirs]
