@@ -148,7 +148,7 @@ struct hlb_gpu_handle {
   LaunchFn launch = nullptr;
   TmaLaunchFn launchTma = nullptr;
   bool useTma = false;  // the mid-domain part through the TMA-staged persistent kernel (HLB_TMA=1; measured slower)
-  int prefetchCtas = 0;  // direct site kernel over a whole part: L2 prefetch distance in CTAs (HLB_PREFETCH)
+  int prefetchSites = 0;  // direct site kernel over a whole part: L2 prefetch distance in sites (HLB_PREFETCH)
   int nSm = 148;
   CUtensorMap mapF[2], mapN;  // f[0], f[1] and the push targets as 2-D tensors (rows = planes), boxes of one tile
   // ---- the product schedule.  Device order: all sites of the mid-domain part sorted by lattice
@@ -985,7 +985,7 @@ int launch_part(hlb_gpu_t h, int part) {
   const bool prof = h->profileBulk && part == 0;
   if (prof && prof_begin(h)) return 1;
   const int64_t gFirst = part ? h->nbMid : 0, gCount = part ? h->NB - h->nbMid : h->nbMid;
-  if (part == 0) A.prefetchCtas = h->prefetchCtas;  // (tile-aligned planes: the part starts at site 0)
+  if (part == 0) A.prefetchSites = h->prefetchSites;  // (line-aligned planes: the part starts at site 0)
   if (part == 0 && h->useTma)
     h->launchTma(h->cfg.wall, h->cfg.inlet, h->cfg.outlet, A, h->mrt.data(), &h->mapF[h->cur], &h->mapN, count, h->nSm,
                  h->bSite, gCount, h->compute);
@@ -1358,9 +1358,11 @@ int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
     const char* t = getenv("HLB_TMA");
     h->useTma = t && t[0] == '1';
     const char* pf = getenv("HLB_PREFETCH");
-    // measured on the 1e8-site tree: 13 070 MLUPS without, 13 830 / 14 080 / 14 118 / 14 095 at 20 / 80 / 150-200 /
-    // 250 CTAs ahead, 13 250 at 600 and 11 000 at 1200 (the lines leave L2 again before they are used)
-    h->prefetchCtas = pf ? atoi(pf) : 160;
+    // measured on the 1e8-site tree (256-thread CTAs): 13 070 MLUPS without, 13 830 / 14 080 / 14 118 / 14 095 at
+    // 5 120 / 20 480 / 38 400-51 200 / 64 000 sites ahead, 13 250 at 153 600 and 11 000 at 307 200 (the lines
+    // leave L2 again before they are used); the optimum in sites is the same for 128- and 64-thread CTAs
+    h->prefetchSites = pf ? atoi(pf) : 40960;
+    h->prefetchSites = h->prefetchSites / 256 * 256;  // whole 128 B lines of every plane
     CU(cudaDeviceGetAttribute(&h->nSm, cudaDevAttrMultiProcessorCount, cfg->device));
   }
   CU(cudaEventCreateWithFlags(&h->evEdge, cudaEventDisableTiming));

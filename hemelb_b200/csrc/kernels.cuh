@@ -25,17 +25,23 @@
 #include <cfloat>
 #include "lattice.cuh"
 
+// D3Q27: ~168 registers -> 384 threads per SM (6 x 64: 11 381 MLUPS on the 1e8-site sac, 3 x 128: 11 275)
 #ifndef HLB_Q27_THREADS
-#define HLB_Q27_THREADS 128
+#define HLB_Q27_THREADS 64
 #endif
 #ifndef HLB_Q27_MIN_CTAS
-#define HLB_Q27_MIN_CTAS 3
+#define HLB_Q27_MIN_CTAS 6
 #endif
+
+// CTA shape of the direct site kernel for Q <= 19: the register file holds 512 threads at 128 registers;
+// measured on the 1.03e8-site tree / the cylinder (MLUPS, L2 prefetch 40 960 sites ahead):
+// 2 x 256 threads 14 118 / 17 391, 4 x 128: 15 242 / 17 280, 8 x 64: 15 491 / 17 052 -- small CTAs
+// retire and are replaced warp by warp, which evens out the mix of loading and computing warps
 #ifndef HLB_MIN_CTAS
-#define HLB_MIN_CTAS 2
+#define HLB_MIN_CTAS 8
 #endif
 #ifndef HLB_SITE_THREADS
-#define HLB_SITE_THREADS 256
+#define HLB_SITE_THREADS 64
 #endif
 
 namespace hlb {
@@ -110,9 +116,9 @@ struct StepArgs {
   const uint32_t* __restrict__ refSiteOf;  // internal site -> reference site id (cache rows), or null
   // optional explicit site list (launches that are not a contiguous run of internal sites)
   const uint32_t* __restrict__ siteList;
-  // contiguous launches of the direct site kernel: every CTA asks L2 for what the CTA `prefetchCtas`
-  // later in the grid will load (0: off)
-  int prefetchCtas;
+  // contiguous launches of the direct site kernel: every CTA asks L2 for what the CTA that starts
+  // `prefetchSites` sites further down the grid will load (0: off)
+  int prefetchSites;
   // fused monitors (C_MONITOR): {min f, min rho, max rho, max u^2} as order-preserving u64 keys
   unsigned long long* __restrict__ monitorSlots;
 };
@@ -477,12 +483,12 @@ __device__ __forceinline__ void gzs_fill(const GzsNode<Q>& N, double (&fneqW)[Q]
 // through shared memory once, the tile's wall links are compacted into a list (so warps are full
 // whatever the wall orientation), and the threads walk the list.
 constexpr int kGzsTile = 128;  // (GzsNode::sf is typed on it)
-constexpr int kGzsThreads = 256;
+constexpr int kGzsThreads = 256;  // MRT and D3Q27 need > 85 registers (two CTAs per SM), the rest 80 (three)
 
 // The launch covers `count` boundary-typed sites: siteList[0 .. count) (a whole part: the part's
 // slice of the boundary-site list), or the consecutive internal sites from `first`.
 template <int Q, int KERNEL>
-__global__ void __launch_bounds__(kGzsThreads, 2) gzs_links_kernel(const StepArgs A, const MrtArgs<Q> M, int64_t first,
+__global__ void __launch_bounds__(kGzsThreads, (KERNEL == K_MRT || Q > 19) ? 2 : 3) gzs_links_kernel(const StepArgs A, const MrtArgs<Q> M, int64_t first,
                                                                int64_t count) {
   constexpr int T = kGzsTile;
   __shared__ double sf[Q][T];
@@ -866,11 +872,11 @@ __global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) collide
   constexpr int T = site_threads<Q>(), RC = brec_words<Q>() / 4;
   __shared__ uint4 srec[RC * T];
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (A.prefetchCtas) {
+  if (A.prefetchSites) {
     // The planes of f_old and of the push targets that a CTA further down the grid will read: one
     // 128 B line per thread and round, into L2.  The loads of this kernel are then mostly L2 hits, and
     // DRAM is kept busy by requests that do not wait for a warp to come round to its load phase.
-    const int64_t site0 = first + ((int64_t)blockIdx.x + A.prefetchCtas) * T;
+    const int64_t site0 = first + (int64_t)blockIdx.x * T + A.prefetchSites;
     if (site0 + T <= first + count) {
       constexpr int fLines = Q * (T * 8 / 128), nLines = (Q - 1) * (T * 4 / 128);
 #pragma unroll

@@ -221,9 +221,21 @@ class DeviceDomain:
         dist, nrm = np.full((N, Q - 1), -1.0), np.full((N, 3), np.inf)
         wall[bs], iol[bs], iid[bs], dist[bs], nrm[bs] = (bt["wallMask"], bt["ioletMask"], bt["ioletId"],
                                                          bt["distanceToWall"], bt["wallNormal"])
+        # geometry::SiteType of every site (FLUID 1, INLET 2, OUTLET 3) from its collision-type range
+        stype = np.ones(N, np.int32)
+        first = 0
+        for counts in (self.mid, self.edge):
+            for t in range(6):
+                n = int(counts[t])
+                if t in (2, 4):
+                    stype[first:first + n] = 2
+                elif t in (3, 5):
+                    stype[first:first + n] = 3
+                first += n
         return dict(N=N, totalSharedFs=self.totalSharedFs, counts=np.concatenate([self.mid, self.edge]),
                     mid=self.mid.copy(), edge=self.edge.copy(), neighbourIndices=self.neighbour_indices(),
-                    wallMask=wall, ioletMask=iol, ioletId=iid, distanceToWall=dist.reshape(-1),
+                    Q=Q, wallMask=wall, ioletMask=iol, siteType=stype, ioletId=iid, distanceToWall=dist.reshape(-1),
+                    inputIndex=np.arange(N, dtype=np.int64),  # (no input list behind an analytic shape)
                     wallNormal=nrm.reshape(-1), globalCoords=self.global_coords().reshape(-1),
                     streamingIndices=self.streamingIndices, procs=self.procs)
 
