@@ -483,12 +483,12 @@ __device__ __forceinline__ void gzs_fill(const GzsNode<Q>& N, double (&fneqW)[Q]
 // through shared memory once, the tile's wall links are compacted into a list (so warps are full
 // whatever the wall orientation), and the threads walk the list.
 constexpr int kGzsTile = 128;  // (GzsNode::sf is typed on it)
-constexpr int kGzsThreads = 256;  // MRT and D3Q27 need > 85 registers (two CTAs per SM), the rest 80 (three)
+constexpr int kGzsThreads = 256;  // LBGK on Q <= 19 fits 85 registers (three CTAs per SM), the rest needs two
 
 // The launch covers `count` boundary-typed sites: siteList[0 .. count) (a whole part: the part's
 // slice of the boundary-site list), or the consecutive internal sites from `first`.
 template <int Q, int KERNEL>
-__global__ void __launch_bounds__(kGzsThreads, (KERNEL == K_MRT || Q > 19) ? 2 : 3) gzs_links_kernel(const StepArgs A, const MrtArgs<Q> M, int64_t first,
+__global__ void __launch_bounds__(kGzsThreads, (KERNEL == K_LBGK && Q <= 19) ? 3 : 2) gzs_links_kernel(const StepArgs A, const MrtArgs<Q> M, int64_t first,
                                                                int64_t count) {
   constexpr int T = kGzsTile;
   __shared__ double sf[Q][T];

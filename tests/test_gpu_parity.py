@@ -343,6 +343,33 @@ def test_equilibrium_initial_condition_matches_the_oracle(Q):
     assert np.array_equal(gpu.get_f()[:dom.N * Q], sim.get_f()[:dom.N * Q])
 
 
+@pytest.mark.parametrize("geom_name,Q,kernel,wall,inlet,outlet", [
+    ("tree", 19, "LBGK", "BFL", "NASH", "NASH"), ("tree", 19, "MRT", "GZS", "LADD", "NASH"),
+    ("sac", 27, "TRT", "BFL", "NASH", "NASH"), ("cylinder", 15, "LBGK", "SBB", "LADD", "NASH")])
+def test_tma_staged_site_kernel_is_bit_identical(monkeypatch, geom_name, Q, kernel, wall, inlet, outlet):
+    """HLB_TMA=1: the mid-domain part through the persistent, TMA-staged form of the site kernel (2-D bulk
+    tensor copies into per-warp shared-memory stages, mbarrier completion) -- opt-in because it is
+    slower (profiles/r02_tma_experiments.md), and bit-identical to the direct form and the oracle."""
+    geom = geometry(geom_name)
+    dom = build_domains(geom, Q)[0]
+    inlets, outlets = iolets_for(geom, inlet, outlet)
+    f0 = anisotropic_f(dom.N, Q, 0)
+    direct = GpuLBM(dom, kernel, wall, inlet, outlet, tau=0.8, inlets=inlets, outlets=outlets)
+    monkeypatch.setenv("HLB_TMA", "1")
+    staged = GpuLBM(dom, kernel, wall, inlet, outlet, tau=0.8, inlets=inlets, outlets=outlets)
+    monkeypatch.delenv("HLB_TMA")
+    sim = O.OracleSim(O.OracleDomains(geom, Q), kernel, wall, inlet, outlet, tau=0.8, inlets=inlets, outlets=outlets)
+    for g in (direct, staged, sim):
+        g.set_f(f0)
+        g.set_cache_mask(255)
+    for g in (direct, staged, sim):
+        g.step(5)
+    assert np.array_equal(staged.get_f(), direct.get_f())
+    assert np.abs(staged.get_f()[:dom.N * Q] - sim.get_f()[:dom.N * Q]).max() <= TOL_F
+    for name in O.CACHE_BITS:
+        assert np.array_equal(staged.get_cache(name), direct.get_cache(name)), name
+
+
 def test_stability_reduction_matches_the_reference_loop():
     """hlb_gpu_stability = the site loop of lb::StabilityTester::PostSendToParent
     (Code/lb/StabilityTester.h:97-141) run where the reference runs it: after the step's streaming,
