@@ -349,7 +349,7 @@ def main():
                 dist.barrier()
                 torch.cuda.synchronize()
 
-        out = {}
+        out = {"target_runs": gpu.target_runs()}
         gpu.step(warmup)
         barrier()
         sampler = ClockSampler(local_rank)
@@ -436,7 +436,11 @@ def main():
                      "kernel": SITE_KERNEL + " over rank 0's mid-domain part (all six collision types in one launch, "
                                "sites in lattice order)",
                      "kernel_source_hash": kernel_source_hash(),
-                     "bytes_per_site": BYTES_PER_SITE, "peak_kind": peak_kind + " HBM copy (burst)",
+                     "bytes_per_site": BYTES_PER_SITE,
+                     "streaming_targets": "read as <= 2 runs per direction (8 B) for %d of rank 0's %d groups of 32 sites, "
+                                          "from the index planes (128 B) for the rest: the kernel moves fewer bytes than the "
+                                          "algorithmic 20 Q per site, so frac can pass 1" % tuple(res["target_runs"]),
+                     "peak_kind": peak_kind + " HBM copy (burst)",
                      "kernel_share_of_step": res["part_ms"] / res["ms"] if res["ms"] else None,
                      "timed_in": "the timed region of `value` itself, CUDA events on the engine's stream",
                      "whole_step_frac": (mlups * 1e6 * BYTES_PER_SITE / 1e9 / world) / peak},

@@ -186,6 +186,7 @@ def main():
     wall_links = None
     line = {"config": "%s, D3Q%d %s + %s walls, %s inlet / %s outlets" % (what, Q, args.kernel, args.wall, args.inlet, args.outlet),
             "gzs_remote_links_rank0": int(gpu.gzs_need.shape[0]),
+            "rank0_target_runs": list(gpu.target_runs()),
             "n_gpus": world, "sites": sum(per_rank), "sites_counted": n_global, "sites_per_rank": per_rank,
             "halo_doubles_per_rank": halo, "neighbours_per_rank": nbrs,
             "decomposition": ("weighted k-way over blocks, %s start (hemelb_b200/partition.py)" % args.partition_start

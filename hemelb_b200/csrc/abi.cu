@@ -168,6 +168,10 @@ struct hlb_gpu_handle {
   uint2* bInfo = nullptr;      // per 32 internal sites {bitmap, ordinal of the first}
   uint32_t* bSite = nullptr;   // internal site of boundary ordinal b
   uint4* bRec = nullptr;       // per boundary-typed site: masks, iolet id, cut distances (StepArgs::bRec)
+  uint2* nbrRuns = nullptr;    // push targets as runs per 32 sites (StepArgs::nbrRuns); HLB_NBR_RUNS=0: not built
+  uint32_t* runFlags = nullptr;
+  bool useRuns = true;
+  int64_t runWords = 0, runWordsTotal = 0;  // 32-site words served by runs / all
   int64_t nbMid = 0;           // boundary-typed sites of the mid-domain part (ordinals [0, nbMid))
   std::vector<int64_t> refOrdToB;  // boundary ordinal in reference order -> device ordinal
   // BFL PostStep links {slot of f_new[site, inv d], slot of f_new[site, d], q}, device site order
@@ -404,6 +408,50 @@ __global__ void boundary_records_kernel(const uint32_t* __restrict__ wallMask, c
   else if (w == 2) v = (uint32_t)ioletId[b];
   else if (w >= 4 && w < 4 + Q - 1) v = __float_as_uint(cut[(int64_t)(w - 4) * bStride + b]);
   rec[tid] = v;
+}
+// The push targets of 32 consecutive device sites as runs (StepArgs::nbrRuns): one warp per word of
+// sites.  Along a lattice row the sites and their neighbours in a direction are both consecutive, so
+// target - lane is constant; a word that covers the end of one row and the start of the next has two
+// such values.  Links the whole-part launch does not push (cut by a wall or an iolet: bRec masks) do
+// not count.  A word whose every direction fits gets its bit in `flags`.
+__global__ void nbr_runs_kernel(const uint32_t* __restrict__ nbr, int64_t stride, int64_t N, int Q,
+                                const uint2* __restrict__ bInfo, const uint4* __restrict__ bRec, int recChunks,
+                                uint2* __restrict__ runs, uint32_t* __restrict__ flags, int64_t nWords) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= nWords) return;
+  const unsigned lane = threadIdx.x & 31u;
+  const int64_t site = w * 32 + lane;
+  const bool valid = site < N;
+  uint32_t cutMask = 0;
+  if (valid) {
+    const uint2 bi = bInfo[w];
+    if ((bi.x >> lane) & 1u) {
+      const uint4 r0 = bRec[(int64_t)(bi.y + __popc(bi.x & ((1u << lane) - 1u))) * recChunks];
+      cutMask = r0.x | r0.y;
+    }
+  }
+  bool ok = true;
+  for (int d = 1; d < Q; ++d) {
+    const uint32_t t = valid ? nbr[(int64_t)(d - 1) * stride + site] : 0u;
+    const bool live = valid && !((cutMask >> (d - 1)) & 1u);
+    const uint32_t delta = t - lane;
+    const unsigned liveMask = __ballot_sync(0xffffffffu, live);
+    uint32_t base = 0, split = 0;
+    int64_t step = 0;
+    if (liveMask) {
+      base = __shfl_sync(0xffffffffu, delta, __ffs(liveMask) - 1);
+      const unsigned diff = __ballot_sync(0xffffffffu, live && delta != base);
+      if (diff) {
+        split = (uint32_t)(__ffs(diff) - 1);
+        const uint32_t second = __shfl_sync(0xffffffffu, delta, (int)split);
+        step = (int64_t)second - (int64_t)base;
+        if (__ballot_sync(0xffffffffu, live && lane >= split && delta != second)) ok = false;
+        if (step < -(1 << 26) || step >= (1 << 26)) ok = false;
+      }
+    }
+    if (lane == 0) runs[w * (Q - 1) + (d - 1)] = make_uint2(base, ok ? (((uint32_t)(int32_t)step) << 5) | split : 0u);
+  }
+  if (lane == 0 && ok && valid) atomicOr(flags + (w >> 5), 1u << (w & 31));
 }
 // BFL PostStep links (BouzidiFirdaousLallemand.h:72-91) of boundary site b: wall link d whose
 // opposite is not a wall link and whose cut distance is below one half
@@ -986,6 +1034,8 @@ int launch_part(hlb_gpu_t h, int part) {
   if (prof && prof_begin(h)) return 1;
   const int64_t gFirst = part ? h->nbMid : 0, gCount = part ? h->NB - h->nbMid : h->nbMid;
   if (part == 0) A.prefetchSites = h->prefetchSites;  // (line-aligned planes: the part starts at site 0)
+  A.nbrRuns = h->nbrRuns;  // every site by its own type, every cut link masked: the runs stand for the target planes
+  A.runFlags = h->runFlags;
   if (part == 0 && h->useTma)
     h->launchTma(h->cfg.wall, h->cfg.inlet, h->cfg.outlet, A, h->mrt.data(), &h->mapF[h->cur], &h->mapN, count, h->nSm,
                  h->bSite, gCount, h->compute);
@@ -1357,6 +1407,8 @@ int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
     h->scheduleDefault = h->schedule;
     const char* t = getenv("HLB_TMA");
     h->useTma = t && t[0] == '1';
+    const char* nr = getenv("HLB_NBR_RUNS");
+    h->useRuns = !(nr && nr[0] == '0');
     const char* pf = getenv("HLB_PREFETCH");
     // measured on the 1e8-site tree (256-thread CTAs): 13 070 MLUPS without, 13 830 / 14 080 / 14 118 / 14 095 at
     // 5 120 / 20 480 / 38 400-51 200 / 64 000 sites ahead, 13 250 at 153 600 and 11 000 at 307 200 (the lines
@@ -1454,6 +1506,8 @@ int hlb_gpu_destroy(hlb_gpu_t h) {
   cudaFree(h->bInfo);
   cudaFree(h->bSite);
   cudaFree(h->bRec);
+  cudaFree(h->nbrRuns);
+  cudaFree(h->runFlags);
   cudaFree(h->postI);
   cudaFree(h->postD);
   cudaFree(h->postQ);
@@ -1810,6 +1864,21 @@ int hlb_gpu_finalise(hlb_gpu_t h) {
     }
   }
   if (build_post_links(h)) return 1;
+  if (h->useRuns && h->N > 0) {
+    const int64_t nWords = (h->N + 31) / 32, nFlagWords = nWords / 32 + 2;
+    const int words = Q == 15 ? brec_words<15>() : (Q == 19 ? brec_words<19>() : brec_words<27>());
+    CU(cudaMalloc(&h->nbrRuns, sizeof(uint2) * (Q - 1) * (nWords + 1)));
+    CU(cudaMalloc(&h->runFlags, sizeof(uint32_t) * nFlagWords));
+    CU(cudaMemset(h->runFlags, 0, sizeof(uint32_t) * nFlagWords));
+    nbr_runs_kernel<<<blocks_for(nWords * 32), 256>>>(h->nbr, h->stride, h->N, Q, h->bInfo, h->bRec, words / 4, h->nbrRuns,
+                                                      h->runFlags, nWords);
+    CU(cudaGetLastError());
+    std::vector<uint32_t> fl(nFlagWords);
+    CU(cudaMemcpy(fl.data(), h->runFlags, sizeof(uint32_t) * nFlagWords, cudaMemcpyDeviceToHost));
+    h->runWordsTotal = nWords;
+    h->runWords = 0;
+    for (uint32_t v : fl) h->runWords += __builtin_popcount(v);
+  }
   if (h->useTma && build_tensor_maps(h)) return 1;
   if (h->coordsAll) {
     cudaFree(h->coordsAll);
@@ -2229,6 +2298,14 @@ int hlb_gpu_stability(hlb_gpu_t h, int with_convergence, double* out2) {
 int hlb_gpu_launch_count(hlb_gpu_t h, int64_t* n) {
   if (!h || !n) return fail("null argument");
   *n = h->launches;
+  return 0;
+}
+
+int hlb_gpu_target_runs(hlb_gpu_t h, int64_t* words_in_runs, int64_t* words) {
+  if (!h || !words_in_runs || !words) return fail("null argument");
+  if (!h->finalised) return fail("hlb_gpu_target_runs before hlb_gpu_finalise");
+  *words_in_runs = h->runWords;
+  *words = h->runWordsTotal;
   return 0;
 }
 

@@ -119,6 +119,14 @@ struct StepArgs {
   // contiguous launches of the direct site kernel: every CTA asks L2 for what the CTA that starts
   // `prefetchSites` sites further down the grid will load (0: off)
   int prefetchSites;
+  // whole-part launches: the push targets of 32 consecutive sites as at most two runs per direction.
+  // runFlags bit w: every direction of sites [32w, 32w+32) is {base, split, delta} in
+  // nbrRuns[w*(Q-1) + d-1] = {base, delta << 5 | split}: target(lane) = base + lane + (lane >= split ? delta : 0)
+  // for every link the launch pushes (cut links are not pushed); else the sites read the nbr planes.
+  // Null: off (sub-range launches apply their streamer's policies to whatever sites they get, and push
+  // the cut links of the others to the rubbish slot through nbr)
+  const uint2* __restrict__ nbrRuns;
+  const uint32_t* __restrict__ runFlags;
   // fused monitors (C_MONITOR): {min f, min rho, max rho, max u^2} as order-preserving u64 keys
   unsigned long long* __restrict__ monitorSlots;
 };
@@ -879,11 +887,22 @@ __global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) collide
     const int64_t site0 = first + (int64_t)blockIdx.x * T + A.prefetchSites;
     if (site0 + T <= first + count) {
       constexpr int fLines = Q * (T * 8 / 128), nLines = (Q - 1) * (T * 4 / 128);
+      constexpr int rLines = (T / 32 * (Q - 1) * 8 + 127) / 128 + 1;  // the CTA's run words, wherever their lines start
+      // (a 128 B line of a target plane = the 32 sites of one run word: not asked for where the runs replace it)
+      uint32_t runBits = 0;
+      if (A.runFlags) runBits = __ldg(A.runFlags + (site0 >> 10)) >> ((site0 >> 5) & 31);  // T / 32 <= 2 words, 64-aligned
 #pragma unroll
-      for (int l = threadIdx.x; l < fLines + nLines; l += T) {
-        const char* p = l < fLines
-            ? (const char*)(A.fOld + (int64_t)(l / (T * 8 / 128)) * A.stride + site0) + (l % (T * 8 / 128)) * 128
-            : (const char*)(A.nbr + (int64_t)((l - fLines) / (T * 4 / 128)) * A.stride + site0) + ((l - fLines) % (T * 4 / 128)) * 128;
+      for (int l = threadIdx.x; l < fLines + nLines + rLines; l += T) {
+        const char* p;
+        if (l < fLines) {
+          p = (const char*)(A.fOld + (int64_t)(l / (T * 8 / 128)) * A.stride + site0) + (l % (T * 8 / 128)) * 128;
+        } else if (l < fLines + nLines) {
+          if ((runBits >> ((l - fLines) % (T * 4 / 128))) & 1u) continue;
+          p = (const char*)(A.nbr + (int64_t)((l - fLines) / (T * 4 / 128)) * A.stride + site0) + ((l - fLines) % (T * 4 / 128)) * 128;
+        } else {
+          if (!A.runFlags) continue;
+          p = (const char*)(A.nbrRuns + (site0 >> 5) * (Q - 1)) + (l - fLines - nLines) * 128;
+        }
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
       }
     }
@@ -897,11 +916,20 @@ __global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) collide
   for (int d = 0; d < Q; ++d) f[d] = __ldcs(A.fOld + (int64_t)d * A.stride + site);
   uint32_t target[Q];
   target[0] = (uint32_t)site;
+  const unsigned lane = (unsigned)site & 31u;
+  if (A.runFlags && ((__ldg(A.runFlags + (site >> 10)) >> ((site >> 5) & 31)) & 1u)) {
+    const uint2* __restrict__ run = A.nbrRuns + (site >> 5) * (Q - 1);
 #pragma unroll
-  for (int d = 1; d < Q; ++d) target[d] = __ldcs(A.nbr + (int64_t)(d - 1) * A.stride + site);
+    for (int d = 1; d < Q; ++d) {
+      const uint2 r = __ldg(run + (d - 1));
+      target[d] = r.x + lane + (lane >= (r.y & 31u) ? (uint32_t)((int32_t)r.y >> 5) : 0u);
+    }
+  } else {
+#pragma unroll
+    for (int d = 1; d < Q; ++d) target[d] = __ldcs(A.nbr + (int64_t)(d - 1) * A.stride + site);
+  }
   int b = -1;
   {
-    const unsigned lane = (unsigned)site & 31u;
     if ((bi.x >> lane) & 1u) {
       b = (int)(bi.y + __popc(bi.x & ((1u << lane) - 1u)));
       const uint4* src = A.bRec + (int64_t)b * RC;

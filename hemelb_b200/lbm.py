@@ -443,6 +443,13 @@ class GpuLBM:
         check(self.L.hlb_gpu_launch_count(self.h, C.byref(n)))
         return int(n.value)
 
+    def target_runs(self):
+        """(groups of 32 device sites whose streaming targets the whole-part launches read in run form,
+        all groups): hlb_gpu_target_runs."""
+        a, b = C.c_int64(), C.c_int64()
+        check(self.L.hlb_gpu_target_runs(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def get_cache(self, name):
         bit = capi.CACHES[name]
         out = np.zeros(capi.CACHE_WIDTH[bit] * self.N)

@@ -181,6 +181,11 @@ int hlb_gpu_monitor(hlb_gpu_t h, double* out4);
 int hlb_gpu_monitor_global(hlb_gpu_t h, double* out4);
 /* number of kernels launched by this handle so far */
 int hlb_gpu_launch_count(hlb_gpu_t h, int64_t* n);
+/* How much of geometry::Domain's neighbourIndices (Code/geometry/Domain.cc:425-505) the whole-part
+ * launches read in run form: of the `words` groups of 32 consecutive device sites, `words_in_runs`
+ * have every streaming target given by at most two runs per direction (8 B per direction and group
+ * instead of 128 B).  0 of 0 with HLB_NBR_RUNS=0.  After hlb_gpu_finalise. */
+int hlb_gpu_target_runs(hlb_gpu_t h, int64_t* words_in_runs, int64_t* words);
 /* lb::StabilityTester<LATTICE>::PostSendToParent's loop over the local sites
  * (Code/lb/StabilityTester.h:97-141) as one device reduction, to be called where that loop runs:
  * after the step's streaming, before SwapOldAndNew.  out2[0] = the number of populations of f_new

@@ -370,6 +370,56 @@ def test_tma_staged_site_kernel_is_bit_identical(monkeypatch, geom_name, Q, kern
         assert np.array_equal(staged.get_cache(name), direct.get_cache(name)), name
 
 
+@pytest.mark.parametrize("geom_name,Q,kernel,wall,inlet,outlet,R", [
+    ("cylinder_long", 19, "LBGK", "BFL", "NASH", "NASH", 1), ("tree", 19, "MRT", "GZS", "LADD", "NASH", 1),
+    ("sac", 27, "TRT", "BFL", "NASH", "NASH", 1), ("tree", 15, "LBGK", "SBB", "LADD", "LADD", 1),
+    ("cylinder_long", 19, "LBGK", "BFL", "NASH", "NASH", 3)])
+def test_streaming_targets_as_runs(monkeypatch, geom_name, Q, kernel, wall, inlet, outlet, R):
+    """The whole-part launches read the streaming targets of 32 consecutive sites as at most two runs per
+    direction where the sites allow it (hlb_gpu_target_runs) and from the index planes elsewhere;
+    HLB_NBR_RUNS=0 reads the planes everywhere.  Same bits both ways and as the oracle, on rank 1 of R
+    too (its domain-edge part streams into the halo slots)."""
+    geom = geometry(geom_name)
+    rank = None if R == 1 else G.slab_decomposition(geom, R)
+    r = R // 2
+    dom = build_domains(geom, Q, rank, R)[r]
+    inlets, outlets = iolets_for(geom, inlet, outlet)
+    f0 = anisotropic_f(dom.N, Q, dom.totalSharedFs)
+    runs = GpuLBM(dom, kernel, wall, inlet, outlet, tau=0.8, inlets=inlets, outlets=outlets)
+    monkeypatch.setenv("HLB_NBR_RUNS", "0")
+    planes = GpuLBM(dom, kernel, wall, inlet, outlet, tau=0.8, inlets=inlets, outlets=outlets)
+    monkeypatch.delenv("HLB_NBR_RUNS")
+    inRuns, words = runs.target_runs()
+    assert words == (dom.N + 31) // 32 and 0 < inRuns <= words
+    if geom_name == "cylinder_long" and R == 1:
+        assert inRuns > 0.5 * words
+    assert planes.target_runs() == (0, 0)
+    for g in (runs, planes):
+        g.set_f(f0)
+        g.set_cache_mask(255)
+        if R == 1:
+            g.step(5)
+        else:  # the halo is not exchanged: the received slots stay as set, the sends are compared
+            for _ in range(3):
+                g.request_comms()
+                g.pre_send()
+                g.pre_receive()
+                g.post_receive()
+                g.end_iteration()
+                g.swap_old_and_new()
+                g.state.increment()
+    assert np.array_equal(runs.get_f(), planes.get_f())
+    for which in (0, 1):
+        assert np.array_equal(runs.get_halo(which=which), planes.get_halo(which=which))
+    for name in O.CACHE_BITS:
+        assert np.array_equal(runs.get_cache(name), planes.get_cache(name)), name
+    if R == 1:
+        sim = O.OracleSim(O.OracleDomains(geom, Q), kernel, wall, inlet, outlet, tau=0.8, inlets=inlets, outlets=outlets)
+        sim.set_f(f0)
+        sim.step(5)
+        _check(runs.get_f()[:dom.N * Q], sim.get_f()[:dom.N * Q], "f_old, targets as runs")
+
+
 def test_stability_reduction_matches_the_reference_loop():
     """hlb_gpu_stability = the site loop of lb::StabilityTester::PostSendToParent
     (Code/lb/StabilityTester.h:97-141) run where the reference runs it: after the step's streaming,
