@@ -880,53 +880,76 @@ __global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) collide
   constexpr int T = site_threads<Q>(), RC = brec_words<Q>() / 4;
   __shared__ uint4 srec[RC * T];
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (A.prefetchSites) {
-    // The planes of f_old and of the push targets that a CTA further down the grid will read: one
-    // 128 B line per thread and round, into L2.  The loads of this kernel are then mostly L2 hits, and
-    // DRAM is kept busy by requests that do not wait for a warp to come round to its load phase.
-    const int64_t site0 = first + (int64_t)blockIdx.x * T + A.prefetchSites;
-    if (site0 + T <= first + count) {
-      constexpr int fLines = Q * (T * 8 / 128), nLines = (Q - 1) * (T * 4 / 128);
-      constexpr int rLines = (T / 32 * (Q - 1) * 8 + 127) / 128 + 1;  // the CTA's run words, wherever their lines start
-      // (a 128 B line of a target plane = the 32 sites of one run word: not asked for where the runs replace it)
-      uint32_t runBits = 0;
-      if (A.runFlags) runBits = __ldg(A.runFlags + (site0 >> 10)) >> ((site0 >> 5) & 31);  // T / 32 <= 2 words, 64-aligned
+  // The planes of f_old and of the push targets that a CTA further down the grid will read: one
+  // 128 B line per thread and round, into L2.  The loads of this kernel are then mostly L2 hits, and
+  // DRAM is kept busy by requests that do not wait for a warp to come round to its load phase.
+  constexpr int fLines = Q * (T * 8 / 128), nLines = (Q - 1) * (T * 4 / 128);
+  constexpr int rLines = (T / 32 * (Q - 1) * 8 + 127) / 128 + 1;  // the CTA's run words, wherever their lines start
+  const int64_t site0 = first + (int64_t)blockIdx.x * T + A.prefetchSites;
+  const bool ahead = A.prefetchSites && site0 + T <= first + count;
+  uint32_t aheadFlags = 0;
+  if (ahead) {
+    // (which of the CTA's T / 32 <= 2 groups over there are in runs: asked for now, looked at once this
+    // thread's own loads are on their way)
+    if (A.runFlags) aheadFlags = __ldg(A.runFlags + (site0 >> 10));
 #pragma unroll
-      for (int l = threadIdx.x; l < fLines + nLines + rLines; l += T) {
-        const char* p;
-        if (l < fLines) {
-          p = (const char*)(A.fOld + (int64_t)(l / (T * 8 / 128)) * A.stride + site0) + (l % (T * 8 / 128)) * 128;
-        } else if (l < fLines + nLines) {
-          if ((runBits >> ((l - fLines) % (T * 4 / 128))) & 1u) continue;
-          p = (const char*)(A.nbr + (int64_t)((l - fLines) / (T * 4 / 128)) * A.stride + site0) + ((l - fLines) % (T * 4 / 128)) * 128;
-        } else {
-          if (!A.runFlags) continue;
-          p = (const char*)(A.nbrRuns + (site0 >> 5) * (Q - 1)) + (l - fLines - nLines) * 128;
-        }
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-      }
+    for (int l = threadIdx.x; l < fLines; l += T) {
+      const char* p = (const char*)(A.fOld + (int64_t)(l / (T * 8 / 128)) * A.stride + site0) + (l % (T * 8 / 128)) * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
     }
   }
   if (tid >= count) return;
   const int64_t site = A.siteList ? (int64_t)A.siteList[tid] : first + tid;
   // is this a boundary-typed site?  One 8 B word per 32 sites, asked for first.
   const uint2 bi = __ldg(A.bInfo + (site >> 5));
+  uint32_t flags = 0;
+  if (A.runFlags) flags = __ldg(A.runFlags + (site >> 10));
   double f[Q];
 #pragma unroll
   for (int d = 0; d < Q; ++d) f[d] = __ldcs(A.fOld + (int64_t)d * A.stride + site);
   uint32_t target[Q];
   target[0] = (uint32_t)site;
   const unsigned lane = (unsigned)site & 31u;
-  if (A.runFlags && ((__ldg(A.runFlags + (site >> 10)) >> ((site >> 5) & 31)) & 1u)) {
+  if (A.runFlags) {
+    // the group's run words are asked for whether or not they stand for its targets (no load waits for the
+    // flag); a group that is not in runs (rare) goes to the index planes once the flag says so
     const uint2* __restrict__ run = A.nbrRuns + (site >> 5) * (Q - 1);
+    uint2 r[Q];
 #pragma unroll
-    for (int d = 1; d < Q; ++d) {
-      const uint2 r = __ldg(run + (d - 1));
-      target[d] = r.x + lane + (lane >= (r.y & 31u) ? (uint32_t)((int32_t)r.y >> 5) : 0u);
+    for (int d = 1; d < Q; ++d) r[d] = __ldg(run + (d - 1));
+    if (ahead) {
+      const uint32_t runBits = aheadFlags >> ((site0 >> 5) & 31);  // (site0 is a multiple of 64)
+#pragma unroll
+      for (int l = threadIdx.x; l < nLines + rLines; l += T) {
+        const char* p;
+        if (l < nLines) {
+          // (a 128 B line of a target plane = the 32 sites of one group: not asked for where the runs replace it)
+          if ((runBits >> (l % (T * 4 / 128))) & 1u) continue;
+          p = (const char*)(A.nbr + (int64_t)(l / (T * 4 / 128)) * A.stride + site0) + (l % (T * 4 / 128)) * 128;
+        } else {
+          p = (const char*)(A.nbrRuns + (site0 >> 5) * (Q - 1)) + (l - nLines) * 128;
+        }
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+      }
+    }
+    if ((flags >> ((site >> 5) & 31)) & 1u) {
+#pragma unroll
+      for (int d = 1; d < Q; ++d)
+        target[d] = r[d].x + lane + (lane >= (r[d].y & 31u) ? (uint32_t)((int32_t)r[d].y >> 5) : 0u);
+    } else {
+#pragma unroll
+      for (int d = 1; d < Q; ++d) target[d] = __ldcs(A.nbr + (int64_t)(d - 1) * A.stride + site);
     }
   } else {
 #pragma unroll
     for (int d = 1; d < Q; ++d) target[d] = __ldcs(A.nbr + (int64_t)(d - 1) * A.stride + site);
+    if (ahead) {
+#pragma unroll
+      for (int l = threadIdx.x; l < nLines; l += T) {
+        const char* p = (const char*)(A.nbr + (int64_t)(l / (T * 4 / 128)) * A.stride + site0) + (l % (T * 4 / 128)) * 128;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+      }
+    }
   }
   int b = -1;
   {

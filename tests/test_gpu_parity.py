@@ -390,7 +390,8 @@ def test_streaming_targets_as_runs(monkeypatch, geom_name, Q, kernel, wall, inle
     planes = GpuLBM(dom, kernel, wall, inlet, outlet, tau=0.8, inlets=inlets, outlets=outlets)
     monkeypatch.delenv("HLB_NBR_RUNS")
     inRuns, words = runs.target_runs()
-    assert words == (dom.N + 31) // 32 and 0 < inRuns <= words
+    assert words == (dom.N + 31) // 32 and 0 <= inRuns <= words
+    assert inRuns > 0 or R > 1   # (a thin slab's rows are a few sites long: no group of 32 is two runs)
     if geom_name == "cylinder_long" and R == 1:
         assert inRuns > 0.5 * words
     assert planes.target_runs() == (0, 0)
