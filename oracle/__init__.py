@@ -87,6 +87,73 @@ def ref_lib(sse3: bool = False):
     return _refs[sse3]
 
 
+_refdom = []
+
+
+def ref_domain_lib():
+    """oracle/_ref/libhemelb_refdom.so -- the reference's unmodified geometry::Domain, LookupTree, DistributedStore
+    and BasicDecomposition over emulated ranks (oracle/ref_domain_driver.cc) -- or None when it was not
+    built / shipped."""
+    if not _refdom:
+        path = os.path.join(HERE, "_ref", "libhemelb_refdom.so")
+        L = None
+        if os.path.exists(path):
+            L = C.CDLL(path)
+            L.hrefdom_run.restype = C.c_void_p
+            L.hrefdom_get.restype = C.c_int64
+            L.hrefdom_get.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p]
+            L.hrefdom_destroy.argtypes = [C.c_void_p]
+        _refdom.append(L)
+    return _refdom[0]
+
+
+class RefDomains:
+    """Per-rank tables from the reference's own ``geometry::Domain`` (R emulated ranks).  ``rank_of_site``
+    None: the blocks go to ranks by the reference's ``BasicDecomposition`` (``block_rank`` = its answer per
+    .gmy block, SITE_OR_BLOCK_SOLID = INT_MIN for solid blocks)."""
+
+    def __init__(self, geom, Q, rank_of_site=None, nranks=1):
+        L = ref_domain_lib()
+        if L is None:
+            raise RuntimeError("oracle/_ref/libhemelb_refdom.so not built")
+        self.L, self.Q, self.R = L, Q, nranks
+        bd = np.ascontiguousarray(geom.block_dims, np.int32)
+        arrs = [np.ascontiguousarray(geom.coords, np.int32), np.ascontiguousarray(geom.bsite, np.int64),
+                np.ascontiguousarray(geom.btype, np.uint8), np.ascontiguousarray(geom.biolet, np.int32),
+                np.ascontiguousarray(geom.bdist, np.float32), np.ascontiguousarray(geom.bnavail, np.uint8),
+                np.ascontiguousarray(geom.bnormal, np.float32)]
+        rk = None if rank_of_site is None else np.ascontiguousarray(rank_of_site, np.int32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.h = C.c_void_p(L.hrefdom_run(Q, nranks, p(bd), int(geom.block_size), C.c_int64(geom.n_sites), p(arrs[0]),
+                                          C.c_int64(arrs[1].size), *[p(a) for a in arrs[1:]], None if rk is None else p(rk)))
+        if not self.h:
+            raise ValueError("more ranks than non-empty blocks: the reference's BasicDecomposition refuses")
+        self.block_rank = self._get(0, "blockRank", np.int32)
+
+    def _get(self, r, name, dt):
+        n = self.L.hrefdom_get(self.h, r, name.encode(), None)
+        a = np.zeros(n, dt)
+        self.L.hrefdom_get(self.h, r, name.encode(), a.ctypes.data_as(C.c_void_p))
+        return a
+
+    def tables(self, r=0):
+        out = {"N": int(self.L.hrefdom_get(self.h, r, b"N", None)),
+               "totalSharedFs": int(self.L.hrefdom_get(self.h, r, b"totalSharedFs", None)), "Q": self.Q}
+        for name, dt in TABLE_DTYPES.items():
+            if name != "inputIndex":  # (the reference keeps global coordinates, not the .gmy index)
+                out[name] = self._get(r, name, dt)
+        out["procs"] = self._get(r, "procs", np.int64).reshape(-1, 3)
+        out["mid"] = out["counts"][:6].copy()
+        out["edge"] = out["counts"][6:].copy()
+        return out
+
+    def __del__(self):
+        try:
+            self.L.hrefdom_destroy(self.h)
+        except Exception:
+            pass
+
+
 def iolet_record(kind=0, normal=(0, 0, 1), position=(0, 0, 0), radius=1.0, max_speed=0.0,
                  density_mean=1.0, density_amp=0.0, phase=0.0, period=1000.0, warmup=0.0,
                  min_density=1.0):

@@ -331,3 +331,31 @@ def test_typed_block_counts_and_weighted_decomposition(name, Q):
         _same(d, host[r], (name, Q, "weighted blocks", r))
         d.close()
     dev.close()
+
+
+@pytest.mark.parametrize("name,Q,R,kind", [("four_cube", 15, 1, None), ("cylinder", 19, 3, "slab"), ("tree", 19, 4, "basic"),
+                                           ("sac", 27, 2, "slab")])
+def test_device_tables_equal_the_reference_domain(name, Q, R, kind):
+    """The device builder (hlb_dom_*) against tables written by the reference's own geometry::Domain
+    (tests/golden/domain_tables_*.npz, tests/test_domain_vs_ref.py), and against that library itself where it
+    travelled with the snapshot."""
+    import os
+    from tests.test_domain_vs_ref import KEYS as REF_KEYS, decomposition
+    geom = geometry(name)
+    rank = decomposition(geom, R, kind)
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "domain_tables_%s_q%d_r%d.npz" % (name, Q, R)))
+    live = O.RefDomains(geom, Q, rank, R) if O.ref_domain_lib() is not None else None
+    for r in range(R):
+        dev = DeviceDomain.from_geometry(geom, Q, rank, r, R)
+        t = dev.tables()
+        bs = dev.boundary_sites()
+        for k in REF_KEYS:
+            for src in ([gold["r%d_%s" % (r, k)]] + ([live.tables(r)[k]] if live else [])):
+                a, b = np.asarray(t[k]), np.asarray(src)
+                if k == "wallNormal":  # (read for boundary-typed sites only)
+                    a, b = a.reshape(-1, 3)[bs], b.reshape(-1, 3)[bs]
+                if k == "siteType":
+                    continue  # the device tables carry the collision type; types are compared through counts
+                assert a.shape == b.shape and np.array_equal(a, b), (name, Q, R, r, k)
+        assert t["N"] == int(gold["r%d_N" % r]) and t["totalSharedFs"] == int(gold["r%d_totalSharedFs" % r])
+        dev.close()

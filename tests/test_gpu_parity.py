@@ -400,11 +400,12 @@ def test_streaming_targets_as_runs(monkeypatch, geom_name, Q, kernel, wall, inle
         g.set_cache_mask(255)
         if R == 1:
             g.step(5)
-        else:  # the halo is not exchanged: the received slots stay as set, the sends are compared
-            for _ in range(3):
+        else:  # no peers here: the received slots are given, the sends are compared
+            for k in range(3):
                 g.request_comms()
                 g.pre_send()
                 g.pre_receive()
+                g.set_halo(0.05 + 0.001 * k + 1e-5 * np.arange(dom.totalSharedFs), which=0)
                 g.post_receive()
                 g.end_iteration()
                 g.swap_old_and_new()
