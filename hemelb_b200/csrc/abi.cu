@@ -171,6 +171,9 @@ struct hlb_gpu_handle {
   uint2* nbrRuns = nullptr;    // push targets as runs per 32 sites (StepArgs::nbrRuns); HLB_NBR_RUNS=0: not built
   uint32_t* runFlags = nullptr;
   bool useRuns = true;
+  bool gzsOverlap = false;     // GuoZhengShi: per-link kernel on `aux`, beside the site kernel (HLB_GZS_OVERLAP=1)
+  cudaStream_t aux = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
   int64_t runWords = 0, runWordsTotal = 0;  // 32-site words served by runs / all
   int64_t nbMid = 0;           // boundary-typed sites of the mid-domain part (ordinals [0, nbMid))
   std::vector<int64_t> refOrdToB;  // boundary ordinal in reference order -> device ordinal
@@ -1039,7 +1042,18 @@ int launch_part(hlb_gpu_t h, int part) {
   if (part == 0 && h->useTma)
     h->launchTma(h->cfg.wall, h->cfg.inlet, h->cfg.outlet, A, h->mrt.data(), &h->mapF[h->cur], &h->mapN, count, h->nSm,
                  h->bSite, gCount, h->compute);
-  else
+  else if (h->gzsOverlap && h->cfg.wall == HLB_WALL_GZS && gCount > 0) {
+    // GuoZhengShi: the per-link kernel (FP64-issue-bound) beside the site kernel (memory-bound).  Both read
+    // f_old; the link kernel writes the wall-link populations of the boundary-typed sites, which the site
+    // kernel leaves alone.  The link kernel goes first, on a high-priority stream, so that its CTAs take
+    // their share of every SM and the site kernel fills the rest.
+    CU(cudaEventRecord(h->evFork, h->compute));
+    CU(cudaStreamWaitEvent(h->aux, h->evFork, 0));
+    h->launch(h->cfg.wall, h->cfg.inlet, h->cfg.outlet, A, h->mrt.data(), first, 0, h->bSite + gFirst, 0, gCount, h->aux);
+    CU(cudaEventRecord(h->evJoin, h->aux));
+    h->launch(h->cfg.wall, h->cfg.inlet, h->cfg.outlet, A, h->mrt.data(), first, count, h->bSite + gFirst, 0, 0, h->compute);
+    CU(cudaStreamWaitEvent(h->compute, h->evJoin, 0));
+  } else
     h->launch(h->cfg.wall, h->cfg.inlet, h->cfg.outlet, A, h->mrt.data(), first, count, h->bSite + gFirst, 0, gCount,
               h->compute);
   h->launches++;
@@ -1407,6 +1421,15 @@ int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
     h->scheduleDefault = h->schedule;
     const char* t = getenv("HLB_TMA");
     h->useTma = t && t[0] == '1';
+    const char* go = getenv("HLB_GZS_OVERLAP");
+    h->gzsOverlap = go && go[0] == '1';
+    {
+      int lo = 0, hi = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CU(cudaStreamCreateWithPriority(&h->aux, cudaStreamNonBlocking, hi));
+      CU(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
+    }
     const char* nr = getenv("HLB_NBR_RUNS");
     h->useRuns = !(nr && nr[0] == '0');
     const char* pf = getenv("HLB_PREFETCH");
@@ -1508,6 +1531,9 @@ int hlb_gpu_destroy(hlb_gpu_t h) {
   cudaFree(h->bRec);
   cudaFree(h->nbrRuns);
   cudaFree(h->runFlags);
+  if (h->aux) cudaStreamDestroy(h->aux);
+  if (h->evFork) cudaEventDestroy(h->evFork);
+  if (h->evJoin) cudaEventDestroy(h->evJoin);
   cudaFree(h->postI);
   cudaFree(h->postD);
   cudaFree(h->postQ);

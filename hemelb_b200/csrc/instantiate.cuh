@@ -2,6 +2,7 @@
 // (wall link, inlet link, outlet link) bundles of the site kernel and the run-time dispatch over
 // them.
 #pragma once
+#include <algorithm>
 #include <cuda_runtime.h>
 #include "kernels.cuh"
 
@@ -10,15 +11,16 @@ namespace hlb {
 template <int Q, int KERNEL>
 void launch_collide_stream(int wall, int inlet, int outlet, const StepArgs& A, const void* mrt, int64_t first,
                            int64_t count, const uint32_t* gzsList, int64_t gzsFirst, int64_t gzsCount, void* stream) {
-  if (count <= 0) return;
+  // (count == 0 with gzsCount > 0: the per-link kernel alone -- the caller runs it on a stream of its own)
+  if (count <= 0 && gzsCount <= 0) return;
   constexpr int T = site_threads<Q>();
   const dim3 block(T);
-  const dim3 grid((unsigned)((count + T - 1) / T));
+  const dim3 grid((unsigned)((std::max<int64_t>(count, 1) + T - 1) / T));
   cudaStream_t s = (cudaStream_t)stream;
   const MrtArgs<Q>& M = *(const MrtArgs<Q>*)mrt;
 #define HLB_CASE(W, I, O)                                                                       \
   if (wall == W && inlet == I && outlet == O) {                                                 \
-    collide_stream_kernel<Q, KERNEL, W, I, O><<<grid, block, 0, s>>>(A, M, first, count);       \
+    if (count > 0) collide_stream_kernel<Q, KERNEL, W, I, O><<<grid, block, 0, s>>>(A, M, first, count); \
     if constexpr (W == W_GZS) {                                                                 \
       if (A.wallOn && gzsCount > 0) {                                                           \
         StepArgs G = A;                                                                         \
