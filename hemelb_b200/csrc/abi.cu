@@ -171,7 +171,7 @@ struct hlb_gpu_handle {
   uint2* nbrRuns = nullptr;    // push targets as runs per 32 sites (StepArgs::nbrRuns); HLB_NBR_RUNS=0: not built
   uint32_t* runFlags = nullptr;
   bool useRuns = true;
-  bool gzsOverlap = false;     // GuoZhengShi: per-link kernel on `aux`, beside the site kernel (HLB_GZS_OVERLAP=1)
+  int gzsOverlap = 0;          // GuoZhengShi: per-link kernel on `aux`, this many CTAs per SM, beside the site kernel (HLB_GZS_OVERLAP)
   cudaStream_t aux = nullptr;
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   int64_t runWords = 0, runWordsTotal = 0;  // 32-site words served by runs / all
@@ -1049,7 +1049,9 @@ int launch_part(hlb_gpu_t h, int part) {
     // their share of every SM and the site kernel fills the rest.
     CU(cudaEventRecord(h->evFork, h->compute));
     CU(cudaStreamWaitEvent(h->aux, h->evFork, 0));
-    h->launch(h->cfg.wall, h->cfg.inlet, h->cfg.outlet, A, h->mrt.data(), first, 0, h->bSite + gFirst, 0, gCount, h->aux);
+    StepArgs G = A;
+    G.gzsGridLimit = h->nSm * h->gzsOverlap;  // resident from the start: the site kernel's CTAs are dispatched beside them
+    h->launch(h->cfg.wall, h->cfg.inlet, h->cfg.outlet, G, h->mrt.data(), first, 0, h->bSite + gFirst, 0, gCount, h->aux);
     CU(cudaEventRecord(h->evJoin, h->aux));
     h->launch(h->cfg.wall, h->cfg.inlet, h->cfg.outlet, A, h->mrt.data(), first, count, h->bSite + gFirst, 0, 0, h->compute);
     CU(cudaStreamWaitEvent(h->compute, h->evJoin, 0));
@@ -1422,7 +1424,7 @@ int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
     const char* t = getenv("HLB_TMA");
     h->useTma = t && t[0] == '1';
     const char* go = getenv("HLB_GZS_OVERLAP");
-    h->gzsOverlap = go && go[0] == '1';
+    h->gzsOverlap = go ? atoi(go) : 0;
     {
       int lo = 0, hi = 0;
       CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));

@@ -25,8 +25,9 @@ void launch_collide_stream(int wall, int inlet, int outlet, const StepArgs& A, c
       if (A.wallOn && gzsCount > 0) {                                                           \
         StepArgs G = A;                                                                         \
         if (gzsList) G.siteList = gzsList;                                                      \
-        gzs_links_kernel<Q, KERNEL><<<(unsigned)((gzsCount + kGzsTile - 1) / kGzsTile), kGzsThreads, 0, s>>>( \
-            G, M, gzsFirst, gzsCount);                                                          \
+        unsigned gzsGrid = (unsigned)((gzsCount + kGzsTile - 1) / kGzsTile);                    \
+        if (A.gzsGridLimit > 0 && gzsGrid > (unsigned)A.gzsGridLimit) gzsGrid = (unsigned)A.gzsGridLimit; \
+        gzs_links_kernel<Q, KERNEL><<<gzsGrid, kGzsThreads, 0, s>>>(G, M, gzsFirst, gzsCount);  \
       }                                                                                         \
     }                                                                                           \
     return;                                                                                     \

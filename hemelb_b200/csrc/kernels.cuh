@@ -127,6 +127,8 @@ struct StepArgs {
   // the cut links of the others to the rubbish slot through nbr)
   const uint2* __restrict__ nbrRuns;
   const uint32_t* __restrict__ runFlags;
+  // GuoZhengShi per-link kernel: at most this many CTAs, each walking several tiles (0: one CTA per tile)
+  int gzsGridLimit;
   // fused monitors (C_MONITOR): {min f, min rho, max rho, max u^2} as order-preserving u64 keys
   unsigned long long* __restrict__ monitorSlots;
 };
@@ -507,7 +509,11 @@ __global__ void __launch_bounds__(kGzsThreads, (KERNEL == K_LBGK && Q <= 19) ? 3
   __shared__ uint16_t slink[T * (Q - 1)];
   __shared__ int soff[(Q - 1) * (T / 32) + 1];
   const int tx = threadIdx.x;
-  const int64_t tile0 = (int64_t)blockIdx.x * T;
+  // (one tile per CTA; or, with a grid smaller than the tiles -- StepArgs::gzsGridLimit: the launch that
+  // shares the SMs with the site kernel -- every CTA walks its tiles)
+  const int nTiles = (int)((count + T - 1) / T);
+  for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+  const int64_t tile0 = (int64_t)tile * T;
   const int nT = (int)((count - tile0) < T ? (count - tile0) : T);
   if (tx < T) {
     uint32_t wall = 0, iol = 0;
@@ -676,6 +682,8 @@ __global__ void __launch_bounds__(kGzsThreads, (KERNEL == K_LBGK && Q <= 19) ? 3
     double out = 0.;
     gzs_pick<Q, KERNEL, 1>(A, M, N, o, sbb, wdensity_1, wmm, mw, fneqW, mneq, out);
     A.fNew[(int64_t)i * A.stride + site] = out;
+  }
+  __syncthreads();  // (the staging area is reused by the CTA's next tile)
   }
 }
 
