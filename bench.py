@@ -28,6 +28,7 @@ import argparse
 import hashlib
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -48,11 +49,15 @@ REFERENCE_SAMPLE_SITES = 2.0e7
 
 
 def kernel_source_hash():
-    """Identifies the site kernel a DRAM-traffic capture belongs to."""
+    """Identifies the site kernel a DRAM-traffic capture belongs to: the kernel sources without their
+    comments and white space (an edited comment does not make a capture stale, an edited statement does)."""
     h = hashlib.sha256()
     for f in ("kernels.cuh", "lattice.cuh", "instantiate.cuh"):
-        with open(os.path.join(ROOT, "hemelb_b200", "csrc", f), "rb") as fh:
-            h.update(fh.read())
+        with open(os.path.join(ROOT, "hemelb_b200", "csrc", f), "r") as fh:
+            text = fh.read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        text = re.sub(r"//[^\n]*", "", text)
+        h.update("".join(text.split()).encode())
     return h.hexdigest()[:16]
 
 

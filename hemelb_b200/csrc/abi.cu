@@ -1435,9 +1435,9 @@ int hlb_gpu_create(const hlb_gpu_config* cfg, hlb_gpu_t* out) {
     const char* nr = getenv("HLB_NBR_RUNS");
     h->useRuns = !(nr && nr[0] == '0');
     const char* pf = getenv("HLB_PREFETCH");
-    // measured on the 1e8-site tree (256-thread CTAs): 13 070 MLUPS without, 13 830 / 14 080 / 14 118 / 14 095 at
-    // 5 120 / 20 480 / 38 400-51 200 / 64 000 sites ahead, 13 250 at 153 600 and 11 000 at 307 200 (the lines
-    // leave L2 again before they are used); the optimum in sites is the same for 128- and 64-thread CTAs
+    // measured on the 1e8-site tree: 16 140 / 16 445 / 16 600 / 16 656 / 16 661 / 16 580 / 16 635 MLUPS at 10 240 /
+    // 20 480 / 30 720 / 40 960 / 51 200 / 61 440 / 81 920 sites ahead (profiles/r02_prefetch_sweep_runs.json);
+    // 15 % less without, and beyond ~150 000 the lines leave L2 again before they are used
     h->prefetchSites = pf ? atoi(pf) : 40960;
     h->prefetchSites = h->prefetchSites / 256 * 256;  // whole 128 B lines of every plane
     CU(cudaDeviceGetAttribute(&h->nSm, cudaDevAttrMultiProcessorCount, cfg->device));

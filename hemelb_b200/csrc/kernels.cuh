@@ -10,6 +10,9 @@
 // population through the 32-bit neighbour table into f_new.  Macroscopic-moment extraction
 // (UpdateCachePostCollision, Common.h:21-130) is fused behind a run-time mask.
 //
+// Where the sites of a group of 32 allow it, the Q-1 push targets are not loaded per site but made
+// from at most two runs per direction (StepArgs::nbrRuns): 8 B per direction and group.
+//
 // Site order on the device: inside the mid-domain part and inside the domain-edge part the sites
 // of ALL six collision types are sorted together by lattice position (x, y, z) -- a wall site sits
 // between the mid-fluid sites of its lattice row, so the 32 pushes of a warp land on consecutive
@@ -18,7 +21,8 @@
 // runs is decided per site from a bitmap of the boundary-typed sites (bInfo: one 8 B word per 32
 // sites) and that site's wall / iolet masks, in the order of StreamerTypeFactory.h:65-79.
 //
-// HBM traffic per site update: Q*8 B read + Q*8 B written + (Q-1)*4 B of indices.
+// Algorithmic HBM traffic per site update: Q*8 B read + Q*8 B written + (Q-1)*4 B of indices
+// (380 B for D3Q19); with the targets as runs the site kernel moves 313 B.
 #pragma once
 #include <cuda.h>  // CUtensorMap
 #include <cstdint>
@@ -688,8 +692,8 @@ __global__ void __launch_bounds__(kGzsThreads, (KERNEL == K_LBGK && Q <= 19) ? 3
 }
 
 // ---------------------------------------------------------------------------------- the site kernel
-// Q <= 19: 256-thread CTAs, two resident per SM (<= 128 registers).  D3Q27 needs ~190 registers:
-// 128-thread CTAs, three resident (<= 168 registers; 12 warps per SM instead of 8).
+// Q <= 19: 64-thread CTAs, eight resident per SM (<= 128 registers).  D3Q27 needs ~190 registers:
+// 64-thread CTAs, six resident (<= 168 registers; 12 warps per SM instead of 16).
 
 // per-site quantities of an iolet link policy (NashZerothOrderPressure.h:27-60 / LaddIolet.h:29-66)
 struct IoletSite {
@@ -882,7 +886,8 @@ __device__ __forceinline__ void site_finish(const StepArgs& A, const MrtArgs<Q>&
 // site needs beyond its populations -- masks, iolet id, cut distances: its bRec record -- is fetched
 // asynchronously (cp.async, 16 B chunks) into the thread's column of `srec` as soon as the bitmap
 // word says the site is boundary-typed: no load depends on another one except through that word
-// (small enough to stay in L2).  Used for the domain-edge part, for sub-ranges and site lists.
+// (small enough to stay in L2).  The product path: whole parts (with the targets as runs where
+// StepArgs::runFlags says so), sub-ranges and site lists.
 template <int Q, int KERNEL, int WALL, int INLET, int OUTLET>
 __global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) collide_stream_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ MrtArgs<Q> M, int64_t first, int64_t count) {
   constexpr int T = site_threads<Q>(), RC = brec_words<Q>() / 4;
@@ -976,6 +981,9 @@ __global__ void __launch_bounds__(site_threads<Q>(), site_min_ctas<Q>()) collide
 }
 
 // ---------------------------------------------------------------------------------- TMA-staged form
+// OPT-IN (HLB_TMA=1), NOT the product path: bit-identical, measured slower than the direct form with its
+// L2 prefetch (8 860 - 12 110 against 15 237 MLUPS on the tree, profiles/r02_tma_experiments.md).  What
+// follows is the reasoning it was built on.
 // The site kernel for a whole part whose first site is tile-aligned (the mid-domain part): a
 // persistent kernel, one CTA per SM, whose warps work independently of one another.  A warp walks
 // its share of the part's tiles of 32 consecutive sites with two shared-memory stages of its own.

@@ -151,22 +151,22 @@ int hlb_gpu_get_cache(hlb_gpu_t h, uint32_t which, double* out);
  *      cosine iolet densities evaluated on the host as InOutLetCosine::GetDensity does */
 int hlb_gpu_step(hlb_gpu_t h, int nsteps);
 int hlb_gpu_get_time_step(hlb_gpu_t h, uint64_t* t);
-/* scheduling knob.  Product schedule (enabled = 1, as created): whole mid-domain range requests
- * (LBM::PreReceive asks one streamer at a time) are deferred until the last non-empty one arrived,
- * then run (a) in slot order with the mid-fluid kernel pre-writing the slots the boundary ranges
- * fill after it (LBGK / TRT, Q <= 19), or (b) as ONE fused kernel ordered by lattice position (MRT,
- * D3Q27), or (c) with the boundary ranges on a second stream (other bundles, single rank) -- see
- * DESIGN.md section 4.  The ranges read f_old and write disjoint slots of f_new, so the result of a
- * step is bit-identical in every schedule; whatever follows the streaming (CopyReceived, PostStep,
- * swap, read-backs) waits for all of it.  enabled = 0: every range its own kernel in the
- * reference's plain write order (A/B comparisons).  Sub-range calls always run plain.
- * Environment at create: HLB_FILL_HOLES=0, HLB_FUSE=0, HLB_OVERLAP=0|1. */
+/* scheduling knob.  Product schedule (enabled = 1, as created): requests for a whole range with that
+ * range's own streamer (what LBM::PreSend / PreReceive make, lb.hpp:176-251) are held and served by ONE
+ * launch of the site kernel per part (domain-edge, mid-domain) in which every site runs the streamer of
+ * its own collision type; the twelve PostStep requests become one launch over the BFL link list
+ * (INTEGRATION.md "Asynchrony").  The ranges read f_old and write disjoint slots of
+ * f_new, so the result of a step is bit-identical in every schedule; whatever reads or orders state
+ * (CopyReceived, swap, read-backs, monitors) first sends off what was held.  enabled = 0: every request
+ * its own launch, in the caller's order (A/B comparisons).  Sub-range requests, and a streamer asked to
+ * run on another type's range, always run at once.  Environment at create: HLB_SCHEDULE=0 (as enabled = 0),
+ * HLB_PREFETCH=<sites>, HLB_NBR_RUNS=0, HLB_TMA=1, HLB_GZS_OVERLAP=k (measurement switches). */
 int hlb_gpu_set_overlap(hlb_gpu_t h, int enabled);
 int hlb_gpu_sync(hlb_gpu_t h);
 /* CUDA-event timing of nsteps whole steps on the engine's own streams (ms) */
 int hlb_gpu_time_steps(hlb_gpu_t h, int nsteps, float* ms);
-/* same, also returning the summed CUDA-event duration of the mid-fluid (bulk) range launches and
- * the number of sites they updated -- the roofline kernel, timed live inside the step */
+/* same, also returning the summed CUDA-event duration of the site-kernel launches over the mid-domain
+ * part and the number of sites they updated -- the roofline kernel, timed live inside the step */
 int hlb_gpu_time_steps_detail(hlb_gpu_t h, int nsteps, float* total_ms, float* bulk_ms, int64_t* bulk_sites);
 /* device-side monitors (StabilityTester / IncompressibilityChecker inputs): {min f, min density,
  * max density, max |u|}; D2H of 4 doubles.  With HLB_CACHE_MONITOR in the step's cache mask the
