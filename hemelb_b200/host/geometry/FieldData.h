@@ -58,6 +58,10 @@ namespace hemelb::geometry {
     struct GzsLink { site_t site; int direction; site_t globalId; };
     std::vector<GzsLink> gzsLinks;
     neighbouring::NeighbouringDataManager* gzsManager = nullptr;
+    // for the monitors that are constructed with the Domain, not the FieldData (lb/IncompressibilityChecker.h):
+    // the engine once it exists, and whether the site kernel should gather density / velocity extrema
+    hlb_gpu_t engine = nullptr;
+    bool monitorRequested = false;
   };
 
   // The six streamers are constructed from InitParams (LBM::InitCollisions, lb.hpp:75-114), which

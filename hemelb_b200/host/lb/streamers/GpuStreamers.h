@@ -138,7 +138,7 @@ namespace hemelb::lb::gpu {
       if (pol.outletValues)
         for (unsigned i = 0; i < pol.outletValues->GetGlobalIoletCount(); ++i) out.push_back(pol.outletValues->GetBoundaryDensity(i));
       const auto t = pol.inletValues ? pol.inletValues->GetTimeStep() : (pol.outletValues ? pol.outletValues->GetTimeStep() : 1);
-      const uint32_t mask = CacheMask(cache);
+      const uint32_t mask = CacheMask(cache) | (pol.monitorRequested ? (uint32_t)HLB_CACHE_MONITOR : 0u);
       if (pol.scalarsPushed && pol.pushedStep == t && pol.pushedMask == mask && pol.pushedIn == in && pol.pushedOut == out)
         return;  // same step, same values: the engine already has them
       geometry::FieldData::Check(hlb_gpu_set_step_scalars(h, t, in.data(), out.data(), mask));
@@ -287,6 +287,7 @@ namespace hemelb::geometry {
     cfg.n_inlets = (int)(rin.size() / HLB_IOLET_RECORD_DOUBLES);
     cfg.n_outlets = (int)(rout.size() / HLB_IOLET_RECORD_DOUBLES);
     Check(hlb_gpu_create(&cfg, &m_gpu));
+    pol.engine = m_gpu;
     Check(hlb_gpu_set_neighbour_indices(m_gpu, 0, N, d.neighbourIndices.data()));
     std::vector<uint32_t> wall(N), iol(N);
     std::vector<int32_t> ioid(N);

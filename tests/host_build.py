@@ -37,7 +37,7 @@ def build_host_binaries(verbose=False):
     host = os.path.join(ROOT, "hemelb_b200", "host")
     deps = [os.path.join(ROOT, "tests", "host_lbm_run.cc"), os.path.join(ROOT, "include", "hemelb_b200.h"),
             os.path.join(host, "geometry", "FieldData.h"), os.path.join(host, "lb", "streamers", "GpuStreamers.h"),
-            os.path.join(host, "lb", "StabilityTester.h"),
+            os.path.join(host, "lb", "StabilityTester.h"), os.path.join(host, "lb", "IncompressibilityChecker.h"),
             os.path.join(host, "geometry", "neighbouring", "NeighbouringDataManager.h"),
             os.path.join(ROOT, "tests", "host_shim", "net", "mixins", "InterfaceDelegationNet.h"), os.path.join(ROOT, "tests", "host_shim", "net", "PhasedBroadcastRegular.h"),
             os.path.join(ROOT, "tests", "host_shim", "reporting", "Timers.h"),

@@ -34,6 +34,7 @@
 #include "lb/SimulationState.h"
 #include "lb/streamers/GpuStreamers.h"
 #include "lb/StabilityTester.h"  // hemelb_b200/host: the device-side stand-in
+#include "lb/IncompressibilityChecker.hpp"  // hemelb_b200/host: likewise
 
 using namespace hemelb;
 namespace g = hemelb::lb::gpu;
@@ -309,6 +310,12 @@ namespace {
       tester = std::make_unique<lb::StabilityTester<Lattice>>(
           std::shared_ptr<const geometry::FieldData>(&fd, [](const geometry::FieldData*) {}), nullptr, &state, timers,
           monitoring);
+    // HLB_HOST_INCOMPRESSIBILITY=1: an lb::IncompressibilityChecker beside it, constructed as
+    // configuration/SimBuilder.h:216-226 constructs it (with the Domain and the property cache)
+    using Checker = lb::IncompressibilityChecker<net::PhasedBroadcastRegular<>>;
+    std::unique_ptr<Checker> checker;
+    if (getenv("HLB_HOST_INCOMPRESSIBILITY"))
+      checker = std::make_unique<Checker>(&fd.GetDomain(), nullptr, &state, cache, timers, 0.05);
     auto t0 = std::chrono::steady_clock::now();
     for (int64_t s = 0; s < steps; ++s) {
       if (timing && s == 1) {
@@ -329,6 +336,12 @@ namespace {
       if (tester) {
         tester->RunCycle();
         fprintf(stderr, "host_lbm_run: step %lld stability %d\n", (long long)s, (int)state.GetStability());
+      }
+      if (checker) {
+        checker->RunCycle();
+        fprintf(stderr, "host_lbm_run: step %lld densities %.17g %.17g speed %.17g within %d\n", (long long)s,
+                checker->GetGlobalSmallestDensity(), checker->GetGlobalLargestDensity(),
+                checker->GetGlobalLargestVelocityMagnitude(), (int)checker->IsDensityDiffWithinRange());
       }
       fd.SwapOldAndNew();
       state.Increment();

@@ -97,6 +97,16 @@ int hlb_gpu_stability(hlb_gpu_t, int conv, double* out2) {
   out2[1] = conv ? 1e-3 : 0.0;
   return 0;
 }
+int hlb_gpu_monitor(hlb_gpu_t, double* out4) {
+  static int calls = 0;  // a density range that widens with every call, as a run's extrema would
+  ++calls;
+  fprintf(out(), "monitor\n");
+  out4[0] = 0.01;
+  out4[1] = 1.0 - 0.001 * calls;
+  out4[2] = 1.0 + 0.002 * calls;
+  out4[3] = 0.003 * calls;
+  return 0;
+}
 int hlb_gpu_edge_done(hlb_gpu_t) { fprintf(out(), "edge_done\n"); return 0; }
 int hlb_gpu_get_cache(hlb_gpu_t h, uint32_t which, double* o) {
   fprintf(out(), "get_cache %u\n", which);

@@ -253,6 +253,41 @@ def test_cxx_stability_tester_moves_sixteen_bytes_a_step(tmp_path, mode):
     assert len(verdicts) == steps and all(v.endswith("stability 1") for v in verdicts)
 
 
+@needs_reference_or_prebuilt
+def test_cxx_incompressibility_checker_moves_thirty_two_bytes_a_step(tmp_path):
+    """hemelb_b200/host/lb/IncompressibilityChecker.h in place of the reference's (constructed with the Domain
+    and the property cache, as configuration/SimBuilder.h:216-226 does): one hlb_gpu_monitor per step after
+    the step's last PostStep and before the swap, the gathering switched on in the step scalars
+    (HLB_CACHE_MONITOR), no cache or distribution read-back; the tracker only ever widens."""
+    build_host_binaries()
+    geom, Q = geometry("cylinder"), 19
+    dom = build_domains(geom, Q)[0]
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    steps, dt = 4, physical_dt(0.8)
+    write_case(tmp_path / "case.bin", dom, "LBGK", "BFL", "NASH", "NASH", inlets, outlets, anisotropic_f(dom.N, Q, 0), steps, 0, dt)
+    env = dict(os.environ, HLB_MOCK_LOG=str(tmp_path / "calls.log"), HLB_HOST_INCOMPRESSIBILITY="1")
+    r = subprocess.run([os.path.join(BUILD, "host_lbm_run_mock"), str(tmp_path / "case.bin"), str(tmp_path / "out.bin")],
+                       env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    log = open(tmp_path / "calls.log").read().splitlines()
+    per_step = log[log.index("finalise") + 1:]
+    assert per_step.count("monitor") == steps
+    assert not [ln for ln in per_step if ln.startswith("get_cache")]
+    assert [ln for ln in per_step if ln.startswith("get_f")] == ["get_f 0"]  # the harness's own final read-back
+    scal = [ln for ln in per_step if ln.startswith("set_step_scalars")]
+    assert len(scal) == steps and all(" mask=256" in ln for ln in scal)
+    k = 0
+    for _ in range(steps):
+        k = per_step.index("monitor", k)
+        assert per_step[k - 1].startswith("post_step 5 ") and per_step[k + 1] == "swap"
+        k += 1
+    lines = [ln.split() for ln in r.stderr.splitlines() if "densities" in ln]
+    assert len(lines) == steps
+    for n, w in enumerate(lines, 1):  # the stand-in ABI reports [1 - 0.001 n, 1 + 0.002 n], speed 0.003 n on its n-th call
+        assert float(w[4]) == 1.0 - 0.001 * n and float(w[5]) == 1.0 + 0.002 * n and float(w[7]) == 0.003 * n
+        assert int(w[9]) == 1  # within the 5 % allowed
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,Q,kernel,wall,inlet,outlet", [
     ("four_cube", 15, "LBGK", "SBB", "NASH", "NASH"),
@@ -279,11 +314,29 @@ def test_cxx_host_runs_on_the_gpu_and_matches_the_oracle(tmp_path, name, Q, kern
     import sysconfig
     extra = ["/usr/local/cuda/lib64", os.path.join(sysconfig.get_paths()["purelib"], "nvidia", "cuda_runtime", "lib")]
     env = dict(os.environ, LD_LIBRARY_PATH=":".join([os.environ.get("LD_LIBRARY_PATH", "")] + extra).strip(":"),
-               HLB_HOST_STABILITY="2")  # lb::StabilityTester (device-side stand-in) assessing every step
+               HLB_HOST_STABILITY="2",  # lb::StabilityTester (device-side stand-in) assessing every step
+               HLB_HOST_INCOMPRESSIBILITY="1")  # and an lb::IncompressibilityChecker (likewise)
     r = subprocess.run([exe, str(tmp_path / "case.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True,
                        timeout=300, env=env)
     assert r.returncode == 0, r.stderr
     verdicts = [int(ln.split()[-1]) for ln in r.stderr.splitlines() if "stability" in ln]
+    # the checker's tracker after every step: extrema, over all steps so far, of the density and speed of
+    # the distributions that entered the step (what UpdateCachePostCollision would have cached)
+    tracked = [[float(w[4]), float(w[5]), float(w[7])] for w in (ln.split() for ln in r.stderr.splitlines() if "densities" in ln)]
+    probe = O.OracleSim(O.OracleDomains(geom, Q), kernel, wall, inlet, outlet, tau=reference_tau(dt), inlets=inlets, outlets=outlets)
+    probe.set_f(f0)
+    cx = np.asarray(O.lattice(Q)[0], np.float64).reshape(Q, 3) if np.asarray(O.lattice(Q)[0]).size == 3 * Q else None
+    lo, hi, sp = np.inf, -np.inf, 0.0
+    assert len(tracked) == steps
+    for s_ in range(steps):
+        fs = probe.get_f()[:dom.N * Q].reshape(dom.N, Q)
+        rho_ = fs.sum(1)
+        lo, hi = min(lo, rho_.min()), max(hi, rho_.max())
+        assert abs(tracked[s_][0] - lo) <= 1e-12 * abs(lo) and abs(tracked[s_][1] - hi) <= 1e-12 * abs(hi), (s_, tracked[s_], lo, hi)
+        if cx is not None:
+            sp = max(sp, (np.linalg.norm(fs @ cx, axis=1) / rho_).max())
+            assert abs(tracked[s_][2] - sp) <= 1e-10 * max(sp, 1e-300), (s_, tracked[s_], sp)
+        probe.step(1)
     out = np.fromfile(tmp_path / "out.bin", np.float64)
     # lb::Unstable = 0, Stable = 1, StableAndConverged = 2.  The anisotropic start is far from equilibrium
     # (populations do go negative in the first steps) and, as in the reference, Unstable sticks until Reset()
