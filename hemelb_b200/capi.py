@@ -30,7 +30,7 @@ SYMBOLS = [
     "hlb_gpu_set_equilibrium", "hlb_gpu_request_comms", "hlb_gpu_copy_received", "hlb_gpu_swap",
     "hlb_gpu_set_step_scalars", "hlb_gpu_stream_and_collide", "hlb_gpu_post_step", "hlb_gpu_edge_done",
     "hlb_gpu_get_cache", "hlb_gpu_step", "hlb_gpu_get_time_step", "hlb_gpu_sync", "hlb_gpu_time_steps", "hlb_gpu_time_steps_detail",
-    "hlb_gpu_monitor", "hlb_gpu_monitor_global", "hlb_gpu_stability", "hlb_gpu_launch_count", "hlb_gpu_target_runs", "hlb_gpu_get_neighbour_indices", "hlb_gpu_set_overlap",
+    "hlb_gpu_monitor", "hlb_gpu_monitor_begin", "hlb_gpu_monitor_end", "hlb_gpu_monitor_global", "hlb_gpu_stability", "hlb_gpu_launch_count", "hlb_gpu_target_runs", "hlb_gpu_get_neighbour_indices", "hlb_gpu_set_overlap",
     # device-side Domain construction
     "hlb_dom_create", "hlb_dom_destroy", "hlb_dom_set_sites", "hlb_dom_set_shape", "hlb_dom_set_roughness", "hlb_dom_gzs_needs", "hlb_dom_lookup_sites", "hlb_dom_set_partition_slabs",
     "hlb_dom_set_partition_blocks", "hlb_dom_count_block_sites", "hlb_dom_count_block_sites_typed", "hlb_dom_build", "hlb_dom_build_seconds",

@@ -202,6 +202,9 @@ struct hlb_gpu_handle {
   int64_t siteListCap = 0;
   double* monitorDev = nullptr;
   double* monitorPinned = nullptr;
+  double* monitorPinnedAsync = nullptr;  // hlb_gpu_monitor_begin / _end
+  cudaEvent_t evMonitor = nullptr;
+  int monitorPending = 0;                // 1: copy in flight (evMonitor), 2: values ready
   unsigned long long* monitorSlots = nullptr;
   bool monitorFused = false;  // the collide kernels of the current step(s) feed the slots
   int64_t monitorLaunches = 0; // collide launches that fed the slots since the last fold
@@ -1519,6 +1522,8 @@ int hlb_gpu_destroy(hlb_gpu_t h) {
   cudaFree(h->siteListDev);
   cudaFree(h->monitorDev);
   if (h->monitorPinned) cudaFreeHost(h->monitorPinned);
+  if (h->monitorPinnedAsync) cudaFreeHost(h->monitorPinnedAsync);
+  if (h->evMonitor) cudaEventDestroy(h->evMonitor);
   cudaFree(h->monitorSlots);
   cudaFree(h->perm);
   cudaFree(h->gzsGhost);
@@ -2233,6 +2238,7 @@ int hlb_gpu_time_steps_detail(hlb_gpu_t h, int nsteps, float* total_ms, float* b
 
 int hlb_gpu_monitor(hlb_gpu_t h, double* out4) {
   if (!h || !out4) return fail("null argument");
+  if (h->monitorPending) return fail("hlb_gpu_monitor while a read-back begun by hlb_gpu_monitor_begin is outstanding");
   CU(cudaSetDevice(h->cfg.device));
   if (join_aux(h)) return 1;
   if (!h->monitorPinned) CU(cudaMallocHost(&h->monitorPinned, sizeof(double) * 4));
@@ -2266,6 +2272,41 @@ int hlb_gpu_monitor(hlb_gpu_t h, double* out4) {
   CU(cudaMemcpyAsync(out4, h->monitorDev + 4, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->compute));
   if (join_aux(h)) return 1;
   CU(cudaStreamSynchronize(h->compute));
+  return 0;
+}
+
+// The same read-back split in two, so that a driver can issue the next time step before it waits for
+// this one's 32 bytes (the values it gets are one step old, as the reference's monitors' are several:
+// their PhasedBroadcast cycles span time steps)
+int hlb_gpu_monitor_begin(hlb_gpu_t h) {
+  if (!h) return fail("null argument");
+  if (h->monitorPending) return fail("hlb_gpu_monitor_begin: the previous read-back has not been collected (hlb_gpu_monitor_end)");
+  CU(cudaSetDevice(h->cfg.device));
+  if (!h->monitorPinnedAsync) CU(cudaMallocHost(&h->monitorPinnedAsync, sizeof(double) * 4));
+  if (!h->evMonitor) CU(cudaEventCreateWithFlags(&h->evMonitor, cudaEventDisableTiming));
+  if (h->monitorFused && h->monitorLaunches > 0) {
+    if (join_aux(h)) return 1;
+    h->monitorLaunches = 0;
+    monitor_fold_decode_kernel<<<1, 256, 0, h->compute>>>(h->monitorSlots, h->monitorDev + 4);
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h->monitorPinnedAsync, h->monitorDev + 4, sizeof(double) * 4, cudaMemcpyDeviceToHost, h->compute));
+    CU(cudaEventRecord(h->evMonitor, h->compute));
+    h->monitorPending = 1;
+    return 0;
+  }
+  // nothing gathered in-kernel since the last read: the one-pass form, which is synchronous
+  if (hlb_gpu_monitor(h, h->monitorPinnedAsync)) return 1;
+  h->monitorPending = 2;
+  return 0;
+}
+
+int hlb_gpu_monitor_end(hlb_gpu_t h, double* out4) {
+  if (!h || !out4) return fail("null argument");
+  if (!h->monitorPending) return fail("hlb_gpu_monitor_end without hlb_gpu_monitor_begin");
+  if (h->monitorPending == 1) CU(cudaEventSynchronize(h->evMonitor));
+  h->monitorPending = 0;
+  for (int k = 0; k < 4; ++k) out4[k] = h->monitorPinnedAsync[k];
   return 0;
 }
 

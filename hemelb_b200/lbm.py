@@ -425,6 +425,16 @@ class GpuLBM:
         check(self.L.hlb_gpu_monitor(self.h, ptr(out, C.c_double)))
         return dict(min_f=out[0], min_density=out[1], max_density=out[2], max_speed=out[3])
 
+    def monitor_begin(self):
+        """First half of :meth:`monitor`: enqueue the reduction and the 32-byte copy, return at once."""
+        check(self.L.hlb_gpu_monitor_begin(self.h))
+
+    def monitor_end(self):
+        """Second half: wait for the values asked for by :meth:`monitor_begin`."""
+        out = np.zeros(4)
+        check(self.L.hlb_gpu_monitor_end(self.h, ptr(out, C.c_double)))
+        return dict(min_f=out[0], min_density=out[1], max_density=out[2], max_speed=out[3])
+
     def monitor_global(self):
         """The same extrema over all ranks (one ncclAllReduce; collective)."""
         out = np.zeros(4)

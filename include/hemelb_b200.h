@@ -173,6 +173,13 @@ int hlb_gpu_time_steps_detail(hlb_gpu_t h, int nsteps, float* total_ms, float* b
  * values were gathered by the collide kernels from the distributions ENTERING the last step(s)
  * since the previous call (no extra pass); otherwise one pass over the current f_old. */
 int hlb_gpu_monitor(hlb_gpu_t h, double* out4);
+/* the same read-back in two halves: _begin enqueues the reduction and the 32-byte copy behind the step
+ * just issued and returns at once; _end waits for them and hands the values out.  Between the two the
+ * caller may issue the next time step, so that the device never idles while the host looks at the
+ * monitors (the values are then one step old; the reference's StabilityTester / IncompressibilityChecker
+ * cycles span several time steps, Code/net/PhasedBroadcast.h).  One read-back outstanding at a time. */
+int hlb_gpu_monitor_begin(hlb_gpu_t h);
+int hlb_gpu_monitor_end(hlb_gpu_t h, double* out4);
 /* the same four values over ALL ranks: one ncclAllReduce on the handle's communicator
  * (hlb_gpu_comm_init) in place of the PhasedBroadcast trees of lb::StabilityTester
  * (Code/lb/StabilityTester.h:51-150) and lb::IncompressibilityChecker

@@ -325,6 +325,49 @@ def test_monitor_matches_numpy():
     assert abs(m4["min_density"] - f2.sum(1).min()) < 1e-12
 
 
+def test_monitor_read_back_in_two_halves():
+    """hlb_gpu_monitor_begin / _end: the values of hlb_gpu_monitor, collected after the next step has been
+    issued; one read-back outstanding at a time."""
+    from hemelb_b200.capi import HlbError
+    geom, Q = geometry("cylinder"), 19
+    dom = build_domains(geom, Q)[0]
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    a = GpuLBM(dom, inlets=inlets, outlets=outlets)
+    b = GpuLBM(dom, inlets=inlets, outlets=outlets)
+    f0 = anisotropic_f(dom.N, Q, 0)
+    for g in (a, b):
+        g.set_f(f0)
+        g.set_cache_mask(256)
+    blocking, lagged = [], []
+    for _ in range(4):
+        a.step(1)
+        blocking.append(a.monitor())
+    pending = False
+    for _ in range(4):
+        b.step(1)
+        if pending:
+            lagged.append(b.monitor_end())
+        b.monitor_begin()
+        pending = True
+    lagged.append(b.monitor_end())
+    assert lagged == blocking
+    assert np.array_equal(a.get_f(), b.get_f())
+    # nothing gathered since the last read: the one-pass form answers, through the same pair of calls
+    b.set_cache_mask(0)
+    b.monitor_begin()
+    assert b.monitor_end() == a.monitor()
+    with pytest.raises(HlbError, match="without hlb_gpu_monitor_begin"):
+        b.monitor_end()
+    b.set_cache_mask(256)
+    b.step(1)
+    b.monitor_begin()
+    with pytest.raises(HlbError, match="has not been collected"):
+        b.monitor_begin()
+    with pytest.raises(HlbError, match="outstanding"):
+        b.monitor()
+    b.monitor_end()
+
+
 @pytest.mark.parametrize("Q", (15, 19, 27))
 def test_equilibrium_initial_condition_matches_the_oracle(Q):
     """EquilibriumInitialCondition::SetFs (Code/lb/InitialCondition.hpp:40-52): f_old = f_new =
