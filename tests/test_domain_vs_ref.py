@@ -57,7 +57,7 @@ def decomposition(geom, R, kind):
 @needs_ref
 @pytest.mark.parametrize("name", ["four_cube", "cylinder", "tree", "sac"])
 @pytest.mark.parametrize("Q", (15, 19, 27))
-@pytest.mark.parametrize("R,kind", [(1, None), (2, "slab"), (3, "slab"), (4, "basic"), (5, "ragged")])
+@pytest.mark.parametrize("R,kind", [(1, None), (2, "slab"), (3, "slab"), (4, "basic"), (5, "ragged"), (8, "basic"), (16, "ragged")])
 def test_oracle_and_product_tables_equal_the_reference_domain(name, Q, R, kind):
     geom = geometry(name)
     if name == "four_cube" and R > 1:
