@@ -65,7 +65,10 @@ def test_oracle_and_product_tables_equal_the_reference_domain(name, Q, R, kind):
             O.RefDomains(geom, Q, None, R)
         return
     rank = decomposition(geom, R, kind)
-    ref = O.RefDomains(geom, Q, rank, R)
+    try:
+        ref = O.RefDomains(geom, Q, rank, R)
+    except ValueError:
+        pytest.skip("fewer non-empty blocks than ranks: the reference refuses (BasicDecomposition.cc:66-67)")
     orc = O.OracleDomains(geom, Q, rank, R)
     mine = build_domains(geom, Q, rank, R)
     for r in range(R):
