@@ -469,6 +469,49 @@ def test_streaming_targets_as_runs(monkeypatch, geom_name, Q, kernel, wall, inle
         _check(runs.get_f()[:dom.N * Q], sim.get_f()[:dom.N * Q], "f_old, targets as runs")
 
 
+@pytest.mark.parametrize("axis", (0, 2))
+def test_runs_with_long_rows_and_a_halo(axis):
+    """A cylinder whose lattice rows (along z) are 160 sites long, cut into two ranks across the rows (axis 2:
+    every row loses an end to the domain-edge part) or along them (axis 0: whole rows are domain-edge and
+    push into halo slots): most groups of 32 sites are in runs, the groups next to the cut are not, and
+    both ranks match the oracle bit for bit through the host-staged halo."""
+    geom, Q, R = G.cylinder(12.3, 160), 19, 2
+    rank = G.slab_decomposition(geom, R, axis=axis)
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    doms = build_domains(geom, Q, rank, R)
+    sim = O.OracleSim(O.OracleDomains(geom, Q, rank, R), "LBGK", "BFL", tau=0.8, inlets=inlets, outlets=outlets)
+    gpus = [GpuLBM(d, "LBGK", "BFL", tau=0.8, inlets=inlets, outlets=outlets) for d in doms]
+    for r, d in enumerate(doms):
+        inRuns, words = gpus[r].target_runs()
+        assert 0.5 * words < inRuns < words, (axis, r, inRuns, words)
+        f0 = anisotropic_f(d.N, Q, d.totalSharedFs, site_offset=11 * r)
+        sim.set_f(f0, r)
+        gpus[r].set_f(f0)
+    for _ in range(4):
+        for g in gpus:
+            g.request_comms()
+            g.pre_send()
+            g.pre_receive()
+        sends = [g.get_halo(which=1) for g in gpus]
+        for r, d in enumerate(doms):
+            recv = np.zeros(d.totalSharedFs)
+            for (p, cnt, first) in d.procs:
+                op = doms[p].procs
+                j = int(np.nonzero(op[:, 0] == r)[0][0])
+                o_first = int(op[j, 2]) - (doms[p].N * Q + 1)
+                m_first = int(first) - (d.N * Q + 1)
+                recv[m_first:m_first + cnt] = sends[p][o_first:o_first + cnt]
+            gpus[r].set_halo(recv, which=0)
+        for g in gpus:
+            g.post_receive()
+            g.end_iteration()
+            g.swap_old_and_new()
+            g.state.increment()
+    sim.step(4)
+    for r, d in enumerate(doms):
+        _check(gpus[r].get_f()[:d.N * Q], sim.get_f(r)[:d.N * Q], "axis %d rank %d f_old" % (axis, r))
+
+
 def test_stability_reduction_matches_the_reference_loop():
     """hlb_gpu_stability = the site loop of lb::StabilityTester::PostSendToParent
     (Code/lb/StabilityTester.h:97-141) run where the reference runs it: after the step's streaming,
