@@ -169,10 +169,10 @@ __device__ __forceinline__ double mon_dec(unsigned long long u) {
 // extrema, max speed): warp-reduce, then one relaxed atomic per value per warp, spread over slots.
 template <int Q>
 __device__ __forceinline__ double min_population(const double (&f)[Q]) {
-  double fmin = f[0];
+  double smallest = f[0];
 #pragma unroll
-  for (int d = 1; d < Q; ++d) fmin = fmin < f[d] ? fmin : f[d];
-  return fmin;
+  for (int d = 1; d < Q; ++d) smallest = fmin(smallest, f[d]);  // (one DMNMX each)
+  return smallest;
 }
 // smallest / largest order-preserving key of a full warp: two 32-bit warp reductions (redux.sync) per
 // value -- the high words first, then the low words of the lanes that hold the winning high word
@@ -188,9 +188,7 @@ __device__ __forceinline__ unsigned long long warp_max_key(unsigned long long k)
   const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? (unsigned)k : 0u);
   return ((unsigned long long)mhi << 32) | mlo;
 }
-__device__ __forceinline__ void fused_monitor(const StepArgs& A, int64_t tid, double fmin, double rho,
-                                              const double (&m)[3]) {
-  const double u2 = (m[0] * m[0] + m[1] * m[1] + m[2] * m[2]) / (rho * rho);
+__device__ __forceinline__ void fused_monitor(const StepArgs& A, int64_t tid, double fmin, double rho, double u2) {
   unsigned long long kf = mon_enc(fmin), krmin = mon_enc(rho), krmax = krmin, ku = mon_enc(u2);
   const unsigned mask = __activemask();
   unsigned long long* slot = A.monitorSlots + 4 * ((tid >> 5) & (kMonitorSlots - 1));
@@ -828,15 +826,19 @@ __device__ __forceinline__ void site_finish(const StepArgs& A, const MrtArgs<Q>&
   double rho, m[3];
   density_momentum<Q>(f, rho, m);
   double fneq[Q], fpost[Q];
+  // (the monitor's smallest population and squared speed are taken now: f dies with the collision, and
+  // 1 / rho is at hand)
+  double fmin = 0.0, u2 = 0.0;
   {
     const double density_1 = 1. / rho;
     const double mm = m[0] * m[0] + m[1] * m[1] + m[2] * m[2];
 #pragma unroll
     for (int d = 0; d < Q; ++d) fneq[d] = f[d] - feq_i<Q>(d, rho, density_1, mm, m);
+    if (A.cacheMask & C_MONITOR) {
+      fmin = min_population<Q>(f);
+      u2 = mm * density_1 * density_1;
+    }
   }
-  // (the monitor's smallest population is taken now: f and f_neq die with the collision)
-  double fmin = 0.0;
-  if (A.cacheMask & C_MONITOR) fmin = min_population<Q>(f);
   collide<Q, KERNEL>(A, M, f, fneq, fpost);
 
   // the record has had the whole collision to arrive
@@ -869,7 +871,7 @@ __device__ __forceinline__ void site_finish(const StepArgs& A, const MrtArgs<Q>&
 
   if (A.cacheMask) {
     // the monitors need eight values that are live anyway; the moment extraction goes through the call
-    if (A.cacheMask & C_MONITOR) fused_monitor(A, DIRECT ? launch_tid_again() : site, fmin, rho, m);
+    if (A.cacheMask & C_MONITOR) fused_monitor(A, DIRECT ? launch_tid_again() : site, fmin, rho, u2);
     if (A.cacheMask & 255u) {
       if constexpr (DIRECT) {
         const int64_t tid = launch_tid_again();
