@@ -78,3 +78,58 @@ def valid_combo(Q, kernel, wall, inlet, outlet, need_ref=False):
         if kernel == "MRT" and wall == "GZS":
             return False  # reference reads an unset m_neq
     return True
+
+
+def square_duct(W: int, L: int):
+    """A W x W x L box of fluid, lattice-aligned: walls half a link outside the x / y faces, an inlet half a
+    link below z-min and an outlet above z-max -- the reference's four_cube recipe at another size (a duct
+    whose walls sit exactly mid-link), in 8^3 blocks.  The iolet planes for ``iolets_for`` are in ``meta``."""
+    from hemelb_b200.geometry import CUT_INLET, CUT_OUTLET, CUT_WALL, NEIGHBOURHOOD, Geometry, IoletPlane
+    B = 8
+    lo = 1
+    coords, bsite, btype, biolet, bdist, bnavail, bnormal = [], [], [], [], [], [], []
+    for i in range(lo, lo + W):
+        for j in range(lo, lo + W):
+            for k in range(lo, lo + L):
+                types = np.zeros(26, np.uint8)
+                ids = np.full(26, -1, np.int32)
+                dists = np.full(26, -1.0, np.float32)
+                for l, c in enumerate(NEIGHBOURHOOD):
+                    ni, nj, nk = i + c[0], j + c[1], k + c[2]
+                    if lo <= ni < lo + W and lo <= nj < lo + W and lo <= nk < lo + L:
+                        continue
+                    if nk < lo:
+                        types[l], ids[l] = CUT_INLET, 0
+                    elif nk >= lo + L:
+                        types[l], ids[l] = CUT_OUTLET, 0
+                    else:
+                        types[l] = CUT_WALL
+                    dists[l] = 0.5
+                if types.any():
+                    normal = np.zeros(3, np.float32)
+                    if i == lo:
+                        normal[:] = (-1, 0, 0)
+                    if i == lo + W - 1:
+                        normal[:] = (1, 0, 0)
+                    if j == lo:
+                        normal[:] = (0, -1, 0)
+                    if j == lo + W - 1:
+                        normal[:] = (0, 1, 0)
+                    iswall = bool((types == CUT_WALL).any())
+                    bsite.append(len(coords))
+                    btype.append(types)
+                    biolet.append(ids)
+                    bdist.append(dists)
+                    bnavail.append(1 if iswall else 0)
+                    bnormal.append(normal if iswall else np.zeros(3, np.float32))
+                coords.append((i, j, k))
+    nb = len(bsite)
+    bd = np.array([(lo + W + B) // B, (lo + W + B) // B, (lo + L + B) // B], np.int32)
+    mid = lo + (W - 1) / 2.0
+    meta = {"kind": "square_duct",
+            "inlets": [IoletPlane(CUT_INLET, 0, np.array([mid, mid, lo - 0.5]), np.array([0.0, 0.0, 1.0]), W / 2.0 + 2)],
+            "outlets": [IoletPlane(CUT_OUTLET, 0, np.array([mid, mid, lo + L - 0.5]), np.array([0.0, 0.0, -1.0]), W / 2.0 + 2)]}
+    g = Geometry(bd, B, np.array(coords, np.int32), np.array(bsite, np.int64), np.array(btype, np.uint8).reshape(nb, 26),
+                 np.array(biolet, np.int32).reshape(nb, 26), np.array(bdist, np.float32).reshape(nb, 26),
+                 np.array(bnavail, np.uint8), np.array(bnormal, np.float32).reshape(nb, 3), meta=meta)
+    return g.gmy_sort()
