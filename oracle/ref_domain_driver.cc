@@ -32,6 +32,7 @@
 #include "lb/lattices/D3Q27.h"
 #include "net/IOCommunicator.h"
 #include "reporting/Dict.h"
+#include "ref_domain_build.h"
 
 namespace hemelb::reporting {
   // reporting/Dict.cc wraps ctemplate (absent here); geometry::Domain::Report is not on the path
@@ -89,17 +90,8 @@ struct RankTables {
   int64_t N = 0, totalSharedFs = 0;
 };
 struct Run {
-  int Q = 0, R = 0, blockSize = 0;
-  int bd[3] = {0, 0, 0};
-  int64_t N = 0, nb = 0;
-  const int32_t* coords = nullptr;
-  const int64_t* bsite = nullptr;
-  const uint8_t* btype = nullptr;
-  const int32_t* biolet = nullptr;
-  const float* bdist = nullptr;
-  const uint8_t* bnavail = nullptr;
-  const float* bnormal = nullptr;
-  const int32_t* siteRank = nullptr;  // null: the reference's BasicDecomposition over blocks
+  int Q = 0, R = 0;
+  refdom::GeometryArrays g;
   std::vector<RankTables> out;
   std::vector<int32_t> blockRank;     // per .gmy block: rank given by BasicDecomposition, or SITE_OR_BLOCK_SOLID
   std::string error;
@@ -115,64 +107,12 @@ lb::LatticeInfo const& lattice_info(int Q) {
 
 void rank_body(int rank, void* arg) {
   Run& run = *static_cast<Run*>(arg);
-  using gmy = io::formats::geometry;
   auto const& info = lattice_info(run.Q);
-  const int B = run.blockSize;
   net::IOCommunicator comms{net::MpiCommunicator::World()};
 
-  geometry::GmyReadResult read(Vec16(run.bd[0], run.bd[1], run.bd[2]), U16(B));
-  read.Blocks.resize(read.GetBlockCount());
-  std::vector<site_t> fluidSitesPerBlock(read.GetBlockCount(), 0);
-  // which input site carries which boundary record
-  std::vector<int64_t> recordOf(run.N, -1);
-  for (int64_t k = 0; k < run.nb; ++k) recordOf[run.bsite[k]] = k;
-  auto block_of = [&](int64_t s) {
-    return read.GetBlockIdFromBlockCoordinates(run.coords[3 * s] / B, run.coords[3 * s + 1] / B, run.coords[3 * s + 2] / B);
-  };
-  for (int64_t s = 0; s < run.N; ++s) {
-    const site_t blk = block_of(s);
-    auto& sites = read.Blocks[blk].Sites;
-    if (sites.empty()) sites.assign(read.GetSitesPerBlock(), geometry::GeometrySite(false));
-    const site_t local = read.GetSiteIdFromSiteCoordinates(run.coords[3 * s] % B, run.coords[3 * s + 1] % B, run.coords[3 * s + 2] % B);
-    geometry::GeometrySite site(true);
-    site.links.resize(info.GetNumVectors() - 1);
-    const int64_t rec = recordOf[s];
-    if (rec >= 0) {
-      int n = 0;
-      for (auto&& dir : gmy::Neighbourhood) {  // the file's 26 directions, matched to the lattice in use
-        geometry::GeometrySiteLink link;
-        link.type = static_cast<gmy::CutType>(run.btype[rec * 26 + n]);
-        if (link.type != gmy::CutType::NONE) {
-          link.distanceToIntersection = run.bdist[rec * 26 + n];
-          if (link.type != gmy::CutType::WALL) link.ioletId = run.biolet[rec * 26 + n];
-        }
-        for (Direction l = 1; l < info.GetNumVectors(); ++l)
-          if (info.GetVector(l) == dir) {
-            site.links[l - 1] = link;
-            break;
-          }
-        ++n;
-      }
-      site.wallNormalAvailable = run.bnavail[rec] != 0;
-      if (site.wallNormalAvailable)
-        site.wallNormal = util::Vector3D<float>(run.bnormal[3 * rec], run.bnormal[3 * rec + 1], run.bnormal[3 * rec + 2]);
-    }
-    sites[local] = site;
-    ++fluidSitesPerBlock[blk];
-  }
-
-  auto blockTree = geometry::octree::build_block_tree(read.GetBlockDimensions().as<geometry::octree::U16>(), fluidSitesPerBlock);
-  std::vector<proc_t> procForEachBlock(read.GetBlockCount());
-  geometry::decomposition::BasicDecomposition basic(read, comms.Size());
-  auto procForBlockOct = basic.Decompose(blockTree, procForEachBlock);
+  std::vector<proc_t> procForEachBlock;
+  geometry::GmyReadResult read = refdom::BuildReadResult(run.g, info, comms, &procForEachBlock);
   if (rank == 0) run.blockRank.assign(procForEachBlock.begin(), procForEachBlock.end());
-  read.block_store = std::make_unique<geometry::octree::DistributedStore>(read.GetSitesPerBlock(), std::move(blockTree),
-                                                                              procForBlockOct, comms);
-  for (int64_t s = 0; s < run.N; ++s) {
-    const site_t blk = block_of(s);
-    const site_t local = read.GetSiteIdFromSiteCoordinates(run.coords[3 * s] % B, run.coords[3 * s + 1] % B, run.coords[3 * s + 2] % B);
-    read.Blocks[blk].Sites[local].targetProcessor = run.siteRank ? run.siteRank[s] : procForEachBlock[blk];
-  }
 
   {
     geometry::Domain domain(info, read, comms);
@@ -231,18 +171,18 @@ void* hrefdom_run(int Q, int R, const int32_t* blockDims, int blockSize, int64_t
   Run* run = new Run;
   run->Q = Q;
   run->R = R;
-  run->blockSize = blockSize;
-  for (int k = 0; k < 3; ++k) run->bd[k] = blockDims[k];
-  run->N = N;
-  run->nb = nb;
-  run->coords = coords;
-  run->bsite = bsite;
-  run->btype = btype;
-  run->biolet = biolet;
-  run->bdist = bdist;
-  run->bnavail = bnavail;
-  run->bnormal = bnormal;
-  run->siteRank = siteRank;
+  run->g.blockSize = blockSize;
+  for (int k = 0; k < 3; ++k) run->g.bd[k] = blockDims[k];
+  run->g.N = N;
+  run->g.nb = nb;
+  run->g.coords = coords;
+  run->g.bsite = bsite;
+  run->g.btype = btype;
+  run->g.biolet = biolet;
+  run->g.bdist = bdist;
+  run->g.bnavail = bnavail;
+  run->g.bnormal = bnormal;
+  run->g.siteRank = siteRank;
   run->out.resize(R);
   fakempi_run(R, rank_body, run);
   return run;
