@@ -7,6 +7,7 @@
 #include <mpi.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -504,6 +505,9 @@ int MPI_Put(const void* origin, int ocount, MPI_Datatype ot, int rank, MPI_Aint 
   return MPI_SUCCESS;
 }
 int MPI_Error_string(int, char* s, int* n) { std::strcpy(s, "fake MPI error"); *n = (int)std::strlen(s); return MPI_SUCCESS; }
+double MPI_Wtime(void) {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 int MPI_Abort(MPI_Comm, int code) { std::fprintf(stderr, "MPI_Abort(%d)\n", code); std::abort(); }
 
 int MPI_Scan(const void*, void*, int, MPI_Datatype, MPI_Op, MPI_Comm) { return unreached("MPI_Scan"); }

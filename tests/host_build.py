@@ -17,6 +17,20 @@ REF_SRCS = ["net/IteratedAction.cc", "geometry/neighbouring/RequiredSiteInformat
             "lb/MacroscopicPropertyCache.cc", "lb/SimulationState.cc", "geometry/SiteDataBare.cc", "util/Matrix3D.cc",
             "util/Vector3D.cc", "lb/kernels/DHumieresD3Q19MRTBasis.cc", "lb/iolets/InOutLet.cc",
             "lb/iolets/InOutLetCosine.cc", "lb/iolets/InOutLetVelocity.cc", "lb/iolets/InOutLetParabolicVelocity.cc"]
+# the real lb::LBM over the real geometry::Domain, net::Net and lb::BoundaryValues, ranks as threads
+# (tests/host_lbm_real.cc): every reference source it links, unmodified
+REAL_LBM_REF_SRCS = [
+    "geometry/Domain.cc", "geometry/LookupTree.cc", "geometry/GmyReadResult.cc", "geometry/Block.cc",
+    "geometry/BlockTraverser.cc", "geometry/SiteTraverser.cc", "geometry/VolumeTraverser.cc", "geometry/SiteDataBare.cc",
+    "geometry/neighbouring/NeighbouringDomain.cc", "geometry/decomposition/BasicDecomposition.cc",
+    "net/MpiCommunicator.cc", "net/MpiGroup.cc", "net/IOCommunicator.cc", "net/MpiError.cc", "net/BaseNet.cc",
+    "net/IteratedAction.cc", "net/mixins/StoringNet.cc", "net/mixins/pointpoint/SeparatedPointPoint.cc",
+    "net/mixins/alltoall/SeparatedAllToAll.cc", "net/mixins/gathers/SeparatedGathers.cc",
+    "util/Vector3D.cc", "util/Vector3DHemeLb.cc", "util/UnitConverter.cc", "util/utilityFunctions.cc", "util/Matrix3D.cc",
+    "lb/iolets/BoundaryValues.cc", "lb/iolets/BoundaryComms.cc", "lb/iolets/BoundaryCommunicator.cc",
+    "lb/iolets/InOutLet.cc", "lb/iolets/InOutLetCosine.cc", "lb/iolets/InOutLetVelocity.cc",
+    "lb/iolets/InOutLetParabolicVelocity.cc", "lb/SimulationState.cc", "lb/MacroscopicPropertyCache.cc",
+    "reporting/Timers.cc"]
 XTR_REF_SRCS = ["util/Vector3D.cc", "extraction/GeometrySelector.cc", "extraction/WholeGeometrySelector.cc",
                 "extraction/GeometrySurfaceSelector.cc", "extraction/PlaneGeometrySelector.cc",
                 "extraction/StraightLineGeometrySelector.cc", "extraction/SurfacePointSelector.cc"]
@@ -72,6 +86,30 @@ def build_host_binaries(verbose=False):
     xtr_src = os.path.join(ROOT, "tests", "host_xtr_run.cc")
     if _stale(xtr, [xtr_src, mock_src, os.path.join(host, "extraction", "GpuPropertyEncoder.h"), deps[1], os.path.abspath(__file__)]):
         subprocess.run(common + [xtr_src, mock_src] + [os.path.join(REF, s) for s in XTR_REF_SRCS] + ["-o", xtr], check=True)
+    # the reference's own lb::LBM driving the GPU policy classes (recording ABI, emulated ranks)
+    real_lbm = os.path.join(BUILD, "libhost_lbm_real.so")
+    real_src = os.path.join(ROOT, "tests", "host_lbm_real.cc")
+    shim_lbm = os.path.join(ROOT, "tests", "host_shim_lbm")
+    oracle = os.path.join(ROOT, "oracle")
+    real_deps = [real_src, mock_src, os.path.join(oracle, "fake_mpi.cc"), os.path.join(oracle, "ref_domain_build.h"),
+                 os.path.join(shim_lbm, "Traits.h"), os.path.join(shim_lbm, "build_info.h"), deps[1], deps[2], deps[3],
+                 os.path.abspath(__file__)]
+    if _stale(real_lbm, real_deps):
+        subprocess.run(["g++", "-std=c++20", "-O1", "-w", "-fPIC", "-shared", "-pthread", "-Wl,--no-undefined",
+                        "-I" + host, "-I" + os.path.join(ROOT, "include"), "-I" + shim_lbm,
+                        "-I" + os.path.join(oracle, "ref_shim_dom"), "-I" + oracle, "-I" + REF, "-o", real_lbm,
+                        real_src, mock_src, os.path.join(oracle, "fake_mpi.cc")]
+                       + [os.path.join(REF, s_) for s_ in REAL_LBM_REF_SRCS], check=True)
+    # the same against the product library (GPU, one rank): results for the oracle
+    real_gpu = os.path.join(BUILD, "libhost_lbm_real_gpu.so")
+    if os.path.exists(lib) and _stale(real_gpu, real_deps + [lib]):
+        subprocess.run(["g++", "-std=c++20", "-O1", "-w", "-fPIC", "-shared", "-pthread", "-DHLB_REAL_ENGINE",
+                        "-I" + host, "-I" + os.path.join(ROOT, "include"), "-I" + shim_lbm,
+                        "-I" + os.path.join(oracle, "ref_shim_dom"), "-I" + oracle, "-I" + REF, "-o", real_gpu,
+                        real_src, os.path.join(oracle, "fake_mpi.cc")]
+                       + [os.path.join(REF, s_) for s_ in REAL_LBM_REF_SRCS]
+                       + ["-L" + os.path.dirname(lib), "-lhemelb_b200", "-Wl,-rpath,$ORIGIN/../../hemelb_b200",
+                          "-Wl,--allow-shlib-undefined"], check=True)
     if verbose:
         print("host binaries in", BUILD)
     return True

@@ -5,12 +5,24 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include "hemelb_b200.h"
 
 struct hlb_gpu_handle { hlb_gpu_config cfg; };
 
 namespace {
+  // one log per process; or, for harnesses whose ranks are threads (tests/host_lbm_real.cc), one per thread:
+  // $HLB_MOCK_LOG.rank<r> once the thread has said which rank it is
+  thread_local int mock_rank = -1;
+  thread_local FILE* mock_fh = nullptr;
   FILE* out() {
+    if (mock_rank >= 0) {
+      if (!mock_fh) {
+        const char* p = getenv("HLB_MOCK_LOG");
+        mock_fh = p ? fopen((std::string(p) + ".rank" + std::to_string(mock_rank)).c_str(), "w") : stderr;
+      }
+      return mock_fh;
+    }
     static FILE* fh = nullptr;
     if (!fh) {
       const char* p = getenv("HLB_MOCK_LOG");
@@ -22,6 +34,11 @@ namespace {
 }
 
 extern "C" {
+void hlb_mock_set_rank(int r) {
+  if (mock_fh && mock_fh != stderr) fclose(mock_fh);
+  mock_fh = nullptr;
+  mock_rank = r;
+}
 const char* hlb_gpu_last_error(void) { return "mock"; }
 int hlb_gpu_device_count(int* n) { *n = 1; return 0; }
 int hlb_gpu_create(const hlb_gpu_config* c, hlb_gpu_t* h) {

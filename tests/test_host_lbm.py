@@ -588,3 +588,116 @@ def test_cxx_property_encoder_translates_the_reference_spec(tmp_path):
     assert log[1:4] == ["xtr_header global=1234 capacity=72", "xtr_encode first=0 n=3 capacity=72", "xtr_destroy"]
     out = r.stdout.splitlines()
     assert out[0] == "sites=3 site_len=24 header_len=72 header0=H records0=R caches=103"
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Code") and not os.path.exists(os.path.join(BUILD, "libhost_lbm_real.so")),
+                    reason="reference checkout absent and no prebuilt tests/_build/libhost_lbm_real.so")
+@pytest.mark.parametrize("name,R,kind", [("cylinder", 1, None), ("cylinder", 2, "slab"), ("tree", 3, "basic"), ("tree", 4, "ragged")])
+def test_the_reference_lbm_itself_drives_the_gpu_classes(tmp_path, name, R, kind):
+    """tests/host_lbm_real.cc: the reference's own lb::LBM<Traits> (lb.h / lb.hpp, unmodified), constructed and
+    stepped as SimulationMaster steps it, over the reference's own geometry::Domain, net::Net, lb::BoundaryValues,
+    SimulationState, LbmParameters and Timers (all compiled unmodified; R ranks = threads over oracle/fake_mpi.cc),
+    with hemelb_b200/host's streamers in the Traits and its FieldData in the reference's place.  Behind the C ABI
+    sits the recording stand-in: on every rank the engine must be created with that rank's tables -- the ones
+    hemelb_b200.domain builds, bit for bit what the reference's Domain holds -- and every time step must be
+    the call sequence of lb.hpp:162-309."""
+    import ctypes as C
+    from hemelb_b200 import geometry as G
+    from tests.test_domain_vs_ref import decomposition
+    build_host_binaries()
+    L = C.CDLL(os.path.join(BUILD, "libhost_lbm_real.so"))
+    geom, Q = geometry(name), 19
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    rank = decomposition(geom, R, kind)
+    doms = build_domains(geom, Q, rank, R)
+    steps, dt = 3, physical_dt(0.8)
+    os.environ["HLB_MOCK_LOG"] = str(tmp_path / "calls.log")
+    try:
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        arrs = [np.ascontiguousarray(geom.coords, np.int32), np.ascontiguousarray(geom.bsite, np.int64),
+                np.ascontiguousarray(geom.btype, np.uint8), np.ascontiguousarray(geom.biolet, np.int32),
+                np.ascontiguousarray(geom.bdist, np.float32), np.ascontiguousarray(geom.bnavail, np.uint8),
+                np.ascontiguousarray(geom.bnormal, np.float32)]
+        bd = np.ascontiguousarray(geom.block_dims, np.int32)
+        rk = None if rank is None else np.ascontiguousarray(rank, np.int32)
+        inr, outr = np.ascontiguousarray(np.stack(inlets)), np.ascontiguousarray(np.stack(outlets))
+        rc = L.hreal_run(R, p(bd), int(geom.block_size), C.c_int64(geom.n_sites), p(arrs[0]), C.c_int64(arrs[1].size),
+                         *[p(a) for a in arrs[1:]], None if rk is None else p(rk), C.c_double(dt), C.c_double(DX),
+                         len(inlets), p(inr), len(outlets), p(outr), C.c_int64(steps), None, None)
+        assert rc == 0
+    finally:
+        del os.environ["HLB_MOCK_LOG"]
+    for r, dom in enumerate(doms):
+        log = open(str(tmp_path / "calls.log") + ".rank%d" % r).read().splitlines()
+        kv = dict(x.split("=") for x in log[0].split()[1:])
+        assert log[0].startswith("create ")
+        assert (int(kv["lattice"]), int(kv["kernel"]), int(kv["wall"]), int(kv["inlet"]), int(kv["outlet"])) == (19, 0, 1, 0, 0)
+        assert float(kv["tau"]) == reference_tau(dt)
+        assert (int(kv["rank"]), int(kv["nranks"]), int(kv["n_sites"]), int(kv["shared"])) == (r, R, dom.N, dom.totalSharedFs)
+        assert [int(x) for x in kv["mid"].split(",")] == [int(x) for x in dom.mid]
+        assert [int(x) for x in kv["edge"].split(",")] == [int(x) for x in dom.edge]
+        assert int(kv["neighbours"]) == dom.procs.shape[0]
+        build = log[:log.index("finalise") + 1]
+        assert build[1] == "set_neighbour_indices 0 %d first=%d" % (dom.N, int(dom.neighbour_indices(0, 1)[0]))
+        if dom.procs.shape[0]:
+            assert "set_neighbours " + " ".join("%d:%d:%d" % tuple(int(x) for x in row) for row in dom.procs) in build
+            w = int((np.arange(1, dom.totalSharedFs + 1, dtype=np.int64) * dom.streamingIndices).sum())
+            assert "set_streaming_indices weighted_sum=%d" % w in build
+        assert "set_site_coords 0 %d" % dom.N in build
+        # (the rank that owns the boundary-condition task keeps every iolet; the table always has them all)
+        assert any(ln.startswith("set_iolets 0 %d kind0=0 " % len(inlets)) for ln in build)
+        assert any(ln.startswith("set_iolets 1 %d kind0=0 " % len(outlets)) for ln in build)
+        got = [ln for ln in log if ln not in build and not ln.startswith("set_f ")]
+        assert got[-1] == "destroy"
+        got = got[:-1]
+        if R > 1:  # the NCCL id travelled over the reference's own communicator (MpiCommunicator::Broadcast)
+            boot = [ln for ln in got if ln.startswith("comm_")]
+            assert boot == ["comm_init"], boot
+            got = [ln for ln in got if not ln.startswith("comm_")]
+        want_calls = expected_calls(dom, steps, len(inlets), len(outlets), 0)
+        assert len(got) == len(want_calls), (r, len(got), len(want_calls))
+        for g_, w_ in zip(got, want_calls):
+            if isinstance(w_, tuple):
+                parts = g_.split()
+                assert parts[0] == "set_step_scalars" and parts[1] == "t=%d" % w_[1] and parts[2] == "mask=%d" % w_[2], g_
+                assert len(parts) == 3 + len(inlets) + len(outlets)
+            else:
+                assert g_ == w_, (r, g_, w_)
+
+
+@pytest.mark.gpu
+def test_the_reference_lbm_itself_on_the_gpu_matches_the_oracle():
+    """The same harness linked against libhemelb_b200.so: the reference's lb::LBM over its own Domain, net::Net and
+    BoundaryValues steps the engine on the GPU; the distributions after five steps equal the oracle's (1e-13)."""
+    import ctypes as C
+    lib = os.path.join(BUILD, "libhost_lbm_real_gpu.so")
+    if not os.path.exists(lib):
+        if not os.path.isdir("/root/reference/Code"):
+            pytest.skip("tests/_build/libhost_lbm_real_gpu.so was not prebuilt (needs the reference sources)")
+        build_host_binaries()
+    import oracle as O
+    from hemelb_b200 import capi
+    capi.lib()  # libhemelb_b200.so first: the harness library names it as a dependency
+    L = C.CDLL(lib)
+    geom, Q = geometry("cylinder"), 19
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    dom = build_domains(geom, Q)[0]
+    steps, dt = 5, physical_dt(0.8)
+    f0 = anisotropic_f(dom.N, Q, 0)
+    fin = np.ascontiguousarray(f0[:dom.N * Q])
+    out = np.zeros(dom.N * Q)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    arrs = [np.ascontiguousarray(geom.coords, np.int32), np.ascontiguousarray(geom.bsite, np.int64),
+            np.ascontiguousarray(geom.btype, np.uint8), np.ascontiguousarray(geom.biolet, np.int32),
+            np.ascontiguousarray(geom.bdist, np.float32), np.ascontiguousarray(geom.bnavail, np.uint8),
+            np.ascontiguousarray(geom.bnormal, np.float32)]
+    bd = np.ascontiguousarray(geom.block_dims, np.int32)
+    inr, outr = np.ascontiguousarray(np.stack(inlets)), np.ascontiguousarray(np.stack(outlets))
+    rc = L.hreal_run(1, p(bd), int(geom.block_size), C.c_int64(geom.n_sites), p(arrs[0]), C.c_int64(arrs[1].size),
+                     *[p(a) for a in arrs[1:]], None, C.c_double(dt), C.c_double(DX), len(inlets), p(inr), len(outlets),
+                     p(outr), C.c_int64(steps), p(fin), p(out))
+    assert rc == 0
+    sim = O.OracleSim(O.OracleDomains(geom, Q), "LBGK", "BFL", "NASH", "NASH", tau=reference_tau(dt), inlets=inlets, outlets=outlets)
+    sim.set_f(f0)
+    sim.step(steps)
+    assert np.abs(out - sim.get_f()[:dom.N * Q]).max() <= 1e-13
