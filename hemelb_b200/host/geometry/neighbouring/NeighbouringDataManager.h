@@ -23,7 +23,7 @@
 #include "geometry/neighbouring/NeighbouringDomain.h"
 #include "geometry/neighbouring/RequiredSiteInformation.h"
 #include "net/IteratedAction.h"
-#include "net/mixins/InterfaceDelegationNet.h"
+#include "net/net.h"  // (as the reference's header does: InterfaceDelegationNet.h alone does not stand on its own)
 
 namespace hemelb::geometry::neighbouring
 {

@@ -22,7 +22,8 @@ REF_SRCS = ["net/IteratedAction.cc", "geometry/neighbouring/RequiredSiteInformat
 REAL_LBM_REF_SRCS = [
     "geometry/Domain.cc", "geometry/LookupTree.cc", "geometry/GmyReadResult.cc", "geometry/Block.cc",
     "geometry/BlockTraverser.cc", "geometry/SiteTraverser.cc", "geometry/VolumeTraverser.cc", "geometry/SiteDataBare.cc",
-    "geometry/neighbouring/NeighbouringDomain.cc", "geometry/decomposition/BasicDecomposition.cc",
+    "geometry/neighbouring/NeighbouringDomain.cc", "geometry/neighbouring/RequiredSiteInformation.cc",
+    "geometry/decomposition/BasicDecomposition.cc",
     "net/MpiCommunicator.cc", "net/MpiGroup.cc", "net/IOCommunicator.cc", "net/MpiError.cc", "net/BaseNet.cc",
     "net/IteratedAction.cc", "net/mixins/StoringNet.cc", "net/mixins/pointpoint/SeparatedPointPoint.cc",
     "net/mixins/alltoall/SeparatedAllToAll.cc", "net/mixins/gathers/SeparatedGathers.cc",

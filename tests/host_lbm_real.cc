@@ -23,6 +23,7 @@
 #include "debug/Debugger.h"
 #include "geometry/Domain.h"
 #include "geometry/FieldData.h"  // hemelb_b200/host
+#include "geometry/neighbouring/NeighbouringDataManager.h"  // hemelb_b200/host
 #include "lb/lb.hpp"
 #include "lb/iolets/BoundaryValues.h"
 #include "lb/iolets/InOutLetCosine.h"
@@ -75,6 +76,7 @@ namespace {
     int nIn = 0, nOut = 0;
     const double *inRec = nullptr, *outRec = nullptr;  // HLB_IOLET_RECORD_DOUBLES per iolet, lattice units
     int64_t steps = 0;
+    int wall = 1;                // HLB_WALL_BFL, or HLB_WALL_GZS: GuoZhengShi walls + the NeighbouringDataManager
     const double* f0 = nullptr;  // rank 0's initial distributions (N * Q, the Domain's site order) or null: 0.05 everywhere
     double* fOut = nullptr;      // rank 0's distributions after the last step, or null
   };
@@ -96,11 +98,16 @@ namespace {
     return out;
   }
 
-  void rank_body(int rank, void* arg) {
-    const Job& job = *static_cast<const Job*>(arg);
+  // tests/host_shim_lbm/Traits.h: D3Q19 LBGK + the gpu:: streamers (BFL, Nash) by default
+  using BflTraits = hemelb::Traits<>;
+  using GzsTraits = hemelb::Traits<lb::D3Q19, lb::LBGK, lb::Normal, lb::gpu::Bulk,
+                                   lb::gpu::Wall<lb::gpu::GuoZhengShi>::template type,
+                                   lb::gpu::Inlet<lb::gpu::NashZerothOrderPressure>::template type,
+                                   lb::gpu::Outlet<lb::gpu::NashZerothOrderPressure>::template type>;
+
+  template <class TraitsT> void run_rank(int rank, const Job& job) {
     hlb_mock_set_rank(rank);
-    using TraitsT = hemelb::Traits<>;  // tests/host_shim_lbm/Traits.h: D3Q19 LBGK + the gpu:: streamers (BFL, Nash)
-    using Lattice = TraitsT::Lattice;
+    using Lattice = typename TraitsT::Lattice;
     auto const& info = Lattice::GetLatticeInfo();
     net::IOCommunicator comms{net::MpiCommunicator::World()};
     {
@@ -117,8 +124,17 @@ namespace {
       reporting::Timers timers(comms);
       net::Net net(comms);
 
-      lb::LBM<TraitsT> lbm(params, &net, &fd, &state, timers, nullptr);
+      // configuration/SimBuilder.h:153-160: the manager exists before the LBM, whose streamers register
+      // their needs with it (GuoZhengShi); :235-236 shares them once everything is constructed
+      std::unique_ptr<geometry::neighbouring::NeighbouringDataManager> ndm;
+      if (job.wall == HLB_WALL_GZS)
+        ndm = std::make_unique<geometry::neighbouring::NeighbouringDataManager>(fd, fd.GetNeighbouringData(), net);
+      lb::LBM<TraitsT> lbm(params, &net, &fd, &state, timers, ndm.get());
       lbm.Initialise(&inletValues, &outletValues);
+      if (ndm) {
+        ndm->ShareNeeds();
+        ndm->TransferNonFieldDependentInformation();
+      }
 
       // an initial condition written through the host view, as lb::InitialCondition does
       const site_t n = dom->GetLocalFluidSiteCount() * Lattice::NUMVECTORS;
@@ -131,6 +147,7 @@ namespace {
       // PreReceive, PostReceive, EndIteration (Code/net/phased/StepManager.cc); SimulationMaster then swaps
       // the arrays and advances the state (SimulationMaster.impl.h:218-223)
       for (int64_t s = 0; s < job.steps; ++s) {
+        if (ndm) ndm->RequestComms();  // phase 0
         inletValues.RequestComms();
         outletValues.RequestComms();
         lbm.RequestComms();
@@ -150,13 +167,19 @@ namespace {
     }  // (the Domain's windows are freed collectively here)
     hlb_mock_set_rank(-1);
   }
+
+  void rank_body(int rank, void* arg) {
+    const Job& job = *static_cast<const Job*>(arg);
+    if (job.wall == HLB_WALL_GZS) run_rank<GzsTraits>(rank, job);
+    else run_rank<BflTraits>(rank, job);
+  }
 }
 
 extern "C" int hreal_run(int R, const int32_t* blockDims, int blockSize, int64_t N, const int32_t* coords, int64_t nb,
                          const int64_t* bsite, const uint8_t* btype, const int32_t* biolet, const float* bdist,
                          const uint8_t* bnavail, const float* bnormal, const int32_t* siteRank, double dt, double dx,
                          int nIn, const double* inRec, int nOut, const double* outRec, int64_t steps, const double* f0,
-                         double* fOut) {
+                         double* fOut, int wall) {
   Job job;
   job.g.blockSize = blockSize;
   for (int k = 0; k < 3; ++k) job.g.bd[k] = blockDims[k];
@@ -179,6 +202,7 @@ extern "C" int hreal_run(int R, const int32_t* blockDims, int blockSize, int64_t
   job.steps = steps;
   job.f0 = f0;
   job.fOut = fOut;
+  job.wall = wall;
   fakempi_run(R, rank_body, &job);
   return 0;
 }

@@ -623,7 +623,7 @@ def test_the_reference_lbm_itself_drives_the_gpu_classes(tmp_path, name, R, kind
         inr, outr = np.ascontiguousarray(np.stack(inlets)), np.ascontiguousarray(np.stack(outlets))
         rc = L.hreal_run(R, p(bd), int(geom.block_size), C.c_int64(geom.n_sites), p(arrs[0]), C.c_int64(arrs[1].size),
                          *[p(a) for a in arrs[1:]], None if rk is None else p(rk), C.c_double(dt), C.c_double(DX),
-                         len(inlets), p(inr), len(outlets), p(outr), C.c_int64(steps), None, None)
+                         len(inlets), p(inr), len(outlets), p(outr), C.c_int64(steps), None, None, 1)
         assert rc == 0
     finally:
         del os.environ["HLB_MOCK_LOG"]
@@ -695,9 +695,79 @@ def test_the_reference_lbm_itself_on_the_gpu_matches_the_oracle():
     inr, outr = np.ascontiguousarray(np.stack(inlets)), np.ascontiguousarray(np.stack(outlets))
     rc = L.hreal_run(1, p(bd), int(geom.block_size), C.c_int64(geom.n_sites), p(arrs[0]), C.c_int64(arrs[1].size),
                      *[p(a) for a in arrs[1:]], None, C.c_double(dt), C.c_double(DX), len(inlets), p(inr), len(outlets),
-                     p(outr), C.c_int64(steps), p(fin), p(out))
+                     p(outr), C.c_int64(steps), p(fin), p(out), 1)
     assert rc == 0
     sim = O.OracleSim(O.OracleDomains(geom, Q), "LBGK", "BFL", "NASH", "NASH", tau=reference_tau(dt), inlets=inlets, outlets=outlets)
     sim.set_f(f0)
     sim.step(steps)
     assert np.abs(out - sim.get_f()[:dom.N * Q]).max() <= 1e-13
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Code") and not os.path.exists(os.path.join(BUILD, "libhost_lbm_real.so")),
+                    reason="reference checkout absent and no prebuilt tests/_build/libhost_lbm_real.so")
+@pytest.mark.parametrize("R", (2, 3))
+def test_the_reference_lbm_with_guo_zheng_shi_walls_across_ranks(tmp_path, R):
+    """The same harness with GuoZhengShi walls: the streamers' constructors ask the reference's own Domain which rank
+    owns the neighbour of every extrapolating wall link (Domain::GetProcIdFromGlobalCoords -> the
+    DistributedStore's one-sided windows) and register the remote ones with hemelb_b200/host's
+    NeighbouringDataManager, whose ShareNeeds runs over the reference's own net::Net (all-to-all + point-to-point).
+    Every rank's engine must be given the link and serve lists of the Python mirror, and the site halo must be
+    exchanged once per time step, before the step's first range."""
+    import ctypes as C
+    from hemelb_b200 import geometry as G
+    from hemelb_b200.domain import DomainBuilder
+    build_host_binaries()
+    L = C.CDLL(os.path.join(BUILD, "libhost_lbm_real.so"))
+    geom, Q = geometry("cylinder_long"), 19
+    ros = G.slab_decomposition(geom, R)
+    builder = DomainBuilder(geom, Q, ros, R)
+    doms = builder.domains
+    need, serve = builder.gzs_site_halo()
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    steps, dt = 3, physical_dt(0.8)
+    os.environ["HLB_MOCK_LOG"] = str(tmp_path / "calls.log")
+    try:
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        arrs = [np.ascontiguousarray(geom.coords, np.int32), np.ascontiguousarray(geom.bsite, np.int64),
+                np.ascontiguousarray(geom.btype, np.uint8), np.ascontiguousarray(geom.biolet, np.int32),
+                np.ascontiguousarray(geom.bdist, np.float32), np.ascontiguousarray(geom.bnavail, np.uint8),
+                np.ascontiguousarray(geom.bnormal, np.float32)]
+        bd = np.ascontiguousarray(geom.block_dims, np.int32)
+        rk = np.ascontiguousarray(ros, np.int32)
+        inr, outr = np.ascontiguousarray(np.stack(inlets)), np.ascontiguousarray(np.stack(outlets))
+        rc = L.hreal_run(R, p(bd), int(geom.block_size), C.c_int64(geom.n_sites), p(arrs[0]), C.c_int64(arrs[1].size),
+                         *[p(a) for a in arrs[1:]], p(rk), C.c_double(dt), C.c_double(DX), len(inlets), p(inr),
+                         len(outlets), p(outr), C.c_int64(steps), None, None, 2)
+        assert rc == 0
+    finally:
+        del os.environ["HLB_MOCK_LOG"]
+    ext = geom.block_dims.astype(np.int64) * geom.block_size
+    total_links = 0
+    for r, dom in enumerate(doms):
+        log = open(str(tmp_path / "calls.log") + ".rank%d" % r).read().splitlines()
+        assert " wall=2 " in log[0]
+        build = log[:log.index("finalise") + 1]
+        got = [ln for ln in build if ln.startswith("set_gzs_remote ")]
+        nd = need[r]
+        total_links += nd.shape[0]
+        if nd.shape[0]:
+            rows = [tuple(int(v) for v in x.split(":")) for x in got[0].split()[2:]]
+            assert sorted(x[:3] for x in rows) == sorted((int(a), int(b), int(c)) for a, b, c, _ in nd)
+            assert [x[2] for x in rows] == sorted(x[2] for x in rows)  # grouped by owner rank
+            inp_of = {(int(builder.rank_of_site[i]), int(builder.local_of_input[i])): i for i in range(geom.n_sites)}
+            for site, direction, owner, key in rows:  # the key is the neighbour's global non-contiguous id
+                c = geom.coords[inp_of[(r, site)]].astype(np.int64) + builder.c[direction]
+                assert key == (c[0] * ext[1] + c[1]) * ext[2] + c[2]
+        else:
+            assert not got
+        got = [ln for ln in build if ln.startswith("set_gzs_serve ")]
+        sv = serve[r]
+        if sv.shape[0]:
+            assert sorted(tuple(int(v) for v in x.split(":")) for x in got[0].split()[2:]) == \
+                sorted((int(a), int(b)) for a, b in sv)
+        after = [ln for ln in log[log.index("finalise") + 1:] if not ln.startswith("set_f ") and ln != "comm_init"]
+        assert after.count("exchange_site_halo") == steps
+        for i in [k for k, ln in enumerate(after) if ln == "exchange_site_halo"]:
+            nxt = after[i + 1]
+            assert nxt.startswith("set_step_scalars") or nxt.startswith("stream_and_collide") or nxt == "request_comms"
+    assert total_links > 0
