@@ -18,6 +18,7 @@
 
 #include <map>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 #include "Exception.h"
@@ -68,11 +69,24 @@ namespace hemelb::geometry {
   // names the Domain but not the FieldData; each constructor files its policy here under the
   // Domain, so that the engine -- built when the first range is asked for -- knows the wall and
   // iolet policies of all six.
+  // (one rank per process in a HemeLB build; the lock is for harnesses whose ranks are threads of one
+  // process -- entries are per Domain, and std::map keeps references to them valid)
   inline std::map<const Domain*, GpuPolicy>& GpuPolicies() {
     static std::map<const Domain*, GpuPolicy> all;
     return all;
   }
-  inline GpuPolicy& GpuPolicyFor(const Domain* d) { return GpuPolicies()[d]; }
+  inline std::mutex& GpuPoliciesLock() {
+    static std::mutex lock;
+    return lock;
+  }
+  inline GpuPolicy& GpuPolicyFor(const Domain* d) {
+    std::lock_guard<std::mutex> guard(GpuPoliciesLock());
+    return GpuPolicies()[d];
+  }
+  inline void ForgetGpuPolicy(const Domain* d) {
+    std::lock_guard<std::mutex> guard(GpuPoliciesLock());
+    GpuPolicies().erase(d);
+  }
 
   class FieldData {
   public:
@@ -82,7 +96,7 @@ namespace hemelb::geometry {
         m_domain{d}, m_force(d->GetLocalFluidSiteCount()),
         m_neighbouringFields{std::make_unique<neighbouring::NeighbouringFieldData>(d->neighbouringData)} {}
 
-    ~FieldData() { if (m_gpu) hlb_gpu_destroy(m_gpu); GpuPolicies().erase(m_domain.get()); }
+    ~FieldData() { if (m_gpu) hlb_gpu_destroy(m_gpu); ForgetGpuPolicy(m_domain.get()); }
     FieldData(FieldData const&) = delete;
 
     domain_type& GetDomain() { return *m_domain; }

@@ -96,8 +96,10 @@ def build_host_binaries(verbose=False):
                  os.path.join(shim_lbm, "Traits.h"), os.path.join(shim_lbm, "build_info.h"), deps[1], deps[2], deps[3],
                  os.path.abspath(__file__)]
     if _stale(real_lbm, real_deps):
+        # (-Bsymbolic: oracle/_ref/libhemelb_refdom.so, which a test process may have loaded before, defines the
+        # same stand-in MPI and reference symbols with a state of its own)
         subprocess.run(["g++", "-std=c++20", "-O1", "-w", "-fPIC", "-shared", "-pthread", "-Wl,--no-undefined",
-                        "-I" + host, "-I" + os.path.join(ROOT, "include"), "-I" + shim_lbm,
+                        "-Wl,-Bsymbolic", "-I" + host, "-I" + os.path.join(ROOT, "include"), "-I" + shim_lbm,
                         "-I" + os.path.join(oracle, "ref_shim_dom"), "-I" + oracle, "-I" + REF, "-o", real_lbm,
                         real_src, mock_src, os.path.join(oracle, "fake_mpi.cc")]
                        + [os.path.join(REF, s_) for s_ in REAL_LBM_REF_SRCS], check=True)
@@ -105,7 +107,7 @@ def build_host_binaries(verbose=False):
     real_gpu = os.path.join(BUILD, "libhost_lbm_real_gpu.so")
     if os.path.exists(lib) and _stale(real_gpu, real_deps + [lib]):
         subprocess.run(["g++", "-std=c++20", "-O1", "-w", "-fPIC", "-shared", "-pthread", "-DHLB_REAL_ENGINE",
-                        "-I" + host, "-I" + os.path.join(ROOT, "include"), "-I" + shim_lbm,
+                        "-Wl,-Bsymbolic", "-I" + host, "-I" + os.path.join(ROOT, "include"), "-I" + shim_lbm,
                         "-I" + os.path.join(oracle, "ref_shim_dom"), "-I" + oracle, "-I" + REF, "-o", real_gpu,
                         real_src, os.path.join(oracle, "fake_mpi.cc")]
                        + [os.path.join(REF, s_) for s_ in REAL_LBM_REF_SRCS]
