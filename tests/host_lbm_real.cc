@@ -25,6 +25,9 @@
 #include "geometry/FieldData.h"  // hemelb_b200/host
 #include "geometry/neighbouring/NeighbouringDataManager.h"  // hemelb_b200/host
 #include "lb/lb.hpp"
+#include "lb/IncompressibilityChecker.hpp"  // hemelb_b200/host, over the reference's own net::PhasedBroadcastRegular
+#include "lb/StabilityTester.h"             // hemelb_b200/host, likewise
+#include "configuration/MonitoringConfig.h"
 #include "lb/iolets/BoundaryValues.h"
 #include "lb/iolets/InOutLetCosine.h"
 #include "lb/SimulationState.h"
@@ -76,6 +79,8 @@ namespace {
     int nIn = 0, nOut = 0;
     const double *inRec = nullptr, *outRec = nullptr;  // HLB_IOLET_RECORD_DOUBLES per iolet, lattice units
     int64_t steps = 0;
+    int monitors = 0;            // 1: an lb::StabilityTester and an lb::IncompressibilityChecker are actions of every step
+    double* monitorOut = nullptr;  // per rank {stability, smallest density, largest density, largest speed, available}
     int wall = 1;                // HLB_WALL_BFL, or HLB_WALL_GZS: GuoZhengShi walls + the NeighbouringDataManager
     const double* f0 = nullptr;  // rank 0's initial distributions (N * Q, the Domain's site order) or null: 0.05 everywhere
     double* fOut = nullptr;      // rank 0's distributions after the last step, or null
@@ -136,6 +141,30 @@ namespace {
         ndm->TransferNonFieldDependentInformation();
       }
 
+      // configuration/SimBuilder.h:207-226: the monitors, actions of the same step manager
+      using Checker = lb::IncompressibilityChecker<net::PhasedBroadcastRegular<>>;
+      // (with the convergence check on: without it the root of the tree, which never looks at sites of its own,
+      // hands down UndefinedStability for a stable run -- StabilityTester.h:192-239 -- and there is nothing to see)
+      configuration::MonitoringConfig monitoring;
+      monitoring.doConvergenceCheck = true;
+      monitoring.convergenceVariable = extraction::source::Velocity{};
+      monitoring.convergenceReferenceValue = 0.01;
+      monitoring.convergenceRelativeTolerance = 1e-9;
+      std::unique_ptr<lb::StabilityTester<Lattice>> tester;
+      std::unique_ptr<Checker> checker;
+      if (job.monitors) {
+        tester = std::make_unique<lb::StabilityTester<Lattice>>(
+            std::shared_ptr<const geometry::FieldData>(&fd, [](const geometry::FieldData*) {}), &net, &state, timers, monitoring);
+        checker = std::make_unique<Checker>(dom.get(), &net, &state, lbm.GetPropertyCache(), timers, 0.05);
+      }
+      std::vector<net::IteratedAction*> actions;
+      if (ndm) actions.push_back(ndm.get());
+      actions.push_back(&inletValues);
+      actions.push_back(&outletValues);
+      actions.push_back(&lbm);
+      if (tester) actions.push_back(tester.get());
+      if (checker) actions.push_back(checker.get());
+
       // an initial condition written through the host view, as lb::InitialCondition does
       const site_t n = dom->GetLocalFluidSiteCount() * Lattice::NUMVECTORS;
       for (site_t i = 0; i < n; ++i) {
@@ -147,18 +176,24 @@ namespace {
       // PreReceive, PostReceive, EndIteration (Code/net/phased/StepManager.cc); SimulationMaster then swaps
       // the arrays and advances the state (SimulationMaster.impl.h:218-223)
       for (int64_t s = 0; s < job.steps; ++s) {
-        if (ndm) ndm->RequestComms();  // phase 0
-        inletValues.RequestComms();
-        outletValues.RequestComms();
-        lbm.RequestComms();
-        lbm.PreSend();
-        lbm.PreReceive();
-        lbm.PostReceive();
-        inletValues.EndIteration();
-        outletValues.EndIteration();
-        lbm.EndIteration();
+        for (auto* a : actions) a->RequestComms();
+        net.Dispatch();  // (one phase here: the step manager sends, receives and waits between the calls below)
+        for (auto* a : actions) a->PreSend();
+        for (auto* a : actions) a->PreReceive();
+        for (auto* a : actions) a->PostReceive();
+        for (auto* a : actions) a->EndIteration();
         fd.SwapOldAndNew();
         state.Increment();
+      }
+      if (job.monitorOut) {
+        double* o = job.monitorOut + 5 * rank;
+        o[0] = (double)state.GetStability();
+        o[4] = checker && checker->AreDensitiesAvailable() ? 1.0 : 0.0;
+        if (o[4] != 0.0) {
+          o[1] = checker->GetGlobalSmallestDensity();
+          o[2] = checker->GetGlobalLargestDensity();
+          o[3] = checker->GetGlobalLargestVelocityMagnitude();
+        }
       }
       if (job.fOut && rank == 0) {
         const distribn_t* f = const_cast<geometry::FieldData const&>(fd).GetFOld(0);
@@ -179,7 +214,7 @@ extern "C" int hreal_run(int R, const int32_t* blockDims, int blockSize, int64_t
                          const int64_t* bsite, const uint8_t* btype, const int32_t* biolet, const float* bdist,
                          const uint8_t* bnavail, const float* bnormal, const int32_t* siteRank, double dt, double dx,
                          int nIn, const double* inRec, int nOut, const double* outRec, int64_t steps, const double* f0,
-                         double* fOut, int wall) {
+                         double* fOut, int wall, int monitors, double* monitorOut) {
   Job job;
   job.g.blockSize = blockSize;
   for (int k = 0; k < 3; ++k) job.g.bd[k] = blockDims[k];
@@ -203,6 +238,8 @@ extern "C" int hreal_run(int R, const int32_t* blockDims, int blockSize, int64_t
   job.f0 = f0;
   job.fOut = fOut;
   job.wall = wall;
+  job.monitors = monitors;
+  job.monitorOut = monitorOut;
   fakempi_run(R, rank_body, &job);
   return 0;
 }

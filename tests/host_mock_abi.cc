@@ -115,13 +115,15 @@ int hlb_gpu_stability(hlb_gpu_t, int conv, double* out2) {
   return 0;
 }
 int hlb_gpu_monitor(hlb_gpu_t, double* out4) {
-  static int calls = 0;  // a density range that widens with every call, as a run's extrema would
+  static int calls = 0;  // one process per rank: a density range that widens with every call, as a run's extrema would
   ++calls;
   fprintf(out(), "monitor\n");
+  // ranks as threads: extrema that tell the ranks apart, so that a test can see whose reached the root
+  const int k = mock_rank >= 0 ? mock_rank + 1 : calls;
   out4[0] = 0.01;
-  out4[1] = 1.0 - 0.001 * calls;
-  out4[2] = 1.0 + 0.002 * calls;
-  out4[3] = 0.003 * calls;
+  out4[1] = 1.0 - 0.001 * k;
+  out4[2] = 1.0 + 0.002 * k;
+  out4[3] = 0.003 * k;
   return 0;
 }
 int hlb_gpu_edge_done(hlb_gpu_t) { fprintf(out(), "edge_done\n"); return 0; }

@@ -623,7 +623,7 @@ def test_the_reference_lbm_itself_drives_the_gpu_classes(tmp_path, name, R, kind
         inr, outr = np.ascontiguousarray(np.stack(inlets)), np.ascontiguousarray(np.stack(outlets))
         rc = L.hreal_run(R, p(bd), int(geom.block_size), C.c_int64(geom.n_sites), p(arrs[0]), C.c_int64(arrs[1].size),
                          *[p(a) for a in arrs[1:]], None if rk is None else p(rk), C.c_double(dt), C.c_double(DX),
-                         len(inlets), p(inr), len(outlets), p(outr), C.c_int64(steps), None, None, 1)
+                         len(inlets), p(inr), len(outlets), p(outr), C.c_int64(steps), None, None, 1, 0, None)
         assert rc == 0
     finally:
         del os.environ["HLB_MOCK_LOG"]
@@ -695,7 +695,7 @@ def test_the_reference_lbm_itself_on_the_gpu_matches_the_oracle():
     inr, outr = np.ascontiguousarray(np.stack(inlets)), np.ascontiguousarray(np.stack(outlets))
     rc = L.hreal_run(1, p(bd), int(geom.block_size), C.c_int64(geom.n_sites), p(arrs[0]), C.c_int64(arrs[1].size),
                      *[p(a) for a in arrs[1:]], None, C.c_double(dt), C.c_double(DX), len(inlets), p(inr), len(outlets),
-                     p(outr), C.c_int64(steps), p(fin), p(out), 1)
+                     p(outr), C.c_int64(steps), p(fin), p(out), 1, 0, None)
     assert rc == 0
     sim = O.OracleSim(O.OracleDomains(geom, Q), "LBGK", "BFL", "NASH", "NASH", tau=reference_tau(dt), inlets=inlets, outlets=outlets)
     sim.set_f(f0)
@@ -737,7 +737,7 @@ def test_the_reference_lbm_with_guo_zheng_shi_walls_across_ranks(tmp_path, R):
         inr, outr = np.ascontiguousarray(np.stack(inlets)), np.ascontiguousarray(np.stack(outlets))
         rc = L.hreal_run(R, p(bd), int(geom.block_size), C.c_int64(geom.n_sites), p(arrs[0]), C.c_int64(arrs[1].size),
                          *[p(a) for a in arrs[1:]], p(rk), C.c_double(dt), C.c_double(DX), len(inlets), p(inr),
-                         len(outlets), p(outr), C.c_int64(steps), None, None, 2)
+                         len(outlets), p(outr), C.c_int64(steps), None, None, 2, 0, None)
         assert rc == 0
     finally:
         del os.environ["HLB_MOCK_LOG"]
@@ -771,3 +771,52 @@ def test_the_reference_lbm_with_guo_zheng_shi_walls_across_ranks(tmp_path, R):
             nxt = after[i + 1]
             assert nxt.startswith("set_step_scalars") or nxt.startswith("stream_and_collide") or nxt == "request_comms"
     assert total_links > 0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Code") and not os.path.exists(os.path.join(BUILD, "libhost_lbm_real.so")),
+                    reason="reference checkout absent and no prebuilt tests/_build/libhost_lbm_real.so")
+@pytest.mark.parametrize("R", (2, 3, 5))
+def test_the_monitor_stand_ins_over_the_reference_broadcast_tree(tmp_path, R):
+    """hemelb_b200/host's lb::StabilityTester and lb::IncompressibilityChecker as actions beside the reference's
+    lb::LBM, their up-and-down passes carried by the reference's own net::PhasedBroadcastRegular / PhasedBroadcast
+    over its net::Net (R ranks as threads).  The recording ABI gives every rank extrema of its own
+    ([1 - 0.001 (r + 1), 1 + 0.002 (r + 1)], speed 0.003 (r + 1)): after a few cycles every rank must hold the
+    extrema of all of them, and a stable verdict."""
+    import ctypes as C
+    from hemelb_b200 import geometry as G
+    build_host_binaries()
+    L = C.CDLL(os.path.join(BUILD, "libhost_lbm_real.so"))
+    geom, Q = geometry("tree"), 19
+    inlets, outlets = iolets_for(geom, "NASH", "NASH")
+    rank = None if R == 1 else G.basic_decomposition(geom, R)
+    steps, dt = 16, physical_dt(0.8)
+    got = np.zeros(5 * R)
+    os.environ["HLB_MOCK_LOG"] = str(tmp_path / "calls.log")
+    try:
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        arrs = [np.ascontiguousarray(geom.coords, np.int32), np.ascontiguousarray(geom.bsite, np.int64),
+                np.ascontiguousarray(geom.btype, np.uint8), np.ascontiguousarray(geom.biolet, np.int32),
+                np.ascontiguousarray(geom.bdist, np.float32), np.ascontiguousarray(geom.bnavail, np.uint8),
+                np.ascontiguousarray(geom.bnormal, np.float32)]
+        bd = np.ascontiguousarray(geom.block_dims, np.int32)
+        rk = None if rank is None else np.ascontiguousarray(rank, np.int32)
+        inr, outr = np.ascontiguousarray(np.stack(inlets)), np.ascontiguousarray(np.stack(outlets))
+        rc = L.hreal_run(R, p(bd), int(geom.block_size), C.c_int64(geom.n_sites), p(arrs[0]), C.c_int64(arrs[1].size),
+                         *[p(a) for a in arrs[1:]], None if rk is None else p(rk), C.c_double(dt), C.c_double(DX),
+                         len(inlets), p(inr), len(outlets), p(outr), C.c_int64(steps), None, None, 1, 1, p(got))
+        assert rc == 0
+    finally:
+        del os.environ["HLB_MOCK_LOG"]
+    got = got.reshape(R, 5)
+    for r in range(R):
+        assert got[r, 4] == 1.0, "no densities on rank %d after %d steps" % (r, steps)
+        # lb::Stable: the recording ABI reports |du| = 1e-3 against a tolerance of 1e-9 x 0.01 -- stable, not converged
+        assert got[r, 0] == 1.0
+        # (as in the reference, the tracker's range always contains the reference density 1)
+        assert got[r, 1] == 1.0 - 0.001 * R and got[r, 2] == 1.0 + 0.002 * R and got[r, 3] == 0.003 * R, got[r]
+        log = open(str(tmp_path / "calls.log") + ".rank%d" % r).read().splitlines()
+        assert not [ln for ln in log if ln.startswith("get_cache") or ln.startswith("get_f")]
+        # as in the reference, the root of the tree never looks at sites of its own (PostSendToParent is for nodes
+        # that have a parent, PhasedBroadcastRegular.h:142-158): only the other ranks ask their engines
+        asked = log.count("monitor") >= 1 and any(ln.startswith("stability ") for ln in log)
+        assert asked == (r > 0)
