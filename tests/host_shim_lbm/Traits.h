@@ -1,7 +1,11 @@
-// Traits.h for the real-lb::LBM harness: hemelb::Traits as Code/Traits.h declares it -- same template
-// parameters, same member names -- but without the defaults that drag in every streamer of the reference
-// (lb/Streamers.h -> JunkYang.h needs boost::ublas; redblood/stencil.h).  A HemeLB build keeps its own
-// Traits.h and names the gpu:: streamers in an instantiation.  Test infrastructure.
+// Test infrastructure: Traits.h for the harness around the reference's own lb::LBM (tests/host_lbm_real.cc).
+//
+// lb::LBM<TRAITS> reads ten member types off its TRAITS (Lattice, Kernel, Collision, Streamer, WallBoundary,
+// InletBoundary, OutletBoundary, WallInletBoundary, WallOutletBoundary, Stencil).  The reference's Traits.h supplies
+// them from seven template template parameters whose *defaults* pull in every streamer it has (lb/Streamers.h ->
+// JunkYang.h needs boost::ublas) and redblood/stencil.h; this one takes the same parameters in the same order,
+// defaults them to D3Q19 / LBGK / Normal and the gpu:: streamers, and includes only what those need.  A HemeLB
+// build keeps its own Traits.h and names the gpu:: streamers in an instantiation.
 #pragma once
 #include "lb/lattices/D3Q15.h"
 #include "lb/lattices/D3Q19.h"
@@ -14,30 +18,28 @@
 #include "lb/streamers/StreamerTypeFactory.h"
 #include "lb/streamers/GpuStreamers.h"
 
-namespace hemelb
-{
-  namespace redblood::stencil { struct FourPoint; }
-  template <
-      typename LATTICE = lb::D3Q19,
-      template<lb::lattice_type> class KERNEL = lb::LBGK,
-      template<class> class COLLISION = lb::Normal,
-      template<class> class STREAMER = lb::gpu::Bulk,
-      template<class> class WALL_BOUNDARY = lb::gpu::Wall<lb::gpu::BouzidiFirdaousLallemand>::template type,
-      template<class> class INLET_BOUNDARY = lb::gpu::Inlet<lb::gpu::NashZerothOrderPressure>::template type,
-      template<class> class OUTLET_BOUNDARY = lb::gpu::Outlet<lb::gpu::NashZerothOrderPressure>::template type,
-      typename STENCIL = redblood::stencil::FourPoint
-  >
-  struct Traits
-  {
-    using Lattice = LATTICE;
-    using Kernel = KERNEL<Lattice>;
-    using Collision = COLLISION<Kernel>;
-    using Streamer = STREAMER<Collision>;
-    using WallBoundary = WALL_BOUNDARY<Collision>;
-    using InletBoundary = INLET_BOUNDARY<Collision>;
-    using OutletBoundary = OUTLET_BOUNDARY<Collision>;
-    using WallInletBoundary = typename lb::CombineWallAndIoletStreamers<WallBoundary, InletBoundary>::type;
-    using WallOutletBoundary = typename lb::CombineWallAndIoletStreamers<WallBoundary, OutletBoundary>::type;
-    using Stencil = STENCIL;
+namespace hemelb {
+  namespace redblood::stencil { struct FourPoint; }  // (named by the last parameter only)
+
+  template <typename L = lb::D3Q19,
+            template <lb::lattice_type> class K = lb::LBGK,
+            template <class> class C = lb::Normal,
+            template <class> class BULK = lb::gpu::Bulk,
+            template <class> class WALL = lb::gpu::Wall<lb::gpu::BouzidiFirdaousLallemand>::template type,
+            template <class> class IN = lb::gpu::Inlet<lb::gpu::NashZerothOrderPressure>::template type,
+            template <class> class OUT = lb::gpu::Outlet<lb::gpu::NashZerothOrderPressure>::template type,
+            typename S = redblood::stencil::FourPoint>
+  struct Traits {
+    typedef L Lattice;
+    typedef K<L> Kernel;
+    typedef C<Kernel> Collision;
+    typedef S Stencil;
+    // the six streamers lb::LBM constructs (lb.h:40-52)
+    typedef BULK<Collision> Streamer;
+    typedef WALL<Collision> WallBoundary;
+    typedef IN<Collision> InletBoundary;
+    typedef OUT<Collision> OutletBoundary;
+    typedef typename lb::CombineWallAndIoletStreamers<WallBoundary, InletBoundary>::type WallInletBoundary;
+    typedef typename lb::CombineWallAndIoletStreamers<WallBoundary, OutletBoundary>::type WallOutletBoundary;
   };
 }
