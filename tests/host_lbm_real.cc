@@ -30,6 +30,7 @@
 #include "configuration/MonitoringConfig.h"
 #include "lb/iolets/BoundaryValues.h"
 #include "lb/iolets/InOutLetCosine.h"
+#include "lb/iolets/InOutLetParabolicVelocity.h"
 #include "lb/SimulationState.h"
 #include "net/net.h"
 #include "reporting/Dict.h"
@@ -79,6 +80,7 @@ namespace {
     int nIn = 0, nOut = 0;
     const double *inRec = nullptr, *outRec = nullptr;  // HLB_IOLET_RECORD_DOUBLES per iolet, lattice units
     int64_t steps = 0;
+    int variant = 0;             // 0: D3Q19 BFL Nash; 1: D3Q15 SBB Nash; 2: D3Q27 BFL Nash; 3: D3Q19 BFL, Ladd velocity inlet
     int monitors = 0;            // 1: an lb::StabilityTester and an lb::IncompressibilityChecker are actions of every step
     double* monitorOut = nullptr;  // per rank {stability, smallest density, largest density, largest speed, available}
     int wall = 1;                // HLB_WALL_BFL, or HLB_WALL_GZS: GuoZhengShi walls + the NeighbouringDataManager
@@ -90,15 +92,25 @@ namespace {
     std::vector<util::clone_ptr<lb::InOutLet>> out;
     for (int i = 0; i < n; ++i) {
       const double* q = rec + (size_t)i * HLB_IOLET_RECORD_DOUBLES;
-      auto c = util::make_clone_ptr<lb::InOutLetCosine>();
-      c->SetDensityMean(q[9]);
-      c->SetDensityAmp(q[10]);
-      c->SetPhase(q[11]);
-      c->SetPeriod(q[12]);
-      c->SetWarmup((unsigned)q[13]);
-      c->SetNormal(util::Vector3D<double>(q[1], q[2], q[3]));
-      c->SetPosition(LatticePosition(q[4], q[5], q[6]));
-      out.emplace_back(std::move(c));
+      if ((int)q[0] == 0) {
+        auto c = util::make_clone_ptr<lb::InOutLetCosine>();
+        c->SetDensityMean(q[9]);
+        c->SetDensityAmp(q[10]);
+        c->SetPhase(q[11]);
+        c->SetPeriod(q[12]);
+        c->SetWarmup((unsigned)q[13]);
+        c->SetNormal(util::Vector3D<double>(q[1], q[2], q[3]));
+        c->SetPosition(LatticePosition(q[4], q[5], q[6]));
+        out.emplace_back(std::move(c));
+      } else {
+        auto v = util::make_clone_ptr<lb::InOutLetParabolicVelocity>();
+        v->SetRadius(q[7]);
+        v->SetMaxSpeed(q[8]);
+        v->SetWarmup((unsigned)q[13]);
+        v->SetNormal(util::Vector3D<double>(q[1], q[2], q[3]));
+        v->SetPosition(LatticePosition(q[4], q[5], q[6]));
+        out.emplace_back(std::move(v));
+      }
     }
     return out;
   }
@@ -109,6 +121,19 @@ namespace {
                                    lb::gpu::Wall<lb::gpu::GuoZhengShi>::template type,
                                    lb::gpu::Inlet<lb::gpu::NashZerothOrderPressure>::template type,
                                    lb::gpu::Outlet<lb::gpu::NashZerothOrderPressure>::template type>;
+  // other lattices and link rules through the same unmodified lb::LBM (Job::variant)
+  using Q15SbbTraits = hemelb::Traits<lb::D3Q15, lb::LBGK, lb::Normal, lb::gpu::Bulk,
+                                      lb::gpu::Wall<lb::gpu::SimpleBounceBack>::template type,
+                                      lb::gpu::Inlet<lb::gpu::NashZerothOrderPressure>::template type,
+                                      lb::gpu::Outlet<lb::gpu::NashZerothOrderPressure>::template type>;
+  using Q27BflTraits = hemelb::Traits<lb::D3Q27, lb::LBGK, lb::Normal, lb::gpu::Bulk,
+                                      lb::gpu::Wall<lb::gpu::BouzidiFirdaousLallemand>::template type,
+                                      lb::gpu::Inlet<lb::gpu::NashZerothOrderPressure>::template type,
+                                      lb::gpu::Outlet<lb::gpu::NashZerothOrderPressure>::template type>;
+  using LaddTraits = hemelb::Traits<lb::D3Q19, lb::LBGK, lb::Normal, lb::gpu::Bulk,
+                                    lb::gpu::Wall<lb::gpu::BouzidiFirdaousLallemand>::template type,
+                                    lb::gpu::Inlet<lb::gpu::LaddIolet>::template type,
+                                    lb::gpu::Outlet<lb::gpu::NashZerothOrderPressure>::template type>;
 
   template <class TraitsT> void run_rank(int rank, const Job& job) {
     hlb_mock_set_rank(rank);
@@ -206,6 +231,9 @@ namespace {
   void rank_body(int rank, void* arg) {
     const Job& job = *static_cast<const Job*>(arg);
     if (job.wall == HLB_WALL_GZS) run_rank<GzsTraits>(rank, job);
+    else if (job.variant == 1) run_rank<Q15SbbTraits>(rank, job);
+    else if (job.variant == 2) run_rank<Q27BflTraits>(rank, job);
+    else if (job.variant == 3) run_rank<LaddTraits>(rank, job);
     else run_rank<BflTraits>(rank, job);
   }
 }
@@ -214,7 +242,7 @@ extern "C" int hreal_run(int R, const int32_t* blockDims, int blockSize, int64_t
                          const int64_t* bsite, const uint8_t* btype, const int32_t* biolet, const float* bdist,
                          const uint8_t* bnavail, const float* bnormal, const int32_t* siteRank, double dt, double dx,
                          int nIn, const double* inRec, int nOut, const double* outRec, int64_t steps, const double* f0,
-                         double* fOut, int wall, int monitors, double* monitorOut) {
+                         double* fOut, int wall, int monitors, double* monitorOut, int variant) {
   Job job;
   job.g.blockSize = blockSize;
   for (int k = 0; k < 3; ++k) job.g.bd[k] = blockDims[k];
@@ -240,6 +268,7 @@ extern "C" int hreal_run(int R, const int32_t* blockDims, int blockSize, int64_t
   job.wall = wall;
   job.monitors = monitors;
   job.monitorOut = monitorOut;
+  job.variant = variant;
   fakempi_run(R, rank_body, &job);
   return 0;
 }

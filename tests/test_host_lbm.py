@@ -623,7 +623,7 @@ def test_the_reference_lbm_itself_drives_the_gpu_classes(tmp_path, name, R, kind
         inr, outr = np.ascontiguousarray(np.stack(inlets)), np.ascontiguousarray(np.stack(outlets))
         rc = L.hreal_run(R, p(bd), int(geom.block_size), C.c_int64(geom.n_sites), p(arrs[0]), C.c_int64(arrs[1].size),
                          *[p(a) for a in arrs[1:]], None if rk is None else p(rk), C.c_double(dt), C.c_double(DX),
-                         len(inlets), p(inr), len(outlets), p(outr), C.c_int64(steps), None, None, 1, 0, None)
+                         len(inlets), p(inr), len(outlets), p(outr), C.c_int64(steps), None, None, 1, 0, None, 0)
         assert rc == 0
     finally:
         del os.environ["HLB_MOCK_LOG"]
@@ -695,7 +695,7 @@ def test_the_reference_lbm_itself_on_the_gpu_matches_the_oracle():
     inr, outr = np.ascontiguousarray(np.stack(inlets)), np.ascontiguousarray(np.stack(outlets))
     rc = L.hreal_run(1, p(bd), int(geom.block_size), C.c_int64(geom.n_sites), p(arrs[0]), C.c_int64(arrs[1].size),
                      *[p(a) for a in arrs[1:]], None, C.c_double(dt), C.c_double(DX), len(inlets), p(inr), len(outlets),
-                     p(outr), C.c_int64(steps), p(fin), p(out), 1, 0, None)
+                     p(outr), C.c_int64(steps), p(fin), p(out), 1, 0, None, 0)
     assert rc == 0
     sim = O.OracleSim(O.OracleDomains(geom, Q), "LBGK", "BFL", "NASH", "NASH", tau=reference_tau(dt), inlets=inlets, outlets=outlets)
     sim.set_f(f0)
@@ -737,7 +737,7 @@ def test_the_reference_lbm_with_guo_zheng_shi_walls_across_ranks(tmp_path, R):
         inr, outr = np.ascontiguousarray(np.stack(inlets)), np.ascontiguousarray(np.stack(outlets))
         rc = L.hreal_run(R, p(bd), int(geom.block_size), C.c_int64(geom.n_sites), p(arrs[0]), C.c_int64(arrs[1].size),
                          *[p(a) for a in arrs[1:]], p(rk), C.c_double(dt), C.c_double(DX), len(inlets), p(inr),
-                         len(outlets), p(outr), C.c_int64(steps), None, None, 2, 0, None)
+                         len(outlets), p(outr), C.c_int64(steps), None, None, 2, 0, None, 0)
         assert rc == 0
     finally:
         del os.environ["HLB_MOCK_LOG"]
@@ -803,7 +803,7 @@ def test_the_monitor_stand_ins_over_the_reference_broadcast_tree(tmp_path, R):
         inr, outr = np.ascontiguousarray(np.stack(inlets)), np.ascontiguousarray(np.stack(outlets))
         rc = L.hreal_run(R, p(bd), int(geom.block_size), C.c_int64(geom.n_sites), p(arrs[0]), C.c_int64(arrs[1].size),
                          *[p(a) for a in arrs[1:]], None if rk is None else p(rk), C.c_double(dt), C.c_double(DX),
-                         len(inlets), p(inr), len(outlets), p(outr), C.c_int64(steps), None, None, 1, 1, p(got))
+                         len(inlets), p(inr), len(outlets), p(outr), C.c_int64(steps), None, None, 1, 1, p(got), 0)
         assert rc == 0
     finally:
         del os.environ["HLB_MOCK_LOG"]
@@ -820,3 +820,59 @@ def test_the_monitor_stand_ins_over_the_reference_broadcast_tree(tmp_path, R):
         # that have a parent, PhasedBroadcastRegular.h:142-158): only the other ranks ask their engines
         asked = log.count("monitor") >= 1 and any(ln.startswith("stability ") for ln in log)
         assert asked == (r > 0)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/Code") and not os.path.exists(os.path.join(BUILD, "libhost_lbm_real.so")),
+                    reason="reference checkout absent and no prebuilt tests/_build/libhost_lbm_real.so")
+@pytest.mark.parametrize("variant,Q,wall,inlet", [(1, 15, "SBB", "NASH"), (2, 27, "BFL", "NASH"), (3, 19, "BFL", "LADD")])
+def test_the_reference_lbm_with_other_lattices_and_link_rules(tmp_path, variant, Q, wall, inlet):
+    """The reference's lb::LBM instantiated with D3Q15 + simple bounce-back, D3Q27 + BFL, and D3Q19 + BFL with a Ladd
+    velocity inlet (the reference's InOutLetParabolicVelocity, warm-up ramp on): two ranks each; the engines are
+    created with those policies and that rank's tables, and stepped in lb.hpp's order."""
+    import ctypes as C
+    from hemelb_b200 import geometry as G
+    build_host_binaries()
+    L = C.CDLL(os.path.join(BUILD, "libhost_lbm_real.so"))
+    geom, R = geometry("tree"), 2
+    inlets, outlets = iolets_for(geom, inlet, "NASH")
+    if inlet == "LADD":
+        inlets[0][13] = 6  # InOutLetParabolicVelocity::SetWarmup
+    rank = G.basic_decomposition(geom, R)
+    doms = build_domains(geom, Q, rank, R)
+    steps, dt = 2, physical_dt(0.8)
+    os.environ["HLB_MOCK_LOG"] = str(tmp_path / "calls.log")
+    try:
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        arrs = [np.ascontiguousarray(geom.coords, np.int32), np.ascontiguousarray(geom.bsite, np.int64),
+                np.ascontiguousarray(geom.btype, np.uint8), np.ascontiguousarray(geom.biolet, np.int32),
+                np.ascontiguousarray(geom.bdist, np.float32), np.ascontiguousarray(geom.bnavail, np.uint8),
+                np.ascontiguousarray(geom.bnormal, np.float32)]
+        bd = np.ascontiguousarray(geom.block_dims, np.int32)
+        rk = np.ascontiguousarray(rank, np.int32)
+        inr, outr = np.ascontiguousarray(np.stack(inlets)), np.ascontiguousarray(np.stack(outlets))
+        rc = L.hreal_run(R, p(bd), int(geom.block_size), C.c_int64(geom.n_sites), p(arrs[0]), C.c_int64(arrs[1].size),
+                         *[p(a) for a in arrs[1:]], p(rk), C.c_double(dt), C.c_double(DX), len(inlets), p(inr),
+                         len(outlets), p(outr), C.c_int64(steps), None, None, WALLS[wall], 0, None, variant)
+        assert rc == 0
+    finally:
+        del os.environ["HLB_MOCK_LOG"]
+    for r, dom in enumerate(doms):
+        log = open(str(tmp_path / "calls.log") + ".rank%d" % r).read().splitlines()
+        kv = dict(x.split("=") for x in log[0].split()[1:])
+        assert (int(kv["lattice"]), int(kv["kernel"]), int(kv["wall"]), int(kv["inlet"]), int(kv["outlet"])) == \
+            (Q, 0, WALLS[wall], IOLETS[inlet], 0)
+        assert (int(kv["n_sites"]), int(kv["shared"])) == (dom.N, dom.totalSharedFs)
+        assert [int(x) for x in kv["mid"].split(",")] == [int(x) for x in dom.mid]
+        assert [int(x) for x in kv["edge"].split(",")] == [int(x) for x in dom.edge]
+        build = log[:log.index("finalise") + 1]
+        assert build[1] == "set_neighbour_indices 0 %d first=%d" % (dom.N, int(dom.neighbour_indices(0, 1)[0]))
+        if inlet == "LADD":  # the warm-up length has no getter: the host classes read it off the ramp
+            assert any(ln.startswith("set_iolets 0 %d kind0=1 " % len(inlets)) and ln.endswith("warmup0=6") for ln in build)
+        got = [ln for ln in log if ln not in build and not ln.startswith("set_f ") and not ln.startswith("comm_")][:-1]
+        want_calls = expected_calls(dom, steps, len(inlets), len(outlets), 0)
+        assert len(got) == len(want_calls)
+        for g_, w_ in zip(got, want_calls):
+            if isinstance(w_, tuple):
+                assert g_.startswith("set_step_scalars t=%d mask=%d" % (w_[1], w_[2]))
+            else:
+                assert g_ == w_, (r, g_, w_)
