@@ -107,6 +107,65 @@ def ref_domain_lib():
     return _refdom[0]
 
 
+_reflbm = []
+
+REF_LBM_VARIANTS = {  # oracle/ref_lbm_driver.cc rank_body: (Q, kernel, wall, inlet, outlet)
+    (19, "LBGK", "BFL", "NASH", "NASH"): 0, (15, "LBGK", "SBB", "NASH", "NASH"): 1, (27, "LBGK", "BFL", "NASH", "NASH"): 2,
+    (19, "LBGK", "BFL", "LADD", "NASH"): 3, (19, "LBGK", "GZS", "NASH", "NASH"): 4, (19, "LBGK", "SBB", "NASH", "NASH"): 5,
+    (19, "LBGK", "GZS", "LADD", "NASH"): 6, (15, "LBGK", "BFL", "NASH", "NASH"): 7, (27, "LBGK", "SBB", "NASH", "NASH"): 8,
+    (19, "MRT", "BFL", "LADD", "LADD"): 9, (15, "MRT", "SBB", "LADD", "LADD"): 10, (19, "LBGK", "BFL", "LADD", "LADD"): 11}
+
+
+def ref_lbm_lib():
+    """oracle/_ref/libhemelb_reflbm.so -- the reference's unmodified lb::LBM<Traits> with its own CPU streamers,
+    FieldData, Domain, NeighbouringDataManager, BoundaryValues, initial condition and StepManager over emulated
+    ranks (oracle/ref_lbm_driver.cc) -- or None when it was not built / shipped."""
+    if not _reflbm:
+        path = os.path.join(HERE, "_ref", "libhemelb_reflbm.so")
+        _reflbm.append(C.CDLL(path) if os.path.exists(path) else None)
+    return _reflbm[0]
+
+
+def ref_lbm_run(geom, Q, wall, inlet, inlets, outlets, dt, dx, steps, sites_per_rank, rank_of_site=None, nranks=1,
+                f0=None, equilibrium=None, kernel="LBGK", outlet="NASH"):
+    """Runs the reference's whole lb::LBM for ``steps`` time steps on ``nranks`` emulated ranks and returns
+    (per-rank f_old after the last swap [N_r * Q each, the Domain's site order], rank 0's iolet densities per step
+    [steps, n_inlets + n_outlets]).  ``sites_per_rank``: the local fluid site counts the caller expects (the driver
+    checks them against the reference Domain's); ``f0``: per-rank initial distributions, or ``equilibrium`` =
+    (rho, (mx, my, mz)) for lb::EquilibriumInitialCondition."""
+    L = ref_lbm_lib()
+    if L is None:
+        raise RuntimeError("oracle/_ref/libhemelb_reflbm.so not built")
+    bd = np.ascontiguousarray(geom.block_dims, np.int32)
+    arrs = [np.ascontiguousarray(geom.coords, np.int32), np.ascontiguousarray(geom.bsite, np.int64),
+            np.ascontiguousarray(geom.btype, np.uint8), np.ascontiguousarray(geom.biolet, np.int32),
+            np.ascontiguousarray(geom.bdist, np.float32), np.ascontiguousarray(geom.bnavail, np.uint8),
+            np.ascontiguousarray(geom.bnormal, np.float32)]
+    rk = None if rank_of_site is None else np.ascontiguousarray(rank_of_site, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    off = np.zeros(nranks + 1, np.int64)
+    off[1:] = np.cumsum(np.asarray(sites_per_rank, np.int64) * Q)
+    fin = None
+    if f0 is not None:
+        fin = np.ascontiguousarray(np.concatenate([np.asarray(f, np.float64)[:int(n) * Q] for f, n in zip(f0, sites_per_rank)]))
+        assert fin.size == off[-1]
+    rho, mom = (1.0, np.zeros(3)) if equilibrium is None else (float(equilibrium[0]), np.ascontiguousarray(equilibrium[1], np.float64))
+    ri, ni = _recs(list(inlets))
+    ro, no = _recs(list(outlets))
+    out = np.zeros(int(off[-1]))
+    n_local = np.zeros(nranks, np.int64)
+    dens = np.zeros((max(steps, 1), ni + no))
+    rc = L.hreflbm_run(nranks, p(bd), int(geom.block_size), C.c_int64(geom.n_sites), p(arrs[0]), C.c_int64(arrs[1].size),
+                       *[p(a) for a in arrs[1:]], None if rk is None else p(rk), C.c_double(dt), C.c_double(dx),
+                       ni, _d(ri), no, _d(ro), C.c_int64(steps), REF_LBM_VARIANTS[(Q, kernel, wall, inlet, outlet)],
+                       0 if equilibrium is None else 1, C.c_double(rho), _d(mom), None if fin is None else _d(fin),
+                       p(off), _d(out), p(n_local), _d(dens))
+    if rc != 0:
+        raise RuntimeError("hreflbm_run failed (%d)" % rc)
+    assert [int(x) for x in n_local] == [int(x) for x in sites_per_rank], (n_local, sites_per_rank)
+    return [out[off[r]:off[r + 1]].copy() for r in range(nranks)], dens
+
+
 class RefDomains:
     """Per-rank tables from the reference's own ``geometry::Domain`` (R emulated ranks).  ``rank_of_site``
     None: the blocks go to ranks by the reference's ``BasicDecomposition`` (``block_rank`` = its answer per
