@@ -264,7 +264,7 @@ def cpu_reference_run(steps, warmup, target_seconds=15.0, sample_sites=REFERENCE
     stepper(steps)
     dtm = time.perf_counter() - t0
     mlups = n_sites * steps / dtm / 1e6
-    sample = "%s (%d sites), D3Q19 LBGK+BFL+Nash, %d steps, %d threads (one emulated rank each, BasicDecomposition), %s build; %s" % (
+    sample = "%s (%d sites), D3Q19 LBGK+BFL+Nash, %d steps, %d threads (one emulated rank each for the whole run, BasicDecomposition, neighbour waits + one barrier per step), %s build; %s" % (
         geom_text, n_sites, steps, cores, "SSE3" if sse3 else "scalar", built)
     return dict(value=mlups, unit="MLUPS", cores=cores, kind=kind, sample=sample, sites=n_sites), dtm / steps * 1e3, steps
 

@@ -116,24 +116,25 @@ REF_LBM_VARIANTS = {  # oracle/ref_lbm_driver.cc rank_body: (Q, kernel, wall, in
     (19, "MRT", "BFL", "LADD", "LADD"): 9, (15, "MRT", "SBB", "LADD", "LADD"): 10, (19, "LBGK", "BFL", "LADD", "LADD"): 11}
 
 
-def ref_lbm_lib():
+def ref_lbm_lib(sse3: bool = False):
     """oracle/_ref/libhemelb_reflbm.so -- the reference's unmodified lb::LBM<Traits> with its own CPU streamers,
     FieldData, Domain, NeighbouringDataManager, BoundaryValues, initial condition and StepManager over emulated
     ranks (oracle/ref_lbm_driver.cc) -- or None when it was not built / shipped."""
-    if not _reflbm:
-        path = os.path.join(HERE, "_ref", "libhemelb_reflbm.so")
+    while len(_reflbm) < 2:
+        path = os.path.join(HERE, "_ref", "libhemelb_reflbm_sse3.so" if _reflbm else "libhemelb_reflbm.so")
         _reflbm.append(C.CDLL(path) if os.path.exists(path) else None)
-    return _reflbm[0]
+    return _reflbm[1 if sse3 else 0]
 
 
 def ref_lbm_run(geom, Q, wall, inlet, inlets, outlets, dt, dx, steps, sites_per_rank, rank_of_site=None, nranks=1,
-                f0=None, equilibrium=None, kernel="LBGK", outlet="NASH"):
+                f0=None, equilibrium=None, kernel="LBGK", outlet="NASH", sse3=False, timing=None):
     """Runs the reference's whole lb::LBM for ``steps`` time steps on ``nranks`` emulated ranks and returns
     (per-rank f_old after the last swap [N_r * Q each, the Domain's site order], rank 0's iolet densities per step
     [steps, n_inlets + n_outlets]).  ``sites_per_rank``: the local fluid site counts the caller expects (the driver
     checks them against the reference Domain's); ``f0``: per-rank initial distributions, or ``equilibrium`` =
-    (rho, (mx, my, mz)) for lb::EquilibriumInitialCondition."""
-    L = ref_lbm_lib()
+    (rho, (mx, my, mz)) for lb::EquilibriumInitialCondition; ``sse3``: the build with the reference's x86-64
+    default vector path; ``timing``: a list that gets rank 0's wall-clock seconds around the step loop appended."""
+    L = ref_lbm_lib(sse3)
     if L is None:
         raise RuntimeError("oracle/_ref/libhemelb_reflbm.so not built")
     bd = np.ascontiguousarray(geom.block_dims, np.int32)
@@ -155,11 +156,14 @@ def ref_lbm_run(geom, Q, wall, inlet, inlets, outlets, dt, dx, steps, sites_per_
     out = np.zeros(int(off[-1]))
     n_local = np.zeros(nranks, np.int64)
     dens = np.zeros((max(steps, 1), ni + no))
+    secs = np.zeros(1)
     rc = L.hreflbm_run(nranks, p(bd), int(geom.block_size), C.c_int64(geom.n_sites), p(arrs[0]), C.c_int64(arrs[1].size),
                        *[p(a) for a in arrs[1:]], None if rk is None else p(rk), C.c_double(dt), C.c_double(dx),
                        ni, _d(ri), no, _d(ro), C.c_int64(steps), REF_LBM_VARIANTS[(Q, kernel, wall, inlet, outlet)],
                        0 if equilibrium is None else 1, C.c_double(rho), _d(mom), None if fin is None else _d(fin),
-                       p(off), _d(out), p(n_local), _d(dens))
+                       p(off), _d(out), p(n_local), _d(dens), _d(secs))
+    if timing is not None:
+        timing.append(float(secs[0]))
     if rc != 0:
         raise RuntimeError("hreflbm_run failed (%d)" % rc)
     assert [int(x) for x in n_local] == [int(x) for x in sites_per_rank], (n_local, sites_per_rank)

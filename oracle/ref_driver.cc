@@ -15,6 +15,8 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <atomic>
+#include <barrier>
 #include <thread>
 #include <tuple>
 #include <vector>
@@ -626,45 +628,48 @@ void href_sim_stream_and_collide(void* sp, int r, int slot, int64_t first, int64
 void href_sim_post_step(void* sp, int r, int slot, int64_t first, int64_t count) {
   ((SimBase*)sp)->PostStep(r, slot, first, count);
 }
-// One std::thread per emulated rank (the reference is one single-threaded MPI process per rank):
-// phases separated by joins stand in for the MPI waits.  Used for the CPU baseline only.
+// One std::thread per emulated rank for the whole call (the reference is one single-threaded MPI process per
+// rank).  Coupling as loose as the reference's: a rank publishes "my domain-edge sites of step k are done" (the
+// send of lb.hpp:196-214), does its mid-domain sites, then waits only for ITS neighbours' flags before it pulls
+// their slices (the wait of the receive), copies them in and runs PostStep; one barrier per step stands in for
+// SimulationState::Increment, which the emulated ranks share.  Used for the CPU baseline only.
 void href_sim_step_mt(void* sp, int n) {
   SimBase* S = (SimBase*)sp;
   const int R = S->R, Q = S->Q;
-  auto par = [&](auto fn) {
-    std::vector<std::thread> th;
-    for (int r = 0; r < R; ++r) th.emplace_back(fn, r);
-    for (auto& t : th) t.join();
-  };
-  for (int it = 0; it < n; ++it) {
-    S->ApplyCacheMask();
-    par([&](int r) {
-      RankState& X = *S->ranks[r];
-      site_t off = 0;
-      for (int t = 0; t < 6; ++t) off += X.mid[t];
+  std::vector<std::atomic<int64_t>> edgeDone(R);
+  for (auto& e : edgeDone) e.store(0);
+  std::barrier stepEnd(R, [S]() noexcept { S->state.Increment(); });
+  S->ApplyCacheMask();
+  auto body = [&](int r) {
+    RankState& X = *S->ranks[r];
+    site_t edge0 = 0;
+    for (int t = 0; t < 6; ++t) edge0 += X.mid[t];
+    for (int64_t it = 1; it <= n; ++it) {
+      site_t off = edge0;
       for (int t = 0; t < 6; ++t) { S->StreamAndCollide(r, t, off, X.edge[t]); off += X.edge[t]; }
+      edgeDone[r].store(it, std::memory_order_release);
       off = 0;
       for (int t = 0; t < 6; ++t) { S->StreamAndCollide(r, t, off, X.mid[t]); off += X.mid[t]; }
-    });
-    par([&](int r) {  // receive side pulls its slices, then CopyReceived + PostStep
-      RankState& X = *S->ranks[r];
       for (auto& p : X.procs) {
+        while (edgeDone[p.rank].load(std::memory_order_acquire) < it) std::this_thread::yield();
         RankState& O = *S->ranks[p.rank];
         for (auto& po : O.procs)
-          if (po.rank == r)
-            for (site_t i = 0; i < p.count; ++i) X.fd.fOld[p.first + i] = O.fd.fNew[po.first + i];
+          if (po.rank == r) std::copy_n(&O.fd.fNew[po.first], p.count, &X.fd.fOld[p.first]);
       }
       for (site_t i = 0; i < X.totalSharedFs; ++i)
         X.fd.fNew[X.streamingIndices[i]] = X.fd.fOld[X.dom.nSites * Q + 1 + i];
-      site_t off = 0;
-      for (int t = 0; t < 6; ++t) off += X.mid[t];
+      off = edge0;
       for (int t = 0; t < 6; ++t) { S->PostStep(r, t, off, X.edge[t]); off += X.edge[t]; }
       off = 0;
       for (int t = 0; t < 6; ++t) { S->PostStep(r, t, off, X.mid[t]); off += X.mid[t]; }
-    });
-    for (int r = 0; r < R; ++r) S->ranks[r]->fd.fOld.swap(S->ranks[r]->fd.fNew);
-    S->state.Increment();
-  }
+      // every neighbour must have pulled this step's slices before the arrays change roles
+      stepEnd.arrive_and_wait();
+      X.fd.fOld.swap(X.fd.fNew);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int r = 0; r < R; ++r) th.emplace_back(body, r);
+  for (auto& t : th) t.join();
 }
 
 void href_sim_step(void* sp, int n) {

@@ -22,6 +22,7 @@
 #include <mpi.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <memory>
@@ -93,6 +94,7 @@ namespace {
     double* fOut = nullptr;          // all ranks' f_old after the last swap, same offsets
     int64_t* nLocal = nullptr;       // per rank: the reference Domain's local fluid site count
     double* densities = nullptr;     // rank 0: GetBoundaryDensity of inlet 0.., outlet 0.. at each step (steps * (nIn+nOut)) or null
+    double* loopSeconds = nullptr;   // rank 0's wall clock around the step loop (barrier on both sides), or null
   };
 
   std::vector<util::clone_ptr<lb::InOutLet>> iolets_from(int n, const double* rec) {
@@ -186,6 +188,8 @@ namespace {
       for (auto [a, phase] : actors) stepManager.RegisterIteratedActorSteps(*a, phase);
       stepManager.RegisterCommsForAllPhases(netConcern);
 
+      MPI_Barrier(MPI_COMM_WORLD);
+      const auto t0 = std::chrono::steady_clock::now();
       for (int64_t s = 0; s < run.steps; ++s) {
         if (run.densities && rank == 0) {
           double* d = run.densities + s * (run.nIn + run.nOut);
@@ -196,6 +200,9 @@ namespace {
         fd->SwapOldAndNew();
         state.Increment();
       }
+      MPI_Barrier(MPI_COMM_WORLD);
+      if (run.loopSeconds && rank == 0)
+        *run.loopSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       if (run.fOut) {
         const distribn_t* f = const_cast<geometry::FieldData const&>(*fd).GetFOld(0);
         std::copy(f, f + nf, run.fOut + run.fOff[rank]);
@@ -230,7 +237,7 @@ extern "C" int hreflbm_run(int R, const int32_t* blockDims, int blockSize, int64
                            const uint8_t* bnavail, const float* bnormal, const int32_t* siteRank, double dt, double dx,
                            int nIn, const double* inRec, int nOut, const double* outRec, int64_t steps, int variant,
                            int init, double rho, const double* momentum, const double* f0, const int64_t* fOff,
-                           double* fOut, int64_t* nLocal, double* densities) {
+                           double* fOut, int64_t* nLocal, double* densities, double* loopSeconds) {
   Run run;
   run.g.blockSize = blockSize;
   for (int k = 0; k < 3; ++k) run.g.bd[k] = blockDims[k];
@@ -260,6 +267,7 @@ extern "C" int hreflbm_run(int R, const int32_t* blockDims, int blockSize, int64
   run.fOut = fOut;
   run.nLocal = nLocal;
   run.densities = densities;
+  run.loopSeconds = loopSeconds;
   if (init == 0 && (!f0 || !fOff)) return 1;
   if (fOut && !fOff) return 1;
   fakempi_run(R, rank_body, &run);

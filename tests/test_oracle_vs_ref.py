@@ -81,12 +81,17 @@ def test_scalar_vs_sse3_reference_paths_within_budget():
     assert np.abs(ra.get_f()[:n] - rb.get_f()[:n]).max() <= 1e-13
 
 
-def test_threaded_reference_step_equals_serial():
-    geom = geometry("cylinder")
-    rank = G.slab_decomposition(geom, 4)
-    a, ra, T = _pair(geom, 19, "LBGK", "BFL", "NASH", "NASH", rank, 4)
-    b, rb, _ = _pair(geom, 19, "LBGK", "BFL", "NASH", "NASH", rank, 4)
-    ra.step(5)
+@pytest.mark.parametrize("name,R,kind", [("cylinder", 4, "slab"), ("tree", 8, "basic"), ("tree", 5, "ragged")])
+def test_threaded_reference_step_equals_serial(name, R, kind):
+    """href_sim_step_mt (the timed CPU baseline: one thread per emulated rank for the whole call, neighbour flags
+    instead of joins, one barrier per step) against the serial phase loop, bit for bit."""
+    from tests.test_domain_vs_ref import decomposition
+    geom = geometry(name)
+    rank = decomposition(geom, R, kind)
+    a, ra, T = _pair(geom, 19, "LBGK", "BFL", "NASH", "NASH", rank, R)
+    b, rb, _ = _pair(geom, 19, "LBGK", "BFL", "NASH", "NASH", rank, R)
+    ra.step(9)
+    rb.step_mt(4)
     rb.step_mt(5)
-    for r in range(4):
+    for r in range(R):
         assert np.array_equal(ra.get_f(r), rb.get_f(r))

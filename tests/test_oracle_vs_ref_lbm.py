@@ -116,10 +116,8 @@ def test_mrt_with_velocity_iolets_through_the_reference_lbm(name, R, kind, Q, ke
         assert np.array_equal(mine[r], ref[r]), (r, float(np.abs(mine[r] - ref[r]).max()))
 
 
-def test_where_the_reference_indexes_its_local_iolet_list_with_a_global_id():
-    """The tree over BasicDecomposition on 3 ranks: ranks 1 and 2 hold outlets {.., k} that are not 0..k-1.  After
-    one step the oracle differs from the reference on those ranks at iolet-typed sites and nowhere else; rank 0 and
-    every non-iolet site are identical."""
+def _defect_case():
+    """(run in a child process: the reference reads past the end of a vector here, which may also end in SIGSEGV)"""
     geom, rank, doms, mine, ref, _, _ = both("tree", 3, "basic", 19, "BFL", "NASH", steps=1)
     ok = local_lists_are_prefixes(geom, np.asarray(rank), 3)
     assert ok[0] and not all(ok)
@@ -135,6 +133,26 @@ def test_where_the_reference_indexes_its_local_iolet_list_with_a_global_id():
         assert set(np.searchsorted(bounds, bad, side="right")) <= set(IOLET_RANGES)
         differing += bad.size
     assert differing > 0  # (if the reference ever looks the iolet up by its global id this test says so)
+    print("DEFECT-CONFINED-TO-IOLET-SITES", differing)
+
+
+def test_where_the_reference_indexes_its_local_iolet_list_with_a_global_id():
+    """The tree over BasicDecomposition on 3 ranks: ranks 1 and 2 hold outlets that are not 0..k-1.  After one step
+    the oracle differs from the reference on those ranks at iolet-typed sites and nowhere else; rank 0 and every
+    non-iolet site are identical.  The out-of-range read is undefined behaviour in the reference: on larger trees
+    over 8 ranks it ends in SIGSEGV inside StreamerTypeFactory<NullLink, NashZerothOrderPressureLink>::StreamAndCollide
+    about one run in three (seen while timing it), so the case runs in a child process and a
+    child killed by SIGSEGV counts as the defect showing itself too."""
+    import signal
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    run = subprocess.run([sys.executable, "-c", "import tests.test_oracle_vs_ref_lbm as t; t._defect_case()"], cwd=root,
+                         capture_output=True, text=True, timeout=300)
+    if run.returncode == -signal.SIGSEGV:
+        return
+    assert run.returncode == 0, run.stderr[-2000:]
+    assert "DEFECT-CONFINED-TO-IOLET-SITES" in run.stdout
 
 
 @pytest.mark.parametrize("name,R,kind,Q", [("cylinder", 1, None, 19), ("tree", 2, "slab", 19), ("cylinder", 2, "slab", 27),
