@@ -185,3 +185,37 @@ def test_warm_up_ramp_of_the_iolets(inlet):
         assert np.array_equal(want, dens[s]), (s, want, dens[s])
         state.increment()
     assert dens[0, -1] != dens[6, -1]
+
+
+@pytest.mark.parametrize("name", ["four_cube", "large_cylinder", "fedosov1c", "cyl_l100_r5"])
+def test_reference_inputs_through_the_reference_lbm(name):
+    """The reference's own .gmy / .xml fixtures (tests/golden/ref_inputs: voxelised walls with genuine cut distances
+    and normals, the XML's step length, voxel size and pressures) through the reference's whole lb::LBM from an
+    lb::EquilibriumInitialCondition at the initial pressure, one bundle per fixture as in
+    tests/test_reference_inputs.py -- on one rank and on as many ranks as keep every rank's iolet list 0..k-1."""
+    import xml.etree.ElementTree as ET
+    from hemelb_b200 import geometry as G
+    from tests.ref_inputs import HERE, load
+    from tests.test_reference_inputs import POLICIES
+    geom, tau, rho0, inlets, outlets = load(name)
+    Q, kernel, wall, inlet, outlet = POLICIES[name]
+    sim_xml = ET.parse(os.path.join(HERE, name + ".xml")).getroot().find("simulation")
+    dt, dx = float(sim_xml.find("step_length").get("value")), float(sim_xml.find("voxel_size").get("value"))
+    steps = 20 if geom.n_sites < 50000 else 6
+    ran_on = []
+    for R in (1, 2, 3):
+        if R > 1 and geom.n_sites < 1000:
+            continue
+        rank = None if R == 1 else G.basic_decomposition(geom, R)
+        if R > 1 and not all(local_lists_are_prefixes(geom, rank, R)):
+            continue
+        doms = build_domains(geom, Q, rank, R)
+        sim = O.OracleSim(O.OracleDomains(geom, Q, rank, R), kernel, wall, inlet, outlet, tau=tau, inlets=inlets, outlets=outlets)
+        sim.set_equilibrium(rho0)
+        sim.step(steps)
+        ref, _ = O.ref_lbm_run(geom, Q, wall, inlet, inlets, outlets, dt, dx, steps, [d.N for d in doms], rank, R,
+                               equilibrium=(rho0, (0.0, 0.0, 0.0)), kernel=kernel, outlet=outlet)
+        for r, d in enumerate(doms):
+            assert np.array_equal(sim.get_f(r)[:d.N * Q], ref[r]), (name, R, r)
+        ran_on.append(R)
+    assert 1 in ran_on and (geom.n_sites < 1000 or len(ran_on) > 1), ran_on
