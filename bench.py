@@ -191,6 +191,32 @@ def workload_text(sites_per_gpu):
 # ------------------------------------------------------------------------------------------------
 # the reference's own code on the host cores
 # ------------------------------------------------------------------------------------------------
+def usable_cores():
+    """Host threads this process may really use: the affinity mask, capped by a cgroup CPU quota when there is one
+    (the emulated ranks of the reference arm poll for their neighbours as MPI ranks do: more threads than cores
+    would cost the reference its rate)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", ):
+        try:
+            quota, period = open(path).read().split()[:2]
+            if quota != "max":
+                n = min(n, max(1, int(float(quota) / float(period))))
+        except (OSError, ValueError):
+            pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0 and per > 0:
+            n = min(n, max(1, q // per))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def cpu_reference_run(steps, warmup, target_seconds=15.0, sample_sites=REFERENCE_SAMPLE_SITES):
     """The reference's own streamers / kernels (oracle/_ref, SSE3 build = the x86-64 default) on all
     host cores: one emulated rank (thread) per core, BasicDecomposition over Morton blocks, in-memory
@@ -199,7 +225,7 @@ def cpu_reference_run(steps, warmup, target_seconds=15.0, sample_sites=REFERENCE
     the only way to get a tree too large for the host caches in seconds; else a small numpy-built tree)."""
     import oracle as O
     from hemelb_b200 import capi
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     sse3 = O.ref_lib(True) is not None
     have_ref = O.ref_lib(sse3) is not None
     R = cores if have_ref else 1
