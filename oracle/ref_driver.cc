@@ -28,6 +28,16 @@
 #include "lb/kernels/MRT.h"
 #include "lb/kernels/DHumieresD3Q15MRTBasis.h"
 #include "lb/kernels/DHumieresD3Q19MRTBasis.h"
+#ifdef HLB_REF_TRT
+// lb/kernels/TRT.h has bit-rotted in the reference (it is not part of any build there): MakeOpposites() counts the
+// rest direction as a pair and overruns its array at compile time (TRT.h:48, `iBar >= i`), and the bodies still use
+// the `.f` member FVector lost when it became a std::array.  oracle/Makefile passes the file through three
+// substitutions into a temporary include directory that comes first on the path (nothing is copied into the
+// repository): `iBar >= i` -> `iBar > i`, `f_neq.f[` -> `f_neq[`, `f_eq.f[` -> `f_eq[`.  Only TRT::Collide is
+// instantiated below -- its arithmetic is the reference's, token for token; CalculateDensityMomentumFeq /
+// CalculateFeq (which call Lattice functions with signatures that no longer exist) never are.
+#include "lb/kernels/TRT.h"
+#endif
 #include "lb/collisions/Normal.h"
 #include "lb/iolets/BoundaryValues.h"
 #include "lb/iolets/InOutLetCosine.h"
@@ -227,6 +237,42 @@ struct RefSim : SimBase {
   }
 };
 
+#ifdef HLB_REF_TRT
+  // The reference's TRT::Collide inside the reference's streamers.  TRT.h's own CalculateDensityMomentumFeq /
+  // CalculateFeq call Lattice functions with signatures that no longer exist (the file is in no build); they state
+  // what LBGK.h:28-53 states, so this kernel takes those two from the text of LBGK.h's form and hands the collision
+  // itself to the reference's TRT<L>::Collide (see the include above for how TRT.h reaches the compiler).
+  template <lb::lattice_type L> class TrtOfTheReference {
+  public:
+    using LatticeType = L;
+    using VarsType = lb::HydroVars<TrtOfTheReference>;
+    TrtOfTheReference(lb::InitParams& ip) : inner(ip) {}
+    void CalculateDensityMomentumFeq(VarsType& hv, site_t) {
+      L::CalculateDensityMomentumFEq(hv.f, hv.density, hv.momentum, hv.velocity, hv.GetFEq());
+      for (unsigned i = 0; i < L::NUMVECTORS; ++i) hv.SetFNeq(i, hv.f[i] - hv.GetFEq()[i]);
+    }
+    void CalculateFeq(VarsType& hv, site_t) {
+      L::CalculateFeq(hv.density, hv.momentum, hv.GetFEq());
+      for (unsigned i = 0; i < L::NUMVECTORS; ++i) hv.SetFNeq(i, hv.f[i] - hv.GetFEq()[i]);
+    }
+    void Collide(const lb::LbmParameters* p, VarsType& hv) {
+      typename lb::TRT<L>::VarsType t(hv.f);
+      t.tau = hv.tau;
+      t.density = hv.density;
+      t.momentum = hv.momentum;
+      t.velocity = hv.velocity;
+      for (unsigned i = 0; i < L::NUMVECTORS; ++i) {
+        t.SetFEq(i, hv.GetFEq()[i]);
+        t.SetFNeq(i, hv.GetFNeq()[i]);
+      }
+      inner.Collide(p, t);
+      for (unsigned i = 0; i < L::NUMVECTORS; ++i) hv.SetFPostCollision(i, t.GetFPostCollision()[i]);
+    }
+  private:
+    lb::TRT<L> inner;
+  };
+#endif
+
 template <class KernelT, template <class> class WallLink>
 SimBase* MakeIo(int inBC, int outBC, bool allowNash) {
   if (inBC == 0 && outBC == 0 && allowNash)
@@ -275,6 +321,13 @@ SimBase* MakeSim(int Q, int kernel, int wall, int inBC, int outBC) {
     if (Q == 15) return MakeWall<lb::MRT<lb::DHumieresD3Q15MRTBasis>, true>(wall, inBC, outBC);
     if (Q == 19) return MakeWall<lb::MRT<lb::DHumieresD3Q19MRTBasis>, true>(wall, inBC, outBC);
   }
+#ifdef HLB_REF_TRT
+  else if (kernel == 2) {
+    if (Q == 15) return MakeWall<TrtOfTheReference<lb::D3Q15>, false>(wall, inBC, outBC);
+    if (Q == 19) return MakeWall<TrtOfTheReference<lb::D3Q19>, false>(wall, inBC, outBC);
+    if (Q == 27) return MakeWall<TrtOfTheReference<lb::D3Q27>, false>(wall, inBC, outBC);
+  }
+#endif
   return nullptr;
 }
 
@@ -305,6 +358,45 @@ void CollideOne(double dt, double dx, double rho, double eta, const double* f, d
     }
   }
 }
+
+#ifdef HLB_REF_TRT
+// f_eq / f_neq as the (pinned) LBGK kernel computes them -- TRT.h:62-92 states the same two calls -- handed to
+// the reference's TRT::Collide through HydroVars' public setters.
+template <class L>
+void TrtCollideOne(double dt, double dx, double rho, double eta, const double* f, double* fpost, double* feq,
+                   double* fneq, double* rmu) {
+  lb::LbmParameters p(dt, dx, rho, eta);
+  lb::InitParams ip;
+  ip.lbmParams = &p;
+  lb::LBGK<L> lbgk(ip);
+  typename lb::LBGK<L>::VarsType base(f);
+  base.tau = p.GetTau();
+  lbgk.CalculateDensityMomentumFeq(base, 0);
+  lb::TRT<L> trt(ip);
+  typename lb::TRT<L>::VarsType hv(f);
+  hv.tau = p.GetTau();
+  hv.density = base.density;
+  hv.momentum = base.momentum;
+  hv.velocity = base.velocity;
+  for (unsigned i = 0; i < L::NUMVECTORS; ++i) {
+    hv.SetFEq(i, base.GetFEq()[i]);
+    hv.SetFNeq(i, base.GetFNeq()[i]);
+  }
+  trt.Collide(&p, hv);
+  for (unsigned i = 0; i < L::NUMVECTORS; ++i) {
+    fpost[i] = hv.GetFPostCollision()[i];
+    if (feq) feq[i] = hv.GetFEq()[i];
+    if (fneq) fneq[i] = hv.GetFNeq()[i];
+  }
+  if (rmu) {
+    rmu[0] = hv.density;
+    for (int k2 = 0; k2 < 3; ++k2) {
+      rmu[1 + k2] = hv.momentum[k2];
+      rmu[4 + k2] = hv.velocity[k2];
+    }
+  }
+}
+#endif
 
 template <class L>
 void StressOne(double rho, double tau, const double* fneq, const double* normal, double* out) {
@@ -380,6 +472,11 @@ int href_collide(int Q, int kernel, double dt, double dx, double rho, double eta
   else if (kernel == 0 && Q == 27) CollideOne<lb::D3Q27, lb::LBGK<lb::D3Q27>>(dt, dx, rho, eta, f, fpost, feq, fneq, rmu, nullptr);
   else if (kernel == 1 && Q == 15) CollideOne<lb::D3Q15, lb::MRT<lb::DHumieresD3Q15MRTBasis>>(dt, dx, rho, eta, f, fpost, feq, fneq, rmu, mrtRates);
   else if (kernel == 1 && Q == 19) CollideOne<lb::D3Q19, lb::MRT<lb::DHumieresD3Q19MRTBasis>>(dt, dx, rho, eta, f, fpost, feq, fneq, rmu, mrtRates);
+#ifdef HLB_REF_TRT
+  else if (kernel == 2 && Q == 15) TrtCollideOne<lb::D3Q15>(dt, dx, rho, eta, f, fpost, feq, fneq, rmu);
+  else if (kernel == 2 && Q == 19) TrtCollideOne<lb::D3Q19>(dt, dx, rho, eta, f, fpost, feq, fneq, rmu);
+  else if (kernel == 2 && Q == 27) TrtCollideOne<lb::D3Q27>(dt, dx, rho, eta, f, fpost, feq, fneq, rmu);
+#endif
   else return 1;
   return 0;
 }

@@ -1,6 +1,8 @@
 """The oracle restatement against the UNMODIFIED reference headers (oracle/_ref): bit-identical
 distributions and property caches on every policy bundle the reference can build.  Skipped where
 oracle/_ref was not built (no /root/reference and no shipped .so)."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -95,3 +97,90 @@ def test_threaded_reference_step_equals_serial(name, R, kind):
     rb.step_mt(5)
     for r in range(R):
         assert np.array_equal(ra.get_f(r), rb.get_f(r))
+
+
+@pytest.mark.parametrize("Q", (15, 19, 27))
+def test_trt_collision_against_the_reference_file(Q):
+    """TRT::Collide as lb/kernels/TRT.h:94-121 states it, compiled from the reference file itself.  The file has
+    bit-rotted there (it is in no build): it reaches the compiler through three substitutions made at build time --
+    `iBar >= i` -> `iBar > i` (MakeOpposites counted the rest direction as a pair and overran its array), and
+    `f_neq.f[` / `f_eq.f[` -> `f_neq[` / `f_eq[` (FVector became a std::array) -- see oracle/Makefile and
+    oracle/ref_driver.cc.  Collide's arithmetic is untouched; f_eq and f_neq come from the pinned LBGK kernel, as
+    TRT.h:62-92 computes them.  Bit-identical to the oracle's TRT, from which the CUDA kernel is checked."""
+    L = O.ref_lib()
+    if L is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(Q)
+    _, w, _ = O.lattice(Q)
+    probe = np.ascontiguousarray(w)
+    try:
+        O.ref_collide(L, Q, "TRT", 100.0, 1.0, 1000.0, 0.004, probe)
+    except ValueError:
+        pytest.skip("oracle/_ref was built without the TRT path")
+    worst = 0.0
+    for tau0 in (0.51, 0.62, 0.8, 1.0, 1.4, 2.5):
+        dt = (tau0 - 0.5) / 3.0 * 1000.0 / 0.004
+        tau = float(L.href_tau(C.c_double(dt), C.c_double(1.0), C.c_double(1000.0), C.c_double(0.004)))
+        for _ in range(40):
+            f = w * (1.0 + 0.2 * rng.uniform(-1, 1, Q))
+            a = O.collide(Q, "TRT", tau, f)
+            b = O.ref_collide(L, Q, "TRT", dt, 1.0, 1000.0, 0.004, f)
+            assert np.array_equal(a["fpost"], b["fpost"]), (tau0, float(np.abs(a["fpost"] - b["fpost"]).max()))
+            assert np.array_equal(a["feq"], b["feq"]) and np.array_equal(a["fneq"], b["fneq"])
+            worst = max(worst, float(np.abs(a["fpost"] - f).max()))
+    assert worst > 1e-3  # (the collision did something)
+    # and it is not LBGK in disguise: at tau != 1 the two differ
+    f = w * (1.0 + 0.2 * rng.uniform(-1, 1, Q))
+    assert not np.array_equal(O.collide(Q, "TRT", 0.62, f)["fpost"], O.collide(Q, "LBGK", 0.62, f)["fpost"])
+
+
+TRT_COMBOS = [(Q, w, i, o) for Q in (15, 19, 27) for w in ("SBB", "BFL", "GZS")
+              for (i, o) in (("NASH", "NASH"), ("LADD", "NASH"), ("LADD", "LADD"))]
+
+
+def _trt_built():
+    L = O.ref_lib()
+    if L is None:
+        return False
+    try:
+        O.ref_collide(L, 19, "TRT", 100.0, 1.0, 1000.0, 0.004, np.ascontiguousarray(O.lattice(19)[1]))
+    except ValueError:
+        return False
+    return True
+
+
+@pytest.mark.parametrize("Q,wall,inlet,outlet", TRT_COMBOS)
+def test_trt_through_the_reference_streamers_four_cube(Q, wall, inlet, outlet):
+    """The reference's TRT::Collide (see test_trt_collision_against_the_reference_file for how TRT.h is compiled)
+    inside the reference's own streamers -- every wall and iolet rule, all three lattices, all eight caches --
+    against the oracle's TRT: configs[4]'s kernel on the whole path, bit for bit."""
+    if not _trt_built():
+        pytest.skip("oracle/_ref was built without the TRT path")
+    sim, ref, T = _pair(geometry("four_cube"), Q, "TRT", wall, inlet, outlet, None, 1)
+    sim.set_cache_mask(255)
+    ref.set_cache_mask(255)
+    sim.step(5)
+    ref.step(5)
+    n = T[0]["N"] * Q
+    assert np.array_equal(sim.get_f()[:n], ref.get_f()[:n])
+    for name in O.CACHE_BITS:
+        assert np.array_equal(sim.get_cache(name), ref.get_cache(name), equal_nan=True), name
+
+
+@pytest.mark.parametrize("name,R,Q,wall,inlet,outlet", [
+    ("sac", 1, 27, "BFL", "NASH", "NASH"),          # configs[4]: D3Q27 TRT + BFL on the rough-walled sac
+    ("sac", 3, 27, "BFL", "NASH", "NASH"),
+    ("cylinder", 3, 19, "GZS", "LADD", "NASH"),
+    ("tree", 3, 19, "BFL", "NASH", "NASH"),
+    ("cylinder", 3, 15, "SBB", "LADD", "LADD")])
+def test_trt_through_the_reference_streamers_multi_rank(name, R, Q, wall, inlet, outlet):
+    if not _trt_built():
+        pytest.skip("oracle/_ref was built without the TRT path")
+    geom = geometry(name)
+    rank = None if R == 1 else G.slab_decomposition(geom, R)
+    sim, ref, T = _pair(geom, Q, "TRT", wall, inlet, outlet, rank, R)
+    sim.step(8)
+    ref.step(8)
+    for r in range(R):
+        n = T[r]["N"] * Q
+        assert np.array_equal(sim.get_f(r)[:n], ref.get_f(r)[:n]), r
