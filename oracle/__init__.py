@@ -64,10 +64,13 @@ def oracle_lib():
 _refs = {}
 
 
-def ref_lib(sse3: bool = False):
-    """The compiled reference, or None when oracle/_ref was not built/shipped."""
+def ref_lib(sse3=False):
+    """The compiled reference, or None when oracle/_ref was not built/shipped.  ``sse3`` True: the build with the
+    reference's x86-64 vector path; "mrtgzs": the build whose GuoZhengShi.h sets the wall node's m_neq before the
+    collision (oracle/Makefile), for the one test that needs MRT + GuoZhengShi to be defined behaviour."""
     if sse3 not in _refs:
-        path = os.path.join(HERE, "_ref", "libhemelb_ref_sse3.so" if sse3 else "libhemelb_ref.so")
+        name = {False: "libhemelb_ref.so", True: "libhemelb_ref_sse3.so", "mrtgzs": "libhemelb_ref_mrtgzs.so"}[sse3]
+        path = os.path.join(HERE, "_ref", name)
         if not os.path.exists(path):
             _refs[sse3] = None
         else:
