@@ -289,6 +289,10 @@ SimBase* MakeIo(int inBC, int outBC, bool allowNash) {
 // MRT + Nash does not compile in the reference (MRT.h:73-86): only instantiate Ladd/Ladd for MRT.
 template <class KernelT, template <class> class WallLink>
 SimBase* MakeIoMrt(int inBC, int outBC) {
+#ifdef HLB_REF_MRT_NASH
+  // (libhemelb_ref_mrtgzs.so only: MRT.h reaches the compiler through the substitutions of oracle/Makefile)
+  return MakeIo<KernelT, WallLink>(inBC, outBC, true);
+#endif
   if (inBC == 1 && outBC == 1)
     return new RefSim<KernelT, WallLink, lb::LaddIoletLink, lb::LaddIoletLink>();
   return nullptr;

@@ -76,3 +76,29 @@ def test_gpu_ranks_with_a_host_staged_halo_equal_the_reference_lbm():
     ref, _ = O.ref_lbm_run(geom, Q, "BFL", "NASH", inlets, outlets, dt, DX, steps, [d.N for d in doms], rank, R, f0=f0)
     for r, d in enumerate(doms):
         assert np.array_equal(gpus[r].get_f()[:d.N * Q], ref[r]), r
+
+
+def _larger_golden_keys():
+    from tests.test_golden import KEYS
+    return [k for k in KEYS if "_R1_" in k and not k.startswith("four_cube_")]
+
+
+@pytest.mark.parametrize("key", _larger_golden_keys())
+def test_gpu_reproduces_the_larger_golden_vectors(key):
+    """configs[3]'s bundle (MRT + GuoZhengShi + Ladd inlet + Nash outlets, tree) and configs[4]'s (D3Q27 TRT + BFL,
+    sac) against vectors written by the reference's own streamers -- around its TRT::Collide, and with its one
+    missing m_neq projection inserted (tests/golden/make_golden_trt.py)."""
+    from tests.cases import anisotropic_f
+    from tests.test_golden import GOLD, STEPS, _parse
+    gname, R, Q, k, w, i, o = _parse(key)
+    geom = geometry(gname)
+    inlets, outlets = iolets_for(geom, i, o)
+    dom = build_domains(geom, Q)[0]
+    gpu = GpuLBM(dom, k, w, i, o, tau=float(GOLD[key + "_tau"][0]), inlets=inlets, outlets=outlets)
+    gpu.set_f(anisotropic_f(dom.N, Q, 0))
+    gpu.set_cache_mask(3)
+    gpu.step(STEPS)
+    f = gpu.get_f()[:dom.N * Q]
+    assert np.abs(f - GOLD[key + "_f0"]).max() <= 1e-13
+    assert np.array_equal(f, GOLD[key + "_f0"])
+    assert np.array_equal(gpu.get_cache("density"), GOLD[key + "_rho0"])
