@@ -11,10 +11,15 @@
 //     LatticeTests.cc, BoundaryTests.cc:31-51, StreamerTests.cc formulas), and
 //   * oracle/_ref/libhemelb_ref.so = the UNMODIFIED reference lattice / kernel / collision /
 //     streamer headers compiled where they lie under /root/reference (oracle/Makefile), with the
-//     outputs committed as fixtures under tests/golden/.
-// TRT, MRT+Nash and MRT+GZS have no buildable / well-defined reference (TRT.h:42-90 and
-// MRT.h:73-86 do not compile; GuoZhengShi.h:269-282 collides an MRT HydroVars whose m_neq was
-// never set).  For those three the oracle states the evident intent and parity is "unpinned".
+//     outputs committed as fixtures under tests/golden/,
+//   * oracle/_ref/libhemelb_refdom.so = the reference's own geometry::Domain for the index tables, and
+//   * oracle/_ref/libhemelb_reflbm.so = the reference's own lb::LBM (CPU streamers, FieldData,
+//     NeighbouringDataManager, BoundaryValues, StepManager) for the whole time step on 1-3 ranks.
+// TRT, MRT+Nash and MRT+GZS have no buildable / well-defined reference as it stands (TRT.h:42-90 and
+// MRT.h:73-86 have bit-rotted and do not compile; GuoZhengShi.h:279 collides an MRT HydroVars whose
+// m_neq was never set).  For those three the oracle states the evident intent; parity is "unpinned"
+// against the unmodified text, and bit-exact against the reference's text with, respectively, three
+// mechanical substitutions, four, and one inserted line (oracle/Makefile).
 //
 // Floating point: follows the reference's *scalar* (non-SSE3) summation order; compile with
 // -ffp-contract=off so no FMA contraction happens.
