@@ -5,7 +5,10 @@
   lbm   the reference's whole lb::LBM over its own net::Net and StepManager (oracle/ref_lbm_driver.cc)
 
 on a cylinder (one inlet, one outlet: the reference's local-iolet lookup is safe on any decomposition) over
-BasicDecomposition, scalar and SSE3 builds, interleaved repetitions.  Output: profiles/r02_reference_arm_ab.txt."""
+BasicDecomposition, scalar and SSE3 builds, interleaved repetitions.  Output: profiles/r02_reference_arm_ab.txt.
+`--json [--sse3-only] [--reps N]`: one JSON object on the last line (bench.py --impl reference runs it that way, in a
+child process, and puts the result into its line as `cross_check`)."""
+import json
 import os
 import sys
 import time
@@ -23,7 +26,17 @@ from hemelb_b200.domain import build_domains  # noqa: E402
 
 def main():
     Q, steps, reps = 19, 20, 3
-    radius, length = (float(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (40.0, 200)
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("radius", nargs="?", type=float, default=40.0)
+    ap.add_argument("length", nargs="?", type=int, default=200)
+    ap.add_argument("--json", action="store_true")
+    ap.add_argument("--sse3-only", action="store_true")
+    ap.add_argument("--reps", type=int, default=reps)
+    args = ap.parse_args()
+    as_json, sse3_only, reps, radius, length = args.json, args.sse3_only, args.reps, args.radius, args.length
+    builds = (True,) if sse3_only else (False, True)
+    result = {"workload": "cylinder r=%g l=%d, D3Q19 LBGK+BFL+Nash, BasicDecomposition" % (radius, length), "steps": steps}
     geom = G.cylinder(radius, length)
     R = usable_cores()
     rank_of = G.basic_decomposition(geom, R) if R > 1 else None
@@ -39,7 +52,7 @@ def main():
         f[:t["N"] * Q] = np.tile(w, t["N"])
         f0.append(f)
     sims = {}
-    for sse3 in (False, True):
+    for sse3 in builds:
         sim = O.RefSim(tables, Q, "LBGK", "BFL", "NASH", "NASH", dt=dt, dx=1.0, rho=1000.0, eta=0.004, inlets=inlets,
                        outlets=outlets, sse3=sse3)
         for r, f in enumerate(f0):
@@ -48,16 +61,22 @@ def main():
         sim.step_mt(2)
         sims[sse3] = sim
     print("cylinder r=%g l=%d: %d sites, %d emulated ranks = threads, %d steps per measurement" % (radius, length, n, R, steps))
+    result.update(sites=int(n), threads=int(R))
     for rep in range(reps):
-        for sse3 in (False, True):
+        for sse3 in builds:
             t0 = time.perf_counter()
             sims[sse3].step_mt(steps)
             arm = n * steps / (time.perf_counter() - t0) / 1e6
             tm = []
             O.ref_lbm_run(geom, Q, "BFL", "NASH", inlets, outlets, dt, 1.0, steps, [d.N for d in doms], rank_of, R, f0=f0,
                           sse3=sse3, timing=tm)
+            tag = "sse3" if sse3 else "scalar"
+            result.setdefault("arm_mlups_" + tag, []).append(round(arm, 2))
+            result.setdefault("reference_lbm_mlups_" + tag, []).append(round(n * steps / tm[0] / 1e6, 2))
             print("rep %d  %-6s  arm %6.1f MLUPS   lbm %6.1f MLUPS   arm / lbm %.2f" % (
                 rep, "SSE3" if sse3 else "scalar", arm, n * steps / tm[0] / 1e6, arm / (n * steps / tm[0] / 1e6)), flush=True)
+    if as_json:
+        print(json.dumps(result), flush=True)
 
 
 if __name__ == "__main__":
