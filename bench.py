@@ -217,6 +217,24 @@ def usable_cores():
     return max(1, n)
 
 
+def reference_cross_check(timeout=300):
+    """Is the timed arm a fair stand-in for the reference?  scripts/reference_arm_ab.py, in a child process (a crash
+    there cannot cost this line): the arm's rank driver against the reference's whole lb::LBM over its own net::Net
+    and StepManager (oracle/_ref/libhemelb_reflbm_sse3.so) on the same 1e6-site cylinder, decomposition and cores,
+    two interleaved repetitions each.  MLUPS lists, or why there are none."""
+    import oracle as O
+    if O.ref_lbm_lib(True) is None:
+        return {"unavailable": "oracle/_ref/libhemelb_reflbm_sse3.so was not built / shipped"}
+    try:
+        run = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "reference_arm_ab.py"), "40", "200", "--json",
+                              "--sse3-only", "--reps", "2"], capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+        if run.returncode != 0:
+            return {"unavailable": "child ended with %d: %s" % (run.returncode, run.stderr.strip()[-200:])}
+        return json.loads(run.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001 -- whatever went wrong, the bench line itself stands
+        return {"unavailable": repr(e)[:200]}
+
+
 def cpu_reference_run(steps, warmup, target_seconds=15.0, sample_sites=REFERENCE_SAMPLE_SITES):
     """The reference's own streamers / kernels (oracle/_ref, SSE3 build = the x86-64 default) on all
     host cores: one emulated rank (thread) per core, BasicDecomposition over Morton blocks, in-memory
@@ -309,6 +327,8 @@ def main():
     ap.add_argument("--length", type=int, default=1500, help="secondary record: cylinder length per GPU")
     ap.add_argument("--no-secondary", action="store_true", help="skip the configs[1] cylinder record")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cross-check", action="store_true",
+                    help="--impl reference: skip the comparison of the timed arm with the reference's whole lb::LBM")
     ap.add_argument("--no-reorder", action="store_true")
     args = ap.parse_args()
     # stdout carries the JSON line and nothing else: whatever a library prints to fd 1 (NCCL's version
@@ -339,6 +359,8 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config,
                 "cpu_baseline": base,
                 "e2e": {"value": base["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        if world == 1 and not args.no_cross_check:
+            line["cross_check"] = reference_cross_check()
         print(json.dumps(line), file=json_out, flush=True)
         return 0
 

@@ -24,6 +24,11 @@ def test_reference_arm_prints_one_contract_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the arm's rank driver held against the reference's whole lb::LBM on the same cores (a child process): figures
+    # when oracle/_ref/libhemelb_reflbm_sse3.so is there, the reason when it is not -- never a lost line
+    cc = d["cross_check"]
+    assert "unavailable" in cc or (len(cc["arm_mlups_sse3"]) == len(cc["reference_lbm_mlups_sse3"]) == 2 and
+                                   min(cc["arm_mlups_sse3"] + cc["reference_lbm_mlups_sse3"]) > 0)
 
 
 def test_reference_arm_other_ranks_stay_silent():
