@@ -83,6 +83,7 @@ struct SimBase {
   std::vector<std::unique_ptr<lb::InOutLet>> inletStore, outletStore;
   lb::BoundaryValues inletValues, outletValues;
   unsigned cacheMask = 0;
+  bool memoryIsRankLocal = false;  // href_sim_step_mt: every rank's arrays re-made by its own (bound) thread
   // coordinate -> (rank, local id, input id) lookup shared by all ranks (GZS)
   std::function<bool(const util::Vector3D<site_t>&, int&, site_t&, site_t&)> lookup;
 
@@ -743,6 +744,7 @@ void href_sim_step_mt(void* sp, int n) {
   std::vector<std::atomic<int64_t>> edgeDone(R);
   for (auto& e : edgeDone) e.store(0);
   std::barrier stepEnd(R, [S]() noexcept { S->state.Increment(); });
+  std::barrier stepEnd0(R);
   S->ApplyCacheMask();
   // One core per emulated rank, as an MPI launcher binds its ranks: fresh threads all start on the caller's core,
   // and while they poll for their neighbours the scheduler took over a second to spread them (measured: the first
@@ -763,8 +765,27 @@ void href_sim_step_mt(void* sp, int n) {
       pthread_setaffinity_np(pthread_self(), sizeof one, &one);
     }
     RankState& X = *S->ranks[r];
+    if (!S->memoryIsRankLocal) {
+      // An MPI rank allocates and first touches its own arrays; here the caller's thread filled them.  On a host
+      // with more than one memory node that would leave most ranks reading remote memory: re-make each array from
+      // the rank's own thread once (values unchanged).
+      auto own = [](auto& v) {
+        std::remove_reference_t<decltype(v)> c(v.begin(), v.end());
+        v.swap(c);
+      };
+      own(X.fd.fOld);
+      own(X.fd.fNew);
+      own(X.dom.neighbourIndices);
+      own(X.dom.distanceToWall);
+      own(X.dom.wallNormalAtSite);
+      own(X.dom.siteData);
+      own(X.dom.globalSiteCoords);
+      own(X.streamingIndices);
+    }
     site_t edge0 = 0;
     for (int t = 0; t < 6; ++t) edge0 += X.mid[t];
+    // (no rank may read a neighbour's arrays while that neighbour is still re-making them)
+    if (!S->memoryIsRankLocal) stepEnd0.arrive_and_wait();
     for (int64_t it = 1; it <= n; ++it) {
       site_t off = edge0;
       for (int t = 0; t < 6; ++t) { S->StreamAndCollide(r, t, off, X.edge[t]); off += X.edge[t]; }
@@ -791,6 +812,7 @@ void href_sim_step_mt(void* sp, int n) {
   std::vector<std::thread> th;
   for (int r = 0; r < R; ++r) th.emplace_back(body, r);
   for (auto& t : th) t.join();
+  S->memoryIsRankLocal = true;
 }
 
 void href_sim_step(void* sp, int n) {
