@@ -32,7 +32,7 @@
 #include "lb/kernels/DHumieresD3Q15MRTBasis.h"
 #include "lb/kernels/DHumieresD3Q19MRTBasis.h"
 #ifdef HLB_REF_TRT
-// lb/kernels/TRT.h has bit-rotted in the reference (it is not part of any build there): MakeOpposites() counts the
+// lb/kernels/TRT.h has bit-rotted in the reference (lb/Kernels.h includes it, but nothing in a default build instantiates TRT): MakeOpposites() counts the
 // rest direction as a pair and overruns its array at compile time (TRT.h:48, `iBar >= i`), and the bodies still use
 // the `.f` member FVector lost when it became a std::array.  oracle/Makefile passes the file through three
 // substitutions into a temporary include directory that comes first on the path (nothing is copied into the
@@ -243,7 +243,7 @@ struct RefSim : SimBase {
 
 #ifdef HLB_REF_TRT
   // The reference's TRT::Collide inside the reference's streamers.  TRT.h's own CalculateDensityMomentumFeq /
-  // CalculateFeq call Lattice functions with signatures that no longer exist (the file is in no build); they state
+  // CalculateFeq call Lattice functions with signatures that no longer exist (no build of the reference instantiates TRT); they state
   // what LBGK.h:28-53 states, so this kernel takes those two from the text of LBGK.h's form and hands the collision
   // itself to the reference's TRT<L>::Collide (see the include above for how TRT.h reaches the compiler).
   template <lb::lattice_type L> class TrtOfTheReference {

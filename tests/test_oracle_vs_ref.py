@@ -102,7 +102,7 @@ def test_threaded_reference_step_equals_serial(name, R, kind):
 @pytest.mark.parametrize("Q", (15, 19, 27))
 def test_trt_collision_against_the_reference_file(Q):
     """TRT::Collide as lb/kernels/TRT.h:94-121 states it, compiled from the reference file itself.  The file has
-    bit-rotted there (it is in no build): it reaches the compiler through three substitutions made at build time --
+    bit-rotted there (lb/Kernels.h includes it, no build instantiates it): it reaches the compiler through three substitutions made at build time --
     `iBar >= i` -> `iBar > i` (MakeOpposites counted the rest direction as a pair and overran its array), and
     `f_neq.f[` / `f_eq.f[` -> `f_neq[` / `f_eq[` (FVector became a std::array) -- see oracle/Makefile and
     oracle/ref_driver.cc.  Collide's arithmetic is untouched; f_eq and f_neq come from the pinned LBGK kernel, as
